@@ -1,0 +1,284 @@
+"""Runs the UNMODIFIED reference (`/root/reference`) and records traces -- TEST INFRASTRUCTURE ONLY.
+
+Works only in the build container (the reference is not present on the GPU box).  The reference is
+imported from where it lies, with `oracle/refshim` standing in for gymnasium, the synthetic TPC-H
+bank written in the reference's own on-disk layout, and instance-level
+instrumentation (no source edits) that records
+
+* the job sequence the reference sampled (arrival time, template, per-stage `num_tasks` and
+  `rough_task_duration` -- used to pin `bank.py`'s restatement of tpch.py:135-187),
+* the duration tape: every value `TPCHDataSampler.task_duration` returned, in call order,
+* every popped event `(t, type, job, stage, task, executor, t_accepted)` (spark_sched_sim.py:326-329),
+* every action and everything `step()` returned, including the whole observation dict,
+* final per-job completion times.
+
+`tests/golden/gen_golden.py` serialises these as fixtures; the C oracle (oracle/sim_oracle.c) is
+pinned against them, and the CUDA path is compared with the oracle.
+"""
+from __future__ import annotations
+
+import hashlib
+import importlib
+import os
+import os.path as osp
+import sys
+import types
+
+import numpy as np
+
+HERE = osp.dirname(osp.abspath(__file__))
+REPO = osp.dirname(HERE)
+REFERENCE = os.environ.get("SSB_REFERENCE", "/root/reference")
+
+EV_JOB_ARRIVAL, EV_TASK_FINISHED, EV_EXECUTOR_READY = 0, 1, 2  # event.py:11-14 order
+
+
+def reference_available() -> bool:
+    return osp.isdir(osp.join(REFERENCE, "spark_sched_sim"))
+
+
+def _import_product_bank():
+    sys.path.insert(0, REPO) if REPO not in sys.path else None
+    import spark_sched_sim_b200.bank as bank  # data preparation only (no simulation code)
+
+    return bank
+
+
+_SETUP_DONE = {}
+
+
+def setup(bank_seed: int = 0) -> str:
+    """Puts the shim + reference on sys.path, writes the synthetic dataset, chdirs next to it."""
+    if bank_seed in _SETUP_DONE:
+        os.chdir(_SETUP_DONE[bank_seed])
+        return _SETUP_DONE[bank_seed]
+    if not reference_available():
+        raise RuntimeError(f"reference not found at {REFERENCE}")
+    for p in (REFERENCE, osp.join(HERE, "refshim")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    # `schedulers/__init__.py` eagerly imports Decima (needs PyG); stub the package so that
+    # `schedulers.heuristics` can be imported on its own.
+    if "schedulers" not in sys.modules:
+        pkg = types.ModuleType("schedulers")
+        pkg.__path__ = [osp.join(REFERENCE, "schedulers")]
+        sys.modules["schedulers"] = pkg
+    bank = _import_product_bank()
+    root = f"/tmp/ssb_refdata_seed{bank_seed}"
+    if not osp.isdir(osp.join(root, "data", "tpch", "100g")):
+        bank.write_tpch_dir(root, bank.make_synthetic_tpch(bank_seed))
+    os.chdir(root)
+    _SETUP_DONE[bank_seed] = root
+    return root
+
+
+def make_policy(name: str, num_executors: int, seed: int = 42):
+    rr = importlib.import_module("schedulers.heuristics.round_robin")
+    rnd = importlib.import_module("schedulers.heuristics.random_scheduler")
+    if name == "fair":
+        return rr.RoundRobinScheduler(num_executors, dynamic_partition=True)
+    if name == "fifo":
+        return rr.RoundRobinScheduler(num_executors, dynamic_partition=False)
+    if name == "random":
+        return rnd.RandomScheduler(seed=seed)
+    raise ValueError(name)
+
+
+def obs_digest(nodes, edge_links, dag_ptr, supplies, ncommit, src) -> int:
+    h = hashlib.sha256()
+    h.update(np.ascontiguousarray(nodes, dtype=np.float32).tobytes())
+    h.update(np.ascontiguousarray(edge_links, dtype=np.int32).tobytes())
+    h.update(np.asarray(dag_ptr, dtype=np.int32).tobytes())
+    h.update(np.asarray(supplies, dtype=np.int32).tobytes())
+    h.update(np.asarray([ncommit, src], dtype=np.int32).tobytes())
+    return int.from_bytes(h.digest()[:8], "little")
+
+
+def events_digest(ev: dict, lo: int, hi: int) -> int:
+    h = hashlib.sha256()
+    for k in ("ev_t", "ev_type", "ev_job", "ev_stage", "ev_task", "ev_exec", "ev_tacc"):
+        h.update(np.ascontiguousarray(ev[k][lo:hi]).tobytes())
+    return int.from_bytes(h.digest()[:8], "little")
+
+
+def run_episode(
+    env_cfg: dict,
+    policy: str = "fair",
+    seed: int = 1234,
+    rng: str = "pcg64",
+    policy_seed: int = 42,
+    time_limit: float | None = None,
+    max_steps: int | None = None,
+    bank_seed: int = 0,
+) -> dict:
+    """One reference episode -> trace dict of numpy arrays (see module docstring)."""
+    setup(bank_seed)
+    import gymnasium
+    from philox_ref import PhiloxNpRandom
+
+    gymnasium.NP_RANDOM_FACTORY = PhiloxNpRandom if rng == "philox" else None
+    env_cfg = dict(env_cfg)
+    env_cfg.setdefault("data_sampler_cls", "TPCHDataSampler")
+    env = gymnasium.make("spark_sched_sim:SparkSchedSimEnv-v0", env_cfg=env_cfg)
+    sched = make_policy(policy, env_cfg["num_executors"], policy_seed)
+    from spark_sched_sim.components.event import Event
+
+    type_map = {
+        Event.Type.JOB_ARRIVAL: EV_JOB_ARRIVAL,
+        Event.Type.TASK_FINISHED: EV_TASK_FINISHED,
+        Event.Type.EXECUTOR_READY: EV_EXECUTOR_READY,
+    }
+
+    tape, tape_meta, events = [], [], []
+    orig_td = env.data_sampler.task_duration
+
+    def task_duration(job, stage, task, executor):
+        d = orig_td(job, stage, task, executor)
+        tape.append(float(d))
+        tape_meta.append((job.id_, stage.id_, task.id_, executor.id_))
+        return d
+
+    env.data_sampler.task_duration = task_duration
+    orig_he = env._handle_event
+
+    def handle_event(event):
+        d = event.data
+        if event.type == Event.Type.JOB_ARRIVAL:
+            row = (env.wall_time, EV_JOB_ARRIVAL, d["job"].id_, -1, -1, -1, np.inf)
+        elif event.type == Event.Type.TASK_FINISHED:
+            t = d["task"]
+            row = (env.wall_time, EV_TASK_FINISHED, d["stage"].job_id, d["stage"].id_,
+                   t.id_, t.executor_id, float(t.t_accepted))
+        else:
+            row = (env.wall_time, EV_EXECUTOR_READY, d["stage"].job_id, d["stage"].id_,
+                   -1, d["executor"].id_, np.inf)
+        events.append(row)
+        return orig_he(event)
+
+    env._handle_event = handle_event
+
+    options = {"time_limit": time_limit} if time_limit is not None else None
+    obs, info = env.reset(seed=seed, options=options)
+
+    jobs = list(env.jobs.values())
+    sizes = ["2g", "5g", "10g", "20g", "50g", "80g", "100g"]
+    job_template = [sizes.index(str(j.query_size)) * 22 + int(j.query_num) - 1 for j in jobs]
+    st_num_tasks = [s.num_tasks for j in jobs for s in j.stages]
+    st_rough = [float(s.most_recent_duration) for j in jobs for s in j.stages]
+
+    rec = {k: [] for k in (
+        "actions", "reward", "wall", "term", "ncommit", "src", "N", "M", "Ja", "ev_count",
+        "nodes", "edges", "dag_ptr", "supplies", "obs_digest")}
+
+    def record_obs(o):
+        g = o["dag_batch"]
+        nodes = np.asarray(g.nodes, np.float32).reshape(-1, 3)
+        el = np.asarray(g.edge_links, np.int64).reshape(-1, 2)
+        rec["N"].append(nodes.shape[0])
+        rec["M"].append(el.shape[0])
+        rec["Ja"].append(len(o["exec_supplies"]))
+        rec["ncommit"].append(int(o["num_committable_execs"]))
+        rec["src"].append(int(o["source_job_idx"]))
+        rec["nodes"].append(nodes.copy())
+        rec["edges"].append(el.astype(np.int32))
+        rec["dag_ptr"].append(np.asarray(o["dag_ptr"], np.int32))
+        rec["supplies"].append(np.asarray(o["exec_supplies"], np.int32))
+        rec["obs_digest"].append(
+            obs_digest(nodes, el, o["dag_ptr"], o["exec_supplies"],
+                       o["num_committable_execs"], o["source_job_idx"]))
+
+    record_obs(obs)  # observation 0 = reset
+    rec["ev_count"].append(len(events))
+    terminated = truncated = False
+    steps = 0
+    while not (terminated or truncated):
+        action, _ = sched.schedule(obs)
+        a = (int(action["stage_idx"]), int(action["num_exec"]))
+        obs, reward, terminated, truncated, info = env.step(
+            {"stage_idx": a[0], "num_exec": a[1]})
+        rec["actions"].append(a)
+        rec["reward"].append(float(reward))
+        rec["wall"].append(float(info["wall_time"]))
+        rec["term"].append(bool(terminated))
+        record_obs(obs)
+        rec["ev_count"].append(len(events))
+        steps += 1
+        if time_limit is not None and info["wall_time"] >= time_limit:
+            truncated = True  # what StochasticTimeLimit.step does (stochastic_time_limit.py:29-30)
+        if max_steps is not None and steps >= max_steps:
+            break
+
+    evarr = np.array(events, dtype=np.float64).reshape(-1, 7)
+    trace = {
+        "num_executors": env_cfg["num_executors"],
+        "moving_delay": float(env_cfg["moving_delay"]),
+        "warmup_delay": float(env_cfg["warmup_delay"]),
+        "job_arrival_rate": float(env_cfg["job_arrival_rate"]),
+        "job_arrival_cap": -1 if env_cfg.get("job_arrival_cap") is None else int(env_cfg["job_arrival_cap"]),
+        "beta": float(env_cfg.get("beta", 0.0)),
+        "time_limit": np.inf if time_limit is None else float(time_limit),
+        "seed": seed,
+        "rng": rng,
+        "policy": policy,
+        "policy_seed": policy_seed,
+        "job_t_arrival": np.array([float(j.t_arrival) for j in jobs], np.float64),
+        "job_template": np.array(job_template, np.int32),
+        "job_t_completed": np.array([float(j.t_completed) for j in jobs], np.float64),
+        "st_num_tasks": np.array(st_num_tasks, np.int32),
+        "st_rough": np.array(st_rough, np.float64),
+        "tape": np.array(tape, np.float64),
+        "tape_meta": np.array(tape_meta, np.int32).reshape(-1, 4),
+        "actions": np.array(rec["actions"], np.int32).reshape(-1, 2),
+        "reward": np.array(rec["reward"], np.float64),
+        "wall": np.array(rec["wall"], np.float64),
+        "term": np.array(rec["term"], np.uint8),
+        "ncommit": np.array(rec["ncommit"], np.int32),
+        "src": np.array(rec["src"], np.int32),
+        "N": np.array(rec["N"], np.int32),
+        "M": np.array(rec["M"], np.int32),
+        "Ja": np.array(rec["Ja"], np.int32),
+        "ev_count": np.array(rec["ev_count"], np.int64),
+        "obs_digest": np.array(rec["obs_digest"], np.uint64),
+        "nodes": np.concatenate(rec["nodes"], 0) if rec["nodes"] else np.zeros((0, 3), np.float32),
+        "edges": np.concatenate(rec["edges"], 0) if rec["edges"] else np.zeros((0, 2), np.int32),
+        "dag_ptr": np.concatenate(rec["dag_ptr"]),
+        "supplies": np.concatenate(rec["supplies"]) if rec["supplies"] else np.zeros(0, np.int32),
+        "ev_t": evarr[:, 0].copy(),
+        "ev_type": evarr[:, 1].astype(np.uint8),
+        "ev_job": evarr[:, 2].astype(np.int16),
+        "ev_stage": evarr[:, 3].astype(np.int16),
+        "ev_task": evarr[:, 4].astype(np.int32),
+        "ev_exec": evarr[:, 5].astype(np.int16),
+        "ev_tacc": evarr[:, 6].copy(),
+        "final_wall": float(env.wall_time),
+        "avg_job_duration_s": float(
+            np.mean([min(j.t_completed, env.wall_time) - j.t_arrival for j in jobs]) * 1e-3),
+    }
+    return trace
+
+
+def slim(trace: dict) -> dict:
+    """Replaces the bulky per-step observations and per-event rows by digests (big episodes)."""
+    t = dict(trace)
+    ec = t["ev_count"]
+    lo = np.concatenate([[0], ec[:-1]])
+    t["ev_digest"] = np.array(
+        [events_digest(trace, int(a), int(b)) for a, b in zip(lo, ec)], np.uint64)
+    for k in ("nodes", "edges", "dag_ptr", "supplies", "ev_t", "ev_type", "ev_job", "ev_stage",
+              "ev_task", "ev_exec", "ev_tacc", "tape_meta"):
+        t.pop(k)
+    t["slim"] = True
+    return t
+
+
+if __name__ == "__main__":
+    import time
+
+    cfg = {"num_executors": 10, "job_arrival_cap": 50, "job_arrival_rate": 4.0e-5,
+           "moving_delay": 2000.0, "warmup_delay": 1000.0}
+    t0 = time.time()
+    tr = run_episode(cfg, "fair", 1234, rng=sys.argv[1] if len(sys.argv) > 1 else "pcg64")
+    dt = time.time() - t0
+    print(f"steps={len(tr['actions'])} events={len(tr['ev_t'])} tasks={len(tr['tape'])} "
+          f"final_wall={tr['final_wall']} avg_jct_s={tr['avg_job_duration_s']:.3f} "
+          f"stages={len(tr['st_num_tasks'])} time={dt:.2f}s")

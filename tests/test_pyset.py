@@ -1,0 +1,63 @@
+"""The oracle's CPython-set emulation against the live interpreter's `set`:
+iteration order, pop order and copy layout decide which executor is moved first
+(spark_sched_sim.py:714-743, executor_tracker.py:134-135)."""
+import random
+import sys
+
+import pytest
+
+from oracle import lib
+
+
+class EmuSet:
+    def __init__(self, h=None):
+        self.L = lib()
+        self.h = h if h is not None else self.L.orc_pyset_new()
+
+    def add(self, k): self.L.orc_pyset_add(self.h, k)
+    def remove(self, k): assert self.L.orc_pyset_remove(self.h, k) == 0
+    def pop(self): return self.L.orc_pyset_pop(self.h)
+    def copy(self): return EmuSet(self.L.orc_pyset_copy(self.h))
+    def __len__(self): return self.L.orc_pyset_len(self.h)
+
+    def list(self):
+        import ctypes as C
+        buf = (C.c_int32 * 4096)()
+        n = self.L.orc_pyset_list(self.h, buf)
+        return list(buf[:n])
+
+    def __del__(self):
+        self.L.orc_pyset_free(self.h)
+
+
+@pytest.mark.skipif(sys.version_info[:2] != (3, 12), reason="layout pinned to CPython 3.12")
+@pytest.mark.parametrize("universe", [3, 10, 50, 100, 200])
+def test_pyset_matches_cpython(universe):
+    rnd = random.Random(universe)
+    for trial in range(200):
+        real, emu = set(), EmuSet()
+        if rnd.random() < 0.5:
+            for i in range(universe):  # set(range(n)) as executor_tracker.py:41
+                real.add(i); emu.add(i)
+        for _ in range(rnd.randrange(1, 120)):
+            op = rnd.random()
+            if op < 0.45:
+                k = rnd.randrange(universe)
+                real.add(k); emu.add(k)
+            elif op < 0.75 and real:
+                k = rnd.choice(sorted(real))
+                real.remove(k); emu.remove(k)
+            elif op < 0.85 and real:
+                assert real.pop() == emu.pop()
+            elif op < 0.95:
+                real, emu = real.copy(), emu.copy()
+            else:  # set(generator) over a copy with a filter (spark_sched_sim.py:720-726)
+                keep = rnd.randrange(2, 5)
+                real = set(x for x in real.copy() if x % keep)
+                src = emu.copy().list()
+                emu = EmuSet()
+                for x in src:
+                    if x % keep:
+                        emu.add(x)
+            assert list(real) == emu.list(), (universe, trial)
+            assert len(real) == len(emu)

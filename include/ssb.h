@@ -1,0 +1,187 @@
+/* include/ssb.h -- C ABI of libssb: the batched, B200-native spark-sched-sim scheduling loop.
+ *
+ * The reference has no FFI: its hot path sits behind the Gymnasium Env API
+ * (spark_sched_sim/spark_sched_sim.py:127 `reset`, :188 `step`) and three plug-in ABCs (Scheduler
+ * schedulers/scheduler.py:10-18, DataSampler data_samplers/data_sampler.py:9-23, wrappers).  This
+ * header is the boundary a binding of that path would use: one `ssb_env` owns B independent
+ * environments on one GPU; every entry point is `extern "C"`, takes plain pointers and sizes,
+ * returns an int status (0 = ok) and never throws.  INTEGRATION.md shows the ctypes stub that
+ * makes `SparkSchedSimEnv` call these.
+ *
+ * Conventions
+ *   - All device work is enqueued on the caller's stream (`stream` = cudaStream_t as void*,
+ *     NULL = default stream).  `*_host` variants take HOST buffers, copy, run and synchronise.
+ *   - The library owns no device memory: the caller passes one workspace allocation
+ *     (`ssb_workspace_bytes` tells how big) -- in Python that is a torch uint8 tensor -- and the
+ *     observation views returned by `ssb_get_views` are pointers into it.
+ *   - Per-environment semantic errors (the reference's ValueError / AssertionError) are reported in
+ *     `ssb_obs_hdr.error`: 1..9 = rejected action or reset (state unchanged, see codes below),
+ *     >= 1000 = violated internal invariant (environment frozen until the next reset).
+ *   - One handle per GPU; a handle is not thread-safe.
+ */
+#ifndef SSB_H
+#define SSB_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSB_ABI_VERSION 1
+
+/* status codes of the entry points */
+enum {
+    SSB_OK = 0,
+    SSB_E_INVALID = -1, /* bad argument / configuration */
+    SSB_E_CUDA = -2,    /* CUDA runtime error (ssb_last_cuda_error) */
+    SSB_E_WORKSPACE = -3
+};
+
+/* per-environment error codes in ssb_obs_hdr.error (mirror the reference's exceptions) */
+enum {
+    SSB_ENV_OK = 0,
+    SSB_ENV_ACTION_SPACE = 1,    /* spark_sched_sim.py:276-277 ValueError */
+    SSB_ENV_STAGE_KEY = 2,       /* :284 KeyError (stage_idx >= number of schedulable stages) */
+    SSB_ENV_NOT_SCHEDULABLE = 3, /* :286-287 */
+    SSB_ENV_ZERO_EXEC = 4,       /* :291-292 */
+    SSB_ENV_TOO_MANY_EXEC = 5,   /* :294-295 */
+    SSB_ENV_NO_LIMIT = 6,        /* :137-138 */
+    SSB_ENV_SAMPLER = 7,         /* tpch.py:106 uncaught KeyError/ValueError */
+    SSB_ENV_TAPE_EXHAUSTED = 8,
+    SSB_ENV_DONE = 9,            /* step() after termination */
+    SSB_ENV_CAPACITY = 10        /* more jobs/stages than the configured capacity */
+};
+
+/* env_cfg of the reference (spark_sched_sim.py:34-57, tpch.py:19-26) + batching/capacity knobs */
+typedef struct {
+    int32_t num_envs;        /* B */
+    int32_t num_executors;   /* env_cfg["num_executors"], 1..128 */
+    int32_t job_arrival_cap; /* env_cfg["job_arrival_cap"]; <= 0: none (time limit required) */
+    int32_t max_jobs;        /* capacity per env; >= job_arrival_cap */
+    int32_t tape_capacity;   /* f64 durations per env for trace replay (0 = no replay support) */
+    int32_t log_capacity;    /* event-log rows per env (0 = no event log) */
+    double moving_delay;     /* ms */
+    double warmup_delay;     /* ms */
+    double job_arrival_rate; /* 1/ms */
+    double beta;             /* continuous discount (trainer.beta_discount), 0 = undiscounted */
+} ssb_config;
+
+/* Flattened template bank (host pointers; copied to the device by ssb_create).  Layout: see
+ * spark-sched-sim_b200/bank.py, which restates tpch.py:118-206. */
+typedef struct {
+    int32_t num_templates;
+    int32_t num_template_stages; /* TS = stage_base[T] */
+    int32_t num_template_edges;  /* edge_base[T] */
+    int64_t num_values;
+    const int32_t *num_stages;    /* [T]   */
+    const int32_t *stage_base;    /* [T+1] */
+    const int32_t *edge_base;     /* [T+1] */
+    const int32_t *edges;         /* [edges][2] (u, v), row-major adjacency order */
+    const int32_t *num_tasks;     /* [TS] */
+    const double *rough_duration; /* [TS] */
+    const uint64_t *parent_mask;  /* [TS] */
+    const uint64_t *child_mask;   /* [TS] */
+    const uint8_t *present;       /* [TS][3] */
+    const uint32_t *dur_off;      /* [TS][3][8] */
+    const uint32_t *dur_cnt;      /* [TS][3][8] */
+    const double *dur_values;     /* [num_values] */
+} ssb_bank;
+
+/* What step()/reset() return besides the graph, one record per environment (device array [B]). */
+typedef struct {
+    double reward;     /* step() reward (spark_sched_sim.py:208-209) */
+    double wall_time;  /* info["wall_time"] */
+    int32_t num_nodes; /* N: rows of dag_batch.nodes */
+    int32_t num_edges; /* M */
+    int32_t num_active_jobs;       /* Ja = len(exec_supplies) */
+    int32_t num_committable_execs; /* obs["num_committable_execs"] */
+    int32_t source_job_idx;        /* obs["source_job_idx"] (== Ja if none) */
+    int32_t num_schedulable;       /* number of valid stage_idx values */
+    int32_t error;                 /* SSB_ENV_* or 1000+line */
+    uint8_t terminated;
+    uint8_t truncated; /* wall_time >= time limit (wrappers/stochastic_time_limit.py:29-30) */
+    uint8_t pad[2];
+} ssb_obs_hdr;
+
+/* Device views of the observation slabs (fixed stride per environment). */
+typedef struct {
+    ssb_obs_hdr *hdr;       /* [B] */
+    float *nodes;           /* [B][node_stride][3]: remaining tasks, most recent duration, schedulable */
+    int32_t *edge_links;    /* [B][edge_stride][2], relabelled to observation node ids */
+    int32_t *dag_ptr;       /* [B][job_stride + 1] */
+    int32_t *exec_supplies; /* [B][job_stride] */
+    int32_t node_stride, edge_stride, job_stride, pad;
+} ssb_views;
+
+/* Counters for measurement (device array [B]); zeroed by ssb_create / ssb_reset_stats. */
+typedef struct {
+    uint64_t decisions;   /* step() calls accepted */
+    uint64_t events;      /* timeline events popped */
+    uint64_t sched_scans; /* full schedulability scans (spark_sched_sim.py:505) */
+    uint64_t sum_nodes, sum_edges, sum_jobs; /* over emitted observations */
+    uint64_t observations;
+    uint64_t episodes;    /* completed (terminated or truncated) */
+} ssb_stats;
+
+typedef struct ssb_env ssb_env;
+
+int ssb_abi_version(void);
+const char *ssb_last_cuda_error(void);
+
+/* bytes of device workspace needed for (cfg, bank) */
+int ssb_workspace_bytes(const ssb_config *cfg, const ssb_bank *bank, size_t *bytes);
+
+/* builds a handle over `workspace` (device memory, >= ssb_workspace_bytes, 256-B aligned) on CUDA
+ * device `device`; uploads the bank.  Replaces SparkSchedSimEnv.__init__ (spark_sched_sim.py:34). */
+int ssb_create(const ssb_config *cfg, const ssb_bank *bank, int device, void *workspace,
+               size_t workspace_bytes, ssb_env **out);
+int ssb_destroy(ssb_env *env);
+
+/* parity mode: give environment `env_index` a pre-sampled job sequence (+ optional duration tape;
+ * tape == NULL keeps the Philox task stream).  HOST pointers.  Takes effect at the next reset. */
+int ssb_load_trace(ssb_env *env, int32_t env_index, int32_t n_jobs, const double *t_arrival,
+                   const int32_t *tmpl, const double *tape, int64_t n_tape);
+int ssb_clear_trace(ssb_env *env, int32_t env_index);
+
+/* reset(seed, options={"time_limit"}) for every env with mask[i] != 0 (mask NULL = all).
+ * DEVICE pointers: seeds u64[B], time_limits f64[B] (NULL = +inf), mask u8[B]. */
+int ssb_reset(ssb_env *env, const uint64_t *seeds, const double *time_limits, const uint8_t *mask,
+              void *stream);
+/* step(action) for every env (mask NULL = all).  DEVICE pointers i32[B]. */
+int ssb_step(ssb_env *env, const int32_t *stage_idx, const int32_t *num_exec, const uint8_t *mask,
+             void *stream);
+
+/* same with HOST buffers: copies in, runs, copies the B observation headers out, synchronises */
+int ssb_reset_host(ssb_env *env, const uint64_t *seeds, const double *time_limits, const uint8_t *mask,
+                   ssb_obs_hdr *hdr_out);
+int ssb_step_host(ssb_env *env, const int32_t *stage_idx, const int32_t *num_exec, const uint8_t *mask,
+                  ssb_obs_hdr *hdr_out);
+
+/* fused rollout: every env takes `num_decisions` decisions with the built-in fair (dynamic_partition
+ * = 1) or FIFO (= 0) policy (round_robin.py:14-49) evaluated on the observation it just wrote.
+ * auto_reset != 0: a finished env re-seeds itself with seed + seed_step * reset_count
+ * (rollout_worker.py:118-120) and continues; otherwise it idles once done. */
+int ssb_rollout_fair(ssb_env *env, int32_t num_decisions, int32_t dynamic_partition, int32_t auto_reset,
+                     uint64_t seed_step, void *stream);
+/* evaluates the built-in policy on the current observations -> DEVICE i32[B] each */
+int ssb_fair_actions(ssb_env *env, int32_t dynamic_partition, int32_t *stage_idx, int32_t *num_exec,
+                     void *stream);
+
+int ssb_get_views(ssb_env *env, ssb_views *out);
+/* device pointer to ssb_stats[B] */
+int ssb_get_stats(ssb_env *env, ssb_stats **out);
+int ssb_reset_stats(ssb_env *env, void *stream);
+
+/* results (HOST outputs, synchronous): per-job arrival/completion time and template of env_index */
+int ssb_get_jobs(ssb_env *env, int32_t env_index, int32_t *n_jobs, double *t_arrival,
+                 double *t_completed, int32_t *tmpl, int32_t capacity);
+/* event log rows [lo, hi) of env_index (needs log_capacity > 0); *n_rows = rows logged so far */
+int ssb_get_log(ssb_env *env, int32_t env_index, int64_t lo, int64_t hi, int64_t *n_rows, double *t,
+                uint8_t *type, int16_t *job, int16_t *stage, int32_t *task, int16_t *exec,
+                double *t_accepted);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,233 @@
+"""BatchedSparkSchedSimEnv: B independent SparkSchedSimEnv episodes on one GPU.
+
+This replaces the reference's "one CPU process per env" rollout workers
+(trainers/trainer.py:264-293, trainers/rollout_worker.py:53-157) by one device-resident batch.
+`reset`/`step` keep the reference's per-environment semantics (spark_sched_sim.py:127-221); the
+observation comes back as device tensors with a fixed stride per environment:
+
+    nodes          f32 [B, S, 3]   rows [0, num_nodes[b])   (remaining, most-recent duration, schedulable)
+    edge_links     i32 [B, M, 2]   rows [0, num_edges[b])   relabelled to observation node ids
+    dag_ptr        i32 [B, J+1]    entries [0, num_active_jobs[b]]
+    exec_supplies  i32 [B, J]
+    hdr            structured [B]  reward, wall_time, counts, num_committable_execs, source_job_idx,
+                                   terminated, truncated, error
+
+PyTorch is used for device memory and streams only; all simulation work happens in libssb.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _native as nat
+from .bank import TemplateBank, synthetic_bank
+
+ERROR_MESSAGES = {
+    1: "invalid action: does not belong to the action space",
+    2: "invalid action: stage index out of range of the schedulable stages",
+    3: "invalid action: stage is not currently schedulable",
+    4: "invalid action: must commit at least one executor",
+    5: "invalid action: too many executors requested",
+    6: "must either have a limit on job arrivals or time.",
+    7: "no task duration data for this stage / executor level",
+    8: "duration tape exhausted",
+    9: "step() called on a finished episode",
+    10: "episode exceeds the configured job/stage capacity",
+}
+
+
+class BatchedSparkSchedSimEnv:
+    def __init__(self, env_cfg: dict, num_envs: int, bank: TemplateBank | None = None,
+                 device: str | torch.device = "cuda:0", max_jobs: int | None = None,
+                 tape_capacity: int = 0, log_capacity: int = 0):
+        self.L = nat.lib()
+        if not torch.cuda.is_available():
+            raise RuntimeError("BatchedSparkSchedSimEnv needs a CUDA device (no CPU fallback)")
+        self.device = torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.bank = bank if bank is not None else synthetic_bank(0)
+        self.num_envs = int(num_envs)
+        self.num_executors = int(env_cfg["num_executors"])
+        cap = env_cfg.get("job_arrival_cap")
+        self.job_arrival_cap = int(cap) if cap else 0
+        if max_jobs is None:
+            max_jobs = self.job_arrival_cap if self.job_arrival_cap > 0 else 256
+        self.max_jobs = int(max_jobs)
+        self.cfg = nat.SsbConfig(
+            self.num_envs, self.num_executors, self.job_arrival_cap, self.max_jobs,
+            int(tape_capacity), int(log_capacity), float(env_cfg["moving_delay"]),
+            float(env_cfg.get("warmup_delay", 0.0)), float(env_cfg["job_arrival_rate"]),
+            float(env_cfg.get("beta", 0.0)))
+        self._bank_struct, self._bank_keep = nat.make_bank_struct(self.bank)
+        nbytes = C.c_size_t()
+        nat.check(self.L.ssb_workspace_bytes(C.byref(self.cfg), C.byref(self._bank_struct),
+                                             C.byref(nbytes)), "ssb_workspace_bytes")
+        self.workspace_bytes = int(nbytes.value)
+        with torch.cuda.device(self.device):
+            self.workspace = torch.empty(self.workspace_bytes, dtype=torch.uint8, device=self.device)
+        self._h = C.c_void_p()
+        nat.check(self.L.ssb_create(C.byref(self.cfg), C.byref(self._bank_struct), self.device.index,
+                                    self.workspace.data_ptr(), self.workspace_bytes,
+                                    C.byref(self._h)), "ssb_create")
+        v = nat.SsbViews()
+        nat.check(self.L.ssb_get_views(self._h, C.byref(v)), "ssb_get_views")
+        B, S, M, J = self.num_envs, v.node_stride, v.edge_stride, v.job_stride
+        self.node_stride, self.edge_stride, self.job_stride = S, M, J
+        self.hdr_bytes = self._view(v.hdr, B * nat.OBS_HDR_DTYPE.itemsize, torch.uint8).view(B, -1)
+        self.nodes = self._view(v.nodes, B * S * 3 * 4, torch.float32).view(B, S, 3)
+        self.edge_links = self._view(v.edge_links, B * M * 2 * 4, torch.int32).view(B, M, 2)
+        self.dag_ptr = self._view(v.dag_ptr, B * (J + 1) * 4, torch.int32).view(B, J + 1)
+        self.exec_supplies = self._view(v.exec_supplies, B * J * 4, torch.int32).view(B, J)
+        sp = C.c_void_p()
+        nat.check(self.L.ssb_get_stats(self._h, C.byref(sp)), "ssb_get_stats")
+        self.stats_bytes = self._view(sp.value, B * nat.STATS_DTYPE.itemsize, torch.uint8).view(B, -1)
+        self._hdr_host = np.zeros(B, nat.OBS_HDR_DTYPE)
+
+    # ---------------------------------------------------------------- plumbing
+    def _view(self, ptr, nbytes, dtype):
+        off = int(ptr) - self.workspace.data_ptr()
+        assert 0 <= off and off + nbytes <= self.workspace_bytes
+        return self.workspace[off:off + nbytes].view(dtype)
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.L.ssb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _dev(self, x, dtype):
+        if x is None:
+            return None
+        if isinstance(x, torch.Tensor):
+            t = x.to(device=self.device, dtype=dtype).contiguous()
+        else:
+            t = torch.as_tensor(np.asarray(x), dtype=dtype).to(self.device)
+        assert t.numel() == self.num_envs
+        return t
+
+    # ---------------------------------------------------------------- device-tensor API
+    def reset(self, seeds, time_limits=None, mask=None):
+        """reset(seed, options={"time_limit"}) per env; arguments are device tensors or arrays."""
+        s = self._dev(torch.as_tensor(np.asarray(seeds, dtype=np.uint64).view(np.int64))
+                      if not isinstance(seeds, torch.Tensor) else seeds, torch.int64)
+        tl = self._dev(time_limits, torch.float64)
+        m = self._dev(mask, torch.uint8)
+        self._keep = (s, tl, m)
+        nat.check(self.L.ssb_reset(self._h, s.data_ptr(), tl.data_ptr() if tl is not None else None,
+                                   m.data_ptr() if m is not None else None, self._stream()), "ssb_reset")
+
+    def step(self, stage_idx, num_exec, mask=None):
+        a = self._dev(stage_idx, torch.int32)
+        n = self._dev(num_exec, torch.int32)
+        m = self._dev(mask, torch.uint8)
+        self._keep = (a, n, m)
+        nat.check(self.L.ssb_step(self._h, a.data_ptr(), n.data_ptr(),
+                                  m.data_ptr() if m is not None else None, self._stream()), "ssb_step")
+
+    def fair_actions(self, dynamic_partition=True):
+        a = torch.empty(self.num_envs, dtype=torch.int32, device=self.device)
+        n = torch.empty(self.num_envs, dtype=torch.int32, device=self.device)
+        nat.check(self.L.ssb_fair_actions(self._h, int(dynamic_partition), a.data_ptr(), n.data_ptr(),
+                                          self._stream()), "ssb_fair_actions")
+        return a, n
+
+    def rollout_fair(self, num_decisions, dynamic_partition=True, auto_reset=True, seed_step=1):
+        nat.check(self.L.ssb_rollout_fair(self._h, int(num_decisions), int(dynamic_partition),
+                                          int(auto_reset), int(seed_step), self._stream()),
+                  "ssb_rollout_fair")
+
+    # ---------------------------------------------------------------- host-buffer API (e2e path)
+    def reset_host(self, seeds: np.ndarray, time_limits: np.ndarray | None = None,
+                   mask: np.ndarray | None = None) -> np.ndarray:
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint64)
+        tl = None if time_limits is None else np.ascontiguousarray(time_limits, dtype=np.float64)
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        nat.check(self.L.ssb_reset_host(self._h, seeds.ctypes.data, tl.ctypes.data if tl is not None else None,
+                                        m.ctypes.data if m is not None else None,
+                                        self._hdr_host.ctypes.data), "ssb_reset_host")
+        return self._hdr_host
+
+    def step_host(self, stage_idx: np.ndarray, num_exec: np.ndarray, mask: np.ndarray | None = None) -> np.ndarray:
+        a = np.ascontiguousarray(stage_idx, dtype=np.int32)
+        n = np.ascontiguousarray(num_exec, dtype=np.int32)
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        nat.check(self.L.ssb_step_host(self._h, a.ctypes.data, n.ctypes.data,
+                                       m.ctypes.data if m is not None else None,
+                                       self._hdr_host.ctypes.data), "ssb_step_host")
+        return self._hdr_host
+
+    # ---------------------------------------------------------------- results
+    def hdr(self) -> np.ndarray:
+        """Structured numpy copy of the B observation headers (synchronises)."""
+        return self.hdr_bytes.cpu().numpy().view(nat.OBS_HDR_DTYPE).reshape(-1)
+
+    def stats(self) -> dict:
+        s = self.stats_bytes.cpu().numpy().view(nat.STATS_DTYPE).reshape(-1)
+        return {f: int(s[f].sum()) for f in nat.STATS_FIELDS}
+
+    def reset_stats(self):
+        nat.check(self.L.ssb_reset_stats(self._h, self._stream()), "ssb_reset_stats")
+
+    def obs(self, b: int = 0, hdr: np.ndarray | None = None) -> dict:
+        """Observation of environment b as host arrays (the pieces of the reference obs dict)."""
+        h = (self.hdr() if hdr is None else hdr)[b]
+        N, M, Ja = int(h["num_nodes"]), int(h["num_edges"]), int(h["num_active_jobs"])
+        return {
+            "nodes": self.nodes[b, :N].cpu().numpy(),
+            "edge_links": self.edge_links[b, :M].cpu().numpy(),
+            "dag_ptr": self.dag_ptr[b, :Ja + 1].cpu().numpy(),
+            "exec_supplies": self.exec_supplies[b, :Ja].cpu().numpy(),
+            "num_committable_execs": int(h["num_committable_execs"]),
+            "source_job_idx": int(h["source_job_idx"]),
+        }
+
+    def load_trace(self, b, t_arrival, template, tape=None):
+        ta = np.ascontiguousarray(t_arrival, np.float64)
+        tm = np.ascontiguousarray(template, np.int32)
+        tp = None if tape is None else np.ascontiguousarray(tape, np.float64)
+        nat.check(self.L.ssb_load_trace(self._h, int(b), len(ta), ta.ctypes.data, tm.ctypes.data,
+                                        tp.ctypes.data if tp is not None else None,
+                                        0 if tp is None else len(tp)), "ssb_load_trace")
+
+    def clear_trace(self, b):
+        nat.check(self.L.ssb_clear_trace(self._h, int(b)), "ssb_clear_trace")
+
+    def jobs(self, b: int = 0):
+        n = C.c_int32()
+        cap = self.max_jobs
+        ta, tc, tm = np.zeros(cap), np.zeros(cap), np.zeros(cap, np.int32)
+        nat.check(self.L.ssb_get_jobs(self._h, int(b), C.byref(n), ta.ctypes.data, tc.ctypes.data,
+                                      tm.ctypes.data, cap), "ssb_get_jobs")
+        k = n.value
+        return ta[:k], tc[:k], tm[:k]
+
+    def log_size(self, b: int = 0) -> int:
+        n = C.c_int64()
+        nat.check(self.L.ssb_get_log(self._h, int(b), 0, 0, C.byref(n), *([None] * 7)), "ssb_get_log")
+        return int(n.value)
+
+    def log(self, b: int = 0, lo: int = 0, hi: int | None = None) -> dict:
+        n = self.log_size(b)
+        hi = n if hi is None else hi
+        k = hi - lo
+        out = {"ev_t": np.zeros(k), "ev_type": np.zeros(k, np.uint8), "ev_job": np.zeros(k, np.int16),
+               "ev_stage": np.zeros(k, np.int16), "ev_task": np.zeros(k, np.int32),
+               "ev_exec": np.zeros(k, np.int16), "ev_tacc": np.zeros(k)}
+        nn = C.c_int64()
+        if k > 0:
+            nat.check(self.L.ssb_get_log(
+                self._h, int(b), lo, hi, C.byref(nn),
+                *[out[x].ctypes.data for x in ("ev_t", "ev_type", "ev_job", "ev_stage", "ev_task",
+                                               "ev_exec", "ev_tacc")]), "ssb_get_log")
+        return out

@@ -1,0 +1,510 @@
+// ssb_api.cu -- kernels and the C ABI of libssb (include/ssb.h).
+//
+// Launch geometry: one warp per environment, 4 environments per 128-thread CTA, grid = ceil(B/4).
+// At B = 4096 that is 1024 CTAs (~7 per SM on 148 SMs), all resident at once; the kernels are
+// latency-bound chains per environment, so residency (warps per SM) is what hides the latency.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "ssb_sim.cuh"
+
+using namespace ssb;
+
+namespace {
+
+constexpr int WARPS_PER_CTA = 4;
+thread_local char g_cuda_err[256] = "";
+
+#define CUDA_TRY(expr)                                                                   \
+    do {                                                                                 \
+        cudaError_t e_ = (expr);                                                         \
+        if (e_ != cudaSuccess) {                                                         \
+            snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", #expr, cudaGetErrorString(e_)); \
+            return SSB_E_CUDA;                                                           \
+        }                                                                                \
+    } while (0)
+
+// ------------------------------------------------------------------------------------ kernels
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+k_reset(Params p, const uint64_t *seeds, const double *time_limits, const uint8_t *mask)
+{
+    const int b = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= p.B) return;
+    if (mask && !mask[b]) return;
+    Sim sim(p, b, lane);
+    const uint64_t seed = seeds ? seeds[b] : 0ull;
+    if (lane == 0) { sim.h->base_seed = seed; sim.h->reset_count = 1; }
+    sim.reset_w(seed, time_limits ? time_limits[b] : INFINITY);
+}
+
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+k_step(Params p, const int32_t *stage_idx, const int32_t *num_exec, const uint8_t *mask)
+{
+    const int b = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= p.B) return;
+    if (mask && !mask[b]) return;
+    Sim sim(p, b, lane);
+    if (lane == 0) sim.oh->error = 0;
+    __syncwarp();
+    sim.step_w(stage_idx[b], num_exec[b]);
+}
+
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+k_fair_actions(Params p, int dynamic_partition, int32_t *stage_idx, int32_t *num_exec)
+{
+    const int b = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= p.B) return;
+    Sim sim(p, b, lane);
+    int a = -1, n = 1;
+    sim.fair_action_w(dynamic_partition != 0, a, n);
+    if (lane == 0) { stage_idx[b] = a; num_exec[b] = n; }
+}
+
+// fused policy + step: `num_decisions` decisions per environment in one launch
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+k_rollout_fair(Params p, int num_decisions, int dynamic_partition, int auto_reset, uint64_t seed_step)
+{
+    const int b = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= p.B) return;
+    Sim sim(p, b, lane);
+    int d = 0;
+    while (d < num_decisions) {
+        if (sim.h->error) break;
+        if (sim.h->done || sim.oh->truncated) {
+            if (!auto_reset) break;
+            // rollout_worker.py:118-120: seed = base_seed + seed_step * reset_count
+            const uint64_t seed = sim.h->base_seed + seed_step * (uint64_t)sim.h->reset_count;
+            const double tl = sim.h->time_limit;
+            const bool was_trunc = !sim.h->done;
+            __syncwarp();
+            if (lane == 0) { sim.h->reset_count += 1; if (was_trunc) sim.stats->episodes++; }
+            sim.reset_w(seed, tl);
+            continue;
+        }
+        int a = -1, n = 1;
+        sim.fair_action_w(dynamic_partition != 0, a, n);
+        sim.step_w(a, n);
+        d++;
+    }
+}
+
+__global__ void k_zero_stats(ssb_stats *s, int n)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) s[i] = ssb_stats{};
+}
+
+// ------------------------------------------------------------------------------------ workspace
+struct Carver {
+    char *base;
+    size_t off = 0;
+    template <typename T>
+    T *take(size_t n)
+    {
+        off = (off + 255) & ~size_t(255);
+        T *ptr = base ? reinterpret_cast<T *>(base + off) : nullptr;
+        off += n * sizeof(T);
+        return ptr;
+    }
+};
+
+struct Dims {
+    int TAB, RT, Sc, Mc, P, Cc, max_stages, max_edges;
+};
+
+int compute_dims(const ssb_config &c, const ssb_bank &bk, Dims &d)
+{
+    if (c.num_envs < 1 || c.num_executors < 1 || c.num_executors > 128) return SSB_E_INVALID;
+    if (c.max_jobs < 1 || c.max_jobs > 16000) return SSB_E_INVALID;
+    if (c.job_arrival_cap > c.max_jobs) return SSB_E_INVALID;
+    if (!(c.job_arrival_rate > 0)) return SSB_E_INVALID;
+    if (bk.num_templates != 154) return SSB_E_INVALID;  // 7 sizes x 22 queries (tpch.py:14-15)
+    int ms = 0, me = 0;
+    for (int t = 0; t < bk.num_templates; t++) {
+        ms = bk.num_stages[t] > ms ? bk.num_stages[t] : ms;
+        int ne = bk.edge_base[t + 1] - bk.edge_base[t];
+        me = ne > me ? ne : me;
+    }
+    if (ms < 1 || ms > 64) return SSB_E_INVALID;
+    d.max_stages = ms;
+    d.max_edges = me;
+    d.TAB = 8;
+    while (d.TAB <= 4 * c.num_executors) d.TAB <<= 1;
+    d.RT = 8;
+    while (d.RT <= 4 * c.max_jobs) d.RT <<= 1;
+    d.Sc = c.max_jobs * ms;
+    d.Mc = c.max_jobs * me;
+    if (d.Sc > 32000) return SSB_E_INVALID;
+    d.P = 2 + c.max_jobs + d.Sc;
+    d.Cc = 2 * c.num_executors + 16;
+    return SSB_OK;
+}
+
+struct BankDev {
+    int32_t *num_stages, *stage_base, *edge_base, *num_tasks;
+    int16_t *edges;
+    double *rough;
+    uint64_t *parent, *child;
+    uint8_t *present;
+    uint2 *dur;
+    double *vals;
+    int16_t *iv;
+};
+
+void carve(Carver &cv, const ssb_config &c, const ssb_bank &bk, const Dims &d, Params &p, BankDev &bd,
+           int32_t **st_a, int32_t **st_n, uint64_t **st_seed, double **st_tl, uint8_t **st_mask)
+{
+    const size_t B = c.num_envs, T = bk.num_templates, TS = bk.num_template_stages;
+    bd.num_stages = cv.take<int32_t>(T);
+    bd.stage_base = cv.take<int32_t>(T + 1);
+    bd.edge_base = cv.take<int32_t>(T + 1);
+    bd.num_tasks = cv.take<int32_t>(TS);
+    bd.edges = cv.take<int16_t>(2 * (size_t)bk.num_template_edges);
+    bd.rough = cv.take<double>(TS);
+    bd.parent = cv.take<uint64_t>(TS);
+    bd.child = cv.take<uint64_t>(TS);
+    bd.present = cv.take<uint8_t>(TS * 4);
+    bd.dur = cv.take<uint2>(TS * 24);
+    bd.vals = cv.take<double>((size_t)bk.num_values + 1);
+    bd.iv = cv.take<int16_t>(2 * ((size_t)c.num_executors + 1));
+    p.hdr = cv.take<EnvHdr>(B);
+    p.exec = cv.take<ExecRec>(B * c.num_executors);
+    p.job = cv.take<JobRec>(B * c.max_jobs);
+    p.stage = cv.take<StageRec>(B * d.Sc);
+    p.active = cv.take<int16_t>(B * c.max_jobs);
+    p.old_act = cv.take<int16_t>(B * c.max_jobs);
+    p.commits = cv.take<Commit>(B * d.Cc);
+    p.pool_hdr = cv.take<PoolHdr>(B * d.P);
+    p.pool_tab = cv.take<uint8_t>(B * d.P * d.TAB);
+    p.scr_tab = cv.take<uint8_t>(B * 3 * d.TAB);
+    p.rset = cv.take<uint16_t>(B * 2 * d.RT);
+    p.trace_t = cv.take<double>(c.tape_capacity > 0 ? B * c.max_jobs : 1);
+    p.trace_tmpl = cv.take<int32_t>(c.tape_capacity > 0 ? B * c.max_jobs : 1);
+    p.tape = cv.take<double>(c.tape_capacity > 0 ? B * (size_t)c.tape_capacity : 1);
+    p.log = cv.take<LogRow>(c.log_capacity > 0 ? B * (size_t)c.log_capacity : 1);
+    p.stats = cv.take<ssb_stats>(B);
+    p.obs_hdr = cv.take<ssb_obs_hdr>(B);
+    p.obs_nodes = cv.take<float>(B * d.Sc * 3);
+    p.obs_edges = cv.take<int32_t>(B * d.Mc * 2);
+    p.obs_dag_ptr = cv.take<int32_t>(B * (c.max_jobs + 1));
+    p.obs_supplies = cv.take<int32_t>(B * c.max_jobs);
+    *st_a = cv.take<int32_t>(B);
+    *st_n = cv.take<int32_t>(B);
+    *st_seed = cv.take<uint64_t>(B);
+    *st_tl = cv.take<double>(B);
+    *st_mask = cv.take<uint8_t>(B);
+}
+
+}  // namespace
+
+struct ssb_env {
+    ssb_config cfg;
+    Dims dims;
+    Params p;
+    BankDev bank;
+    int device;
+    char *ws;
+    size_t ws_bytes;
+    cudaStream_t own_stream;
+    int32_t *st_a, *st_n;  // staging for the *_host entry points
+    uint64_t *st_seed;
+    double *st_tl;
+    uint8_t *st_mask;
+    int grid;
+};
+
+extern "C" {
+
+int ssb_abi_version(void) { return SSB_ABI_VERSION; }
+const char *ssb_last_cuda_error(void) { return g_cuda_err; }
+
+int ssb_workspace_bytes(const ssb_config *cfg, const ssb_bank *bank, size_t *bytes)
+{
+    if (!cfg || !bank || !bytes) return SSB_E_INVALID;
+    Dims d;
+    int rc = compute_dims(*cfg, *bank, d);
+    if (rc) return rc;
+    Carver cv{nullptr};
+    Params p{};
+    BankDev bd{};
+    int32_t *a, *n; uint64_t *s; double *tl; uint8_t *m;
+    carve(cv, *cfg, *bank, d, p, bd, &a, &n, &s, &tl, &m);
+    *bytes = (cv.off + 255) & ~size_t(255);
+    return SSB_OK;
+}
+
+int ssb_create(const ssb_config *cfg, const ssb_bank *bk, int device, void *workspace,
+               size_t workspace_bytes, ssb_env **out)
+{
+    if (!cfg || !bk || !workspace || !out) return SSB_E_INVALID;
+    if (reinterpret_cast<uintptr_t>(workspace) & 255) return SSB_E_WORKSPACE;
+    Dims d;
+    int rc = compute_dims(*cfg, *bk, d);
+    if (rc) return rc;
+    size_t need = 0;
+    ssb_workspace_bytes(cfg, bk, &need);
+    if (workspace_bytes < need) return SSB_E_WORKSPACE;
+    CUDA_TRY(cudaSetDevice(device));
+    ssb_env *env = new (std::nothrow) ssb_env();
+    if (!env) return SSB_E_INVALID;
+    env->cfg = *cfg;
+    env->dims = d;
+    env->device = device;
+    env->ws = static_cast<char *>(workspace);
+    env->ws_bytes = workspace_bytes;
+    Carver cv{env->ws};
+    Params &p = env->p;
+    p = Params{};
+    carve(cv, *cfg, *bk, d, p, env->bank, &env->st_a, &env->st_n, &env->st_seed, &env->st_tl, &env->st_mask);
+    p.B = cfg->num_envs; p.E = cfg->num_executors; p.Jc = cfg->max_jobs; p.Sc = d.Sc; p.Mc = d.Mc;
+    p.TAB = d.TAB; p.RT = d.RT; p.P = d.P; p.Cc = d.Cc; p.max_stages = d.max_stages;
+    p.tape_cap = cfg->tape_capacity; p.log_cap = cfg->log_capacity;
+    p.job_arrival_cap = cfg->job_arrival_cap;
+    p.moving_delay = cfg->moving_delay; p.warmup_delay = cfg->warmup_delay;
+    p.mean_interarrival = 1 / cfg->job_arrival_rate;  // tpch.py:42
+    p.beta = cfg->beta;
+    env->grid = (cfg->num_envs + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    // ---- bank upload
+    const size_t T = bk->num_templates, TS = bk->num_template_stages, ME = bk->num_template_edges;
+    BankDev &bd = env->bank;
+    CUDA_TRY(cudaMemcpy(bd.num_stages, bk->num_stages, T * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(bd.stage_base, bk->stage_base, (T + 1) * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(bd.edge_base, bk->edge_base, (T + 1) * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(bd.num_tasks, bk->num_tasks, TS * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(bd.rough, bk->rough_duration, TS * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(bd.parent, bk->parent_mask, TS * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(bd.child, bk->child_mask, TS * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(bd.vals, bk->dur_values, (size_t)bk->num_values * 8, cudaMemcpyHostToDevice));
+    {
+        std::vector<int16_t> e16(2 * ME);
+        for (size_t i = 0; i < 2 * ME; i++) e16[i] = (int16_t)bk->edges[i];
+        CUDA_TRY(cudaMemcpy(bd.edges, e16.data(), e16.size() * 2, cudaMemcpyHostToDevice));
+        std::vector<uint8_t> pr(TS * 4, 0);
+        for (size_t i = 0; i < TS; i++)
+            for (int w = 0; w < 3; w++) pr[i * 4 + w] = bk->present[i * 3 + w];
+        CUDA_TRY(cudaMemcpy(bd.present, pr.data(), pr.size(), cudaMemcpyHostToDevice));
+        std::vector<uint2> du(TS * 24);
+        for (size_t i = 0; i < TS * 24; i++) du[i] = make_uint2(bk->dur_off[i], bk->dur_cnt[i]);
+        CUDA_TRY(cudaMemcpy(bd.dur, du.data(), du.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+        for (size_t i = 0; i < TS; i++)
+            if (bk->num_tasks[i] < 1 || bk->num_tasks[i] > 65535) { delete env; return SSB_E_INVALID; }
+        // _init_executor_intervals (tpch.py:237-262) as integer levels
+        const int LV[8] = {5, 10, 20, 40, 50, 60, 80, 100};
+        const int cap = cfg->num_executors;
+        std::vector<int16_t> iv(2 * (cap + 1), 0);
+        for (int i = 0; i <= LV[0] && i <= cap; i++) iv[2 * i] = iv[2 * i + 1] = LV[0];
+        for (int i = 0; i < 7; i++) {
+            for (int r = LV[i] + 1; r < LV[i + 1] && r <= cap; r++) { iv[2 * r] = LV[i]; iv[2 * r + 1] = LV[i + 1]; }
+            if (LV[i + 1] > cap) break;
+            iv[2 * LV[i + 1]] = iv[2 * LV[i + 1] + 1] = LV[i + 1];
+        }
+        if (cap > LV[7]) for (int r = LV[7] + 1; r < cap; r++) iv[2 * r] = iv[2 * r + 1] = LV[7];
+        CUDA_TRY(cudaMemcpy(bd.iv, iv.data(), iv.size() * 2, cudaMemcpyHostToDevice));
+    }
+    p.b_num_stages = bd.num_stages; p.b_stage_base = bd.stage_base; p.b_edge_base = bd.edge_base;
+    p.b_num_tasks = bd.num_tasks; p.b_edges = bd.edges; p.b_rough = bd.rough; p.b_parent = bd.parent;
+    p.b_child = bd.child; p.b_present = bd.present; p.b_dur = bd.dur; p.b_vals = bd.vals; p.iv = bd.iv;
+    CUDA_TRY(cudaMemset(p.hdr, 0, sizeof(EnvHdr) * (size_t)p.B));
+    CUDA_TRY(cudaMemset(p.stats, 0, sizeof(ssb_stats) * (size_t)p.B));
+    CUDA_TRY(cudaMemset(p.obs_hdr, 0, sizeof(ssb_obs_hdr) * (size_t)p.B));
+    CUDA_TRY(cudaStreamCreateWithFlags(&env->own_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaDeviceSynchronize());
+    *out = env;
+    return SSB_OK;
+}
+
+int ssb_destroy(ssb_env *env)
+{
+    if (!env) return SSB_E_INVALID;
+    cudaSetDevice(env->device);
+    cudaStreamSynchronize(env->own_stream);
+    cudaStreamDestroy(env->own_stream);
+    delete env;
+    return SSB_OK;
+}
+
+int ssb_load_trace(ssb_env *env, int32_t b, int32_t n_jobs, const double *t_arrival, const int32_t *tmpl,
+                   const double *tape, int64_t n_tape)
+{
+    if (!env || b < 0 || b >= env->p.B || n_jobs < 1 || n_jobs > env->p.Jc || !t_arrival || !tmpl)
+        return SSB_E_INVALID;
+    if (env->cfg.tape_capacity <= 0) return SSB_E_INVALID;
+    if (tape && n_tape > env->cfg.tape_capacity) return SSB_E_INVALID;
+    if (t_arrival[0] != 0.0) return SSB_E_INVALID;  // spark_sched_sim.py:150
+    for (int j = 0; j < n_jobs; j++)
+        if (tmpl[j] < 0 || tmpl[j] >= 154) return SSB_E_INVALID;
+    CUDA_TRY(cudaSetDevice(env->device));
+    const Params &p = env->p;
+    CUDA_TRY(cudaMemcpy(p.trace_t + (size_t)b * p.Jc, t_arrival, n_jobs * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(p.trace_tmpl + (size_t)b * p.Jc, tmpl, n_jobs * 4, cudaMemcpyHostToDevice));
+    int32_t tl = tape ? (int32_t)n_tape : -1;
+    if (tape && n_tape > 0)
+        CUDA_TRY(cudaMemcpy(p.tape + (size_t)b * p.tape_cap, tape, n_tape * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(&p.hdr[b].trace_jobs, &n_jobs, 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(&p.hdr[b].tape_len, &tl, 4, cudaMemcpyHostToDevice));
+    return SSB_OK;
+}
+
+int ssb_clear_trace(ssb_env *env, int32_t b)
+{
+    if (!env || b < 0 || b >= env->p.B) return SSB_E_INVALID;
+    CUDA_TRY(cudaSetDevice(env->device));
+    int32_t z = 0;
+    CUDA_TRY(cudaMemcpy(&env->p.hdr[b].trace_jobs, &z, 4, cudaMemcpyHostToDevice));
+    return SSB_OK;
+}
+
+int ssb_reset(ssb_env *env, const uint64_t *seeds, const double *time_limits, const uint8_t *mask, void *stream)
+{
+    if (!env) return SSB_E_INVALID;
+    k_reset<<<env->grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(env->p, seeds, time_limits, mask);
+    CUDA_TRY(cudaGetLastError());
+    return SSB_OK;
+}
+
+int ssb_step(ssb_env *env, const int32_t *stage_idx, const int32_t *num_exec, const uint8_t *mask, void *stream)
+{
+    if (!env || !stage_idx || !num_exec) return SSB_E_INVALID;
+    k_step<<<env->grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(env->p, stage_idx, num_exec, mask);
+    CUDA_TRY(cudaGetLastError());
+    return SSB_OK;
+}
+
+int ssb_reset_host(ssb_env *env, const uint64_t *seeds, const double *time_limits, const uint8_t *mask,
+                   ssb_obs_hdr *hdr_out)
+{
+    if (!env) return SSB_E_INVALID;
+    CUDA_TRY(cudaSetDevice(env->device));
+    cudaStream_t s = env->own_stream;
+    const size_t B = env->p.B;
+    if (seeds) CUDA_TRY(cudaMemcpyAsync(env->st_seed, seeds, B * 8, cudaMemcpyHostToDevice, s));
+    if (time_limits) CUDA_TRY(cudaMemcpyAsync(env->st_tl, time_limits, B * 8, cudaMemcpyHostToDevice, s));
+    if (mask) CUDA_TRY(cudaMemcpyAsync(env->st_mask, mask, B, cudaMemcpyHostToDevice, s));
+    int rc = ssb_reset(env, seeds ? env->st_seed : nullptr, time_limits ? env->st_tl : nullptr,
+                       mask ? env->st_mask : nullptr, s);
+    if (rc) return rc;
+    if (hdr_out) CUDA_TRY(cudaMemcpyAsync(hdr_out, env->p.obs_hdr, B * sizeof(ssb_obs_hdr), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return SSB_OK;
+}
+
+int ssb_step_host(ssb_env *env, const int32_t *stage_idx, const int32_t *num_exec, const uint8_t *mask,
+                  ssb_obs_hdr *hdr_out)
+{
+    if (!env || !stage_idx || !num_exec) return SSB_E_INVALID;
+    CUDA_TRY(cudaSetDevice(env->device));
+    cudaStream_t s = env->own_stream;
+    const size_t B = env->p.B;
+    CUDA_TRY(cudaMemcpyAsync(env->st_a, stage_idx, B * 4, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(env->st_n, num_exec, B * 4, cudaMemcpyHostToDevice, s));
+    if (mask) CUDA_TRY(cudaMemcpyAsync(env->st_mask, mask, B, cudaMemcpyHostToDevice, s));
+    int rc = ssb_step(env, env->st_a, env->st_n, mask ? env->st_mask : nullptr, s);
+    if (rc) return rc;
+    if (hdr_out) CUDA_TRY(cudaMemcpyAsync(hdr_out, env->p.obs_hdr, B * sizeof(ssb_obs_hdr), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return SSB_OK;
+}
+
+int ssb_rollout_fair(ssb_env *env, int32_t num_decisions, int32_t dynamic_partition, int32_t auto_reset,
+                     uint64_t seed_step, void *stream)
+{
+    if (!env || num_decisions < 0) return SSB_E_INVALID;
+    k_rollout_fair<<<env->grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(
+        env->p, num_decisions, dynamic_partition, auto_reset, seed_step);
+    CUDA_TRY(cudaGetLastError());
+    return SSB_OK;
+}
+
+int ssb_fair_actions(ssb_env *env, int32_t dynamic_partition, int32_t *stage_idx, int32_t *num_exec, void *stream)
+{
+    if (!env || !stage_idx || !num_exec) return SSB_E_INVALID;
+    k_fair_actions<<<env->grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(env->p, dynamic_partition,
+                                                                               stage_idx, num_exec);
+    CUDA_TRY(cudaGetLastError());
+    return SSB_OK;
+}
+
+int ssb_get_views(ssb_env *env, ssb_views *out)
+{
+    if (!env || !out) return SSB_E_INVALID;
+    out->hdr = env->p.obs_hdr;
+    out->nodes = env->p.obs_nodes;
+    out->edge_links = env->p.obs_edges;
+    out->dag_ptr = env->p.obs_dag_ptr;
+    out->exec_supplies = env->p.obs_supplies;
+    out->node_stride = env->p.Sc;
+    out->edge_stride = env->p.Mc;
+    out->job_stride = env->p.Jc;
+    out->pad = 0;
+    return SSB_OK;
+}
+
+int ssb_get_stats(ssb_env *env, ssb_stats **out)
+{
+    if (!env || !out) return SSB_E_INVALID;
+    *out = env->p.stats;
+    return SSB_OK;
+}
+
+int ssb_reset_stats(ssb_env *env, void *stream)
+{
+    if (!env) return SSB_E_INVALID;
+    k_zero_stats<<<(env->p.B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(env->p.stats, env->p.B);
+    CUDA_TRY(cudaGetLastError());
+    return SSB_OK;
+}
+
+int ssb_get_jobs(ssb_env *env, int32_t b, int32_t *n_jobs, double *t_arrival, double *t_completed,
+                 int32_t *tmpl, int32_t capacity)
+{
+    if (!env || b < 0 || b >= env->p.B || !n_jobs) return SSB_E_INVALID;
+    CUDA_TRY(cudaSetDevice(env->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    EnvHdr h;
+    CUDA_TRY(cudaMemcpy(&h, env->p.hdr + b, sizeof(EnvHdr), cudaMemcpyDeviceToHost));
+    *n_jobs = h.n_jobs;
+    int n = h.n_jobs < capacity ? h.n_jobs : capacity;
+    std::vector<JobRec> jr(n > 0 ? n : 1);
+    if (n > 0)
+        CUDA_TRY(cudaMemcpy(jr.data(), env->p.job + (size_t)b * env->p.Jc, sizeof(JobRec) * n, cudaMemcpyDeviceToHost));
+    for (int j = 0; j < n; j++) {
+        if (t_arrival) t_arrival[j] = jr[j].t_arrival;
+        if (t_completed) t_completed[j] = jr[j].t_completed;
+        if (tmpl) tmpl[j] = jr[j].tmpl;
+    }
+    return SSB_OK;
+}
+
+int ssb_get_log(ssb_env *env, int32_t b, int64_t lo, int64_t hi, int64_t *n_rows, double *t, uint8_t *type,
+                int16_t *job, int16_t *stage, int32_t *task, int16_t *exec, double *t_accepted)
+{
+    if (!env || b < 0 || b >= env->p.B || !n_rows) return SSB_E_INVALID;
+    CUDA_TRY(cudaSetDevice(env->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    EnvHdr h;
+    CUDA_TRY(cudaMemcpy(&h, env->p.hdr + b, sizeof(EnvHdr), cudaMemcpyDeviceToHost));
+    *n_rows = h.log_n;
+    if (hi <= lo) return SSB_OK;
+    if (env->p.log_cap <= 0 || lo < 0 || hi > h.log_n || hi > env->p.log_cap) return SSB_E_INVALID;
+    std::vector<LogRow> rows(hi - lo);
+    CUDA_TRY(cudaMemcpy(rows.data(), env->p.log + (size_t)b * env->p.log_cap + lo, sizeof(LogRow) * (hi - lo),
+                        cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < hi - lo; i++) {
+        const LogRow &r = rows[i];
+        if (t) t[i] = r.t;
+        if (type) type[i] = r.type;
+        if (job) job[i] = r.job;
+        if (stage) stage[i] = r.stage;
+        if (task) task[i] = r.task;
+        if (exec) exec[i] = r.exec;
+        if (t_accepted) t_accepted[i] = r.t_acc;
+    }
+    return SSB_OK;
+}
+
+}  // extern "C"

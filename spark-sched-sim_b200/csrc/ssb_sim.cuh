@@ -1,0 +1,1182 @@
+// ssb_sim.cuh -- the scheduling loop of one environment, executed by one warp.
+//
+// Work split inside the warp:
+//   * wide, regular work is warp-cooperative: selecting the next timeline event (arg-min over the
+//     executors' pending events and the arrival cursor by shuffles), the schedulability scan over
+//     active jobs, building the observation (prefix sums + ballots for compaction), the fair policy;
+//   * the irregular state machine of one event (executor motion, commitments, pool membership with
+//     CPython set order) runs on lane 0 while the other lanes wait at the next __syncwarp().
+// Functions suffixed _w must be called by all 32 lanes with uniform arguments; all others are
+// lane-0 code.  Reference citations are spark_sched_sim/spark_sched_sim.py unless another file is named.
+#pragma once
+#include "ssb_types.cuh"
+
+namespace ssb {
+
+#define FULL 0xffffffffu
+#define SSB_CHK(cond)                         \
+    do {                                      \
+        if (!(cond)) {                        \
+            fail(1000 + __LINE__);            \
+            return;                           \
+        }                                     \
+    } while (0)
+#define SSB_CHKR(cond, ret)                   \
+    do {                                      \
+        if (!(cond)) {                        \
+            fail(1000 + __LINE__);            \
+            return ret;                       \
+        }                                     \
+    } while (0)
+
+// ---------------------------------------------------------------- Philox4x32-10 (Random123)
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                uint32_t k0, uint32_t k1)
+{
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+__device__ __forceinline__ uint32_t bounded(uint32_t w, uint32_t n) { return __umulhi(w, n); }
+
+// -ln((w+1) * 2^-32) from IEEE +,-,*,/ only, never fused (oracle/philox_ref.py:neglog_u32).
+__device__ __forceinline__ double neglog_u32(uint32_t w)
+{
+    unsigned long long k = (unsigned long long)w + 1ull;
+    int e = 63 - __clzll((long long)k);
+    double m = __ddiv_rn((double)k, (double)(1ull << e));
+    if (m > 1.4142135623730951) { m = __dmul_rn(m, 0.5); e += 1; }
+    double s = __ddiv_rn(__dadd_rn(m, -1.0), __dadd_rn(m, 1.0));
+    double z = __dmul_rn(s, s);
+    const double D[11] = {21.0, 19.0, 17.0, 15.0, 13.0, 11.0, 9.0, 7.0, 5.0, 3.0, 1.0};
+    double p = __ddiv_rn(1.0, 23.0);
+#pragma unroll
+    for (int i = 0; i < 11; i++) p = __dadd_rn(__dmul_rn(p, z), __ddiv_rn(1.0, D[i]));
+    double lnm = __dmul_rn(__dmul_rn(2.0, s), p);
+    double el = __dmul_rn((double)(e - 32), 0.6931471805599453);
+    return -__dadd_rn(lnm, el);
+}
+
+// ---------------------------------------------------------------- CPython 3.12 set look-alike
+// Objects/setobject.c for small non-negative int keys (hash(i) == i); see SURVEY.md App. B.
+template <typename T>
+struct PSet {
+    int mask, fill, used, finger;
+    T *t;
+    static constexpr int EMPTY = (T)~(T)0;
+    static constexpr int DUMMY = (T)(~(T)0 - 1);
+};
+
+template <typename T>
+__device__ inline void ps_insert_clean(T *t, int mask, int key)  // set_insert_clean
+{
+    unsigned perturb = (unsigned)key, i = (unsigned)key & mask;
+    for (;;) {
+        if (t[i] == PSet<T>::EMPTY) { t[i] = (T)key; return; }
+        if (i + 9 <= (unsigned)mask) {
+            for (int j = 1; j <= 9; j++)
+                if (t[i + j] == PSet<T>::EMPTY) { t[i + j] = (T)key; return; }
+        }
+        perturb >>= 5;
+        i = (i * 5 + 1 + perturb) & mask;
+    }
+}
+template <typename T>
+__device__ inline void ps_resize(PSet<T> &s, int minused, T *tmp)  // set_table_resize
+{
+    int newsize = 8;
+    while (newsize <= minused) newsize <<= 1;
+    int oldmask = s.mask;
+    if (newsize == 8 && oldmask == 7 && s.fill == s.used) return;
+    for (int i = 0; i <= oldmask; i++) tmp[i] = s.t[i];
+    for (int i = 0; i < newsize; i++) s.t[i] = (T)PSet<T>::EMPTY;
+    s.mask = newsize - 1;
+    s.fill = s.used;
+    for (int i = 0; i <= oldmask; i++)
+        if (tmp[i] < PSet<T>::DUMMY) ps_insert_clean(s.t, s.mask, tmp[i]);
+}
+template <typename T>
+__device__ inline void ps_add(PSet<T> &s, int key, T *tmp)  // set_add_entry
+{
+    int mask = s.mask, freeslot = -1;
+    unsigned perturb = (unsigned)key, i = (unsigned)key & mask;
+    for (;;) {
+        int probes = (i + 9 <= (unsigned)mask) ? 9 : 0;
+        for (int j = 0; j <= probes; j++) {
+            int v = s.t[i + j];
+            if (v == PSet<T>::EMPTY) {
+                if (freeslot >= 0) { s.used++; s.t[freeslot] = (T)key; return; }
+                s.fill++; s.used++;
+                s.t[i + j] = (T)key;
+                if (s.fill * 5 < mask * 3) return;
+                ps_resize(s, s.used * 4, tmp);
+                return;
+            }
+            if (v == key) return;
+            if (v == PSet<T>::DUMMY) freeslot = (int)(i + j);
+        }
+        perturb >>= 5;
+        i = (i * 5 + 1 + perturb) & mask;
+    }
+}
+template <typename T>
+__device__ inline int ps_find(const PSet<T> &s, int key)  // set_lookkey
+{
+    int mask = s.mask;
+    unsigned perturb = (unsigned)key, i = (unsigned)key & mask;
+    for (;;) {
+        int probes = (i + 9 <= (unsigned)mask) ? 9 : 0;
+        for (int j = 0; j <= probes; j++) {
+            int v = s.t[i + j];
+            if (v == PSet<T>::EMPTY) return -1;
+            if (v == key) return (int)(i + j);
+        }
+        perturb >>= 5;
+        i = (i * 5 + 1 + perturb) & mask;
+    }
+}
+template <typename T>
+__device__ inline bool ps_remove(PSet<T> &s, int key)
+{
+    int slot = ps_find(s, key);
+    if (slot < 0) return false;
+    s.t[slot] = (T)PSet<T>::DUMMY;
+    s.used--;
+    return true;
+}
+template <typename T>
+__device__ inline int ps_pop(PSet<T> &s)  // set_pop
+{
+    if (s.used == 0) return -1;
+    int i = s.finger & s.mask;
+    while (s.t[i] >= PSet<T>::DUMMY) {
+        i++;
+        if (i > s.mask) i = 0;
+    }
+    int key = s.t[i];
+    s.t[i] = (T)PSet<T>::DUMMY;
+    s.used--;
+    s.finger = i + 1;
+    return key;
+}
+template <typename T>
+__device__ inline void ps_init(PSet<T> &s, T *table)
+{
+    s.mask = 7; s.fill = s.used = s.finger = 0; s.t = table;
+    for (int i = 0; i < 8; i++) table[i] = (T)PSet<T>::EMPTY;
+}
+// set.copy(): make_new_set + set_merge into an empty set
+template <typename T>
+__device__ inline void ps_copy_into(PSet<T> &dst, T *table, const PSet<T> &other, T *tmp)
+{
+    ps_init(dst, table);
+    if (other.used == 0) return;
+    if (other.used * 5 >= 7 * 3) ps_resize(dst, other.used * 2, tmp);
+    if (dst.mask == other.mask && other.fill == other.used) {
+        for (int i = 0; i <= other.mask; i++) dst.t[i] = other.t[i];
+        dst.fill = other.fill; dst.used = other.used;
+        return;
+    }
+    dst.fill = dst.used = other.used;
+    for (int i = 0; i <= other.mask; i++)
+        if (other.t[i] < PSet<T>::DUMMY) ps_insert_clean(dst.t, dst.mask, other.t[i]);
+}
+
+__device__ __forceinline__ int popc64(uint64_t x) { return __popcll(x); }
+__device__ __forceinline__ int ffs64(uint64_t x) { return __ffsll((long long)x) - 1; }
+__device__ __forceinline__ uint64_t bit64(int s) { return 1ull << s; }
+
+// ================================================================ one environment, one warp
+struct Sim {
+    const Params &p;
+    const int b, lane;
+    EnvHdr *h;
+    ExecRec *ex;
+    JobRec *jb;
+    StageRec *st;
+    int16_t *act;
+    Commit *cm;
+    PoolHdr *ph;
+    uint8_t *pt;
+    uint8_t *scr;
+    ssb_stats *stats;
+    ssb_obs_hdr *oh;
+
+    __device__ Sim(const Params &p_, int b_, int lane_) : p(p_), b(b_), lane(lane_)
+    {
+        h = p.hdr + b;
+        ex = p.exec + (size_t)b * p.E;
+        jb = p.job + (size_t)b * p.Jc;
+        st = p.stage + (size_t)b * p.Sc;
+        act = p.active + (size_t)b * p.Jc;
+        cm = p.commits + (size_t)b * p.Cc;
+        ph = p.pool_hdr + (size_t)b * p.P;
+        pt = p.pool_tab + (size_t)b * p.P * p.TAB;
+        scr = p.scr_tab + (size_t)b * 3 * p.TAB;
+        stats = p.stats + b;
+        oh = p.obs_hdr + b;
+    }
+
+    __device__ void fail(int code)
+    {
+        if (!h->error) h->error = code;
+    }
+
+    // ------------------------------------------------------------ pool helpers (executor_tracker.py)
+    __device__ int pool_of_job(int j) const { return 2 + j; }
+    __device__ int pool_of_stage(int j, int s) const { return 2 + p.Jc + jb[j].node_base + s; }
+    __device__ int pool_job(int pool) const  // pool_key[0], -1 == None
+    {
+        if (pool < 2) return -1;
+        if (pool < 2 + p.Jc) return pool - 2;
+        return st[pool - 2 - p.Jc].job;
+    }
+    __device__ int pool_stage(int pool) const  // pool_key[1], -1 == None
+    {
+        if (pool < 2 + p.Jc) return -1;
+        int node = pool - 2 - p.Jc;
+        return node - jb[st[node].job].node_base;
+    }
+    __device__ PSet<uint8_t> ps_load(int pool) const
+    {
+        PSet<uint8_t> s;
+        PoolHdr hd = ph[pool];
+        s.mask = hd.mask; s.fill = hd.fill; s.used = hd.used; s.finger = hd.finger;
+        s.t = pt + (size_t)pool * p.TAB;
+        return s;
+    }
+    __device__ void ps_store(int pool, const PSet<uint8_t> &s)
+    {
+        PoolHdr hd;
+        hd.mask = (uint16_t)s.mask; hd.fill = (uint16_t)s.fill; hd.used = (uint16_t)s.used;
+        hd.finger = (uint16_t)s.finger;
+        ph[pool] = hd;
+    }
+    __device__ int pool_size(int pool) const { return ph[pool].used; }
+    __device__ int commit_from(int pool) const
+    {
+        if (pool == POOL_NONE) return 0;
+        if (pool == POOL_COMMON) return h->commit_from_common;
+        if (pool < 2 + p.Jc) return jb[pool - 2].commit_from;
+        return st[pool - 2 - p.Jc].commit_from;
+    }
+    __device__ void add_commit_from(int pool, int d)
+    {
+        if (pool == POOL_COMMON) h->commit_from_common += d;
+        else if (pool < 2 + p.Jc) jb[pool - 2].commit_from += d;
+        else st[pool - 2 - p.Jc].commit_from += d;
+    }
+    __device__ void add_total(int job, int d)  // _total_executor_count[job], job -1 == None
+    {
+        if (job < 0) h->total_none += d;
+        else jb[job].supply += d;
+    }
+    // demand <= 0  (_get_executor_demand :566-578, _is_stage_saturated :580-582)
+    __device__ void update_sat(int j, int s)
+    {
+        const StageRec &r = st[jb[j].node_base + s];
+        int demand = (int)r.remaining - ((int)r.moving_to + (int)r.commit_to);
+        if (demand <= 0) jb[j].sat |= bit64(s);
+        else jb[j].sat &= ~bit64(s);
+    }
+    __device__ void add_commit_to(int pool, int d)
+    {
+        if (pool == POOL_COMMON) { h->commit_to_common += d; return; }
+        StageRec &r = st[pool - 2 - p.Jc];
+        r.commit_to += d;
+        update_sat(r.job, pool_stage(pool));
+    }
+    __device__ int source_job_id() const  // executor_tracker.py:99-103
+    {
+        int s = h->source;
+        if (s == POOL_NONE || s == POOL_COMMON) return -1;
+        return pool_job(s);
+    }
+    __device__ int num_committable() const  // executor_tracker.py:105-111
+    {
+        int s = h->source;
+        if (s == POOL_NONE) return 0;
+        return (int)ph[s].used - commit_from(s);
+    }
+    __device__ Commit *find_commit(int src, int dst)
+    {
+        int n = h->n_commits;
+        for (int i = 0; i < n; i++)
+            if (cm[i].src == src && cm[i].dst == dst) return cm + i;
+        return nullptr;
+    }
+    __device__ void add_commitment(int n, int dst)  // executor_tracker.py:146-154, :224-236
+    {
+        int src = h->source;
+        SSB_CHK(src != POOL_NONE);
+        Commit *c = find_commit(src, dst);
+        if (c) c->n += n;
+        else {
+            SSB_CHK(h->n_commits < p.Cc);
+            Commit nc; nc.src = src; nc.dst = dst; nc.n = n;
+            cm[h->n_commits++] = nc;
+        }
+        add_commit_from(src, n);
+        add_commit_to(dst, n);
+        SSB_CHK(pool_size(src) >= commit_from(src));
+        int sj = pool_job(src), dj = pool_job(dst);
+        if (dj != sj) add_total(dj, n);
+    }
+    __device__ int remove_commitment(int e, int dst)  // executor_tracker.py:156-173, :238-249
+    {
+        int src = ex[e].loc;
+        SSB_CHKR(src != POOL_NONE, POOL_NONE);
+        Commit *c = find_commit(src, dst);
+        SSB_CHKR(c != nullptr, POOL_NONE);
+        c->n -= 1;
+        add_commit_from(src, -1);
+        add_commit_to(dst, -1);
+        SSB_CHKR(commit_from(src) >= 0, POOL_NONE);
+        if (c->n == 0) {
+            int idx = (int)(c - cm), n = h->n_commits;
+            for (int i = idx; i + 1 < n; i++) cm[i] = cm[i + 1];
+            h->n_commits = n - 1;
+        }
+        int sj = pool_job(src), dj = pool_job(dst);
+        if (dj != sj) {
+            add_total(dj, -1);
+            SSB_CHKR(dj < 0 ? h->total_none >= 0 : jb[dj].supply >= 0, POOL_NONE);
+        }
+        return src;
+    }
+    __device__ int peek_commitment(int pool)  // executor_tracker.py:175-180
+    {
+        int n = h->n_commits;
+        for (int i = 0; i < n; i++)
+            if (cm[i].src == pool) return cm[i].dst;
+        return POOL_NONE;
+    }
+    __device__ void move_executor_to_pool(int e, int new_pool, bool send)  // executor_tracker.py:186-220
+    {
+        int old = ex[e].loc;
+        if (old != POOL_NONE) {
+            PSet<uint8_t> s = ps_load(old);
+            bool ok = ps_remove(s, e);
+            ps_store(old, s);
+            SSB_CHK(ok);
+            ex[e].loc = POOL_NONE;
+        }
+        if (!send) {
+            ex[e].loc = new_pool;
+            PSet<uint8_t> s = ps_load(new_pool);
+            ps_add(s, e, scr + 2 * p.TAB);
+            ps_store(new_pool, s);
+            return;
+        }
+        SSB_CHK(new_pool >= 2 + p.Jc);
+        StageRec &r = st[new_pool - 2 - p.Jc];
+        r.moving_to += 1;
+        update_sat(r.job, pool_stage(new_pool));
+        int old_job = old != POOL_NONE ? pool_job(old) : -1, new_job = r.job;
+        SSB_CHK(old_job != new_job);
+        jb[new_job].supply += 1;
+        if (old_job != -1) {
+            jb[old_job].supply -= 1;
+            SSB_CHK(jb[old_job].supply >= 0);
+        }
+    }
+
+    // ------------------------------------------------------------ sampler (data_samplers/tpch.py)
+    __device__ bool sample_wave(int ts, int wave, int lvl, uint32_t w1, bool warmup, double &out)  // :208-214
+    {
+        if (lvl < 0 || !((p.b_present[ts * 4 + wave] >> lvl) & 1)) return false;  // KeyError
+        uint2 oc = p.b_dur[(ts * 3 + wave) * 8 + lvl];
+        if (oc.y == 0) return false;  // ValueError: choice from an empty list
+        double d = p.b_vals[oc.x + bounded(w1, oc.y)];
+        if (warmup) d = __dadd_rn(d, p.warmup_delay);
+        out = d;
+        return true;
+    }
+    __device__ double task_duration(int j, int s, int e)  // tpch.py:75-106
+    {
+        uint32_t li = h->launch_idx;
+        if (h->use_tape) {
+            if ((int)li >= h->tape_len) { fail(SSB_ENV_TAPE_EXHAUSTED); return 1.0; }
+            return p.tape[(size_t)b * p.tape_cap + li];
+        }
+        int n_local = jb[j].n_local;
+        SSB_CHKR(n_local > 0 && n_local <= p.E, 1.0);
+        uint4 w = philox4x32_10(li, 0u, 2u, 0u, (uint32_t)h->seed, (uint32_t)(h->seed >> 32));
+        int left = p.iv[2 * n_local], right = p.iv[2 * n_local + 1], key;  // _sample_executor_key :216-235
+        if (left == right) key = left;
+        else {
+            double u = __dmul_rn((double)w.x, 1.0 / 4294967296.0);
+            int rand_pt = 1 + (int)__dmul_rn(u, (double)(right - left));
+            key = (rand_pt <= n_local - left) ? left : right;
+        }
+        int ts = jb[j].ts_base + s;
+        int lvl = -1;
+        {
+            const int LV[8] = {5, 10, 20, 40, 50, 60, 80, 100};
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                if (LV[i] == key) lvl = i;
+        }
+        int fw = p.b_present[ts * 4 + 1];
+        if (lvl < 0 || !((fw >> lvl) & 1)) lvl = fw ? 31 - __clz(fw) : -1;  // max(data["first_wave"])
+        double d;
+        if (!ex[e].has_task) {  // executor.is_idle
+            if (sample_wave(ts, 0, lvl, w.y, false, d)) return d;
+            if (sample_wave(ts, 1, lvl, w.y, true, d)) return d;
+            fail(SSB_ENV_SAMPLER);
+            return 1.0;
+        }
+        if (ex[e].task_stage == s)
+            if (sample_wave(ts, 2, lvl, w.y, false, d)) return d;
+        if (sample_wave(ts, 1, lvl, w.y, false, d)) return d;
+        if (sample_wave(ts, 0, lvl, w.y, false, d)) return d;
+        fail(SSB_ENV_SAMPLER);
+        return 1.0;
+    }
+
+    // ------------------------------------------------------------ schedulability (:505-555)
+    // Schedulable stages of job j as a bitmask: ready (unsaturated, all parents saturated), not yet
+    // selected this round, job not saturated with executors unless it is the source job.
+    __device__ uint64_t job_sched_mask(int j, int source_job) const
+    {
+        const JobRec &J = jb[j];
+        if (!(j == source_job || J.supply < p.E)) return 0;
+        uint64_t sat = J.sat, cand = J.active & ~J.selected & ~sat, out = 0;
+        const uint64_t *pm = p.b_parent + J.ts_base;
+        while (cand) {
+            int s = ffs64(cand);
+            cand &= cand - 1;
+            if ((pm[s] & ~sat) == 0) out |= bit64(s);
+        }
+        return out;
+    }
+    // _find_schedulable_stages over all active jobs; writes every active job's `sched` mask
+    __device__ int find_schedulable_all_w()
+    {
+        int src_job = source_job_id();
+        int n_active = h->n_active, total = 0;
+        for (int base = 0; base < n_active; base += 32) {
+            int i = base + lane, cnt = 0;
+            if (i < n_active) {
+                int j = act[i];
+                uint64_t m = job_sched_mask(j, src_job);
+                jb[j].sched = m;
+                cnt = popc64(m);
+            }
+            total += __reduce_add_sync(FULL, cnt);
+        }
+        __syncwarp();
+        if (lane == 0) { h->n_sched = total; stats->sched_scans++; }
+        return total;
+    }
+    __device__ void clear_sched_w()
+    {
+        int n_active = h->n_active;
+        for (int i = lane; i < n_active; i += 32) jb[act[i]].sched = 0;
+        if (lane == 0) h->n_sched = 0;
+        __syncwarp();
+    }
+    // first schedulable stage of the job-id list semantics used by _find_backup_stage (:821-845)
+    __device__ bool first_schedulable(bool only_job, int job, int source_job_arg, int &oj, int &os)
+    {
+        int src_job = source_job_arg <= 0 ? source_job_id() : source_job_arg;  // `if not source_job_id`
+        if (only_job) {
+            uint64_t m = job_sched_mask(job, src_job);
+            if (!m) return false;
+            oj = job; os = ffs64(m);
+            return true;
+        }
+        // other_job_ids = active jobs except `job`; an EMPTY list means "all active jobs" (:518-519)
+        int n_active = h->n_active;
+        bool all = true;
+        for (int i = 0; i < n_active; i++) if (act[i] != job) { all = false; break; }
+        for (int i = 0; i < n_active; i++) {
+            int j = act[i];
+            if (!all && j == job) continue;
+            uint64_t m = job_sched_mask(j, src_job);
+            if (m) { oj = j; os = ffs64(m); return true; }
+        }
+        return false;
+    }
+
+    // ------------------------------------------------------------ executor motion
+    __device__ void detach_executor(int j, int e)  // job.py:86-89
+    {
+        SSB_CHK(jb[j].n_local > 0);
+        jb[j].n_local -= 1;
+        ex[e].job_id = -1;
+        ex[e].has_task = 0;
+    }
+    __device__ void push_event(int e, double t, int kind, int j, int s, int task)
+    {
+        ExecRec &x = ex[e];
+        x.ev_t = t; x.ev_seq = h->seq++; x.ev_kind = (uint8_t)kind;
+        x.ev_job = (int16_t)j; x.ev_stage = (int16_t)s; x.ev_task = task;
+        x.t_acc = h->wall_time;
+    }
+    __device__ void execute_next_task(int e, int j, int s)  // :584-615
+    {
+        StageRec &r = st[jb[j].node_base + s];
+        SSB_CHK(r.remaining > 0);
+        SSB_CHK(ex[e].job_id == j);
+        SSB_CHK(!ex[e].is_executing);
+        int task_id = r.remaining - 1;  // stage.py:53-58: tasks pop from the end
+        r.remaining -= 1;
+        if (r.remaining == 0) jb[j].sat_count += 1;
+        update_sat(j, s);
+        double d = task_duration(j, s, e);
+        h->launch_idx += 1;
+        ex[e].has_task = 1; ex[e].task_stage = (int16_t)s; ex[e].is_executing = 1;
+        r.mrd = (float)d;
+        push_event(e, __dadd_rn(h->wall_time, d), EV_TASK_FINISHED, j, s, task_id);
+    }
+    __device__ void send_executor(int e, int j, int s)  // :617-637
+    {
+        SSB_CHK(!ex[e].is_executing);
+        SSB_CHK(ex[e].job_id != j);
+        move_executor_to_pool(e, pool_of_stage(j, s), true);
+        if (ex[e].job_id != -1) detach_executor(ex[e].job_id, e);
+        push_event(e, __dadd_rn(h->wall_time, p.moving_delay), EV_EXECUTOR_READY, j, s, -1);
+    }
+    // _get_idle_source_executors (:714-728): set(generator) over a copy of the pool; result in scr[1]
+    __device__ PSet<uint8_t> idle_executors(int pool)
+    {
+        PSet<uint8_t> src = ps_load(pool), cp, idle;
+        ps_copy_into(cp, scr, src, scr + 2 * p.TAB);
+        ps_init(idle, scr + p.TAB);
+        for (int i = 0; i <= cp.mask; i++) {
+            int v = cp.t[i];
+            if (v < PSet<uint8_t>::DUMMY && !ex[v].is_executing) ps_add(idle, v, scr + 2 * p.TAB);
+        }
+        return idle;
+    }
+    // _move_idle_executors (:745-782).  e >= 0: that single executor; e < 0: all idle ones at src
+    __device__ void move_idle_executors(int src, int e)
+    {
+        if (src == POOL_NONE) src = h->source;
+        SSB_CHK(src != POOL_NONE);
+        if (src == POOL_COMMON) return;
+        uint8_t ids[128];
+        int n = 0;
+        if (e >= 0) ids[n++] = (uint8_t)e;
+        else {
+            PSet<uint8_t> idle = idle_executors(src);
+            for (int i = 0; i <= idle.mask && n < 128; i++)
+                if (idle.t[i] < PSet<uint8_t>::DUMMY) ids[n++] = idle.t[i];
+        }
+        SSB_CHK(n > 0);
+        int j = pool_job(src), s = pool_stage(src);
+        SSB_CHK(j >= 0);
+        bool sat = jb[j].sat_count == jb[j].n_stages;  // job.saturated, job.py:54-55
+        if (s < 0 && !sat) return;
+        int dst = sat ? POOL_COMMON : pool_of_job(j);
+        for (int i = 0; i < n; i++) {
+            move_executor_to_pool(ids[i], dst, false);
+            if (dst == POOL_COMMON) detach_executor(j, ids[i]);
+        }
+    }
+    // _move_executor_to_stage (:799-819) with _try_backup_schedule (:784-797) unrolled into a loop
+    __device__ void move_executor_to_stage(int e, int j, int s)
+    {
+        for (int guard = 0; guard < 4; guard++) {
+            StageRec &r = st[jb[j].node_base + s];
+            if (r.remaining == 0) {
+                int me = ex[e].job_id, bj, bs;
+                SSB_CHK(me != -1);  // _find_backup_stage :823
+                if (first_schedulable(true, me, me, bj, bs) || first_schedulable(false, me, me, bj, bs)) {
+                    j = bj; s = bs;
+                    continue;
+                }
+                move_idle_executors(ex[e].loc, e);
+                return;
+            }
+            if (ex[e].job_id != j) { send_executor(e, j, s); return; }
+            if (!(jb[j].frontier & bit64(s))) {
+                ex[e].has_task = 0;
+                move_executor_to_pool(e, pool_of_job(j), false);
+                return;
+            }
+            move_executor_to_pool(e, pool_of_stage(j, s), false);
+            execute_next_task(e, j, s);
+            return;
+        }
+        fail(1000 + __LINE__);
+    }
+    __device__ void fulfill_commitment(int e, int dst)  // :699-712
+    {
+        int src = remove_commitment(e, dst);
+        if (h->error) return;
+        if (dst == POOL_COMMON) { move_idle_executors(src, e); return; }
+        SSB_CHK(dst >= 2 + p.Jc);
+        move_executor_to_stage(e, pool_job(dst), pool_stage(dst));
+    }
+    __device__ void commit_remaining_executors()  // :487-503
+    {
+        int n = num_committable();
+        SSB_CHK(n >= 0);
+        if (n > 0) add_commitment(n, POOL_COMMON);
+    }
+    __device__ void fulfill_commitments_from_source()  // :730-743
+    {
+        int src = h->source;
+        SSB_CHK(src != POOL_NONE);
+        PSet<uint8_t> idle = idle_executors(src);
+        // snapshot of the source's commitments in insertion order (get_source_commitments(): dict.copy())
+        int16_t sn[136];
+        int32_t sd[136];
+        int ns = 0;
+        for (int i = 0; i < h->n_commits && ns < 136; i++)
+            if (cm[i].src == src) { sd[ns] = cm[i].dst; sn[ns] = (int16_t)cm[i].n; ns++; }
+        for (int k = 0; k < ns; k++) {
+            int want = sn[k];
+            SSB_CHK(want > 0);
+            while (want > 0 && idle.used > 0) {
+                int e = ps_pop(idle);
+                fulfill_commitment(e, sd[k]);
+                if (h->error) return;
+                want--;
+            }
+        }
+        SSB_CHK(idle.used == 0);
+    }
+
+    // ------------------------------------------------------------ event handlers
+    __device__ void handle_job_arrival(int j)  // :428-438 (pools were initialised at reset)
+    {
+        act[h->n_active++] = (int16_t)j;
+        jb[j].state = JOB_ACTIVE;
+        if (pool_size(POOL_COMMON) > 0) h->source = POOL_COMMON;
+    }
+    __device__ void handle_executor_arrival(int e, int j, int s)  // :440-450
+    {
+        SSB_CHK(!ex[e].has_task);  // job.py:82
+        jb[j].n_local += 1;
+        ex[e].job_id = (int16_t)j;
+        StageRec &r = st[jb[j].node_base + s];
+        SSB_CHK(r.moving_to > 0);
+        r.moving_to -= 1;  // record_executor_arrival
+        update_sat(j, s);
+        move_executor_to_pool(e, pool_of_job(j), false);
+        move_executor_to_stage(e, j, s);
+    }
+    __device__ bool record_stage_completion(int j, int s)  // job.py:65-73, :113-128
+    {
+        JobRec &J = jb[j];
+        J.active &= ~bit64(s);
+        SSB_CHKR(J.frontier & bit64(s), false);
+        J.frontier &= ~bit64(s);
+        uint64_t kids = p.b_child[J.ts_base + s] & J.active, fresh = 0;
+        const uint64_t *pm = p.b_parent + J.ts_base;
+        while (kids) {
+            int c = ffs64(kids);
+            kids &= kids - 1;
+            if ((pm[c] & J.active) == 0) fresh |= bit64(c);  // all parents completed
+        }
+        J.frontier |= fresh;
+        return fresh != 0;
+    }
+    __device__ void process_job_completion(int j)  // :682-697
+    {
+        if (pool_size(pool_of_job(j)) > 0) move_idle_executors(pool_of_job(j), -1);
+        SSB_CHK(pool_size(pool_of_job(j)) == 0);
+        int n = h->n_active, idx = -1;
+        for (int i = 0; i < n; i++) if (act[i] == j) { idx = i; break; }
+        SSB_CHK(idx >= 0);
+        for (int i = idx; i + 1 < n; i++) act[i] = act[i + 1];
+        h->n_active = n - 1;
+        h->n_completed += 1;
+        jb[j].state = JOB_COMPLETED;
+        jb[j].sched = 0;
+        jb[j].t_completed = h->wall_time;
+    }
+    __device__ void handle_task_completion(int e, int j, int s)  // :452-483
+    {
+        StageRec &r = st[jb[j].node_base + s];
+        SSB_CHK(r.completed < r.num_tasks);
+        r.completed += 1;
+        ex[e].is_executing = 0;
+        if (r.remaining > 0) { execute_next_task(e, j, s); return; }
+        bool frontier_changed = false;
+        if (r.completed == r.num_tasks) frontier_changed = record_stage_completion(j, s);
+        if (jb[j].active == 0) process_job_completion(j);
+        if (h->error) return;
+        // _handle_released_executor (:639-660)
+        bool had = false;
+        int dst = peek_commitment(pool_of_stage(j, s));
+        if (dst != POOL_NONE) { fulfill_commitment(e, dst); had = true; }
+        else {
+            ex[e].has_task = 0;
+            if (frontier_changed) move_idle_executors(pool_of_stage(j, s), e);
+        }
+        // _update_executor_source (:662-674)
+        if (frontier_changed) h->source = pool_of_job(j);
+        else if (!had) h->source = pool_of_stage(j, s);
+    }
+    __device__ void log_event(int type, int j, int s, int task, int e, double tacc)
+    {
+        if (p.log_cap > 0 && h->log_n < p.log_cap) {
+            LogRow r;
+            r.t = h->wall_time; r.t_acc = tacc; r.task = task; r.job = (int16_t)j; r.stage = (int16_t)s;
+            r.exec = (int16_t)e; r.type = (uint8_t)type; r.pad = 0; r.pad1 = 0;
+            p.log[(size_t)b * p.log_cap + h->log_n] = r;
+        }
+        h->log_n += 1;
+    }
+    // handles popped event `idx` (executor id, or E for the next job arrival) at time t
+    __device__ void handle_event(int idx, double t)  // :317-318, :327-329
+    {
+        h->wall_time = t;
+        stats->events++;
+        if (idx == p.E) {
+            int j = h->next_arrival++;
+            log_event(EV_JOB_ARRIVAL, j, -1, -1, -1, __longlong_as_double(0x7ff0000000000000ll));
+            handle_job_arrival(j);
+            return;
+        }
+        ExecRec &x = ex[idx];
+        int kind = x.ev_kind, j = x.ev_job, s = x.ev_stage;
+        x.ev_kind = 0;
+        if (kind == EV_TASK_FINISHED) {
+            log_event(kind, j, s, x.ev_task, idx, x.t_acc);
+            handle_task_completion(idx, j, s);
+        } else {
+            log_event(kind, j, s, -1, idx, __longlong_as_double(0x7ff0000000000000ll));
+            handle_executor_arrival(idx, j, s);
+        }
+    }
+
+    // ------------------------------------------------------------ timeline: next event by (t, seq)
+    __device__ int pop_min_w(double &t_out)
+    {
+        unsigned long long kt = 0x7ff8000000000000ull;  // > every finite time and +inf
+        uint32_t ks = 0xffffffffu;
+        int idx = -1;
+        for (int e = lane; e < p.E; e += 32) {
+            const ExecRec &x = ex[e];
+            if (x.ev_kind) {
+                unsigned long long t = (unsigned long long)__double_as_longlong(x.ev_t);
+                if (t < kt || (t == kt && x.ev_seq < ks)) { kt = t; ks = x.ev_seq; idx = e; }
+            }
+        }
+        if (lane == 31) {  // arrival cursor: arrivals were "pushed" first, seq = job id (:152-154)
+            int na = h->next_arrival;
+            if (na < h->n_jobs) {
+                unsigned long long t = (unsigned long long)__double_as_longlong(jb[na].t_arrival);
+                if (t < kt || (t == kt && (uint32_t)na < ks)) { kt = t; ks = (uint32_t)na; idx = p.E; }
+            }
+        }
+#pragma unroll
+        for (int off = 16; off; off >>= 1) {
+            unsigned long long ot = __shfl_xor_sync(FULL, kt, off);
+            uint32_t os = __shfl_xor_sync(FULL, ks, off);
+            int oi = __shfl_xor_sync(FULL, idx, off);
+            if (ot < kt || (ot == kt && os < ks)) { kt = ot; ks = os; idx = oi; }
+        }
+        t_out = __longlong_as_double((long long)kt);
+        return idx;
+    }
+
+    // ------------------------------------------------------------ _resume_simulation (:320-343)
+    __device__ void resume_simulation_w()
+    {
+        clear_sched_w();
+        for (;;) {
+            double t;
+            int idx = pop_min_w(t);
+            if (idx < 0) break;
+            if (lane == 0) handle_event(idx, t);
+            __syncwarp();
+            if (h->error) break;
+            if (num_committable() <= 0) continue;
+            int n = find_schedulable_all_w();
+            if (n) break;
+            if (lane == 0) { move_idle_executors(POOL_NONE, -1); h->source = POOL_NONE; }
+            __syncwarp();
+            if (h->error) break;
+        }
+    }
+
+    // ------------------------------------------------------------ reward (:847-874), lane 0
+    __device__ double compute_jobtime()
+    {
+        double wall = h->wall_time, wall_old = h->wall_old;
+        if (wall - wall_old == 0.0) return 0.0;
+        uint16_t *tab = p.rset + (size_t)b * 2 * p.RT, *tmp = tab + p.RT;
+        PSet<uint16_t> ids;  // set(active_old + active_new): iteration order == CPython's
+        ps_init(ids, tab);
+        const int16_t *old = p.old_act + (size_t)b * p.Jc;
+        for (int i = 0; i < h->n_old_active; i++) ps_add(ids, old[i], tmp);
+        for (int i = 0; i < h->n_active; i++) ps_add(ids, act[i], tmp);
+        double jt = 0.0, beta = p.beta;
+        for (int i = 0; i <= ids.mask; i++) {
+            int j = ids.t[i];
+            if (j >= PSet<uint16_t>::DUMMY) continue;
+            double start = fmax(jb[j].t_arrival, wall_old), end = fmin(jb[j].t_completed, wall);
+            if (beta == 0.0) jt = __dadd_rn(jt, __dadd_rn(end, -start));
+            else
+                jt += exp(-beta * 1e-3 * (start - wall_old)) - exp(-beta * 1e-3 * (end - wall_old));
+        }
+        if (beta > 0.0) jt /= beta;
+        return jt;
+    }
+
+    // ------------------------------------------------------------ _observe (:345-406, utils.py:5-22)
+    __device__ void observe_w(double reward, bool terminated)
+    {
+        const int n_active = h->n_active;
+        float *nodes = p.obs_nodes + (size_t)b * p.Sc * 3;
+        int32_t *edges = p.obs_edges + (size_t)b * p.Mc * 2;
+        int32_t *dag_ptr = p.obs_dag_ptr + (size_t)b * (p.Jc + 1);
+        int32_t *sup = p.obs_supplies + (size_t)b * p.Jc;
+        const int src_job = source_job_id();
+        int src_idx = n_active, N = 0;
+        // dag_ptr / exec_supplies / source_job_idx: exclusive scan of per-job active-stage counts
+        for (int base = 0; base < n_active; base += 32) {
+            int i = base + lane, cnt = 0, j = -1;
+            if (i < n_active) {
+                j = act[i];
+                cnt = popc64(jb[j].active);
+                sup[i] = jb[j].supply;
+            }
+            int incl = cnt;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                int v = __shfl_up_sync(FULL, incl, off);
+                if (lane >= off) incl += v;
+            }
+            if (i < n_active) dag_ptr[i + 1] = N + incl;
+            unsigned hit = __ballot_sync(FULL, j >= 0 && j == src_job);
+            if (hit) src_idx = base + __ffs(hit) - 1;
+            N += __shfl_sync(FULL, incl, 31);
+        }
+        if (lane == 0) dag_ptr[0] = 0;
+        __syncwarp();
+        // nodes and edges, one active job at a time, lanes over its stages / template edges
+        int M = 0;
+        for (int i = 0; i < n_active; i++) {
+            const int j = act[i];
+            const JobRec &J = jb[j];
+            const uint64_t active = J.active, sched = J.sched;
+            const int nbase = dag_ptr[i], ns = J.n_stages;
+            for (int s = lane; s < ns; s += 32) {
+                if (active & bit64(s)) {
+                    const StageRec r = st[J.node_base + s];
+                    int rank = nbase + popc64(active & (bit64(s) - 1));
+                    nodes[rank * 3 + 0] = (float)r.remaining;
+                    nodes[rank * 3 + 1] = r.mrd;
+                    nodes[rank * 3 + 2] = (sched & bit64(s)) ? 1.0f : 0.0f;
+                }
+            }
+            const int eb = p.b_edge_base[J.tmpl], ne = p.b_edge_base[J.tmpl + 1] - eb;
+            for (int k0 = 0; k0 < ne; k0 += 32) {
+                int k = k0 + lane, u = 0, v = 0;
+                bool keep = false;
+                if (k < ne) {
+                    u = p.b_edges[2 * (eb + k)];
+                    v = p.b_edges[2 * (eb + k) + 1];
+                    keep = (active & bit64(u)) && (active & bit64(v));
+                }
+                unsigned m = __ballot_sync(FULL, keep);
+                if (keep) {
+                    int pos = M + __popc(m & ((1u << lane) - 1));
+                    edges[2 * pos] = nbase + popc64(active & (bit64(u) - 1));
+                    edges[2 * pos + 1] = nbase + popc64(active & (bit64(v) - 1));
+                }
+                M += __popc(m);
+            }
+        }
+        if (lane == 0) {
+            ssb_obs_hdr o;
+            o.reward = reward;
+            o.wall_time = h->wall_time;
+            o.num_nodes = N; o.num_edges = M; o.num_active_jobs = n_active;
+            o.num_committable_execs = num_committable();
+            o.source_job_idx = src_idx;
+            o.num_schedulable = h->n_sched;
+            o.error = h->error;
+            o.terminated = terminated ? 1 : 0;
+            o.truncated = (h->wall_time >= h->time_limit) ? 1 : 0;
+            o.pad[0] = o.pad[1] = 0;
+            *oh = o;
+            stats->observations++;
+            stats->sum_nodes += N; stats->sum_edges += M; stats->sum_jobs += n_active;
+        }
+        __syncwarp();
+    }
+
+    // ------------------------------------------------------------ _take_action (:275-315), lane 0
+    // returns 1: round finished (advance the simulation), 0: same round continues, -1: rejected
+    __device__ int take_action(int stage_idx, int num_exec)
+    {
+        if (!(stage_idx >= -1 && stage_idx < oh->num_nodes && num_exec >= 1 && num_exec <= p.E))
+            return -SSB_ENV_ACTION_SPACE;
+        if (stage_idx == -1) {
+            commit_remaining_executors();
+            return (num_committable() > 0 && h->n_sched > 0) ? 0 : 1;
+        }
+        if (stage_idx >= h->n_sched) return -SSB_ENV_STAGE_KEY;
+        // stage_selection_map[stage_idx]: the stage_idx-th schedulable stage in (job, stage) order
+        int j = -1, s = -1, rem = stage_idx;
+        for (int i = 0; i < h->n_active; i++) {
+            uint64_t m = jb[act[i]].sched;
+            int c = popc64(m);
+            if (rem < c) {
+                j = act[i];
+                while (rem--) m &= m - 1;
+                s = ffs64(m);
+                break;
+            }
+            rem -= c;
+        }
+        if (j < 0) return -SSB_ENV_STAGE_KEY;
+        if (num_exec > num_committable()) return -SSB_ENV_TOO_MANY_EXEC;
+        const StageRec &r = st[jb[j].node_base + s];
+        int demand = (int)r.remaining - ((int)r.moving_to + (int)r.commit_to);  // _adjust_num_executors
+        int n = num_exec < demand ? num_exec : demand;
+        if (n <= 0) { fail(1000 + __LINE__); return 1; }
+        add_commitment(n, pool_of_stage(j, s));
+        jb[j].selected |= bit64(s);
+        // re-derive this job's schedulable stages only (bisect splice :306-315)
+        int before = popc64(jb[j].sched);
+        uint64_t m = job_sched_mask(j, source_job_id());
+        jb[j].sched = m;
+        h->n_sched += popc64(m) - before;
+        return (num_committable() > 0 && h->n_sched > 0) ? 0 : 1;
+    }
+
+    // ------------------------------------------------------------ step() (:188-221)
+    __device__ void step_w(int stage_idx, int num_exec)
+    {
+        if (h->error >= 1000) { if (lane == 0) oh->error = h->error; __syncwarp(); return; }
+        if (h->done) { if (lane == 0) oh->error = SSB_ENV_DONE; __syncwarp(); return; }
+        int rc = 0;
+        if (lane == 0) rc = take_action(stage_idx, num_exec);
+        rc = __shfl_sync(FULL, rc, 0);
+        __syncwarp();
+        if (rc < 0) {  // ValueError / KeyError: state untouched, report and let the caller retry
+            if (lane == 0) oh->error = -rc;
+            __syncwarp();
+            return;
+        }
+        if (lane == 0) stats->decisions++;
+        if (rc == 0) { observe_w(0.0, false); return; }
+        // commitment round has completed (:195-199)
+        const int n_active0 = h->n_active;
+        for (int i = lane; i < n_active0; i += 32) p.old_act[(size_t)b * p.Jc + i] = act[i];
+        __syncwarp();
+        if (lane == 0) {
+            commit_remaining_executors();
+            fulfill_commitments_from_source();
+            h->source = POOL_NONE;
+            h->wall_old = h->wall_time;
+            h->n_old_active = n_active0;
+        }
+        __syncwarp();
+        // selected_stages.clear() comes AFTER the fulfilment: backup scheduling during it must still
+        // see this round's selections (:197-199, :825-839)
+        for (int i = lane; i < n_active0; i += 32) jb[act[i]].selected = 0;
+        __syncwarp();
+        if (!h->error) resume_simulation_w();
+        double reward = 0.0;
+        bool terminated = false;
+        if (lane == 0) {
+            reward = -compute_jobtime();
+            terminated = h->n_completed == h->n_jobs;
+            if (terminated) { h->done = 1; stats->episodes++; }
+            else if (!h->error && !(num_committable() > 0 && h->n_sched > 0)) fail(1000 + __LINE__);
+        }
+        reward = __shfl_sync(FULL, reward, 0);
+        terminated = __shfl_sync(FULL, (int)terminated, 0);
+        __syncwarp();
+        observe_w(reward, terminated);
+    }
+
+    // ------------------------------------------------------------ reset() (:127-186)
+    __device__ void reset_w(uint64_t seed, double time_limit)
+    {
+        const int Jc = p.Jc;
+        int n_jobs = 0, err = 0;
+        const bool trace = h->trace_jobs > 0;
+        if (trace) {
+            n_jobs = h->trace_jobs;
+            for (int j = lane; j < n_jobs; j += 32) {
+                jb[j].t_arrival = p.trace_t[(size_t)b * Jc + j];
+                jb[j].tmpl = p.trace_tmpl[(size_t)b * Jc + j];
+            }
+        } else {
+            // job_sequence (tpch.py:54-73) on the Philox job stream: draws in parallel, the running
+            // sum of inter-arrival times sequentially (same f64 additions as `t += ...`)
+            const int cap = p.job_arrival_cap;
+            if (isinf(time_limit) && cap <= 0) err = SSB_ENV_NO_LIMIT;  // :137-138
+            const int lim = cap > 0 ? min(cap, Jc) : Jc;
+            for (int j = lane; j < lim; j += 32) {
+                uint4 w = philox4x32_10((uint32_t)j, 0u, 1u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32));
+                jb[j].tmpl = (int)bounded(w.y, 7) * 22 + (int)bounded(w.x, 22);  // tpch.py:177-178
+                jb[j].t_completed = __dmul_rn(p.mean_interarrival, neglog_u32(w.z));  // stash x_j
+            }
+            __syncwarp();
+            if (lane == 0 && !err) {
+                double t = 0.0;
+                int j = 0;
+                while (t < time_limit && (cap <= 0 || j < cap)) {
+                    if (j >= Jc) { err = SSB_ENV_CAPACITY; break; }
+                    double x = jb[j].t_completed;
+                    jb[j].t_arrival = t;
+                    t = __dadd_rn(t, x);
+                    j++;
+                }
+                n_jobs = j;
+            }
+            n_jobs = __shfl_sync(FULL, n_jobs, 0);
+            err = __shfl_sync(FULL, err, 0);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            int nb = 0, eb = 0;
+            for (int j = 0; j < n_jobs; j++) {
+                int t = jb[j].tmpl;
+                jb[j].node_base = nb; jb[j].edge_base = eb;
+                nb += p.b_num_stages[t];
+                eb += p.b_edge_base[t + 1] - p.b_edge_base[t];
+            }
+            if (nb > p.Sc || eb > p.Mc) err = SSB_ENV_CAPACITY;
+            EnvHdr &H = *h;
+            H.wall_time = 0.0; H.time_limit = time_limit; H.wall_old = 0.0;
+            H.seed = seed; H.log_n = 0; H.launch_idx = 0; H.seq = (uint32_t)n_jobs;
+            H.n_jobs = n_jobs; H.next_arrival = 0; H.n_active = 0; H.n_completed = 0;
+            H.source = POOL_COMMON; H.n_sched = 0; H.n_commits = 0; H.n_old_active = 0;
+            H.commit_from_common = 0; H.commit_to_common = 0; H.total_none = 0;
+            H.error = err; H.done = 0; H.n_nodes_total = nb; H.n_edges_total = eb;
+            H.use_tape = (trace && H.tape_len >= 0) ? 1 : 0;
+        }
+        __syncwarp();
+        if (h->error) {
+            if (lane == 0) {
+                ssb_obs_hdr o = {};
+                o.error = h->error;
+                *oh = o;
+                if (h->error < 1000) { h->done = 1; }
+            }
+            __syncwarp();
+            return;
+        }
+        // jobs
+        for (int j = lane; j < n_jobs; j += 32) {
+            JobRec &J = jb[j];
+            int t = J.tmpl, ns = p.b_num_stages[t];
+            J.ts_base = p.b_stage_base[t];
+            J.n_stages = (int16_t)ns;
+            J.t_completed = __longlong_as_double(0x7ff0000000000000ll);
+            J.active = ns >= 64 ? ~0ull : (bit64(ns) - 1);
+            uint64_t fr = 0;
+            for (int s = 0; s < ns; s++)
+                if (p.b_parent[J.ts_base + s] == 0) fr |= bit64(s);  // job.py:93-111 in-degree 0
+            J.frontier = fr;
+            J.sat = 0; J.sched = 0; J.selected = 0;
+            J.n_local = 0; J.supply = 0; J.commit_from = 0; J.sat_count = 0; J.state = JOB_PENDING;
+        }
+        __syncwarp();
+        // stages + their pools
+        for (int j = 0; j < n_jobs; j++) {
+            const JobRec &J = jb[j];
+            for (int s = lane; s < J.n_stages; s += 32) {
+                StageRec r;
+                int nt = p.b_num_tasks[J.ts_base + s];
+                r.remaining = (uint16_t)nt; r.completed = 0; r.num_tasks = (uint16_t)nt; r.job = (int16_t)j;
+                r.commit_to = r.moving_to = r.commit_from = r.pad = 0;
+                r.mrd = (float)p.b_rough[J.ts_base + s];
+                st[J.node_base + s] = r;
+            }
+        }
+        // pools: fresh `set()` everywhere (executor_tracker.py:39-42, :77, :90)
+        const int n_pools = 2 + Jc + h->n_nodes_total;
+        for (int q = lane; q < n_pools; q += 32) {
+            PoolHdr hd; hd.mask = 7; hd.fill = 0; hd.used = 0; hd.finger = 0;
+            ph[q] = hd;
+            uint8_t *t = pt + (size_t)q * p.TAB;
+            *reinterpret_cast<unsigned long long *>(t) = ~0ull;  // 8 EMPTY slots
+        }
+        for (int e = lane; e < p.E; e += 32) {
+            ExecRec x = {};
+            x.job_id = -1; x.task_stage = -1; x.loc = POOL_COMMON; x.ev_task = -1;
+            ex[e] = x;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            PSet<uint8_t> c = ps_load(POOL_COMMON);  // set(range(num_executors))
+            for (int e = 0; e < p.E; e++) ps_add(c, e, scr + 2 * p.TAB);
+            ps_store(POOL_COMMON, c);
+            // _load_initial_jobs (:260-273): arrivals with t <= 0, wall_time stays 0
+            while (h->next_arrival < n_jobs && jb[h->next_arrival].t_arrival <= 0.0)
+                handle_job_arrival(h->next_arrival++);
+        }
+        __syncwarp();
+        find_schedulable_all_w();
+        observe_w(0.0, false);
+    }
+
+    // ------------------------------------------------------------ fair / FIFO policy
+    // RoundRobinScheduler.schedule (schedulers/heuristics/round_robin.py:14-49) with
+    // preprocess_obs/find_stage (heuristics/utils.py:5-37).  "Frontier" there means "no incoming
+    // edge in the observed sub-graph", i.e. every parent completed == Job.frontier_stages.
+    __device__ void fair_action_w(bool dynamic_partition, int &stage_idx, int &num_exec)
+    {
+        const int Ja = h->n_active, ncommit = num_committable();
+        const int src_job = source_job_id();
+        const int cap = dynamic_partition ? (p.E + max(1, Ja) - 1) / max(1, Ja) : p.E;
+        int best_i = 0x7fffffff, best_stage = -1, best_n = ncommit, src_i = Ja;
+        int run = 0, best_rank = -1;
+        for (int base = 0; base < Ja; base += 32) {
+            int i = base + lane, j = -1, cnt = 0, sel = -1, supply = 0;
+            uint64_t m = 0;
+            if (i < Ja) {
+                j = act[i];
+                m = jb[j].sched;
+                cnt = popc64(m);
+                supply = jb[j].supply;
+                if (m) {  // find_stage: first schedulable frontier stage, else first schedulable
+                    uint64_t f = m & jb[j].frontier;
+                    sel = ffs64(f ? f : m);
+                }
+            }
+            int incl = cnt;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                int v = __shfl_up_sync(FULL, incl, off);
+                if (lane >= off) incl += v;
+            }
+            int rank = sel >= 0 ? run + incl - cnt + popc64(m & (bit64(sel) - 1)) : -1;
+            bool is_src = j >= 0 && j == src_job;
+            unsigned srcb = __ballot_sync(FULL, is_src);
+            if (srcb) {
+                int l = __ffs(srcb) - 1;
+                src_i = base + l;
+                int r = __shfl_sync(FULL, rank, l);
+                if (r >= 0) { stage_idx = r; num_exec = ncommit; return; }  // source job first
+            }
+            bool ok = (i < Ja) && !is_src && supply < cap && sel >= 0;
+            unsigned okb = __ballot_sync(FULL, ok);
+            if (okb && best_rank < 0) {
+                int l = __ffs(okb) - 1;
+                best_i = base + l;
+                best_rank = __shfl_sync(FULL, rank, l);
+                int sp = __shfl_sync(FULL, supply, l);
+                best_n = min(ncommit, cap - sp);
+            }
+            run += __shfl_sync(FULL, incl, 31);
+        }
+        (void)best_i; (void)best_stage; (void)src_i;
+        if (best_rank >= 0) { stage_idx = best_rank; num_exec = best_n; return; }
+        stage_idx = -1;
+        num_exec = ncommit;
+    }
+};
+
+}  // namespace ssb

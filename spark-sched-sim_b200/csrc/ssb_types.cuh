@@ -1,0 +1,141 @@
+// ssb_types.cuh -- device-side state layout of the batched scheduling simulator (libssb).
+//
+// One environment = one episode of the reference's SparkSchedSimEnv (spark_sched_sim.py:29).
+// State is env-major in HBM: every array below is [B][stride] so that the warp that owns an
+// environment reads its jobs / stages / executors with consecutive lanes on consecutive records
+// (16-byte vector loads for StageRec).  Python objects of the reference collapse as follows:
+//   EventQueue (event.py:19)      -> one pending-event slot per executor (every executor has at
+//                                    most one TASK_FINISHED/EXECUTOR_READY in flight) + a cursor
+//                                    over the pre-sampled, time-ordered job arrivals
+//   Job/Stage DAG (job.py, stage.py) -> u64 bitmasks per job (active, frontier, saturated,
+//                                    schedulable, selected) + 16-byte counters per stage; the DAG
+//                                    itself (parent/child masks) stays in the shared template bank
+//   ExecutorTracker pools (executor_tracker.py:38-42) -> CPython-set look-alike tables (u8 slots),
+//                                    because set iteration/pop order decides which executor moves
+//   _commitments dict-of-dicts    -> one insertion-ordered record list per environment
+#pragma once
+#include <stdint.h>
+
+#include "../../include/ssb.h"
+
+namespace ssb {
+
+enum : int { EV_JOB_ARRIVAL = 0, EV_TASK_FINISHED = 1, EV_EXECUTOR_READY = 2 };
+enum : int { POOL_NONE = 0, POOL_COMMON = 1 };  // job j -> 2 + j, stage node v -> 2 + Jc + v
+enum : int { JOB_PENDING = 0, JOB_ACTIVE = 1, JOB_COMPLETED = 2 };
+
+struct __align__(16) StageRec {  // stage.py:8-18 + tracker counters keyed by the stage's pool
+    uint16_t remaining;          // num_remaining_tasks
+    uint16_t completed;          // num_completed_tasks
+    uint16_t num_tasks;
+    int16_t job;
+    uint8_t commit_to;    // _num_commitments_to_stage
+    uint8_t moving_to;    // _num_moving_to_stage
+    uint8_t commit_from;  // _num_commitments_from[(job, stage)]
+    uint8_t pad;
+    float mrd;  // most_recent_duration as the observation sees it (float32)
+};
+static_assert(sizeof(StageRec) == 16, "StageRec must be one 128-bit load");
+
+struct __align__(16) ExecRec {  // executor.py:4-20 + its pending timeline event
+    double ev_t;                // event key (t, seq), event.py:34-35
+    double t_acc;               // task.t_accepted (event log only)
+    uint32_t ev_seq;
+    int32_t ev_task;
+    int16_t ev_job, ev_stage;
+    int16_t job_id;      // executor.job_id, -1 = None
+    int16_t task_stage;  // executor.task.stage_id
+    int32_t loc;         // _executor_locations: pool id, POOL_NONE while moving
+    uint8_t ev_kind;     // 0 = no pending event, else EV_*
+    uint8_t is_executing;
+    uint8_t has_task;  // executor.task is not None
+    uint8_t pad0;
+    int32_t pad1[2];
+};
+static_assert(sizeof(ExecRec) == 48, "ExecRec layout");
+
+struct __align__(16) JobRec {  // job.py:12-40 + tracker counters keyed by the job
+    double t_arrival, t_completed;
+    uint64_t active;    // incomplete stages (active_stages)
+    uint64_t frontier;  // frontier_stages
+    uint64_t sat;       // stages with executor demand <= 0 (spark_sched_sim.py:580-582)
+    uint64_t sched;     // this job's slice of self.schedulable_stages
+    uint64_t selected;  // this job's slice of self.selected_stages
+    int32_t tmpl, node_base, edge_base, ts_base;
+    int16_t n_stages;
+    int16_t n_local;      // len(local_executors)
+    int16_t supply;       // _total_executor_count[job]
+    int16_t commit_from;  // _num_commitments_from[(job, None)]
+    uint8_t sat_count;    // saturated_stage_count
+    uint8_t state;
+    uint8_t pad[6];
+};
+static_assert(sizeof(JobRec) == 96, "JobRec layout");
+
+struct Commit {  // one (src pool -> dst pool: n) entry; list order == dict insertion order
+    int32_t src, dst, n;
+};
+
+struct PoolHdr {  // PySetObject: mask, fill, used, finger (Objects/setobject.c)
+    uint16_t mask, fill, used, finger;
+};
+
+struct __align__(16) LogRow {
+    double t, t_acc;
+    int32_t task;
+    int16_t job, stage, exec;
+    uint8_t type, pad;
+    int32_t pad1;
+};
+static_assert(sizeof(LogRow) == 32, "LogRow layout");
+
+struct __align__(16) EnvHdr {
+    double wall_time, time_limit, wall_old;
+    uint64_t seed, base_seed;
+    int64_t log_n;
+    uint32_t launch_idx, seq;
+    int32_t n_jobs, next_arrival, n_active, n_completed;
+    int32_t source, n_sched, n_commits, n_old_active;
+    int32_t commit_from_common, commit_to_common, total_none, error;
+    int32_t done, trace_jobs, tape_len, n_nodes_total;
+    int32_t n_edges_total, reset_count, use_tape, pad;
+};
+
+// Everything a kernel needs, passed by value.
+struct Params {
+    int B, E, Jc, Sc, Mc, TAB, RT, P, Cc, max_stages;
+    int tape_cap, log_cap, job_arrival_cap;
+    double moving_delay, warmup_delay, mean_interarrival, beta;
+    // template bank (read-only)
+    const int32_t *b_num_stages, *b_stage_base, *b_edge_base, *b_num_tasks;
+    const int16_t *b_edges;  // [edges][2]
+    const double *b_rough;
+    const uint64_t *b_parent, *b_child;
+    const uint8_t *b_present;  // [TS][4] (3 used)
+    const uint2 *b_dur;        // [TS][3][8] (offset, count)
+    const double *b_vals;
+    const int16_t *iv;  // [E+1][2] executor-interval levels (tpch.py:237-262)
+    // state
+    EnvHdr *hdr;
+    ExecRec *exec;     // [B][E]
+    JobRec *job;       // [B][Jc]
+    StageRec *stage;   // [B][Sc]
+    int16_t *active;   // [B][Jc]  active_job_ids
+    int16_t *old_act;  // [B][Jc]
+    Commit *commits;   // [B][Cc]
+    PoolHdr *pool_hdr; // [B][P]
+    uint8_t *pool_tab; // [B][P][TAB]
+    uint8_t *scr_tab;  // [B][3][TAB]  copy / idle / resize scratch
+    uint16_t *rset;    // [B][2][RT]   reward job-id set + resize scratch
+    double *trace_t;   // [B][Jc]
+    int32_t *trace_tmpl;  // [B][Jc]
+    double *tape;      // [B][tape_cap]
+    LogRow *log;       // [B][log_cap]
+    ssb_stats *stats;  // [B]
+    // observation slabs
+    ssb_obs_hdr *obs_hdr;
+    float *obs_nodes;
+    int32_t *obs_edges, *obs_dag_ptr, *obs_supplies;
+};
+
+}  // namespace ssb

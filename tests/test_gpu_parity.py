@@ -1,0 +1,204 @@
+"""GPU parity: the CUDA path, called through the C ABI, against (1) the committed reference traces
+and (2) the CPU oracle on seeded inputs.  Bit-exact: event order, executor assignments,
+observations, f64 wall/completion times; rewards bit-exact for beta == 0 and 1e-12 relative for
+beta > 0 (exp())."""
+import numpy as np
+import pytest
+
+from helpers import golden_names, load_golden, replay_and_compare
+
+pytestmark = pytest.mark.gpu
+
+
+def env_cfg_of(tr):
+    return {"num_executors": tr["num_executors"],
+            "job_arrival_cap": tr["job_arrival_cap"] if tr["job_arrival_cap"] > 0 else None,
+            "job_arrival_rate": tr["job_arrival_rate"], "moving_delay": tr["moving_delay"],
+            "warmup_delay": tr["warmup_delay"], "beta": tr["beta"]}
+
+
+class CudaAdapter:
+    """Presents one slot of a BatchedSparkSchedSimEnv with the OracleEnv interface; every step goes
+    through ssb_step_host (host buffers in, observation headers out)."""
+
+    def __init__(self, bank, tr, B=3, slot=1):
+        from spark_sched_sim_b200.batched_env import BatchedSparkSchedSimEnv
+
+        self.B, self.slot, self.tr = B, slot, tr
+        self.env = BatchedSparkSchedSimEnv(
+            env_cfg_of(tr), num_envs=B, bank=bank, max_jobs=len(tr["job_template"]) + 4,
+            tape_capacity=len(tr["tape"]) + 8, log_capacity=int(tr["ev_count"][-1]) + 64)
+        self.hdr = None
+
+    def reset_trace(self, ta, tm, tape):
+        for b in range(self.B):
+            self.env.load_trace(b, ta, tm, tape)
+        self.hdr = self.env.reset_host(np.full(self.B, self.tr["seed"], np.uint64)).copy()
+        assert (self.hdr["error"] == 0).all(), self.hdr["error"]
+        return self.obs()
+
+    def reset_seed(self, seed, time_limit=np.inf):
+        self.hdr = self.env.reset_host(np.full(self.B, seed, np.uint64),
+                                       np.full(self.B, time_limit, np.float64)).copy()
+        assert (self.hdr["error"] == 0).all(), self.hdr["error"]
+        return self.obs()
+
+    def step(self, a, n):
+        self.hdr = self.env.step_host(np.full(self.B, a, np.int32), np.full(self.B, n, np.int32)).copy()
+        h = self.hdr[self.slot]
+        return int(h["error"]), float(h["reward"]), bool(h["terminated"])
+
+    def obs(self):
+        return self.env.obs(self.slot, self.hdr)
+
+    @property
+    def wall_time(self):
+        return float(self.hdr[self.slot]["wall_time"])
+
+    def log_size(self):
+        return self.env.log_size(self.slot)
+
+    def log(self):
+        return self.env.log(self.slot)
+
+    def job_times(self):
+        return self.env.jobs(self.slot)
+
+    def fair_action(self, dynamic_partition):
+        a, n = self.env.fair_actions(dynamic_partition)
+        return int(a[self.slot].item()), int(n[self.slot].item())
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_cuda_replays_reference_tape(bank, name):
+    tr = load_golden(name)
+    env = CudaAdapter(bank, tr)
+    replay_and_compare(env, tr, "tape", check_policy=env.fair_action,
+                       reward_rtol=1e-12 if tr["beta"] > 0 else 0.0)
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if "philox" in n])
+def test_cuda_replays_reference_from_seed(bank, name):
+    """On-device Philox sampling of jobs and durations against the Philox-plugged reference run."""
+    tr = load_golden(name)
+    env = CudaAdapter(bank, tr)
+    replay_and_compare(env, tr, "seed", check_policy=env.fair_action,
+                       reward_rtol=1e-12 if tr["beta"] > 0 else 0.0)
+
+
+def test_cuda_invalid_actions(bank):
+    tr = load_golden("e10_j8_fair_s2_philox")
+    env = CudaAdapter(bank, tr)
+    obs = env.reset_seed(tr["seed"])
+    N = obs["nodes"].shape[0]
+    nsched = int(obs["nodes"][:, 2].sum())
+    wall0, h0 = env.wall_time, env.hdr.copy()
+    assert env.step(N, 1)[0] == 1
+    assert env.step(0, 0)[0] == 1
+    assert env.step(0, 11)[0] == 1
+    if nsched < N:
+        assert env.step(nsched, 1)[0] == 2
+    # rejected actions leave the state untouched: the recorded episode still replays exactly
+    replay_and_compare(CudaAdapter(bank, tr), tr, "seed")
+    assert env.wall_time == wall0
+    rc, _, _ = env.step(int(tr["actions"][0][0]), int(tr["actions"][0][1]))
+    assert rc == 0
+
+
+@pytest.mark.parametrize("E,J,policy", [(10, 50, "fair"), (10, 20, "fifo"), (50, 30, "fair"), (3, 10, "fair")])
+def test_fused_rollout_matches_oracle(bank, E, J, policy):
+    """Fused on-device policy+step episodes vs the CPU oracle from the same seeds: every job's
+    arrival/completion time, the final wall time, and the decision/event counts."""
+    from oracle import OracleEnv
+    from spark_sched_sim_b200.batched_env import BatchedSparkSchedSimEnv
+
+    B = 16
+    cfg = {"num_executors": E, "job_arrival_cap": J, "job_arrival_rate": 4.0e-5,
+           "moving_delay": 2000.0, "warmup_delay": 1000.0}
+    env = BatchedSparkSchedSimEnv(cfg, num_envs=B, bank=bank)
+    seeds = np.arange(1000, 1000 + B, dtype=np.uint64)
+    env.reset_host(seeds)
+    env.rollout_fair(1_000_000, dynamic_partition=(policy == "fair"), auto_reset=False)
+    hdr = env.hdr()
+    assert (hdr["error"] == 0).all(), hdr["error"]
+    assert (hdr["terminated"] == 1).all()
+    tot_dec = tot_ev = 0
+    for b in range(B):
+        orc = OracleEnv(bank, E, J, 2000.0, 1000.0, 4.0e-5)
+        dec, ev = orc.run_fair_episode(int(seeds[b]), policy == "fair")
+        tot_dec += dec
+        tot_ev += ev
+        ta, tc, tm = orc.job_times()
+        gta, gtc, gtm = env.jobs(b)
+        assert np.array_equal(tm, gtm) and np.array_equal(ta, gta), b
+        assert np.array_equal(tc, gtc), (b, "job completion times")
+        assert hdr["wall_time"][b] == orc.wall_time
+    st = env.stats()
+    assert st["decisions"] == tot_dec and st["events"] == tot_ev
+    assert st["episodes"] == B
+
+
+def test_full_size_batch_properties(bank):
+    """BASELINE config 2 at full size (4096 envs, 50 jobs x 10 executors): no env errors, every
+    episode terminates, envs sharing a seed are identical, a sample matches the oracle, and the
+    run is deterministic."""
+    from oracle import OracleEnv
+    from spark_sched_sim_b200.batched_env import BatchedSparkSchedSimEnv
+
+    B = 4096
+    cfg = {"num_executors": 10, "job_arrival_cap": 50, "job_arrival_rate": 4.0e-5,
+           "moving_delay": 2000.0, "warmup_delay": 1000.0}
+    env = BatchedSparkSchedSimEnv(cfg, num_envs=B, bank=bank)
+    seeds = (1234 + np.arange(B) // 2).astype(np.uint64)  # pairs share a job sequence
+    walls = []
+    for rep in range(2):
+        env.reset_stats()
+        env.reset_host(seeds)
+        env.rollout_fair(1_000_000, True, auto_reset=False)
+        hdr = env.hdr()
+        assert (hdr["error"] == 0).all()
+        assert (hdr["terminated"] == 1).all()
+        walls.append(hdr["wall_time"].copy())
+    assert np.array_equal(walls[0], walls[1])
+    assert np.array_equal(walls[0][0::2], walls[0][1::2])
+    st = env.stats()
+    assert st["episodes"] == B and st["decisions"] > 400 * B
+    for b in (0, 1777, 4095):
+        orc = OracleEnv(bank, 10, 50, 2000.0, 1000.0, 4.0e-5)
+        orc.run_fair_episode(int(seeds[b]), True)
+        assert np.array_equal(orc.job_times()[1], env.jobs(b)[1])
+
+
+def test_auto_reset_rollout(bank):
+    """auto_reset: a finished env re-seeds itself with seed + seed_step * reset_count
+    (rollout_worker.py:118-120) and keeps deciding; decisions per env are exact."""
+    from oracle import OracleEnv
+    from spark_sched_sim_b200.batched_env import BatchedSparkSchedSimEnv
+
+    B, K = 8, 700
+    cfg = {"num_executors": 10, "job_arrival_cap": 8, "job_arrival_rate": 4.0e-5,
+           "moving_delay": 2000.0, "warmup_delay": 1000.0}
+    env = BatchedSparkSchedSimEnv(cfg, num_envs=B, bank=bank)
+    seeds = np.arange(50, 50 + B, dtype=np.uint64)
+    env.reset_host(seeds)
+    env.rollout_fair(K, True, auto_reset=True, seed_step=100)
+    st = env.stats()
+    assert st["decisions"] == B * K
+    hdr = env.hdr()
+    assert (hdr["error"] == 0).all()
+    # replay env 3 on the oracle: K decisions across episodes seeded 53, 153, 253, ...
+    orc = OracleEnv(bank, 10, 8, 2000.0, 1000.0, 4.0e-5)
+    k, ep = 0, 0
+    while k < K:
+        orc.reset_seed(53 + 100 * ep)
+        term = False
+        while not term and k < K:
+            a, n = orc.fair_action(True)
+            rc, _, term = orc.step(a, n)
+            assert rc == 0
+            k += 1
+        ep += 1
+    assert hdr["wall_time"][3] == orc.wall_time
+    o, g = orc.obs(), env.obs(3, hdr)
+    for key in ("nodes", "edge_links", "dag_ptr", "exec_supplies"):
+        assert np.array_equal(o[key], g[key]), key

@@ -1,0 +1,355 @@
+"""bench.py -- scheduling decisions/sec of the batched env on N B200s (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1], "C2"): 4096 environments per GPU, 50 jobs x 10 executors,
+fair scheduler (RoundRobinScheduler(10, dynamic_partition=True)), synthetic TPC-H-shaped bank
+(SURVEY.md App. D), env seeds 1234 + i, auto-reset with seed + 4096 * reset_count.
+One "step" = every environment takes DECISIONS_PER_STEP scheduling decisions (policy evaluation,
+step(), observation construction, amortised resets included).
+
+  value : decisions/s of the fused on-device rollout (state resident in HBM; one launch per step)
+  e2e   : decisions/s through the host-buffer C ABI: per decision batch, actions are read back to
+          pinned host memory, passed to ssb_step_host (H2D), and the B observation headers
+          (reward/terminated/...) are copied D2H -- all inside the timed region
+  roofline : algorithmic HBM bytes of the rollout kernel (SURVEY.md 8d formula, counters measured
+          by the kernel itself) / its CUDA-event duration, against MEASURED_PEAKS.json
+  cpu_baseline : the C oracle port (oracle/sim_oracle.c) on the box's host cores, same workload
+  --impl reference : only that CPU arm, as its own JSON line
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import os.path as osp
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = osp.dirname(osp.abspath(__file__))
+for _p in (REPO, osp.join(REPO, "oracle")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+ENVS_PER_GPU = 4096
+DECISIONS_PER_STEP = 128
+E2E_DECISIONS_PER_STEP = 32
+ENV_CFG = {"num_executors": 10, "job_arrival_cap": 50, "job_arrival_rate": 4.0e-5,
+           "moving_delay": 2000.0, "warmup_delay": 1000.0}  # examples.py:15-23
+METRIC = "scheduling decisions/sec (batched envs)"
+WORKLOAD = "C2: 4096 envs/GPU x (50 jobs, 10 executors), fair scheduler, synthetic TPC-H bank"
+
+
+def peaks():
+    path = osp.join(REPO, "MEASURED_PEAKS.json")
+    if osp.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_bytes(st: dict) -> float:
+    """B_dec = 80*eps + 20*N*sigma + (12 N + 8 M + 8 Ja + 16), summed over the
+    observations / events / schedulability scans the kernel counted."""
+    obs = max(st["observations"], 1)
+    mean_nodes = st["sum_nodes"] / obs
+    return (80.0 * st["events"] + 20.0 * mean_nodes * st["sched_scans"]
+            + 12.0 * st["sum_nodes"] + 8.0 * st["sum_edges"] + 8.0 * st["sum_jobs"] + 16.0 * obs)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for nm, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_arm(seconds: float, threads: int | None = None) -> dict:
+    """The CPU oracle port on host threads: fair C2 episodes back to back, seeds 1234 + i."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import OracleEnv
+    from spark_sched_sim_b200.bank import synthetic_bank
+
+    bank = synthetic_bank(0)
+    P = threads or os.cpu_count() or 1
+    envs = [OracleEnv(bank, ENV_CFG["num_executors"], ENV_CFG["job_arrival_cap"],
+                      ENV_CFG["moving_delay"], ENV_CFG["warmup_delay"], ENV_CFG["job_arrival_rate"])
+            for _ in range(P)]
+    envs[0].run_fair_episode(1234)  # warm-up
+    deadline = time.perf_counter() + seconds
+
+    def work(rank):
+        dec = ev = eps = 0
+        k = 0
+        while time.perf_counter() < deadline:
+            d, e = envs[rank].run_fair_episode(1234 + rank + P * k)  # ctypes releases the GIL
+            dec += d; ev += e; eps += 1; k += 1
+        return dec, ev, eps
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(P) as ex:
+        res = list(ex.map(work, range(P)))
+    dt = time.perf_counter() - t0
+    dec = sum(r[0] for r in res); ev = sum(r[1] for r in res); eps = sum(r[2] for r in res)
+    return {"value": dec / dt, "unit": "decisions/s", "cores": P, "kind": "port",
+            "sample": f"{eps} fair C2 episodes ({dec} decisions, {ev} events) in {dt:.1f} s on {P} "
+                      f"host threads, oracle/sim_oracle.c incl. reset and observation building",
+            "events_per_s": ev / dt}
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    per_step = 2.0
+    vals = []
+    for _ in range(args.warmup):
+        cpu_arm(0.5)
+    t0 = time.perf_counter()
+    last = None
+    for _ in range(args.steps):
+        last = cpu_arm(per_step)
+        vals.append(last["value"])
+    dt = time.perf_counter() - t0
+    v = float(np.mean(vals))
+    last["value"] = v
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "decisions/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64+int",
+        "data": "synthetic", "config": {"workload": WORKLOAD, "step": f"{per_step} s of CPU episodes"},
+        "cpu_baseline": last,
+        "e2e": {"value": v, "unit": "decisions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "the reference is pure Python and cannot travel to the GPU box; this arm times the C "
+                "port of it (oracle/), which is ~250x faster per core than the Python original "
+                "(BASELINE.md: 160-210 decisions/s/core)",
+    }))
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=ENVS_PER_GPU)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from spark_sched_sim_b200.batched_env import BatchedSparkSchedSimEnv
+    from spark_sched_sim_b200.bank import synthetic_bank
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W = max(args.warmup, 3)
+    K = args.steps
+    B = args.envs
+    D = DECISIONS_PER_STEP
+
+    bank = synthetic_bank(0)
+    env = BatchedSparkSchedSimEnv(ENV_CFG, num_envs=B, bank=bank, device=dev)
+    seeds = (1234 + rank * B + np.arange(B)).astype(np.uint64)  # envs shard over ranks: disjoint seeds
+    seed_step = B * world
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    stats_vec = torch.zeros(8, dtype=torch.float64, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allreduce_stats():
+        # the path's only exchange step: rollout statistics summed over ranks
+        if world > 1:
+            dist.all_reduce(stats_vec)
+
+    # ---------------- device-resident rollout ("value")
+    env.reset_host(seeds)
+    for _ in range(W):
+        env.rollout_fair(D, True, True, seed_step)
+    env.reset_stats()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    launches = 0
+    for k in range(K):
+        flush.fill_(k & 0xFF)  # evict L2 between timed iterations (untimed)
+        ev0[k].record()
+        env.rollout_fair(D, True, True, seed_step)
+        launches += 1
+        allreduce_stats()
+        ev1[k].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if rank == 0 else None
+    kern_ms = sum(a.elapsed_time(b) for a, b in zip(ev0, ev1))
+    st = env.stats()
+    hdr = env.hdr()
+    n_err = int((hdr["error"] != 0).sum())
+    t = torch.tensor([kern_ms], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([float(st["decisions"]), float(st["events"]), float(st["episodes"]), float(n_err)],
+                       dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt)
+    max_ms = float(t.item())
+    total_dec, total_ev, total_eps, total_err = (float(x) for x in cnt.tolist())
+    value = total_dec / (max_ms * 1e-3)
+
+    # ---------------- roofline of the rollout kernel (this rank's launches)
+    peak, peak_src = peaks()
+    alg_bytes = algorithmic_bytes(st)
+    achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = osp.join(REPO, "profiles", "rollout_traffic.json")
+    if osp.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    obs = max(st["observations"], 1)
+    roofline = {
+        "bound": "hbm", "kernel": "k_rollout_fair", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": alg_bytes / max(launches, 1),
+        "bytes_per_decision": alg_bytes / max(st["decisions"], 1),
+        "events_per_decision": st["events"] / max(st["decisions"], 1),
+        "sched_scans_per_decision": st["sched_scans"] / max(st["decisions"], 1),
+        "mean_nodes": st["sum_nodes"] / obs, "mean_edges": st["sum_edges"] / obs,
+        "mean_active_jobs": st["sum_jobs"] / obs,
+        "note": "latency/dependency-bound event chains: the HBM fraction is expected to be small",
+    }
+
+    # ---------------- e2e through the host-buffer C ABI
+    e2e = None
+    if not args.no_e2e:
+        De = E2E_DECISIONS_PER_STEP
+        a_pin = torch.empty(B, dtype=torch.int32).pin_memory()
+        n_pin = torch.empty(B, dtype=torch.int32).pin_memory()
+
+        def e2e_step():
+            for _ in range(De):
+                a, n = env.fair_actions(True)        # policy on the observation just written
+                a_pin.copy_(a, non_blocking=True)    # D2H: the actions a host-side caller sees
+                n_pin.copy_(n, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                h = env.step_host(a_pin.numpy(), n_pin.numpy())  # H2D actions, step, D2H headers
+                done = (h["terminated"] != 0) | (h["truncated"] != 0)
+                if done.any():                       # per-env reset(seed) exactly as a caller would
+                    env.reset_host(seeds + np.uint64(seed_step) * np.uint64(e2e_step.resets),
+                                   mask=done.astype(np.uint8))
+                    e2e_step.resets += 1
+        e2e_step.resets = 1
+
+        env.reset_host(seeds)
+        for _ in range(2):
+            e2e_step()
+        env.reset_stats()
+        Ke = max(2, min(K, 5))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(Ke):
+            e2e_step()
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dd = torch.tensor([float(env.stats()["decisions"])], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(dd)
+        e2e = {"value": float(dd.item()) / float(tt.item()), "unit": "decisions/s",
+               "h2d_bytes_per_step": De * 2 * 4 * B, "d2h_bytes_per_step": De * (2 * 4 + 48) * B,
+               "steps": Ke, "decisions_per_env_per_step": De,
+               "path": "ssb_fair_actions -> D2H actions (pinned) -> ssb_step_host (H2D, step, D2H headers)",
+               "gpu_launches": Ke * De * 2}
+        launches_e2e = Ke * De * 2
+    else:
+        launches_e2e = 0
+
+    cpu = None
+    if rank == 0 and world == 1 and args.cpu_seconds > 0:
+        cpu = cpu_arm(args.cpu_seconds)
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": "decisions/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": max_ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64 event times + integer state", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "envs_per_gpu": B, "decisions_per_env_per_step": D,
+                       "policy": "fair (on-device, fused)", "auto_reset": True,
+                       "l2": "256 MiB flush write between timed iterations; workspace "
+                             f"{env.workspace_bytes >> 20} MiB per GPU",
+                       "parallelism": f"envs sharded over {world} GPU(s); all-reduce of rollout stats only"},
+            "events_per_s": total_ev / (max_ms * 1e-3), "episodes": total_eps, "env_errors": total_err,
+            "wall_s_timed_region": t_wall,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+            "gpu_launches": launches + launches_e2e,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

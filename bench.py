@@ -182,6 +182,8 @@ def main() -> None:
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-budget", type=int, default=64,
+                    help="max timeline events per env per ssb_step_host call (0 = run to next decision)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -294,7 +296,9 @@ def main() -> None:
                 a_pin.copy_(a, non_blocking=True)    # D2H: the actions a host-side caller sees
                 n_pin.copy_(n, non_blocking=True)
                 torch.cuda.current_stream().synchronize()
-                h = env.step_host(a_pin.numpy(), n_pin.numpy())  # H2D actions, step, D2H headers
+                # H2D actions, bounded step (envs still simulating come back "pending" and simply
+                # continue next call -- no env waits for the batch's longest event chain), D2H headers
+                h = env.step_host(a_pin.numpy(), n_pin.numpy(), max_events=args.e2e_budget)
                 done = (h["terminated"] != 0) | (h["truncated"] != 0)
                 if done.any():                       # per-env reset(seed) exactly as a caller would
                     env.reset_host(seeds + np.uint64(seed_step) * np.uint64(e2e_step.resets),
@@ -320,7 +324,7 @@ def main() -> None:
             dist.all_reduce(dd)
         e2e = {"value": float(dd.item()) / float(tt.item()), "unit": "decisions/s",
                "h2d_bytes_per_step": De * 2 * 4 * B, "d2h_bytes_per_step": De * (2 * 4 + 48) * B,
-               "steps": Ke, "decisions_per_env_per_step": De,
+               "steps": Ke, "calls_per_step": De, "max_events_per_call": args.e2e_budget,
                "path": "ssb_fair_actions -> D2H actions (pinned) -> ssb_step_host (H2D, step, D2H headers)",
                "gpu_launches": Ke * De * 2}
         launches_e2e = Ke * De * 2

@@ -101,7 +101,8 @@ typedef struct {
     int32_t error;                 /* SSB_ENV_* or 1000+line */
     uint8_t terminated;
     uint8_t truncated; /* wall_time >= time limit (wrappers/stochastic_time_limit.py:29-30) */
-    uint8_t pad[2];
+    uint8_t pending;   /* budgeted step only: next decision not reached yet, observation not rewritten */
+    uint8_t pad;
 } ssb_obs_hdr;
 
 /* Device views of the observation slabs (fixed stride per environment). */
@@ -148,15 +149,21 @@ int ssb_clear_trace(ssb_env *env, int32_t env_index);
  * DEVICE pointers: seeds u64[B], time_limits f64[B] (NULL = +inf), mask u8[B]. */
 int ssb_reset(ssb_env *env, const uint64_t *seeds, const double *time_limits, const uint8_t *mask,
               void *stream);
-/* step(action) for every env (mask NULL = all).  DEVICE pointers i32[B]. */
+/* step(action) for every env (mask NULL = all).  DEVICE pointers i32[B].
+ * max_events <= 0: reference semantics -- every env runs until its next scheduling decision.
+ * max_events  > 0: asynchronous-vector-env mode -- each env processes at most that many timeline
+ *   events in this call; an env that has not reached its next decision is flagged
+ *   ssb_obs_hdr.pending = 1 (observation left as it was) and the next ssb_step call on it ignores
+ *   its action and continues.  Results per env are identical to the unbounded call; only the
+ *   interleaving across envs changes (no env waits for the batch's longest event chain). */
 int ssb_step(ssb_env *env, const int32_t *stage_idx, const int32_t *num_exec, const uint8_t *mask,
-             void *stream);
+             int32_t max_events, void *stream);
 
 /* same with HOST buffers: copies in, runs, copies the B observation headers out, synchronises */
 int ssb_reset_host(ssb_env *env, const uint64_t *seeds, const double *time_limits, const uint8_t *mask,
                    ssb_obs_hdr *hdr_out);
 int ssb_step_host(ssb_env *env, const int32_t *stage_idx, const int32_t *num_exec, const uint8_t *mask,
-                  ssb_obs_hdr *hdr_out);
+                  int32_t max_events, ssb_obs_hdr *hdr_out);
 
 /* fused rollout: every env takes `num_decisions` decisions with the built-in fair (dynamic_partition
  * = 1) or FIFO (= 0) policy (round_robin.py:14-49) evaluated on the observation it just wrote.
@@ -173,9 +180,10 @@ int ssb_get_views(ssb_env *env, ssb_views *out);
 int ssb_get_stats(ssb_env *env, ssb_stats **out);
 int ssb_reset_stats(ssb_env *env, void *stream);
 
-/* results (HOST outputs, synchronous): per-job arrival/completion time and template of env_index */
+/* results (HOST outputs, synchronous): per-job arrival/completion time, template and state
+ * (0 = not arrived yet, 1 = active, 2 = completed) of env_index; any output may be NULL */
 int ssb_get_jobs(ssb_env *env, int32_t env_index, int32_t *n_jobs, double *t_arrival,
-                 double *t_completed, int32_t *tmpl, int32_t capacity);
+                 double *t_completed, int32_t *tmpl, uint8_t *state, int32_t capacity);
 /* event log rows [lo, hi) of env_index (needs log_capacity > 0); *n_rows = rows logged so far */
 int ssb_get_log(ssb_env *env, int32_t env_index, int64_t lo, int64_t hi, int64_t *n_rows, double *t,
                 uint8_t *type, int16_t *job, int16_t *stage, int32_t *task, int16_t *exec,

@@ -76,7 +76,8 @@ OBS_HDR_DTYPE = np.dtype(
         ("error", "<i4"),
         ("terminated", "u1"),
         ("truncated", "u1"),
-        ("pad", "u1", (2,)),
+        ("pending", "u1"),
+        ("pad", "u1"),
     ]
 )
 assert OBS_HDR_DTYPE.itemsize == 48
@@ -115,15 +116,15 @@ def lib():
     L.ssb_load_trace.argtypes = [vp, i32, i32, vp, vp, vp, i64]
     L.ssb_clear_trace.argtypes = [vp, i32]
     L.ssb_reset.argtypes = [vp, vp, vp, vp, vp]
-    L.ssb_step.argtypes = [vp, vp, vp, vp, vp]
+    L.ssb_step.argtypes = [vp, vp, vp, vp, i32, vp]
     L.ssb_reset_host.argtypes = [vp, vp, vp, vp, vp]
-    L.ssb_step_host.argtypes = [vp, vp, vp, vp, vp]
+    L.ssb_step_host.argtypes = [vp, vp, vp, vp, i32, vp]
     L.ssb_rollout_fair.argtypes = [vp, i32, i32, i32, u64, vp]
     L.ssb_fair_actions.argtypes = [vp, i32, vp, vp, vp]
     L.ssb_get_views.argtypes = [vp, C.POINTER(SsbViews)]
     L.ssb_get_stats.argtypes = [vp, C.POINTER(vp)]
     L.ssb_reset_stats.argtypes = [vp, vp]
-    L.ssb_get_jobs.argtypes = [vp, i32, C.POINTER(i32), vp, vp, vp, i32]
+    L.ssb_get_jobs.argtypes = [vp, i32, C.POINTER(i32), vp, vp, vp, vp, i32]
     L.ssb_get_log.argtypes = [vp, i32, i64, i64, C.POINTER(i64)] + [vp] * 7
     if L.ssb_abi_version() != ABI_VERSION:
         raise ImportError("libssb ABI version mismatch; rebuild")

@@ -127,13 +127,17 @@ class BatchedSparkSchedSimEnv:
         nat.check(self.L.ssb_reset(self._h, s.data_ptr(), tl.data_ptr() if tl is not None else None,
                                    m.data_ptr() if m is not None else None, self._stream()), "ssb_reset")
 
-    def step(self, stage_idx, num_exec, mask=None):
+    def step(self, stage_idx, num_exec, mask=None, max_events=0):
+        """step(action) per env.  max_events > 0: each env processes at most that many timeline
+        events; envs that have not reached their next decision come back with hdr["pending"] = 1
+        and continue (ignoring their action) at the next call."""
         a = self._dev(stage_idx, torch.int32)
         n = self._dev(num_exec, torch.int32)
         m = self._dev(mask, torch.uint8)
         self._keep = (a, n, m)
         nat.check(self.L.ssb_step(self._h, a.data_ptr(), n.data_ptr(),
-                                  m.data_ptr() if m is not None else None, self._stream()), "ssb_step")
+                                  m.data_ptr() if m is not None else None, int(max_events),
+                                  self._stream()), "ssb_step")
 
     def fair_actions(self, dynamic_partition=True):
         a = torch.empty(self.num_envs, dtype=torch.int32, device=self.device)
@@ -158,12 +162,13 @@ class BatchedSparkSchedSimEnv:
                                         self._hdr_host.ctypes.data), "ssb_reset_host")
         return self._hdr_host
 
-    def step_host(self, stage_idx: np.ndarray, num_exec: np.ndarray, mask: np.ndarray | None = None) -> np.ndarray:
+    def step_host(self, stage_idx: np.ndarray, num_exec: np.ndarray, mask: np.ndarray | None = None,
+                  max_events: int = 0) -> np.ndarray:
         a = np.ascontiguousarray(stage_idx, dtype=np.int32)
         n = np.ascontiguousarray(num_exec, dtype=np.int32)
         m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
         nat.check(self.L.ssb_step_host(self._h, a.ctypes.data, n.ctypes.data,
-                                       m.ctypes.data if m is not None else None,
+                                       m.ctypes.data if m is not None else None, int(max_events),
                                        self._hdr_host.ctypes.data), "ssb_step_host")
         return self._hdr_host
 
@@ -203,13 +208,17 @@ class BatchedSparkSchedSimEnv:
     def clear_trace(self, b):
         nat.check(self.L.ssb_clear_trace(self._h, int(b)), "ssb_clear_trace")
 
-    def jobs(self, b: int = 0):
+    def jobs(self, b: int = 0, with_state: bool = False):
+        """(t_arrival, t_completed, template[, state]) of every job of environment b."""
         n = C.c_int32()
         cap = self.max_jobs
         ta, tc, tm = np.zeros(cap), np.zeros(cap), np.zeros(cap, np.int32)
+        st = np.zeros(cap, np.uint8)
         nat.check(self.L.ssb_get_jobs(self._h, int(b), C.byref(n), ta.ctypes.data, tc.ctypes.data,
-                                      tm.ctypes.data, cap), "ssb_get_jobs")
+                                      tm.ctypes.data, st.ctypes.data, cap), "ssb_get_jobs")
         k = n.value
+        if with_state:
+            return ta[:k], tc[:k], tm[:k], st[:k]
         return ta[:k], tc[:k], tm[:k]
 
     def log_size(self, b: int = 0) -> int:

@@ -43,7 +43,7 @@ k_reset(Params p, const uint64_t *seeds, const double *time_limits, const uint8_
 }
 
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
-k_step(Params p, const int32_t *stage_idx, const int32_t *num_exec, const uint8_t *mask)
+k_step(Params p, const int32_t *stage_idx, const int32_t *num_exec, const uint8_t *mask, int max_events)
 {
     const int b = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (b >= p.B) return;
@@ -51,7 +51,7 @@ k_step(Params p, const int32_t *stage_idx, const int32_t *num_exec, const uint8_
     Sim sim(p, b, lane);
     if (lane == 0) sim.oh->error = 0;
     __syncwarp();
-    sim.step_w(stage_idx[b], num_exec[b]);
+    sim.step_w(stage_idx[b], num_exec[b], max_events);
 }
 
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
@@ -367,10 +367,12 @@ int ssb_reset(ssb_env *env, const uint64_t *seeds, const double *time_limits, co
     return SSB_OK;
 }
 
-int ssb_step(ssb_env *env, const int32_t *stage_idx, const int32_t *num_exec, const uint8_t *mask, void *stream)
+int ssb_step(ssb_env *env, const int32_t *stage_idx, const int32_t *num_exec, const uint8_t *mask,
+             int32_t max_events, void *stream)
 {
     if (!env || !stage_idx || !num_exec) return SSB_E_INVALID;
-    k_step<<<env->grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(env->p, stage_idx, num_exec, mask);
+    k_step<<<env->grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(env->p, stage_idx, num_exec, mask,
+                                                                       max_events);
     CUDA_TRY(cudaGetLastError());
     return SSB_OK;
 }
@@ -394,7 +396,7 @@ int ssb_reset_host(ssb_env *env, const uint64_t *seeds, const double *time_limit
 }
 
 int ssb_step_host(ssb_env *env, const int32_t *stage_idx, const int32_t *num_exec, const uint8_t *mask,
-                  ssb_obs_hdr *hdr_out)
+                  int32_t max_events, ssb_obs_hdr *hdr_out)
 {
     if (!env || !stage_idx || !num_exec) return SSB_E_INVALID;
     CUDA_TRY(cudaSetDevice(env->device));
@@ -403,7 +405,7 @@ int ssb_step_host(ssb_env *env, const int32_t *stage_idx, const int32_t *num_exe
     CUDA_TRY(cudaMemcpyAsync(env->st_a, stage_idx, B * 4, cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaMemcpyAsync(env->st_n, num_exec, B * 4, cudaMemcpyHostToDevice, s));
     if (mask) CUDA_TRY(cudaMemcpyAsync(env->st_mask, mask, B, cudaMemcpyHostToDevice, s));
-    int rc = ssb_step(env, env->st_a, env->st_n, mask ? env->st_mask : nullptr, s);
+    int rc = ssb_step(env, env->st_a, env->st_n, mask ? env->st_mask : nullptr, max_events, s);
     if (rc) return rc;
     if (hdr_out) CUDA_TRY(cudaMemcpyAsync(hdr_out, env->p.obs_hdr, B * sizeof(ssb_obs_hdr), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
@@ -460,7 +462,7 @@ int ssb_reset_stats(ssb_env *env, void *stream)
 }
 
 int ssb_get_jobs(ssb_env *env, int32_t b, int32_t *n_jobs, double *t_arrival, double *t_completed,
-                 int32_t *tmpl, int32_t capacity)
+                 int32_t *tmpl, uint8_t *state, int32_t capacity)
 {
     if (!env || b < 0 || b >= env->p.B || !n_jobs) return SSB_E_INVALID;
     CUDA_TRY(cudaSetDevice(env->device));
@@ -476,6 +478,7 @@ int ssb_get_jobs(ssb_env *env, int32_t b, int32_t *n_jobs, double *t_arrival, do
         if (t_arrival) t_arrival[j] = jr[j].t_arrival;
         if (t_completed) t_completed[j] = jr[j].t_completed;
         if (tmpl) tmpl[j] = jr[j].tmpl;
+        if (state) state[j] = jr[j].state;
     }
     return SSB_OK;
 }

@@ -784,13 +784,16 @@ struct Sim {
     }
 
     // ------------------------------------------------------------ _resume_simulation (:320-343)
-    __device__ void resume_simulation_w()
+    // Returns false when `max_events` (> 0) events were processed without reaching the next
+    // scheduling decision: the environment is then "pending" and a later call continues here.
+    __device__ bool resume_simulation_w(int max_events)
     {
-        clear_sched_w();
+        int budget = max_events > 0 ? max_events : 0x7fffffff;
         for (;;) {
             double t;
             int idx = pop_min_w(t);
             if (idx < 0) break;
+            if (budget-- == 0) return false;
             if (lane == 0) handle_event(idx, t);
             __syncwarp();
             if (h->error) break;
@@ -801,6 +804,7 @@ struct Sim {
             __syncwarp();
             if (h->error) break;
         }
+        return true;
     }
 
     // ------------------------------------------------------------ reward (:847-874), lane 0
@@ -903,7 +907,7 @@ struct Sim {
             o.error = h->error;
             o.terminated = terminated ? 1 : 0;
             o.truncated = (h->wall_time >= h->time_limit) ? 1 : 0;
-            o.pad[0] = o.pad[1] = 0;
+            o.pending = 0; o.pad = 0;
             *oh = o;
             stats->observations++;
             stats->sum_nodes += N; stats->sum_edges += M; stats->sum_jobs += n_active;
@@ -952,41 +956,59 @@ struct Sim {
     }
 
     // ------------------------------------------------------------ step() (:188-221)
-    __device__ void step_w(int stage_idx, int num_exec)
+    // max_events > 0 bounds the simulation work of this call: an environment that has not reached
+    // its next decision yet is left "pending" (ssb_obs_hdr.pending = 1) and the next step_w() call on it
+    // ignores its action arguments and simply continues.  max_events <= 0: reference semantics.
+    __device__ void step_w(int stage_idx, int num_exec, int max_events = 0)
     {
         if (h->error >= 1000) { if (lane == 0) oh->error = h->error; __syncwarp(); return; }
         if (h->done) { if (lane == 0) oh->error = SSB_ENV_DONE; __syncwarp(); return; }
-        int rc = 0;
-        if (lane == 0) rc = take_action(stage_idx, num_exec);
-        rc = __shfl_sync(FULL, rc, 0);
-        __syncwarp();
-        if (rc < 0) {  // ValueError / KeyError: state untouched, report and let the caller retry
-            if (lane == 0) oh->error = -rc;
+        if (!h->pending) {
+            int rc = 0;
+            if (lane == 0) rc = take_action(stage_idx, num_exec);
+            rc = __shfl_sync(FULL, rc, 0);
+            __syncwarp();
+            if (rc < 0) {  // ValueError / KeyError: state untouched, report and let the caller retry
+                if (lane == 0) oh->error = -rc;
+                __syncwarp();
+                return;
+            }
+            if (lane == 0) stats->decisions++;
+            if (rc == 0) { observe_w(0.0, false); return; }
+            // commitment round has completed (:195-199)
+            const int n_active0 = h->n_active;
+            for (int i = lane; i < n_active0; i += 32) p.old_act[(size_t)b * p.Jc + i] = act[i];
+            __syncwarp();
+            if (lane == 0) {
+                commit_remaining_executors();
+                fulfill_commitments_from_source();
+                h->source = POOL_NONE;
+                h->wall_old = h->wall_time;
+                h->n_old_active = n_active0;
+            }
+            __syncwarp();
+            // selected_stages.clear() comes AFTER the fulfilment: backup scheduling during it must
+            // still see this round's selections (:197-199, :825-839)
+            for (int i = lane; i < n_active0; i += 32) jb[act[i]].selected = 0;
+            __syncwarp();
+            clear_sched_w();
+        }
+        bool reached = true;
+        if (!h->error) reached = resume_simulation_w(max_events);
+        if (!reached) {
+            if (lane == 0) {
+                h->pending = 1;
+                oh->pending = 1;
+                oh->reward = 0.0;
+                oh->wall_time = h->wall_time;
+            }
             __syncwarp();
             return;
         }
-        if (lane == 0) stats->decisions++;
-        if (rc == 0) { observe_w(0.0, false); return; }
-        // commitment round has completed (:195-199)
-        const int n_active0 = h->n_active;
-        for (int i = lane; i < n_active0; i += 32) p.old_act[(size_t)b * p.Jc + i] = act[i];
-        __syncwarp();
-        if (lane == 0) {
-            commit_remaining_executors();
-            fulfill_commitments_from_source();
-            h->source = POOL_NONE;
-            h->wall_old = h->wall_time;
-            h->n_old_active = n_active0;
-        }
-        __syncwarp();
-        // selected_stages.clear() comes AFTER the fulfilment: backup scheduling during it must still
-        // see this round's selections (:197-199, :825-839)
-        for (int i = lane; i < n_active0; i += 32) jb[act[i]].selected = 0;
-        __syncwarp();
-        if (!h->error) resume_simulation_w();
         double reward = 0.0;
         bool terminated = false;
         if (lane == 0) {
+            h->pending = 0;
             reward = -compute_jobtime();
             terminated = h->n_completed == h->n_jobs;
             if (terminated) { h->done = 1; stats->episodes++; }
@@ -1055,6 +1077,7 @@ struct Sim {
             H.commit_from_common = 0; H.commit_to_common = 0; H.total_none = 0;
             H.error = err; H.done = 0; H.n_nodes_total = nb; H.n_edges_total = eb;
             H.use_tape = (trace && H.tape_len >= 0) ? 1 : 0;
+            H.pending = 0;
         }
         __syncwarp();
         if (h->error) {

@@ -98,7 +98,7 @@ struct __align__(16) EnvHdr {
     int32_t source, n_sched, n_commits, n_old_active;
     int32_t commit_from_common, commit_to_common, total_none, error;
     int32_t done, trace_jobs, tape_len, n_nodes_total;
-    int32_t n_edges_total, reset_count, use_tape, pad;
+    int32_t n_edges_total, reset_count, use_tape, pending;
 };
 
 // Everything a kernel needs, passed by value.

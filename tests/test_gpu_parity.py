@@ -21,10 +21,10 @@ class CudaAdapter:
     """Presents one slot of a BatchedSparkSchedSimEnv with the OracleEnv interface; every step goes
     through ssb_step_host (host buffers in, observation headers out)."""
 
-    def __init__(self, bank, tr, B=3, slot=1):
+    def __init__(self, bank, tr, B=3, slot=1, max_events=0):
         from spark_sched_sim_b200.batched_env import BatchedSparkSchedSimEnv
 
-        self.B, self.slot, self.tr = B, slot, tr
+        self.B, self.slot, self.tr, self.max_events = B, slot, tr, max_events
         self.env = BatchedSparkSchedSimEnv(
             env_cfg_of(tr), num_envs=B, bank=bank, max_jobs=len(tr["job_template"]) + 4,
             tape_capacity=len(tr["tape"]) + 8, log_capacity=int(tr["ev_count"][-1]) + 64)
@@ -44,7 +44,14 @@ class CudaAdapter:
         return self.obs()
 
     def step(self, a, n):
-        self.hdr = self.env.step_host(np.full(self.B, a, np.int32), np.full(self.B, n, np.int32)).copy()
+        self.hdr = self.env.step_host(np.full(self.B, a, np.int32), np.full(self.B, n, np.int32),
+                                      max_events=self.max_events).copy()
+        calls = 1
+        while self.hdr[self.slot]["pending"]:  # budgeted mode: continue; the action is ignored now
+            self.hdr = self.env.step_host(np.full(self.B, -7, np.int32), np.full(self.B, -7, np.int32),
+                                          max_events=self.max_events).copy()
+            calls += 1
+            assert calls < 100000
         h = self.hdr[self.slot]
         return int(h["error"]), float(h["reward"]), bool(h["terminated"])
 
@@ -202,3 +209,55 @@ def test_auto_reset_rollout(bank):
     o, g = orc.obs(), env.obs(3, hdr)
     for key in ("nodes", "edge_links", "dag_ptr", "exec_supplies"):
         assert np.array_equal(o[key], g[key]), key
+
+
+@pytest.mark.parametrize("name,budget", [("e10_j8_random_s5_philox", 1), ("e10_j8_fair_s2_philox", 7),
+                                         ("e50_j8_random_s8_philox", 33), ("c2_fair_s1234_philox", 64)])
+def test_budgeted_step_is_equivalent(bank, name, budget):
+    """max_events > 0 (asynchronous-vector-env mode) only changes how the work is sliced over calls:
+    the trajectory is bit-identical to the reference trace."""
+    tr = load_golden(name)
+    env = CudaAdapter(bank, tr, max_events=budget)
+    replay_and_compare(env, tr, "seed", reward_rtol=1e-12 if tr["beta"] > 0 else 0.0)
+
+
+@pytest.mark.parametrize("name", ["e10_j8_fair_s2_philox", "e10_j8_fifo_s3_philox", "e50_j8_fair_s7_philox",
+                                  "c2_fair_s1234_philox"])
+def test_facade_runs_like_examples_py(bank, name):
+    """examples.py:84-102 with the drop-in classes: gym-style env + host RoundRobinScheduler reproduce
+    the reference run (same actions from the same observations, same rewards, same avg job duration)."""
+    from spark_sched_sim_b200 import metrics
+    from spark_sched_sim_b200.env import SparkSchedSimEnv
+    from spark_sched_sim_b200.schedulers import RoundRobinScheduler
+
+    tr = load_golden(name)
+    cfg = env_cfg_of(tr)
+    cfg["data_sampler_cls"] = "TPCHDataSampler"
+    env = SparkSchedSimEnv(cfg, bank=bank)
+    scheduler = RoundRobinScheduler(cfg["num_executors"], dynamic_partition=(tr["policy"] == "fair"))
+    obs, _ = env.reset(seed=tr["seed"], options=None)
+    terminated = truncated = False
+    k = 0
+    while not (terminated or truncated):
+        action, _ = scheduler.schedule(obs)
+        assert (action["stage_idx"], action["num_exec"]) == tuple(tr["actions"][k]), k
+        obs, reward, terminated, truncated, info = env.step(action)
+        assert reward == tr["reward"][k] and info["wall_time"] == tr["wall"][k]
+        assert obs["dag_batch"].nodes.shape[0] == tr["N"][k + 1]
+        assert len(obs["exec_supplies"]) == tr["Ja"][k + 1]
+        k += 1
+    assert k == len(tr["actions"])
+    assert metrics.avg_job_duration(env) * 1e-3 == pytest.approx(
+        np.mean(tr["job_t_completed"] - tr["job_t_arrival"]) * 1e-3, rel=1e-12)
+    assert env.num_completed_jobs == len(tr["job_template"]) and env.all_jobs_complete
+    # error conventions of the reference (spark_sched_sim.py:276-295)
+    env.reset(seed=tr["seed"])
+    with pytest.raises(ValueError):
+        env.step({"stage_idx": 0, "num_exec": 0})
+    with pytest.raises(ValueError):
+        env.step({"stage_idx": 0})
+    with pytest.raises(ValueError):
+        env.step({"stage_idx": 0, "num_exec": cfg["num_executors"] + 1})
+    with pytest.raises(ValueError):
+        SparkSchedSimEnv(dict(cfg, job_arrival_cap=None), bank=bank).reset(seed=1)
+    env.close()

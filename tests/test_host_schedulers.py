@@ -1,0 +1,46 @@
+"""Host-side scheduler plug-ins (same interface as schedulers/heuristics in the reference) against
+the observations and actions recorded from the reference run (no GPU needed)."""
+import numpy as np
+import pytest
+
+from helpers import golden_names, load_golden
+from spark_sched_sim_b200.gym_compat import GraphInstance
+from spark_sched_sim_b200.schedulers import RandomScheduler, RoundRobinScheduler, make_scheduler
+
+
+def recorded_obs(tr):
+    n = e = d = s = 0
+    for k in range(len(tr["N"])):
+        N, M, Ja = int(tr["N"][k]), int(tr["M"][k]), int(tr["Ja"][k])
+        yield {
+            "dag_batch": GraphInstance(tr["nodes"][n:n + N], np.zeros(M, int),
+                                       tr["edges"][e:e + M].astype(np.int64)),
+            "dag_ptr": tr["dag_ptr"][d:d + Ja + 1].tolist(),
+            "num_committable_execs": int(tr["ncommit"][k]),
+            "source_job_idx": int(tr["src"][k]),
+            "exec_supplies": tr["supplies"][s:s + Ja].tolist(),
+        }
+        n += N; e += M; d += Ja + 1; s += Ja
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names(slim=False)])
+def test_host_policies_reproduce_recorded_actions(name):
+    tr = load_golden(name)
+    if tr["policy"] in ("fair", "fifo"):
+        sched = RoundRobinScheduler(tr["num_executors"], dynamic_partition=(tr["policy"] == "fair"))
+    else:
+        sched = RandomScheduler(seed=tr["policy_seed"])
+    assert sched.env_wrapper_cls is None and sched.name in ("Fair", "FIFO", "Random")
+    for k, obs in enumerate(recorded_obs(tr)):
+        if k == len(tr["actions"]):
+            break
+        action, info = sched.schedule(obs)
+        assert (int(action["stage_idx"]), int(action["num_exec"])) == tuple(tr["actions"][k]), k
+        assert info == {}
+
+
+def test_make_scheduler_factory():
+    s = make_scheduler({"agent_cls": "RoundRobinScheduler", "num_executors": 10, "dynamic_partition": False})
+    assert s.name == "FIFO"
+    with pytest.raises(AssertionError):
+        make_scheduler({"agent_cls": "Nope"})

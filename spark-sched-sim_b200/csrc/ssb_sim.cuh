@@ -401,13 +401,23 @@ struct Sim {
     }
     __device__ double task_duration(int j, int s, int e)  // tpch.py:75-106
     {
-        uint32_t li = h->launch_idx;
+        double d = 1.0;
+        int rc = sample_duration(j, s, h->launch_idx, !ex[e].has_task, ex[e].task_stage == s, d);
+        if (rc) fail(rc);
+        return d;
+    }
+    // Duration of launch number `li` of the episode; `idle`: executor.task is None; `same_stage`:
+    // executor.task.stage_id == stage id.  Returns 0 or an SSB_ENV_* code WITHOUT touching the
+    // environment, so the batched fast path may call it speculatively from any lane.
+    __device__ int sample_duration(int j, int s, uint32_t li, bool idle, bool same_stage, double &d)
+    {
         if (h->use_tape) {
-            if ((int)li >= h->tape_len) { fail(SSB_ENV_TAPE_EXHAUSTED); return 1.0; }
-            return p.tape[(size_t)b * p.tape_cap + li];
+            if ((int)li >= h->tape_len) return SSB_ENV_TAPE_EXHAUSTED;
+            d = p.tape[(size_t)b * p.tape_cap + li];
+            return 0;
         }
         int n_local = jb[j].n_local;
-        SSB_CHKR(n_local > 0 && n_local <= p.E, 1.0);
+        if (!(n_local > 0 && n_local <= p.E)) return 1000 + __LINE__;
         uint4 w = philox4x32_10(li, 0u, 2u, 0u, (uint32_t)h->seed, (uint32_t)(h->seed >> 32));
         int left = p.iv[2 * n_local], right = p.iv[2 * n_local + 1], key;  // _sample_executor_key :216-235
         if (left == right) key = left;
@@ -426,19 +436,16 @@ struct Sim {
         }
         int fw = p.b_present[ts * 4 + 1];
         if (lvl < 0 || !((fw >> lvl) & 1)) lvl = fw ? 31 - __clz(fw) : -1;  // max(data["first_wave"])
-        double d;
-        if (!ex[e].has_task) {  // executor.is_idle
-            if (sample_wave(ts, 0, lvl, w.y, false, d)) return d;
-            if (sample_wave(ts, 1, lvl, w.y, true, d)) return d;
-            fail(SSB_ENV_SAMPLER);
-            return 1.0;
+        if (idle) {  // executor.is_idle
+            if (sample_wave(ts, 0, lvl, w.y, false, d)) return 0;
+            if (sample_wave(ts, 1, lvl, w.y, true, d)) return 0;
+            return SSB_ENV_SAMPLER;
         }
-        if (ex[e].task_stage == s)
-            if (sample_wave(ts, 2, lvl, w.y, false, d)) return d;
-        if (sample_wave(ts, 1, lvl, w.y, false, d)) return d;
-        if (sample_wave(ts, 0, lvl, w.y, false, d)) return d;
-        fail(SSB_ENV_SAMPLER);
-        return 1.0;
+        if (same_stage)
+            if (sample_wave(ts, 2, lvl, w.y, false, d)) return 0;
+        if (sample_wave(ts, 1, lvl, w.y, false, d)) return 0;
+        if (sample_wave(ts, 0, lvl, w.y, false, d)) return 0;
+        return SSB_ENV_SAMPLER;
     }
 
     // ------------------------------------------------------------ schedulability (:505-555)
@@ -784,12 +791,135 @@ struct Sim {
     }
 
     // ------------------------------------------------------------ _resume_simulation (:320-343)
+    // ------------------------------------------------------------ batched fast path (E <= 32)
+    // ~99 % of the timeline events are "executor finishes a task and takes the next task of the same
+    // stage" (:464-467).  Such events only touch their own executor and their stage's counters, so
+    // the longest prefix (in (t, seq) order) of pending events that are all of this kind, that leave
+    // their stage's saturation unchanged, and that precede every event they themselves create (and
+    // the next job arrival) can be handled in ONE warp iteration, one event per lane:
+    //   rank_e      = number of pending events ordered before lane e's event       (all-pairs shuffles)
+    //   launch idx  = launch_idx + rank_e   (the Philox counter / tape index of that launch)
+    //   remaining_e = stage.remaining - (# same-stage events ordered before e)
+    // The result is identical to handling the events one by one.  Returns the prefix length (0 => the
+    // next event needs the general path).  Measured on C2: 3.8 events per iteration.
+    __device__ int fast_batch_w(int budget)
+    {
+        const uint64_t INF_BITS = 0x7ff0000000000000ull;
+        if (num_committable() != 0) return 0;
+        const bool has = lane < p.E;
+        unsigned long long kt = 0x7ff8000000000000ull;
+        uint32_t ks = 0xffffffffu;
+        int kind = 0, j = 0, s = 0, node = -1 - lane, old_task = -1;
+        double t_acc = 0.0;
+        if (has) {
+            const ExecRec &x = ex[lane];
+            kind = x.ev_kind;
+            if (kind) {
+                kt = (unsigned long long)__double_as_longlong(x.ev_t);
+                ks = x.ev_seq; j = x.ev_job; s = x.ev_stage; old_task = x.ev_task; t_acc = x.t_acc;
+                node = jb[j].node_base + s;
+            }
+        }
+        const bool pending = kind != 0;
+        const unsigned pend_mask = __ballot_sync(FULL, pending);
+        if (!pend_mask) return 0;
+        unsigned long long t_arr = INF_BITS;
+        {
+            int na = h->next_arrival;
+            if (na < h->n_jobs) t_arr = (unsigned long long)__double_as_longlong(jb[na].t_arrival);
+        }
+        int rank = 0, before_same = 0;
+        for (int i = 0; i < p.E; i++) {
+            unsigned long long ot = __shfl_sync(FULL, kt, i);
+            uint32_t os = __shfl_sync(FULL, ks, i);
+            int on = __shfl_sync(FULL, node, i);
+            bool less = ot < kt || (ot == kt && os < ks);
+            rank += less;
+            before_same += less && on == node;
+        }
+        // eligibility: TASK_FINISHED before the next arrival (an arrival at the same time pops first,
+        // its seq is smaller), tasks left after this launch, saturation bit of the stage unchanged
+        bool elig = pending && kind == EV_TASK_FINISHED && kt < t_arr;
+        int rem = 0;
+        if (elig) {
+            const StageRec r = st[node];
+            rem = (int)r.remaining - before_same;
+            int mc = (int)r.moving_to + (int)r.commit_to;
+            elig = rem > 1 && ((rem <= mc) == (rem - 1 <= mc));
+        }
+        const double t = __longlong_as_double((long long)kt);
+        double d = 0.0, newt = __longlong_as_double((long long)INF_BITS);
+        if (elig) {  // speculative: a failing draw just ends the prefix; the general path reports it
+            if (sample_duration(j, s, h->launch_idx + (uint32_t)rank, false, true, d) != 0) elig = false;
+            else newt = __dadd_rn(t, d);
+        }
+        // longest valid prefix: every earlier event eligible and t_r <= all event times created so far
+        int m = 0;
+        {
+            double minnew = __longlong_as_double((long long)INF_BITS);
+            int n_pending = __popc(pend_mask);
+            if (n_pending > budget) n_pending = budget;
+            for (int r = 0; r < n_pending; r++) {
+                unsigned bm = __ballot_sync(FULL, pending && rank == r);
+                int l = __ffs(bm) - 1;
+                int ok = __shfl_sync(FULL, (int)elig, l);
+                double tr = __shfl_sync(FULL, t, l);
+                double nt = __shfl_sync(FULL, newt, l);
+                if (!ok || tr > minnew) break;
+                minnew = fmin(minnew, nt);
+                m++;
+            }
+        }
+        if (m == 0) return 0;
+        const bool member = pending && rank < m;
+        const unsigned mem_mask = __ballot_sync(FULL, member);
+        const uint32_t seq0 = h->seq;
+        const long long log0 = h->log_n;
+        if (member) {
+            if (p.log_cap > 0 && log0 + rank < p.log_cap) {
+                LogRow r;
+                r.t = t; r.t_acc = t_acc; r.task = old_task; r.job = (int16_t)j; r.stage = (int16_t)s;
+                r.exec = (int16_t)lane; r.type = (uint8_t)EV_TASK_FINISHED; r.pad = 0; r.pad1 = 0;
+                p.log[(size_t)b * p.log_cap + log0 + rank] = r;
+            }
+            ExecRec &x = ex[lane];
+            x.ev_t = newt; x.t_acc = t; x.ev_seq = seq0 + (uint32_t)rank; x.ev_task = rem - 1;
+            const unsigned peers = __match_any_sync(mem_mask, node);
+            const int cnt = __popc(peers);
+            if (before_same == cnt - 1) {  // last launch of this stage in the batch: it owns the counters
+                StageRec &r = st[node];
+                r.remaining -= (uint16_t)cnt;
+                r.completed += (uint16_t)cnt;
+                r.mrd = (float)d;
+            }
+        }
+        const double t_last = __shfl_sync(FULL, t, __ffs(__ballot_sync(FULL, member && rank == m - 1)) - 1);
+        __syncwarp();
+        if (lane == 0) {
+            h->launch_idx += (uint32_t)m;
+            h->seq = seq0 + (uint32_t)m;
+            h->log_n = log0 + m;
+            h->wall_time = t_last;
+            stats->events += (unsigned long long)m;
+        }
+        __syncwarp();
+        return m;
+    }
+
     // Returns false when `max_events` (> 0) events were processed without reaching the next
     // scheduling decision: the environment is then "pending" and a later call continues here.
     __device__ bool resume_simulation_w(int max_events)
     {
         int budget = max_events > 0 ? max_events : 0x7fffffff;
         for (;;) {
+            if (p.E <= 32 && budget > 0) {
+                int m = fast_batch_w(budget);
+                if (m) {
+                    budget -= m;
+                    if (h->error) break;
+                    continue;
+                }
+            }
             double t;
             int idx = pop_min_w(t);
             if (idx < 0) break;

@@ -100,12 +100,15 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    if not osp.exists(LIB_PATH):
+    import os
+
+    path = os.environ.get("SSB_LIB", LIB_PATH)  # SSB_LIB: A/B-test another build of the same library
+    if not osp.exists(path):
         raise ImportError(
-            f"{LIB_PATH} not found: the CUDA library has not been built "
+            f"{path} not found: the CUDA library has not been built "
             "(run `python -c 'import __graft_entry__ as g; g.build()'`). There is no CPU fallback."
         )
-    L = C.CDLL(LIB_PATH)
+    L = C.CDLL(path)
     vp, i32, i64, u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64
     L.ssb_abi_version.restype = C.c_int
     L.ssb_last_cuda_error.restype = C.c_char_p

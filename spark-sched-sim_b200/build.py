@@ -1,4 +1,8 @@
-"""Builds libssb.so in-tree with nvcc for sm_100a (no JIT cache, no torch extension machinery)."""
+"""Builds libssb.so in-tree with nvcc for sm_100a (no JIT cache, no torch extension machinery).
+
+`build()` produces the product library `_lib/libssb.so`.  `build(variant="x", extra=[...])` produces
+`_lib/libssb_x.so` with extra nvcc flags -- a development aid for A/B timing on the GPU box
+(`SSB_LIB=/path/to/libssb_x.so python bench.py`)."""
 from __future__ import annotations
 
 import os
@@ -18,14 +22,16 @@ NVCC_FLAGS = [
 ]
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and osp.exists(OUT) and all(osp.getmtime(d) <= osp.getmtime(OUT) for d in DEPS):
-        return OUT
-    os.makedirs(osp.dirname(OUT), exist_ok=True)
+def build(force: bool = False, verbose: bool = False, variant: str | None = None,
+          extra: list[str] | None = None) -> str:
+    out = OUT if variant is None else osp.join(PKG_DIR, "_lib", f"libssb_{variant}.so")
+    if not force and osp.exists(out) and all(osp.getmtime(d) <= osp.getmtime(out) for d in DEPS):
+        return out
+    os.makedirs(osp.dirname(out), exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SRC
+    cmd = [nvcc] + NVCC_FLAGS + (extra or []) + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + SRC
     subprocess.check_call(cmd)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":

@@ -153,7 +153,7 @@ struct BankDev {
     uint8_t *present;
     uint2 *dur;
     double *vals;
-    int16_t *iv;
+    short4 *iv;
 };
 
 void carve(Carver &cv, const ssb_config &c, const ssb_bank &bk, const Dims &d, Params &p, BankDev &bd,
@@ -171,7 +171,7 @@ void carve(Carver &cv, const ssb_config &c, const ssb_bank &bk, const Dims &d, P
     bd.present = cv.take<uint8_t>(TS * 4);
     bd.dur = cv.take<uint2>(TS * 24);
     bd.vals = cv.take<double>((size_t)bk.num_values + 1);
-    bd.iv = cv.take<int16_t>(2 * ((size_t)c.num_executors + 1));
+    bd.iv = cv.take<short4>((size_t)c.num_executors + 1);
     p.hdr = cv.take<EnvHdr>(B);
     p.exec = cv.take<ExecRec>(B * c.num_executors);
     p.job = cv.take<JobRec>(B * c.max_jobs);
@@ -304,7 +304,16 @@ int ssb_create(const ssb_config *cfg, const ssb_bank *bk, int device, void *work
             iv[2 * LV[i + 1]] = iv[2 * LV[i + 1] + 1] = LV[i + 1];
         }
         if (cap > LV[7]) for (int r = LV[7] + 1; r < cap; r++) iv[2 * r] = iv[2 * r + 1] = LV[7];
-        CUDA_TRY(cudaMemcpy(bd.iv, iv.data(), iv.size() * 2, cudaMemcpyHostToDevice));
+        std::vector<short4> iv4(cap + 1);
+        for (int r = 0; r <= cap; r++) {
+            int li = -1, ri = -1;  // level value -> level index (-1: not a data level, e.g. the 0 rows)
+            for (int q = 0; q < 8; q++) {
+                if (LV[q] == iv[2 * r]) li = q;
+                if (LV[q] == iv[2 * r + 1]) ri = q;
+            }
+            iv4[r] = make_short4(iv[2 * r], iv[2 * r + 1], (short)li, (short)ri);
+        }
+        CUDA_TRY(cudaMemcpy(bd.iv, iv4.data(), iv4.size() * sizeof(short4), cudaMemcpyHostToDevice));
     }
     p.b_num_stages = bd.num_stages; p.b_stage_base = bd.stage_base; p.b_edge_base = bd.edge_base;
     p.b_num_tasks = bd.num_tasks; p.b_edges = bd.edges; p.b_rough = bd.rough; p.b_parent = bd.parent;

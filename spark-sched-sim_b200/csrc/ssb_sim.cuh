@@ -14,6 +14,11 @@
 namespace ssb {
 
 #define FULL 0xffffffffu
+// rarely executed state-machine pieces (executor motion, set emulation) are kept out of line so the
+// hot event loop stays compact in the instruction cache
+#ifndef SSB_COLD
+#define SSB_COLD __noinline__
+#endif
 #define SSB_CHK(cond)                         \
     do {                                      \
         if (!(cond)) {                        \
@@ -89,7 +94,7 @@ __device__ inline void ps_insert_clean(T *t, int mask, int key)  // set_insert_c
     }
 }
 template <typename T>
-__device__ inline void ps_resize(PSet<T> &s, int minused, T *tmp)  // set_table_resize
+__device__ SSB_COLD void ps_resize(PSet<T> &s, int minused, T *tmp)  // set_table_resize
 {
     int newsize = 8;
     while (newsize <= minused) newsize <<= 1;
@@ -103,7 +108,7 @@ __device__ inline void ps_resize(PSet<T> &s, int minused, T *tmp)  // set_table_
         if (tmp[i] < PSet<T>::DUMMY) ps_insert_clean(s.t, s.mask, tmp[i]);
 }
 template <typename T>
-__device__ inline void ps_add(PSet<T> &s, int key, T *tmp)  // set_add_entry
+__device__ SSB_COLD void ps_add(PSet<T> &s, int key, T *tmp)  // set_add_entry
 {
     int mask = s.mask, freeslot = -1;
     unsigned perturb = (unsigned)key, i = (unsigned)key & mask;
@@ -174,7 +179,7 @@ __device__ inline void ps_init(PSet<T> &s, T *table)
 }
 // set.copy(): make_new_set + set_merge into an empty set
 template <typename T>
-__device__ inline void ps_copy_into(PSet<T> &dst, T *table, const PSet<T> &other, T *tmp)
+__device__ SSB_COLD void ps_copy_into(PSet<T> &dst, T *table, const PSet<T> &other, T *tmp)
 {
     ps_init(dst, table);
     if (other.used == 0) return;
@@ -312,7 +317,7 @@ struct Sim {
             if (cm[i].src == src && cm[i].dst == dst) return cm + i;
         return nullptr;
     }
-    __device__ void add_commitment(int n, int dst)  // executor_tracker.py:146-154, :224-236
+    __device__ SSB_COLD void add_commitment(int n, int dst)  // executor_tracker.py:146-154, :224-236
     {
         int src = h->source;
         SSB_CHK(src != POOL_NONE);
@@ -329,7 +334,7 @@ struct Sim {
         int sj = pool_job(src), dj = pool_job(dst);
         if (dj != sj) add_total(dj, n);
     }
-    __device__ int remove_commitment(int e, int dst)  // executor_tracker.py:156-173, :238-249
+    __device__ SSB_COLD int remove_commitment(int e, int dst)  // executor_tracker.py:156-173, :238-249
     {
         int src = ex[e].loc;
         SSB_CHKR(src != POOL_NONE, POOL_NONE);
@@ -358,7 +363,7 @@ struct Sim {
             if (cm[i].src == pool) return cm[i].dst;
         return POOL_NONE;
     }
-    __device__ void move_executor_to_pool(int e, int new_pool, bool send)  // executor_tracker.py:186-220
+    __device__ SSB_COLD void move_executor_to_pool(int e, int new_pool, bool send)  // executor_tracker.py:186-220
     {
         int old = ex[e].loc;
         if (old != POOL_NONE) {
@@ -409,30 +414,29 @@ struct Sim {
     // Duration of launch number `li` of the episode; `idle`: executor.task is None; `same_stage`:
     // executor.task.stage_id == stage id.  Returns 0 or an SSB_ENV_* code WITHOUT touching the
     // environment, so the batched fast path may call it speculatively from any lane.
-    __device__ int sample_duration(int j, int s, uint32_t li, bool idle, bool same_stage, double &d)
+    __device__ __forceinline__ int sample_duration(int j, int s, uint32_t li, bool idle, bool same_stage,
+                                                    double &d)
+    {
+        return sample_duration_ts(jb[j].ts_base + s, jb[j].n_local, li, idle, same_stage, d);
+    }
+    // same, with the template-stage row and len(job.local_executors) already in registers
+    __device__ __forceinline__ int sample_duration_ts(int ts, int n_local, uint32_t li, bool idle,
+                                                       bool same_stage, double &d)
     {
         if (h->use_tape) {
             if ((int)li >= h->tape_len) return SSB_ENV_TAPE_EXHAUSTED;
             d = p.tape[(size_t)b * p.tape_cap + li];
             return 0;
         }
-        int n_local = jb[j].n_local;
         if (!(n_local > 0 && n_local <= p.E)) return 1000 + __LINE__;
         uint4 w = philox4x32_10(li, 0u, 2u, 0u, (uint32_t)h->seed, (uint32_t)(h->seed >> 32));
-        int left = p.iv[2 * n_local], right = p.iv[2 * n_local + 1], key;  // _sample_executor_key :216-235
-        if (left == right) key = left;
-        else {
+        // _sample_executor_key :216-235; iv row = (left level, right level, left index, right index)
+        const short4 iv = p.iv[n_local];
+        int lvl = iv.z;
+        if (iv.x != iv.y) {
             double u = __dmul_rn((double)w.x, 1.0 / 4294967296.0);
-            int rand_pt = 1 + (int)__dmul_rn(u, (double)(right - left));
-            key = (rand_pt <= n_local - left) ? left : right;
-        }
-        int ts = jb[j].ts_base + s;
-        int lvl = -1;
-        {
-            const int LV[8] = {5, 10, 20, 40, 50, 60, 80, 100};
-#pragma unroll
-            for (int i = 0; i < 8; i++)
-                if (LV[i] == key) lvl = i;
+            int rand_pt = 1 + (int)__dmul_rn(u, (double)(iv.y - iv.x));
+            lvl = (rand_pt <= n_local - iv.x) ? iv.z : iv.w;
         }
         int fw = p.b_present[ts * 4 + 1];
         if (lvl < 0 || !((fw >> lvl) & 1)) lvl = fw ? 31 - __clz(fw) : -1;  // max(data["first_wave"])
@@ -565,7 +569,7 @@ struct Sim {
         return idle;
     }
     // _move_idle_executors (:745-782).  e >= 0: that single executor; e < 0: all idle ones at src
-    __device__ void move_idle_executors(int src, int e)
+    __device__ SSB_COLD void move_idle_executors(int src, int e)
     {
         if (src == POOL_NONE) src = h->source;
         SSB_CHK(src != POOL_NONE);
@@ -590,7 +594,7 @@ struct Sim {
         }
     }
     // _move_executor_to_stage (:799-819) with _try_backup_schedule (:784-797) unrolled into a loop
-    __device__ void move_executor_to_stage(int e, int j, int s)
+    __device__ SSB_COLD void move_executor_to_stage(int e, int j, int s)
     {
         for (int guard = 0; guard < 4; guard++) {
             StageRec &r = st[jb[j].node_base + s];
@@ -790,136 +794,208 @@ struct Sim {
         return idx;
     }
 
-    // ------------------------------------------------------------ _resume_simulation (:320-343)
     // ------------------------------------------------------------ batched fast path (E <= 32)
     // ~99 % of the timeline events are "executor finishes a task and takes the next task of the same
-    // stage" (:464-467).  Such events only touch their own executor and their stage's counters, so
-    // the longest prefix (in (t, seq) order) of pending events that are all of this kind, that leave
-    // their stage's saturation unchanged, and that precede every event they themselves create (and
-    // the next job arrival) can be handled in ONE warp iteration, one event per lane:
-    //   rank_e      = number of pending events ordered before lane e's event       (all-pairs shuffles)
-    //   launch idx  = launch_idx + rank_e   (the Philox counter / tape index of that launch)
-    //   remaining_e = stage.remaining - (# same-stage events ordered before e)
-    // The result is identical to handling the events one by one.  Returns the prefix length (0 => the
-    // next event needs the general path).  Measured on C2: 3.8 events per iteration.
-    __device__ int fast_batch_w(int budget)
+    // stage" (:464-467).  Such events only touch their own executor and their stage's counters, so a
+    // prefix (in (t, seq) order) of the pending events that are all of this kind, that leave their
+    // stage's saturation unchanged, and that precede every event the batch itself creates (and the
+    // next job arrival) can be handled in ONE warp iteration, one event per lane:
+    //   less_e      = bitmask of lanes whose pending event is ordered before lane e's   (all-pairs)
+    //   rank_e      = popc(less_e)            launch idx = launch_idx + rank_e (Philox counter / tape)
+    //   remaining_e = stage.remaining - popc(less_e & lanes on the same stage)
+    //   G           = min over all eligible lanes of their NEW event time
+    //   member_e    = eligible, t_e <= G, and no ineligible / later-than-G lane ordered before e
+    // The result is identical to handling the events one by one (a shorter prefix is always valid).
+    // Measured on C2: 3.8 events per iteration.  Between general-path events everything the loop
+    // needs lives in registers, one executor per lane: the pending event, the stage's counters and
+    // the two rest-wave duration-table rows the executor-level draw can select; per iteration a lane
+    // issues one global load (the sampled duration) and its stores.
+    struct HotLane {
+        unsigned long long kt;  // event time (f64 bits) and push counter
+        double t_acc;
+        uint32_t ks;
+        int kind, j, s, node, task;
+        int rem, comp, mc;   // stage: remaining, completed, moving_to + commit_to
+        uint2 oc_a, oc_b;    // rest-wave (offset, count) for the left / right executor level
+        int thr, range;      // _sample_executor_key: key = left iff 1 + int(u * range) <= thr
+        bool fast_ok;        // this executor's next launch can be sampled without the fallback chain
+    };
+    struct HotEnv {  // uniform per-environment scalars
+        unsigned long long t_arr;
+        double wall;
+        long long log_n;
+        uint32_t launch_idx, seq;
+        int events;
+        bool quiet;  // no committable executors at the current (possibly stale) source
+    };
+    __device__ SSB_COLD void hot_load(HotLane &L, HotEnv &H)
     {
-        const uint64_t INF_BITS = 0x7ff0000000000000ull;
-        if (num_committable() != 0) return 0;
-        const bool has = lane < p.E;
-        unsigned long long kt = 0x7ff8000000000000ull;
-        uint32_t ks = 0xffffffffu;
-        int kind = 0, j = 0, s = 0, node = -1 - lane, old_task = -1;
-        double t_acc = 0.0;
-        if (has) {
+        L.kt = 0x7ff8000000000000ull; L.ks = 0xffffffffu; L.kind = 0; L.j = 0; L.s = 0;
+        L.node = -1 - lane; L.task = -1; L.t_acc = 0.0; L.rem = L.comp = L.mc = 0;
+        L.oc_a = L.oc_b = make_uint2(0u, 0u); L.thr = L.range = 0; L.fast_ok = false;
+        if (lane < p.E) {
             const ExecRec &x = ex[lane];
-            kind = x.ev_kind;
-            if (kind) {
-                kt = (unsigned long long)__double_as_longlong(x.ev_t);
-                ks = x.ev_seq; j = x.ev_job; s = x.ev_stage; old_task = x.ev_task; t_acc = x.t_acc;
-                node = jb[j].node_base + s;
+            L.kind = x.ev_kind;
+            if (L.kind) {
+                L.kt = (unsigned long long)__double_as_longlong(x.ev_t);
+                L.ks = x.ev_seq; L.j = x.ev_job; L.s = x.ev_stage; L.task = x.ev_task; L.t_acc = x.t_acc;
+                const JobRec &J = jb[L.j];
+                L.node = J.node_base + L.s;
+                const StageRec r = st[L.node];
+                L.rem = r.remaining; L.comp = r.completed; L.mc = (int)r.moving_to + (int)r.commit_to;
+                if (L.kind == EV_TASK_FINISHED) {
+                    const int ts = J.ts_base + L.s, n_local = J.n_local;
+                    if (h->use_tape) L.fast_ok = true;
+                    else if (n_local > 0 && n_local <= p.E) {
+                        const short4 iv = p.iv[n_local];
+                        const int fw = p.b_present[ts * 4 + 1], rw = p.b_present[ts * 4 + 2];
+                        const int top = fw ? 31 - __clz(fw) : -1;  // max(data["first_wave"])
+                        int la = iv.z, lb = iv.w;
+                        if (la < 0 || !((fw >> la) & 1)) la = top;
+                        if (lb < 0 || !((fw >> lb) & 1)) lb = top;
+                        if (la >= 0 && ((rw >> la) & 1)) L.oc_a = p.b_dur[(ts * 3 + 2) * 8 + la];
+                        if (lb >= 0 && ((rw >> lb) & 1)) L.oc_b = p.b_dur[(ts * 3 + 2) * 8 + lb];
+                        L.range = iv.y - iv.x;
+                        L.thr = n_local - iv.x;
+                        // the rest-wave list must exist for every level the draw can pick
+                        L.fast_ok = L.oc_a.y > 0 && (L.range == 0 || L.oc_b.y > 0);
+                    }
+                }
             }
         }
-        const bool pending = kind != 0;
-        const unsigned pend_mask = __ballot_sync(FULL, pending);
-        if (!pend_mask) return 0;
-        unsigned long long t_arr = INF_BITS;
-        {
-            int na = h->next_arrival;
-            if (na < h->n_jobs) t_arr = (unsigned long long)__double_as_longlong(jb[na].t_arrival);
+        H.t_arr = 0x7ff0000000000000ull;
+        int na = h->next_arrival;
+        if (na < h->n_jobs) H.t_arr = (unsigned long long)__double_as_longlong(jb[na].t_arrival);
+        H.wall = h->wall_time; H.log_n = h->log_n; H.launch_idx = h->launch_idx; H.seq = h->seq;
+        H.events = 0;
+        H.quiet = num_committable() == 0;
+    }
+    __device__ void hot_flush(const HotEnv &H)
+    {
+        if (lane == 0 && H.events) {
+            h->wall_time = H.wall; h->log_n = H.log_n; h->launch_idx = H.launch_idx; h->seq = H.seq;
+            stats->events += (unsigned long long)H.events;
         }
-        int rank = 0, before_same = 0;
+        __syncwarp();
+    }
+    // exact (t, seq) order, used when two pending events agree in the upper half of their timestamps
+    __device__ SSB_COLD unsigned exact_less_w(unsigned long long kt, uint32_t ks)
+    {
+        unsigned less = 0;
         for (int i = 0; i < p.E; i++) {
             unsigned long long ot = __shfl_sync(FULL, kt, i);
             uint32_t os = __shfl_sync(FULL, ks, i);
-            int on = __shfl_sync(FULL, node, i);
-            bool less = ot < kt || (ot == kt && os < ks);
-            rank += less;
-            before_same += less && on == node;
+            less |= (unsigned)(ot < kt || (ot == kt && os < ks)) << i;
         }
+        return less;
+    }
+    __device__ SSB_COLD void log_batch_row(const HotLane &L, long long row, double t)
+    {
+        if (row >= p.log_cap) return;
+        LogRow r;
+        r.t = t; r.t_acc = L.t_acc; r.task = L.task; r.job = (int16_t)L.j; r.stage = (int16_t)L.s;
+        r.exec = (int16_t)lane; r.type = (uint8_t)EV_TASK_FINISHED; r.pad = 0; r.pad1 = 0;
+        p.log[(size_t)b * p.log_cap + row] = r;
+    }
+    __device__ int fast_batch_w(HotLane &L, HotEnv &H, int budget)
+    {
+        const unsigned long long INF_BITS = 0x7ff0000000000000ull;
+        if (!H.quiet) return 0;
+        const bool pending = L.kind != 0;
+        const unsigned pend_mask = __ballot_sync(FULL, pending);
+        if (!pend_mask) return 0;
+        // order of the pending events by (t, push counter) (event.py:34-35).  The upper 32 bits of the
+        // timestamps almost always decide; ties there take the exact path.
+        const uint32_t hi = (uint32_t)(L.kt >> 32);
+        unsigned less = 0;
+#pragma unroll
+        for (int i = 0; i < 16; i++) less |= (__shfl_sync(FULL, hi, i) < hi) ? (1u << i) : 0u;
+        if (p.E > 16) {
+#pragma unroll
+            for (int i = 16; i < 32; i++) less |= (__shfl_sync(FULL, hi, i) < hi) ? (1u << i) : 0u;
+        }
+        {
+            const unsigned eq = __match_any_sync(FULL, hi) & pend_mask;
+            if (__any_sync(FULL, pending && (eq & (eq - 1)))) less = exact_less_w(L.kt, L.ks);
+        }
+        less &= pend_mask;
+        const int rank = __popc(less);
+        const unsigned same_node = __match_any_sync(FULL, L.node);
+        const int before_same = __popc(less & same_node);
         // eligibility: TASK_FINISHED before the next arrival (an arrival at the same time pops first,
         // its seq is smaller), tasks left after this launch, saturation bit of the stage unchanged
-        bool elig = pending && kind == EV_TASK_FINISHED && kt < t_arr;
-        int rem = 0;
+        const int rem = L.rem - before_same;
+        bool elig = pending && L.fast_ok && L.kt < H.t_arr && rank < budget && rem > 1 &&
+                    ((rem <= L.mc) == (rem - 1 <= L.mc));
+        const double t = __longlong_as_double((long long)L.kt);
+        double d = 0.0;
+        unsigned long long nt = INF_BITS;
         if (elig) {
-            const StageRec r = st[node];
-            rem = (int)r.remaining - before_same;
-            int mc = (int)r.moving_to + (int)r.commit_to;
-            elig = rem > 1 && ((rem <= mc) == (rem - 1 <= mc));
-        }
-        const double t = __longlong_as_double((long long)kt);
-        double d = 0.0, newt = __longlong_as_double((long long)INF_BITS);
-        if (elig) {  // speculative: a failing draw just ends the prefix; the general path reports it
-            if (sample_duration(j, s, h->launch_idx + (uint32_t)rank, false, true, d) != 0) elig = false;
-            else newt = __dadd_rn(t, d);
-        }
-        // longest valid prefix: every earlier event eligible and t_r <= all event times created so far
-        int m = 0;
-        {
-            double minnew = __longlong_as_double((long long)INF_BITS);
-            int n_pending = __popc(pend_mask);
-            if (n_pending > budget) n_pending = budget;
-            for (int r = 0; r < n_pending; r++) {
-                unsigned bm = __ballot_sync(FULL, pending && rank == r);
-                int l = __ffs(bm) - 1;
-                int ok = __shfl_sync(FULL, (int)elig, l);
-                double tr = __shfl_sync(FULL, t, l);
-                double nt = __shfl_sync(FULL, newt, l);
-                if (!ok || tr > minnew) break;
-                minnew = fmin(minnew, nt);
-                m++;
+            const uint32_t li = H.launch_idx + (uint32_t)rank;
+            if (h->use_tape) {
+                if ((int)li < h->tape_len) d = p.tape[(size_t)b * p.tape_cap + li];
+                else elig = false;  // the general path reports the exhausted tape
+            } else {  // tpch.py:75-106 for an executor continuing on its stage: rest_wave[level]
+                const uint4 w = philox4x32_10(li, 0u, 2u, 0u, (uint32_t)h->seed, (uint32_t)(h->seed >> 32));
+                uint2 oc = L.oc_a;
+                if (L.range) {
+                    double u = __dmul_rn((double)w.x, 1.0 / 4294967296.0);
+                    int rand_pt = 1 + (int)__dmul_rn(u, (double)L.range);
+                    if (rand_pt > L.thr) oc = L.oc_b;
+                }
+                d = p.b_vals[oc.x + bounded(w.y, oc.y)];
             }
+            if (elig) nt = (unsigned long long)__double_as_longlong(__dadd_rn(t, d));
         }
-        if (m == 0) return 0;
-        const bool member = pending && rank < m;
+        // G = earliest event the batch could create (non-negative doubles order like their bit patterns)
+        const uint32_t ghi = __reduce_min_sync(FULL, (uint32_t)(nt >> 32));
+        const uint32_t glo = __reduce_min_sync(FULL, (uint32_t)(nt >> 32) == ghi ? (uint32_t)nt : 0xffffffffu);
+        const unsigned long long G = ((unsigned long long)ghi << 32) | glo;
+        const unsigned bad = __ballot_sync(FULL, pending && (!elig || L.kt > G));
+        const bool member = pending && !((bad >> lane) & 1) && !(less & bad);
         const unsigned mem_mask = __ballot_sync(FULL, member);
-        const uint32_t seq0 = h->seq;
-        const long long log0 = h->log_n;
+        const int m = __popc(mem_mask);
+        if (m == 0) return 0;
+        const int cnt = __popc(same_node & mem_mask);  // launches of my stage in this batch
         if (member) {
-            if (p.log_cap > 0 && log0 + rank < p.log_cap) {
-                LogRow r;
-                r.t = t; r.t_acc = t_acc; r.task = old_task; r.job = (int16_t)j; r.stage = (int16_t)s;
-                r.exec = (int16_t)lane; r.type = (uint8_t)EV_TASK_FINISHED; r.pad = 0; r.pad1 = 0;
-                p.log[(size_t)b * p.log_cap + log0 + rank] = r;
-            }
+            if (p.log_cap > 0) log_batch_row(L, H.log_n + rank, t);
+            L.kt = nt; L.t_acc = t; L.ks = H.seq + (uint32_t)rank; L.task = rem - 1;
             ExecRec &x = ex[lane];
-            x.ev_t = newt; x.t_acc = t; x.ev_seq = seq0 + (uint32_t)rank; x.ev_task = rem - 1;
-            const unsigned peers = __match_any_sync(mem_mask, node);
-            const int cnt = __popc(peers);
+            x.ev_t = __longlong_as_double((long long)nt); x.t_acc = t; x.ev_seq = L.ks; x.ev_task = L.task;
             if (before_same == cnt - 1) {  // last launch of this stage in the batch: it owns the counters
-                StageRec &r = st[node];
-                r.remaining -= (uint16_t)cnt;
-                r.completed += (uint16_t)cnt;
+                StageRec &r = st[L.node];
+                r.remaining = (uint16_t)(L.rem - cnt);
+                r.completed = (uint16_t)(L.comp + cnt);
                 r.mrd = (float)d;
             }
         }
-        const double t_last = __shfl_sync(FULL, t, __ffs(__ballot_sync(FULL, member && rank == m - 1)) - 1);
-        __syncwarp();
-        if (lane == 0) {
-            h->launch_idx += (uint32_t)m;
-            h->seq = seq0 + (uint32_t)m;
-            h->log_n = log0 + m;
-            h->wall_time = t_last;
-            stats->events += (unsigned long long)m;
-        }
-        __syncwarp();
+        L.rem -= cnt; L.comp += cnt;  // every lane on that stage tracks its counters
+        // wall time = time of the last member (members are a prefix, so it is their maximum)
+        const uint32_t thi = (uint32_t)(__double_as_longlong(t) >> 32), tlo = (uint32_t)__double_as_longlong(t);
+        const uint32_t whi = __reduce_max_sync(FULL, member ? thi : 0u);
+        const uint32_t wlo = __reduce_max_sync(FULL, (member && thi == whi) ? tlo : 0u);
+        H.wall = __longlong_as_double((long long)(((unsigned long long)whi << 32) | wlo));
+        H.launch_idx += (uint32_t)m; H.seq += (uint32_t)m; H.log_n += m; H.events += m;
         return m;
     }
 
+    // ------------------------------------------------------------ _resume_simulation (:320-343)
     // Returns false when `max_events` (> 0) events were processed without reaching the next
     // scheduling decision: the environment is then "pending" and a later call continues here.
     __device__ bool resume_simulation_w(int max_events)
     {
         int budget = max_events > 0 ? max_events : 0x7fffffff;
+        const bool use_fast = p.E <= 32;
+        HotLane L;
+        HotEnv H;
+        bool hot = false;
         for (;;) {
-            if (p.E <= 32 && budget > 0) {
-                int m = fast_batch_w(budget);
-                if (m) {
-                    budget -= m;
-                    if (h->error) break;
-                    continue;
-                }
+            if (use_fast && budget > 0) {
+                if (!hot) { hot_load(L, H); hot = true; }
+                int m = fast_batch_w(L, H, budget);
+                if (m) { budget -= m; continue; }
             }
+            if (hot) { hot_flush(H); hot = false; }
             double t;
             int idx = pop_min_w(t);
             if (idx < 0) break;

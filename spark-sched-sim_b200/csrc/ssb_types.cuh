@@ -114,7 +114,7 @@ struct Params {
     const uint8_t *b_present;  // [TS][4] (3 used)
     const uint2 *b_dur;        // [TS][3][8] (offset, count)
     const double *b_vals;
-    const int16_t *iv;  // [E+1][2] executor-interval levels (tpch.py:237-262)
+    const short4 *iv;  // [E+1] executor intervals (tpch.py:237-262): left/right level, left/right level index
     // state
     EnvHdr *hdr;
     ExecRec *exec;     // [B][E]

@@ -38,7 +38,7 @@ namespace ssb {
 __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                                 uint32_t k0, uint32_t k1)
 {
-#pragma unroll
+#pragma unroll 2
     for (int r = 0; r < 10; r++) {
         uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
         uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
@@ -80,12 +80,13 @@ struct PSet {
 };
 
 template <typename T>
-__device__ inline void ps_insert_clean(T *t, int mask, int key)  // set_insert_clean
+__device__ SSB_COLD void ps_insert_clean(T *t, int mask, int key)  // set_insert_clean
 {
     unsigned perturb = (unsigned)key, i = (unsigned)key & mask;
     for (;;) {
         if (t[i] == PSet<T>::EMPTY) { t[i] = (T)key; return; }
         if (i + 9 <= (unsigned)mask) {
+#pragma unroll 1
             for (int j = 1; j <= 9; j++)
                 if (t[i + j] == PSet<T>::EMPTY) { t[i + j] = (T)key; return; }
         }
@@ -100,10 +101,13 @@ __device__ SSB_COLD void ps_resize(PSet<T> &s, int minused, T *tmp)  // set_tabl
     while (newsize <= minused) newsize <<= 1;
     int oldmask = s.mask;
     if (newsize == 8 && oldmask == 7 && s.fill == s.used) return;
+#pragma unroll 1
     for (int i = 0; i <= oldmask; i++) tmp[i] = s.t[i];
+#pragma unroll 1
     for (int i = 0; i < newsize; i++) s.t[i] = (T)PSet<T>::EMPTY;
     s.mask = newsize - 1;
     s.fill = s.used;
+#pragma unroll 1
     for (int i = 0; i <= oldmask; i++)
         if (tmp[i] < PSet<T>::DUMMY) ps_insert_clean(s.t, s.mask, tmp[i]);
 }
@@ -114,6 +118,7 @@ __device__ SSB_COLD void ps_add(PSet<T> &s, int key, T *tmp)  // set_add_entry
     unsigned perturb = (unsigned)key, i = (unsigned)key & mask;
     for (;;) {
         int probes = (i + 9 <= (unsigned)mask) ? 9 : 0;
+#pragma unroll 1
         for (int j = 0; j <= probes; j++) {
             int v = s.t[i + j];
             if (v == PSet<T>::EMPTY) {
@@ -138,6 +143,7 @@ __device__ inline int ps_find(const PSet<T> &s, int key)  // set_lookkey
     unsigned perturb = (unsigned)key, i = (unsigned)key & mask;
     for (;;) {
         int probes = (i + 9 <= (unsigned)mask) ? 9 : 0;
+#pragma unroll 1
         for (int j = 0; j <= probes; j++) {
             int v = s.t[i + j];
             if (v == PSet<T>::EMPTY) return -1;
@@ -185,11 +191,13 @@ __device__ SSB_COLD void ps_copy_into(PSet<T> &dst, T *table, const PSet<T> &oth
     if (other.used == 0) return;
     if (other.used * 5 >= 7 * 3) ps_resize(dst, other.used * 2, tmp);
     if (dst.mask == other.mask && other.fill == other.used) {
+#pragma unroll 1
         for (int i = 0; i <= other.mask; i++) dst.t[i] = other.t[i];
         dst.fill = other.fill; dst.used = other.used;
         return;
     }
     dst.fill = dst.used = other.used;
+#pragma unroll 1
     for (int i = 0; i <= other.mask; i++)
         if (other.t[i] < PSet<T>::DUMMY) ps_insert_clean(dst.t, dst.mask, other.t[i]);
 }
@@ -229,7 +237,7 @@ struct Sim {
         oh = p.obs_hdr + b;
     }
 
-    __device__ void fail(int code)
+    __device__ SSB_COLD void fail(int code)
     {
         if (!h->error) h->error = code;
     }
@@ -420,8 +428,8 @@ struct Sim {
         return sample_duration_ts(jb[j].ts_base + s, jb[j].n_local, li, idle, same_stage, d);
     }
     // same, with the template-stage row and len(job.local_executors) already in registers
-    __device__ __forceinline__ int sample_duration_ts(int ts, int n_local, uint32_t li, bool idle,
-                                                       bool same_stage, double &d)
+    __device__ SSB_COLD int sample_duration_ts(int ts, int n_local, uint32_t li, bool idle,
+                                                bool same_stage, double &d)
     {
         if (h->use_tape) {
             if ((int)li >= h->tape_len) return SSB_ENV_TAPE_EXHAUSTED;
@@ -455,7 +463,7 @@ struct Sim {
     // ------------------------------------------------------------ schedulability (:505-555)
     // Schedulable stages of job j as a bitmask: ready (unsaturated, all parents saturated), not yet
     // selected this round, job not saturated with executors unless it is the source job.
-    __device__ uint64_t job_sched_mask(int j, int source_job) const
+    __device__ SSB_COLD uint64_t job_sched_mask(int j, int source_job) const
     {
         const JobRec &J = jb[j];
         if (!(j == source_job || J.supply < p.E)) return 0;
@@ -469,7 +477,7 @@ struct Sim {
         return out;
     }
     // _find_schedulable_stages over all active jobs; writes every active job's `sched` mask
-    __device__ int find_schedulable_all_w()
+    __device__ SSB_COLD int find_schedulable_all_w()
     {
         int src_job = source_job_id();
         int n_active = h->n_active, total = 0;
@@ -557,7 +565,7 @@ struct Sim {
         push_event(e, __dadd_rn(h->wall_time, p.moving_delay), EV_EXECUTOR_READY, j, s, -1);
     }
     // _get_idle_source_executors (:714-728): set(generator) over a copy of the pool; result in scr[1]
-    __device__ PSet<uint8_t> idle_executors(int pool)
+    __device__ SSB_COLD PSet<uint8_t> idle_executors(int pool)
     {
         PSet<uint8_t> src = ps_load(pool), cp, idle;
         ps_copy_into(cp, scr, src, scr + 2 * p.TAB);
@@ -828,7 +836,8 @@ struct Sim {
         int events;
         bool quiet;  // no committable executors at the current (possibly stale) source
     };
-    __device__ SSB_COLD void hot_load(HotLane &L, HotEnv &H)
+    // (must inline: a non-inlined callee taking L/H by reference would pin them in local memory)
+    __device__ __forceinline__ void hot_load(HotLane &L, HotEnv &H)
     {
         L.kt = 0x7ff8000000000000ull; L.ks = 0xffffffffu; L.kind = 0; L.j = 0; L.s = 0;
         L.node = -1 - lane; L.task = -1; L.t_acc = 0.0; L.rem = L.comp = L.mc = 0;
@@ -870,7 +879,7 @@ struct Sim {
         H.events = 0;
         H.quiet = num_committable() == 0;
     }
-    __device__ void hot_flush(const HotEnv &H)
+    __device__ __forceinline__ void hot_flush(const HotEnv &H)
     {
         if (lane == 0 && H.events) {
             h->wall_time = H.wall; h->log_n = H.log_n; h->launch_idx = H.launch_idx; h->seq = H.seq;
@@ -889,15 +898,15 @@ struct Sim {
         }
         return less;
     }
-    __device__ SSB_COLD void log_batch_row(const HotLane &L, long long row, double t)
+    __device__ SSB_COLD void log_batch_row(long long row, double t, double t_acc, int task, int j, int s)
     {
         if (row >= p.log_cap) return;
         LogRow r;
-        r.t = t; r.t_acc = L.t_acc; r.task = L.task; r.job = (int16_t)L.j; r.stage = (int16_t)L.s;
+        r.t = t; r.t_acc = t_acc; r.task = task; r.job = (int16_t)j; r.stage = (int16_t)s;
         r.exec = (int16_t)lane; r.type = (uint8_t)EV_TASK_FINISHED; r.pad = 0; r.pad1 = 0;
         p.log[(size_t)b * p.log_cap + row] = r;
     }
-    __device__ int fast_batch_w(HotLane &L, HotEnv &H, int budget)
+    __device__ __forceinline__ int fast_batch_w(HotLane &L, HotEnv &H, int budget)
     {
         const unsigned long long INF_BITS = 0x7ff0000000000000ull;
         if (!H.quiet) return 0;
@@ -908,12 +917,9 @@ struct Sim {
         // timestamps almost always decide; ties there take the exact path.
         const uint32_t hi = (uint32_t)(L.kt >> 32);
         unsigned less = 0;
-#pragma unroll
-        for (int i = 0; i < 16; i++) less |= (__shfl_sync(FULL, hi, i) < hi) ? (1u << i) : 0u;
-        if (p.E > 16) {
-#pragma unroll
-            for (int i = 16; i < 32; i++) less |= (__shfl_sync(FULL, hi, i) < hi) ? (1u << i) : 0u;
-        }
+        // (kept rolled on purpose: the kernel is instruction-fetch bound, see profiles/)
+#pragma unroll 1
+        for (int i = 0; i < p.E; i++) less |= (__shfl_sync(FULL, hi, i) < hi) ? (1u << i) : 0u;
         {
             const unsigned eq = __match_any_sync(FULL, hi) & pend_mask;
             if (__any_sync(FULL, pending && (eq & (eq - 1)))) less = exact_less_w(L.kt, L.ks);
@@ -958,7 +964,7 @@ struct Sim {
         if (m == 0) return 0;
         const int cnt = __popc(same_node & mem_mask);  // launches of my stage in this batch
         if (member) {
-            if (p.log_cap > 0) log_batch_row(L, H.log_n + rank, t);
+            if (p.log_cap > 0) log_batch_row(H.log_n + rank, t, L.t_acc, L.task, L.j, L.s);
             L.kt = nt; L.t_acc = t; L.ks = H.seq + (uint32_t)rank; L.task = rem - 1;
             ExecRec &x = ex[lane];
             x.ev_t = __longlong_as_double((long long)nt); x.t_acc = t; x.ev_seq = L.ks; x.ev_task = L.task;
@@ -986,16 +992,19 @@ struct Sim {
     {
         int budget = max_events > 0 ? max_events : 0x7fffffff;
         const bool use_fast = p.E <= 32;
-        HotLane L;
-        HotEnv H;
-        bool hot = false;
         for (;;) {
             if (use_fast && budget > 0) {
-                if (!hot) { hot_load(L, H); hot = true; }
-                int m = fast_batch_w(L, H, budget);
-                if (m) { budget -= m; continue; }
+                // registers only: L and H die before the general path below is entered
+                HotLane L;
+                HotEnv H;
+                hot_load(L, H);
+                for (;;) {
+                    int m = fast_batch_w(L, H, budget);
+                    budget -= m;
+                    if (m == 0 || budget == 0) break;
+                }
+                hot_flush(H);
             }
-            if (hot) { hot_flush(H); hot = false; }
             double t;
             int idx = pop_min_w(t);
             if (idx < 0) break;
@@ -1014,31 +1023,66 @@ struct Sim {
     }
 
     // ------------------------------------------------------------ reward (:847-874), lane 0
-    __device__ double compute_jobtime()
+    // continuously discounted job-time of one job over [a, b] after the step's start (:866-869)
+    __device__ SSB_COLD double discounted_term(double a, double b) const
+    {
+        return exp(-p.beta * 1e-3 * a) - exp(-p.beta * 1e-3 * b);
+    }
+    __device__ SSB_COLD double compute_jobtime()
     {
         double wall = h->wall_time, wall_old = h->wall_old;
         if (wall - wall_old == 0.0) return 0.0;
-        uint16_t *tab = p.rset + (size_t)b * 2 * p.RT, *tmp = tab + p.RT;
-        PSet<uint16_t> ids;  // set(active_old + active_new): iteration order == CPython's
-        ps_init(ids, tab);
         const int16_t *old = p.old_act + (size_t)b * p.Jc;
-        for (int i = 0; i < h->n_old_active; i++) ps_add(ids, old[i], tmp);
-        for (int i = 0; i < h->n_active; i++) ps_add(ids, act[i], tmp);
+        const int n_old = h->n_old_active, n_new = h->n_active;
         double jt = 0.0, beta = p.beta;
+        // The sum runs over set(active_old + active_new) in CPython's iteration order (:855-858).  Both
+        // lists ascend and jobs that arrived during the step have larger ids than every old one, so the
+        // distinct ids are inserted in ascending order; the table sizes go 8 -> 32 -> 128 -> 512 -> ...
+        // at 5, 19, 77, 307, ... elements, and once every id is smaller than the final table size each
+        // id sits in its own slot => iteration is ascending.  (tests/test_pyset.py checks this claim
+        // against the interpreter.)  Otherwise emulate the set.
+        {
+            const int last_old = n_old ? old[n_old - 1] : -1;
+            int n = n_old;
+            for (int i = n_new - 1; i >= 0 && act[i] > last_old; i--) n++;
+            const int max_id = n_new && act[n_new - 1] > last_old ? act[n_new - 1] : last_old;
+            const int F = n < 5 ? 8 : n < 19 ? 32 : n < 77 ? 128 : n < 307 ? 512 : n < 1229 ? 2048 : 0;
+            if (max_id < F) {
+                int a = 0, c = 0;
+                while (a < n_old || c < n_new) {  // ascending merge of the two lists
+                    int j;
+                    if (c >= n_new || (a < n_old && old[a] <= act[c])) {
+                        j = old[a++];
+                        if (c < n_new && act[c] == j) c++;
+                    } else j = act[c++];
+                    double start = fmax(jb[j].t_arrival, wall_old), end = fmin(jb[j].t_completed, wall);
+                    if (beta == 0.0) jt = __dadd_rn(jt, __dadd_rn(end, -start));
+                    else jt += discounted_term(start - wall_old, end - wall_old);
+                }
+                if (beta > 0.0) jt /= beta;
+                return jt;
+            }
+        }
+        uint16_t *tab = p.rset + (size_t)b * 2 * p.RT, *tmp = tab + p.RT;
+        PSet<uint16_t> ids;
+        ps_init(ids, tab);
+#pragma unroll 1
+        for (int i = 0; i < n_old; i++) ps_add(ids, old[i], tmp);
+#pragma unroll 1
+        for (int i = 0; i < n_new; i++) ps_add(ids, act[i], tmp);
         for (int i = 0; i <= ids.mask; i++) {
             int j = ids.t[i];
             if (j >= PSet<uint16_t>::DUMMY) continue;
             double start = fmax(jb[j].t_arrival, wall_old), end = fmin(jb[j].t_completed, wall);
             if (beta == 0.0) jt = __dadd_rn(jt, __dadd_rn(end, -start));
-            else
-                jt += exp(-beta * 1e-3 * (start - wall_old)) - exp(-beta * 1e-3 * (end - wall_old));
+            else jt += discounted_term(start - wall_old, end - wall_old);
         }
         if (beta > 0.0) jt /= beta;
         return jt;
     }
 
     // ------------------------------------------------------------ _observe (:345-406, utils.py:5-22)
-    __device__ void observe_w(double reward, bool terminated)
+    __device__ SSB_COLD void observe_w(double reward, bool terminated)
     {
         const int n_active = h->n_active;
         float *nodes = p.obs_nodes + (size_t)b * p.Sc * 3;
@@ -1227,7 +1271,7 @@ struct Sim {
     }
 
     // ------------------------------------------------------------ reset() (:127-186)
-    __device__ void reset_w(uint64_t seed, double time_limit)
+    __device__ SSB_COLD void reset_w(uint64_t seed, double time_limit)
     {
         const int Jc = p.Jc;
         int n_jobs = 0, err = 0;

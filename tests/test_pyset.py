@@ -31,6 +31,30 @@ class EmuSet:
 
 
 @pytest.mark.skipif(sys.version_info[:2] != (3, 12), reason="layout pinned to CPython 3.12")
+def test_reward_set_ascending_shortcut():
+    """The kernel's reward sum (ssb_sim.cuh compute_jobtime) iterates set(active_old + active_new)
+    in ascending order whenever max(id) < F(n), F = 8/32/128/512/2048 for n < 5/19/77/307/1229
+    distinct ids inserted in ascending order.  Check that claim against the interpreter."""
+    def final_size(n):
+        return 8 if n < 5 else 32 if n < 19 else 128 if n < 77 else 512 if n < 307 else 2048 if n < 1229 else 0
+
+    rnd = random.Random(7)
+    used = 0
+    for _ in range(20000):
+        J = rnd.choice([8, 50, 200, 1000])
+        pool = sorted(rnd.sample(range(J), rnd.randint(0, min(J, 320))))
+        cut = rnd.randint(0, len(pool))
+        old = pool[:cut]
+        new = [x for x in old if rnd.random() > 0.1] + pool[cut:][:rnd.randint(0, 5)]
+        s = set(old + new)
+        ids = sorted(s)
+        if ids and ids[-1] < final_size(len(ids)):
+            used += 1
+            assert list(s) == ids
+    assert used > 5000
+
+
+@pytest.mark.skipif(sys.version_info[:2] != (3, 12), reason="layout pinned to CPython 3.12")
 @pytest.mark.parametrize("universe", [3, 10, 50, 100, 200])
 def test_pyset_matches_cpython(universe):
     rnd = random.Random(universe)

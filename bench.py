@@ -182,7 +182,7 @@ def main() -> None:
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-budget", type=int, default=64,
+    ap.add_argument("--e2e-budget", type=int, default=192,
                     help="max timeline events per env per ssb_step_host call (0 = run to next decision)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -209,8 +209,9 @@ def main() -> None:
 
     bank = synthetic_bank(0)
     env = BatchedSparkSchedSimEnv(ENV_CFG, num_envs=B, bank=bank, device=dev)
-    seeds = (1234 + rank * B + np.arange(B)).astype(np.uint64)  # envs shard over ranks: disjoint seeds
-    seed_step = B * world
+    from spark_sched_sim_b200 import parallel
+
+    seeds, seed_step = parallel.shard_seeds(1234, B, rank, world)  # envs shard over ranks: disjoint seeds
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     stats_vec = torch.zeros(8, dtype=torch.float64, device=dev)
 

@@ -63,6 +63,25 @@ def setup(bank_seed: int = 0) -> str:
         pkg = types.ModuleType("schedulers")
         pkg.__path__ = [osp.join(REFERENCE, "schedulers")]
         sys.modules["schedulers"] = pkg
+    # the Decima *observation wrapper* needs only numpy + networkx, but its package imports PyG at
+    # module level; empty stand-ins are enough to import it (the GNN itself is not executed here)
+    class _Stub(types.ModuleType):
+        def __getattr__(self, item):  # pyg.data.Batch etc. in annotations evaluated at import time
+            if item.startswith("__"):
+                raise AttributeError(item)
+            return _Stub(f"{self.__name__}.{item}")
+
+        def __or__(self, other):
+            return self
+
+        __ror__ = __or__
+
+    for name in ("torch_geometric", "torch_sparse", "torch_scatter"):
+        if name not in sys.modules:
+            try:
+                importlib.import_module(name)
+            except ImportError:
+                sys.modules[name] = _Stub(name)
     bank = _import_product_bank()
     root = f"/tmp/ssb_refdata_seed{bank_seed}"
     if not osp.isdir(osp.join(root, "data", "tpch", "100g")):
@@ -110,6 +129,7 @@ def run_episode(
     time_limit: float | None = None,
     max_steps: int | None = None,
     bank_seed: int = 0,
+    decima: bool = False,
 ) -> dict:
     """One reference episode -> trace dict of numpy arrays (see module docstring)."""
     setup(bank_seed)
@@ -121,6 +141,9 @@ def run_episode(
     env_cfg.setdefault("data_sampler_cls", "TPCHDataSampler")
     env = gymnasium.make("spark_sched_sim:SparkSchedSimEnv-v0", env_cfg=env_cfg)
     sched = make_policy(policy, env_cfg["num_executors"], policy_seed)
+    dec_wrapper = None
+    if decima:  # the reference's own DecimaObsWrapper, evaluated on every base observation
+        dec_wrapper = importlib.import_module("schedulers.decima.env_wrapper").DecimaObsWrapper(env)
     from spark_sched_sim.components.event import Event
 
     type_map = {
@@ -168,7 +191,8 @@ def run_episode(
 
     rec = {k: [] for k in (
         "actions", "reward", "wall", "term", "ncommit", "src", "N", "M", "Ja", "ev_count",
-        "nodes", "edges", "dag_ptr", "supplies", "obs_digest")}
+        "nodes", "edges", "dag_ptr", "supplies", "obs_digest",
+        "dec_feat", "dec_caps", "dec_depth", "dec_edge_bits", "dec_stage_mask")}
 
     def record_obs(o):
         g = o["dag_batch"]
@@ -186,6 +210,26 @@ def run_episode(
         rec["obs_digest"].append(
             obs_digest(nodes, el, o["dag_ptr"], o["exec_supplies"],
                        o["num_committable_execs"], o["source_job_idx"]))
+
+    def record_decima(o):
+        d = dec_wrapper.observation(o)
+        feat = np.asarray(d["dag_batch"].nodes, np.float32).reshape(-1, 5)
+        em = np.asarray(d["edge_masks"], bool)  # (depth - 1, M)
+        bits = np.zeros(em.shape[1], np.uint64)
+        for k in range(em.shape[0]):
+            bits |= em[k].astype(np.uint64) << np.uint64(k)
+        rec["dec_feat"].append(feat.copy())
+        rec["dec_caps"].append(np.asarray(d["exec_mask"], bool).sum(1).astype(np.int32))
+        rec["dec_depth"].append(em.shape[0])
+        rec["dec_edge_bits"].append(bits)
+        rec["dec_stage_mask"].append(np.asarray(d["stage_mask"], np.uint8))
+
+    _record_base = record_obs
+
+    def record_obs(o):  # noqa: F811
+        _record_base(o)
+        if dec_wrapper is not None:
+            record_decima(o)
 
     record_obs(obs)  # observation 0 = reset
     rec["ev_count"].append(len(events))
@@ -243,6 +287,11 @@ def run_episode(
         "edges": np.concatenate(rec["edges"], 0) if rec["edges"] else np.zeros((0, 2), np.int32),
         "dag_ptr": np.concatenate(rec["dag_ptr"]),
         "supplies": np.concatenate(rec["supplies"]) if rec["supplies"] else np.zeros(0, np.int32),
+        "dec_feat": np.concatenate(rec["dec_feat"], 0) if rec["dec_feat"] else np.zeros((0, 5), np.float32),
+        "dec_caps": np.concatenate(rec["dec_caps"]) if rec["dec_caps"] else np.zeros(0, np.int32),
+        "dec_depth": np.array(rec["dec_depth"], np.int32),
+        "dec_edge_bits": np.concatenate(rec["dec_edge_bits"]) if rec["dec_edge_bits"] else np.zeros(0, np.uint64),
+        "dec_stage_mask": np.concatenate(rec["dec_stage_mask"]) if rec["dec_stage_mask"] else np.zeros(0, np.uint8),
         "ev_t": evarr[:, 0].copy(),
         "ev_type": evarr[:, 1].astype(np.uint8),
         "ev_job": evarr[:, 2].astype(np.int16),
@@ -265,7 +314,8 @@ def slim(trace: dict) -> dict:
     t["ev_digest"] = np.array(
         [events_digest(trace, int(a), int(b)) for a, b in zip(lo, ec)], np.uint64)
     for k in ("nodes", "edges", "dag_ptr", "supplies", "ev_t", "ev_type", "ev_job", "ev_stage",
-              "ev_task", "ev_exec", "ev_tacc", "tape_meta"):
+              "ev_task", "ev_exec", "ev_tacc", "tape_meta", "dec_feat", "dec_caps", "dec_depth",
+              "dec_edge_bits", "dec_stage_mask"):
         t.pop(k)
     t["slim"] = True
     return t

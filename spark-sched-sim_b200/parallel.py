@@ -1,0 +1,59 @@
+"""Multi-GPU plumbing: environments shard over ranks, nothing else crosses GPUs.
+
+The reference parallelises rollouts as `num_sequences x num_rollouts` CPU processes
+(trainers/trainer.py:264-293): worker `i` uses `base_seed = seed + i // num_rollouts` and re-seeds
+with `base_seed + num_sequences * reset_count` (trainers/rollout_worker.py:118-120), then sends its
+statistics to the learner over a Pipe (rollout_worker.py:122-129).  Here one process per GPU owns a
+contiguous block of environments; the only exchange step is an all-reduce (sum) of the statistics
+vector -- NCCL on device tensors in production, gloo on CPU tensors in the tests.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+STAT_KEYS = ("decisions", "events", "sched_scans", "sum_nodes", "sum_edges", "sum_jobs",
+             "observations", "episodes")
+
+
+def shard_range(total_envs: int, rank: int, world: int) -> tuple[int, int]:
+    """[lo, hi) of the global environment ids owned by `rank` (contiguous, sizes differ by <= 1)."""
+    base, rem = divmod(total_envs, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_seeds(base_seed: int, envs_per_rank: int, rank: int, world: int) -> tuple[np.ndarray, int]:
+    """Seeds of this rank's environments and the auto-reset seed step: env g (global id) plays
+    episodes seeded base_seed + g + (envs_per_rank * world) * k, k = 0, 1, ... -- disjoint over
+    ranks, envs and resets."""
+    g = rank * envs_per_rank + np.arange(envs_per_rank, dtype=np.uint64)
+    return (np.uint64(base_seed) + g).astype(np.uint64), envs_per_rank * world
+
+
+def reference_worker_seeds(seed: int, num_sequences: int, num_rollouts: int) -> tuple[np.ndarray, int]:
+    """The reference trainer's scheme for `num_sequences * num_rollouts` environments: rollouts of
+    the same job sequence share a seed (trainer.py:268-270); seed step = num_sequences."""
+    i = np.arange(num_sequences * num_rollouts)
+    return (seed + i // num_rollouts).astype(np.uint64), num_sequences
+
+
+def allreduce_stats(stats: dict, device: torch.device | str = "cpu", group=None) -> dict:
+    """Sums the per-rank statistics dict over all ranks (no-op without an initialised group)."""
+    vec = torch.tensor([float(stats[k]) for k in STAT_KEYS], dtype=torch.float64, device=device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(vec, op=dist.ReduceOp.SUM, group=group)
+    return {k: float(v) for k, v in zip(STAT_KEYS, vec.tolist())}
+
+
+def rollout_summary(sum_job_time: float, sum_wall_time: float, num_completed: float,
+                    num_arrived: float, sum_completed_duration: float) -> dict:
+    """collect_stats (rollout_worker.py:122-129) from sums that can be all-reduced:
+    avg_num_jobs = total job-time / total wall time (metrics.py:15-16)."""
+    return {
+        "avg_job_duration": (sum_completed_duration / num_completed * 1e-3) if num_completed else float("nan"),
+        "avg_num_jobs": (sum_job_time / sum_wall_time) if sum_wall_time else float("nan"),
+        "num_completed_jobs": num_completed,
+        "num_job_arrivals": num_arrived,
+    }

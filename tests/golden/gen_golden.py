@@ -60,7 +60,8 @@ def main(argv):
     checksum = bankmod.synthetic_bank(0).checksum()
     for name in names:
         env_cfg, policy, seed, rng, tl, slim = CASES[name]
-        tr = refrun.run_episode(env_cfg, policy, seed, rng=rng, time_limit=tl)
+        # small cases also record what the reference's DecimaObsWrapper makes of every observation
+        tr = refrun.run_episode(env_cfg, policy, seed, rng=rng, time_limit=tl, decima=not slim)
         if slim:
             tr = refrun.slim(tr)
         tr["bank_checksum"] = checksum

@@ -1,0 +1,85 @@
+"""N > 1 host logic on CPU: world_size-2 gloo processes shard the environments, run their share on
+the CPU oracle (stand-in for the per-GPU env), and all-reduce the rollout statistics -- the same
+helpers bench.py uses with NCCL."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from spark_sched_sim_b200 import parallel
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, envs_per_rank, out):
+    import sys
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    for p in (os.path.dirname(here), os.path.join(os.path.dirname(here), "oracle")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from oracle import OracleEnv
+    from spark_sched_sim_b200.bank import synthetic_bank
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    seeds, step = parallel.shard_seeds(1234, envs_per_rank, rank, world)
+    bank = synthetic_bank(0)
+    env = OracleEnv(bank, 10, 4, 2000.0, 1000.0, 4.0e-5)
+    stats = {k: 0 for k in parallel.STAT_KEYS}
+    for s in seeds:
+        dec, ev = env.run_fair_episode(int(s), True)
+        stats["decisions"] += dec
+        stats["events"] += ev
+        stats["episodes"] += 1
+    total = parallel.allreduce_stats(stats)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (seeds.tolist(), step, stats))
+    if rank == 0:
+        out.put((total, gathered))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharding_and_stats_allreduce():
+    world, envs_per_rank = 2, 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, envs_per_rank, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    total, gathered = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    seeds = [s for g in gathered for s in g[0]]
+    assert sorted(seeds) == list(range(1234, 1234 + world * envs_per_rank))  # disjoint, contiguous
+    assert all(g[1] == world * envs_per_rank for g in gathered)
+    assert total["decisions"] == sum(g[2]["decisions"] for g in gathered) > 0
+    assert total["events"] == sum(g[2]["events"] for g in gathered)
+    assert total["episodes"] == world * envs_per_rank
+
+
+def test_shard_range_and_reference_seeds():
+    for total in (1, 7, 4096, 65536):
+        for world in (1, 2, 3, 8):
+            spans = [parallel.shard_range(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+    seeds, step = parallel.reference_worker_seeds(42, num_sequences=4, num_rollouts=4)
+    assert step == 4 and seeds.tolist() == [42] * 4 + [43] * 4 + [44] * 4 + [45] * 4
+    s = parallel.rollout_summary(10.0, 5.0, 2, 3, 4000.0)
+    assert s["avg_num_jobs"] == 2.0 and s["avg_job_duration"] == 2.0
+    assert parallel.allreduce_stats({k: 1 for k in parallel.STAT_KEYS})["events"] == 1.0

@@ -65,7 +65,11 @@ typedef struct {
     double warmup_delay;     /* ms */
     double job_arrival_rate; /* 1/ms */
     double beta;             /* continuous discount (trainer.beta_discount), 0 = undiscounted */
+    int32_t flags;           /* SSB_FLAG_* */
+    int32_t pad;
 } ssb_config;
+
+#define SSB_FLAG_DECIMA_OBS 1 /* allocate the Decima observation buffers (ssb_decima_obs) */
 
 /* Flattened template bank (host pointers; copied to the device by ssb_create).  Layout: see
  * spark-sched-sim_b200/bank.py, which restates tpch.py:118-206. */
@@ -176,6 +180,21 @@ int ssb_fair_actions(ssb_env *env, int32_t dynamic_partition, int32_t *stage_idx
                      void *stream);
 
 int ssb_get_views(ssb_env *env, ssb_views *out);
+
+/* Decima's observation adapter on the device (schedulers/decima/env_wrapper.py:69-143 and
+ * make_dag_layer_edge_masks, schedulers/decima/utils.py:238-267), computed from the current state
+ * of every env; needs SSB_FLAG_DECIMA_OBS.  Same node/edge/job order as the base observation. */
+typedef struct {
+    float *features;        /* [B][node_stride][5]: cap/E, +-1 source flag, supply/E, remaining/200,
+                               remaining*duration/1e5 (float32 arithmetic as in the reference) */
+    uint8_t *stage_mask;    /* [B][node_stride] schedulable flag */
+    int32_t *commit_caps;   /* [B][job_stride]: exec_mask[j] = first commit_caps[j] of E entries */
+    uint64_t *edge_bits;    /* [B][edge_stride]: bit k set <=> edge in edge_masks[k] */
+    int32_t *depth;         /* [B]: number of edge masks (message passing depth) */
+    int32_t node_stride, edge_stride, job_stride, pad;
+} ssb_decima_views;
+int ssb_decima_obs(ssb_env *env, void *stream);
+int ssb_get_decima_views(ssb_env *env, ssb_decima_views *out);
 /* device pointer to ssb_stats[B] */
 int ssb_get_stats(ssb_env *env, ssb_stats **out);
 int ssb_reset_stats(ssb_env *env, void *stream);

@@ -24,6 +24,25 @@ class SsbConfig(C.Structure):
         ("warmup_delay", C.c_double),
         ("job_arrival_rate", C.c_double),
         ("beta", C.c_double),
+        ("flags", C.c_int32),
+        ("pad", C.c_int32),
+    ]
+
+
+FLAG_DECIMA_OBS = 1
+
+
+class SsbDecimaViews(C.Structure):
+    _fields_ = [
+        ("features", C.c_void_p),
+        ("stage_mask", C.c_void_p),
+        ("commit_caps", C.c_void_p),
+        ("edge_bits", C.c_void_p),
+        ("depth", C.c_void_p),
+        ("node_stride", C.c_int32),
+        ("edge_stride", C.c_int32),
+        ("job_stride", C.c_int32),
+        ("pad", C.c_int32),
     ]
 
 
@@ -89,7 +108,7 @@ EXPORTS = [
     "ssb_abi_version", "ssb_last_cuda_error", "ssb_workspace_bytes", "ssb_create", "ssb_destroy",
     "ssb_load_trace", "ssb_clear_trace", "ssb_reset", "ssb_step", "ssb_reset_host", "ssb_step_host",
     "ssb_rollout_fair", "ssb_fair_actions", "ssb_get_views", "ssb_get_stats", "ssb_reset_stats",
-    "ssb_get_jobs", "ssb_get_log",
+    "ssb_get_jobs", "ssb_get_log", "ssb_decima_obs", "ssb_get_decima_views",
 ]
 
 _lib = None
@@ -125,6 +144,8 @@ def lib():
     L.ssb_rollout_fair.argtypes = [vp, i32, i32, i32, u64, vp]
     L.ssb_fair_actions.argtypes = [vp, i32, vp, vp, vp]
     L.ssb_get_views.argtypes = [vp, C.POINTER(SsbViews)]
+    L.ssb_decima_obs.argtypes = [vp, vp]
+    L.ssb_get_decima_views.argtypes = [vp, C.POINTER(SsbDecimaViews)]
     L.ssb_get_stats.argtypes = [vp, C.POINTER(vp)]
     L.ssb_reset_stats.argtypes = [vp, vp]
     L.ssb_get_jobs.argtypes = [vp, i32, C.POINTER(i32), vp, vp, vp, vp, i32]

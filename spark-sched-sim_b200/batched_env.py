@@ -41,7 +41,7 @@ ERROR_MESSAGES = {
 class BatchedSparkSchedSimEnv:
     def __init__(self, env_cfg: dict, num_envs: int, bank: TemplateBank | None = None,
                  device: str | torch.device = "cuda:0", max_jobs: int | None = None,
-                 tape_capacity: int = 0, log_capacity: int = 0):
+                 tape_capacity: int = 0, log_capacity: int = 0, decima_obs: bool = False):
         self.L = nat.lib()
         if not torch.cuda.is_available():
             raise RuntimeError("BatchedSparkSchedSimEnv needs a CUDA device (no CPU fallback)")
@@ -60,7 +60,7 @@ class BatchedSparkSchedSimEnv:
             self.num_envs, self.num_executors, self.job_arrival_cap, self.max_jobs,
             int(tape_capacity), int(log_capacity), float(env_cfg["moving_delay"]),
             float(env_cfg.get("warmup_delay", 0.0)), float(env_cfg["job_arrival_rate"]),
-            float(env_cfg.get("beta", 0.0)))
+            float(env_cfg.get("beta", 0.0)), nat.FLAG_DECIMA_OBS if decima_obs else 0, 0)
         self._bank_struct, self._bank_keep = nat.make_bank_struct(self.bank)
         nbytes = C.c_size_t()
         nat.check(self.L.ssb_workspace_bytes(C.byref(self.cfg), C.byref(self._bank_struct),
@@ -85,6 +85,15 @@ class BatchedSparkSchedSimEnv:
         nat.check(self.L.ssb_get_stats(self._h, C.byref(sp)), "ssb_get_stats")
         self.stats_bytes = self._view(sp.value, B * nat.STATS_DTYPE.itemsize, torch.uint8).view(B, -1)
         self._hdr_host = np.zeros(B, nat.OBS_HDR_DTYPE)
+        self.has_decima_obs = bool(decima_obs)
+        if decima_obs:
+            dv = nat.SsbDecimaViews()
+            nat.check(self.L.ssb_get_decima_views(self._h, C.byref(dv)), "ssb_get_decima_views")
+            self.dec_features = self._view(dv.features, B * S * 5 * 4, torch.float32).view(B, S, 5)
+            self.dec_stage_mask = self._view(dv.stage_mask, B * S, torch.uint8).view(B, S)
+            self.dec_commit_caps = self._view(dv.commit_caps, B * J * 4, torch.int32).view(B, J)
+            self.dec_edge_bits = self._view(dv.edge_bits, B * M * 8, torch.int64).view(B, M)
+            self.dec_depth = self._view(dv.depth, B * 4, torch.int32)
 
     # ---------------------------------------------------------------- plumbing
     def _view(self, ptr, nbytes, dtype):
@@ -195,6 +204,30 @@ class BatchedSparkSchedSimEnv:
             "exec_supplies": self.exec_supplies[b, :Ja].cpu().numpy(),
             "num_committable_execs": int(h["num_committable_execs"]),
             "source_job_idx": int(h["source_job_idx"]),
+        }
+
+    def decima_obs(self):
+        """Launches the Decima observation adapter (env_wrapper.py:69-143, utils.py:238-267) for all
+        envs; results land in dec_features / dec_stage_mask / dec_commit_caps / dec_edge_bits /
+        dec_depth (device tensors, same node/edge/job order as the base observation)."""
+        nat.check(self.L.ssb_decima_obs(self._h, self._stream()), "ssb_decima_obs")
+
+    def decima_obs_host(self, b: int = 0, hdr: np.ndarray | None = None) -> dict:
+        """Decima observation of env b as host arrays, in the reference's shapes."""
+        h = (self.hdr() if hdr is None else hdr)[b]
+        N, M, Ja = int(h["num_nodes"]), int(h["num_edges"]), int(h["num_active_jobs"])
+        depth = int(self.dec_depth[b].item())
+        bits = self.dec_edge_bits[b, :M].cpu().numpy().view(np.uint64)
+        caps = self.dec_commit_caps[b, :Ja].cpu().numpy()
+        k = np.arange(depth, dtype=np.uint64)[:, None]
+        return {
+            "features": self.dec_features[b, :N].cpu().numpy(),
+            "stage_mask": self.dec_stage_mask[b, :N].cpu().numpy().astype(bool),
+            "commit_caps": caps,
+            "exec_mask": np.arange(self.num_executors)[None, :] < caps[:, None],
+            "edge_bits": bits,
+            "depth": depth,
+            "edge_masks": ((bits[None, :] >> k) & np.uint64(1)).astype(bool),
         }
 
     def load_trace(self, b, t_arrival, template, tape=None):

@@ -93,6 +93,15 @@ k_rollout_fair(Params p, int num_decisions, int dynamic_partition, int auto_rese
     }
 }
 
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_decima_obs(Params p)
+{
+    __shared__ uint64_t Sk[WARPS_PER_CTA][64];
+    const int b = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= p.B) return;
+    Sim sim(p, b, lane);
+    sim.decima_obs_w(Sk[threadIdx.x >> 5]);
+}
+
 __global__ void k_zero_stats(ssb_stats *s, int n)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -193,6 +202,13 @@ void carve(Carver &cv, const ssb_config &c, const ssb_bank &bk, const Dims &d, P
     p.obs_edges = cv.take<int32_t>(B * d.Mc * 2);
     p.obs_dag_ptr = cv.take<int32_t>(B * (c.max_jobs + 1));
     p.obs_supplies = cv.take<int32_t>(B * c.max_jobs);
+    if (c.flags & SSB_FLAG_DECIMA_OBS) {
+        p.dec_feat = cv.take<float>(B * d.Sc * 5);
+        p.dec_stage_mask = cv.take<uint8_t>(B * d.Sc);
+        p.dec_caps = cv.take<int32_t>(B * c.max_jobs);
+        p.dec_edge_bits = cv.take<uint64_t>(B * d.Mc);
+        p.dec_depth = cv.take<int32_t>(B);
+    }
     *st_a = cv.take<int32_t>(B);
     *st_n = cv.take<int32_t>(B);
     *st_seed = cv.take<uint64_t>(B);
@@ -448,6 +464,29 @@ int ssb_get_views(ssb_env *env, ssb_views *out)
     out->edge_links = env->p.obs_edges;
     out->dag_ptr = env->p.obs_dag_ptr;
     out->exec_supplies = env->p.obs_supplies;
+    out->node_stride = env->p.Sc;
+    out->edge_stride = env->p.Mc;
+    out->job_stride = env->p.Jc;
+    out->pad = 0;
+    return SSB_OK;
+}
+
+int ssb_decima_obs(ssb_env *env, void *stream)
+{
+    if (!env || !env->p.dec_feat) return SSB_E_INVALID;  // needs SSB_FLAG_DECIMA_OBS
+    k_decima_obs<<<env->grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(env->p);
+    CUDA_TRY(cudaGetLastError());
+    return SSB_OK;
+}
+
+int ssb_get_decima_views(ssb_env *env, ssb_decima_views *out)
+{
+    if (!env || !out || !env->p.dec_feat) return SSB_E_INVALID;
+    out->features = env->p.dec_feat;
+    out->stage_mask = env->p.dec_stage_mask;
+    out->commit_caps = env->p.dec_caps;
+    out->edge_bits = env->p.dec_edge_bits;
+    out->depth = env->p.dec_depth;
     out->node_stride = env->p.Sc;
     out->edge_stride = env->p.Mc;
     out->job_stride = env->p.Jc;

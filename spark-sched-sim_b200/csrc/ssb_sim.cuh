@@ -1395,6 +1395,89 @@ struct Sim {
         observe_w(0.0, false);
     }
 
+    // ------------------------------------------------------------ Decima observation adapter
+    // DecimaObsWrapper.observation (schedulers/decima/env_wrapper.py:69-143): commit caps, the five
+    // node features, stage mask; make_dag_layer_edge_masks (schedulers/decima/utils.py:238-267):
+    // topological generations of the active graph, mask k = edges with both ends in L_k U succ(L_k),
+    // emitted per edge as a bit set over k.  Jobs are disjoint DAGs, so generations are found per
+    // job on u64 masks: L_k = active unassigned stages without an active unassigned parent.
+    // Sk: per-warp shared scratch (>= 64 entries).
+    __device__ SSB_COLD void decima_obs_w(uint64_t *Sk)
+    {
+        const int n_active = h->n_active, ncommit = num_committable(), src_job = source_job_id();
+        float *feat = p.dec_feat + (size_t)b * p.Sc * 5;
+        uint8_t *smask = p.dec_stage_mask + (size_t)b * p.Sc;
+        int32_t *caps = p.dec_caps + (size_t)b * p.Jc;
+        uint64_t *ebits = p.dec_edge_bits + (size_t)b * p.Mc;
+        const double Ed = (double)p.E;
+        int N = 0, M = 0, D = 0;
+        for (int i = 0; i < n_active; i++) {
+            const int j = act[i];
+            const JobRec &J = jb[j];
+            const uint64_t active = J.active, sched = J.sched;
+            const int supply = J.supply, ns = J.n_stages;
+            int cap = min(max(p.E - supply, 0), ncommit);  // :74-77
+            if (j == src_job) cap = ncommit;               // :81-82
+            if (lane == 0) caps[i] = cap;
+            const float f0 = (float)((double)cap / Ed), f1 = (j == src_job) ? 1.0f : -1.0f,
+                        f2 = (float)((double)supply / Ed);
+            for (int s = lane; s < ns; s += 32) {
+                if (!((active >> s) & 1)) continue;
+                const StageRec r = st[J.node_base + s];
+                const int rank = N + popc64(active & (bit64(s) - 1));
+                const float rem = (float)r.remaining;
+                float *f = feat + (size_t)rank * 5;
+                f[0] = f0; f[1] = f1; f[2] = f2;
+                f[3] = __fdiv_rn(rem, 200.0f);                          // float32 / num_tasks_scale (:137)
+                f[4] = __fdiv_rn(__fmul_rn(rem, r.mrd), 100000.0f);     // float32 * float32 / work_scale (:141)
+                smask[rank] = (uint8_t)((sched >> s) & 1);
+            }
+            const uint64_t *pm = p.b_parent + J.ts_base, *cm = p.b_child + J.ts_base;
+            uint64_t assigned = 0;
+            int dj = 0;
+            while (assigned != active && dj < 64) {
+                const uint64_t open = active & ~assigned;
+                const int s0 = lane, s1 = lane + 32;
+                const bool r0 = s0 < ns && ((open >> s0) & 1) && (pm[s0] & open) == 0;
+                const bool r1 = s1 < ns && ((open >> s1) & 1) && (pm[s1] & open) == 0;
+                const uint64_t Lk = (uint64_t)__ballot_sync(FULL, r0) | ((uint64_t)__ballot_sync(FULL, r1) << 32);
+                const uint64_t mine = ((r0 ? cm[s0] : 0ull) | (r1 ? cm[s1] : 0ull)) & active;
+                const uint64_t succ = (uint64_t)__reduce_or_sync(FULL, (uint32_t)mine) |
+                                      ((uint64_t)__reduce_or_sync(FULL, (uint32_t)(mine >> 32)) << 32);
+                if (lane == 0) Sk[dj] = Lk | succ;
+                assigned |= Lk;
+                dj++;
+                if (Lk == 0) break;  // cannot happen in a DAG
+            }
+            __syncwarp();
+            D = max(D, dj);
+            const int eb = p.b_edge_base[J.tmpl], ne = p.b_edge_base[J.tmpl + 1] - eb;
+            for (int k0 = 0; k0 < ne; k0 += 32) {
+                const int k = k0 + lane;
+                int u = 0, v = 0;
+                bool keep = false;
+                if (k < ne) {
+                    u = p.b_edges[2 * (eb + k)];
+                    v = p.b_edges[2 * (eb + k) + 1];
+                    keep = ((active >> u) & 1) && ((active >> v) & 1);
+                }
+                const unsigned m = __ballot_sync(FULL, keep);
+                if (keep) {
+                    uint64_t bits = 0;
+                    for (int q = 0; q < dj; q++) {
+                        const uint64_t S = Sk[q];
+                        if (((S >> u) & 1) && ((S >> v) & 1)) bits |= bit64(q);
+                    }
+                    ebits[M + __popc(m & ((1u << lane) - 1))] = bits;
+                }
+                M += __popc(m);
+            }
+            __syncwarp();
+            N += popc64(active);
+        }
+        if (lane == 0) p.dec_depth[b] = D > 1 ? D - 1 : 0;
+    }
+
     // ------------------------------------------------------------ fair / FIFO policy
     // RoundRobinScheduler.schedule (schedulers/heuristics/round_robin.py:14-49) with
     // preprocess_obs/find_stage (heuristics/utils.py:5-37).  "Frontier" there means "no incoming

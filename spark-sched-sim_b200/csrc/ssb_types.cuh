@@ -136,6 +136,12 @@ struct Params {
     ssb_obs_hdr *obs_hdr;
     float *obs_nodes;
     int32_t *obs_edges, *obs_dag_ptr, *obs_supplies;
+    // Decima observation adapter outputs (nullptr unless SSB_FLAG_DECIMA_OBS)
+    float *dec_feat;          // [B][Sc][5]
+    uint8_t *dec_stage_mask;  // [B][Sc]
+    int32_t *dec_caps;        // [B][Jc]
+    uint64_t *dec_edge_bits;  // [B][Mc]
+    int32_t *dec_depth;       // [B]
 };
 
 }  // namespace ssb

@@ -29,7 +29,7 @@ class SparkSchedSimEnv(Env):
     metadata = {"render_modes": [], "render_fps": 30}
 
     def __init__(self, env_cfg: dict[str, Any], bank=None, device="cuda:0", max_jobs: int | None = None,
-                 tape_capacity: int = 0, log_capacity: int = 0):
+                 tape_capacity: int = 0, log_capacity: int = 0, decima_obs: bool = False):
         self.num_executors: int = env_cfg["num_executors"]
         self.moving_delay = env_cfg["moving_delay"]
         self.beta: float = env_cfg.get("beta", 0)
@@ -42,7 +42,7 @@ class SparkSchedSimEnv(Env):
             raise ValueError(f"'{sampler}' is not a valid data sampler.")
         self._batched = BatchedSparkSchedSimEnv(env_cfg, num_envs=1, bank=bank, device=device,
                                                 max_jobs=max_jobs, tape_capacity=tape_capacity,
-                                                log_capacity=log_capacity)
+                                                log_capacity=log_capacity, decima_obs=decima_obs)
         self.wall_time: float = 0
         self.jobs: dict[int, SimpleNamespace] = {}
         self.active_job_ids: list[int] = []

@@ -27,8 +27,9 @@ def test_struct_sizes_match_header():
 
     assert _native.OBS_HDR_DTYPE.itemsize == 48
     assert _native.STATS_DTYPE.itemsize == 64
-    assert ctypes.sizeof(_native.SsbConfig) == 56
+    assert ctypes.sizeof(_native.SsbConfig) == 64
     assert ctypes.sizeof(_native.SsbViews) == 56
+    assert ctypes.sizeof(_native.SsbDecimaViews) == 56
 
 
 def test_workspace_bytes_no_gpu(bank):
@@ -40,5 +41,9 @@ def test_workspace_bytes_no_gpu(bank):
     n = ctypes.c_size_t()
     assert nat.lib().ssb_workspace_bytes(ctypes.byref(cfg), ctypes.byref(bs), ctypes.byref(n)) == 0
     assert 100e6 < n.value < 2e9
+    dec = nat.SsbConfig(4096, 10, 50, 50, 0, 0, 2000.0, 1000.0, 4e-5, 0.0, nat.FLAG_DECIMA_OBS, 0)
+    n2 = ctypes.c_size_t()
+    assert nat.lib().ssb_workspace_bytes(ctypes.byref(dec), ctypes.byref(bs), ctypes.byref(n2)) == 0
+    assert n2.value > n.value  # the Decima observation buffers are only allocated on request
     bad = nat.SsbConfig(4096, 500, 50, 50, 0, 0, 2000.0, 1000.0, 4e-5, 0.0)
     assert nat.lib().ssb_workspace_bytes(ctypes.byref(bad), ctypes.byref(bs), ctypes.byref(n)) == -1

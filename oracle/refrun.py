@@ -100,6 +100,24 @@ def make_policy(name: str, num_executors: int, seed: int = 42):
         return rr.RoundRobinScheduler(num_executors, dynamic_partition=False)
     if name == "random":
         return rnd.RandomScheduler(seed=seed)
+    if name == "decima":
+        # the reference's DecimaScheduler with the shipped weights and the agent section of
+        # config/decima_tpch.yaml:66-77 (examples.py:64-72); PyG comes from oracle/refshim
+        import random
+
+        import torch
+
+        random.seed(seed)  # utils.sample draws with python's `random` (decima/utils.py:19-23)
+        torch.manual_seed(seed)
+        dec = importlib.import_module("schedulers.decima.scheduler")
+        sched = dec.DecimaScheduler(
+            num_executors=num_executors, embed_dim=16,
+            gnn_mlp_kwargs={"hid_dims": [32, 16], "act_cls": "LeakyReLU",
+                            "act_kwargs": {"inplace": True, "negative_slope": 0.2}},
+            policy_mlp_kwargs={"hid_dims": [64, 64], "act_cls": "Tanh"},
+            state_dict_path=osp.join(REFERENCE, "models", "decima", "model.pt"))
+        sched.eval()
+        return sched
     raise ValueError(name)
 
 
@@ -180,8 +198,32 @@ def run_episode(
 
     env._handle_event = handle_event
 
+    # A policy with an env wrapper (Decima) steps the reference's own wrapper stack; the base
+    # observation underneath is captured at `_observe` so every trace has the same layout.
+    last_base = {}
+    orig_observe = env._observe
+
+    def observe():
+        o = orig_observe()
+        last_base["obs"] = o
+        return o
+
+    env._observe = observe
+    wenv = sched.env_wrapper_cls(env) if getattr(sched, "env_wrapper_cls", None) else env
+    pol_rec = {"stage_logits": [], "exec_logits": [], "dec_actions": [], "lgprob": []}
+    if policy == "decima":
+        dutils = importlib.import_module("schedulers.decima.utils")
+        orig_sample = dutils.sample
+        calls = []
+
+        def sample(logits):  # records the scores the policy networks produced for this decision
+            calls.append(np.asarray(logits.detach().cpu().numpy(), np.float32).copy())
+            return orig_sample(logits)
+
+        dutils.sample = sample
+
     options = {"time_limit": time_limit} if time_limit is not None else None
-    obs, info = env.reset(seed=seed, options=options)
+    obs, info = wenv.reset(seed=seed, options=options)
 
     jobs = list(env.jobs.values())
     sizes = ["2g", "5g", "10g", "20g", "50g", "80g", "100g"]
@@ -194,7 +236,7 @@ def run_episode(
         "nodes", "edges", "dag_ptr", "supplies", "obs_digest",
         "dec_feat", "dec_caps", "dec_depth", "dec_edge_bits", "dec_stage_mask")}
 
-    def record_obs(o):
+    def record_base(o):
         g = o["dag_batch"]
         nodes = np.asarray(g.nodes, np.float32).reshape(-1, 3)
         el = np.asarray(g.edge_links, np.int64).reshape(-1, 2)
@@ -224,33 +266,44 @@ def run_episode(
         rec["dec_edge_bits"].append(bits)
         rec["dec_stage_mask"].append(np.asarray(d["stage_mask"], np.uint8))
 
-    _record_base = record_obs
-
-    def record_obs(o):  # noqa: F811
-        _record_base(o)
+    def record_obs():
+        o = last_base["obs"]
+        record_base(o)
         if dec_wrapper is not None:
             record_decima(o)
 
-    record_obs(obs)  # observation 0 = reset
+    record_obs()  # observation 0 = reset
     rec["ev_count"].append(len(events))
     terminated = truncated = False
     steps = 0
     while not (terminated or truncated):
-        action, _ = sched.schedule(obs)
-        a = (int(action["stage_idx"]), int(action["num_exec"]))
-        obs, reward, terminated, truncated, info = env.step(
-            {"stage_idx": a[0], "num_exec": a[1]})
+        action, pinfo = sched.schedule(obs)
+        if policy == "decima":
+            # env action as DecimaActWrapper forms it (env_wrapper.py:33-34)
+            a = (int(action["stage_idx"]), 1 + int(action["num_exec"]))
+            pol_rec["stage_logits"].append(calls[-2])
+            pol_rec["exec_logits"].append(calls[-1])
+            pol_rec["dec_actions"].append((int(action["stage_idx"]), int(action["job_idx"]),
+                                           int(action["num_exec"])))
+            pol_rec["lgprob"].append(float(pinfo["lgprob"]))
+            obs, reward, terminated, truncated, info = wenv.step(action)
+        else:
+            a = (int(action["stage_idx"]), int(action["num_exec"]))
+            obs, reward, terminated, truncated, info = wenv.step(
+                {"stage_idx": a[0], "num_exec": a[1]})
         rec["actions"].append(a)
         rec["reward"].append(float(reward))
         rec["wall"].append(float(info["wall_time"]))
         rec["term"].append(bool(terminated))
-        record_obs(obs)
+        record_obs()
         rec["ev_count"].append(len(events))
         steps += 1
         if time_limit is not None and info["wall_time"] >= time_limit:
             truncated = True  # what StochasticTimeLimit.step does (stochastic_time_limit.py:29-30)
         if max_steps is not None and steps >= max_steps:
             break
+    if policy == "decima":
+        dutils.sample = orig_sample
 
     evarr = np.array(events, dtype=np.float64).reshape(-1, 7)
     trace = {
@@ -292,6 +345,14 @@ def run_episode(
         "dec_depth": np.array(rec["dec_depth"], np.int32),
         "dec_edge_bits": np.concatenate(rec["dec_edge_bits"]) if rec["dec_edge_bits"] else np.zeros(0, np.uint64),
         "dec_stage_mask": np.concatenate(rec["dec_stage_mask"]) if rec["dec_stage_mask"] else np.zeros(0, np.uint8),
+        "pol_stage_logits": (np.concatenate(pol_rec["stage_logits"]) if pol_rec["stage_logits"]
+                             else np.zeros(0, np.float32)),
+        "pol_stage_count": np.array([len(x) for x in pol_rec["stage_logits"]], np.int32),
+        "pol_exec_logits": (np.concatenate(pol_rec["exec_logits"]) if pol_rec["exec_logits"]
+                            else np.zeros(0, np.float32)),
+        "pol_exec_count": np.array([len(x) for x in pol_rec["exec_logits"]], np.int32),
+        "pol_actions": np.array(pol_rec["dec_actions"], np.int32).reshape(-1, 3),
+        "pol_lgprob": np.array(pol_rec["lgprob"], np.float64),
         "ev_t": evarr[:, 0].copy(),
         "ev_type": evarr[:, 1].astype(np.uint8),
         "ev_job": evarr[:, 2].astype(np.int16),

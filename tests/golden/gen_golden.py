@@ -49,7 +49,19 @@ CASES = {
     "e10_tl_random_s11_philox": (cfg(10, None), "random", 11, "philox", 5.0e5, False),
     "e3_j5_random_s12_philox": (cfg(3, 5), "random", 12, "philox", None, False),
     "e1_j3_fair_s13_philox": (cfg(1, 3), "fair", 13, "philox", None, False),
+    # driven by the reference's DecimaScheduler with the shipped models/decima/model.pt; these also
+    # hold the policy's stage / executor-count scores for every decision (`pol_*`)
+    "decima_e10_j8_s5_philox": (cfg(10, 8), "decima", 5, "philox", None, False),
+    "decima_e50_j6_s3_philox": (cfg(50, 6), "decima", 3, "philox", None, False),
 }
+
+
+def export_decima_weights():
+    """models/decima/model.pt (42 tensors, 20 802 fp32 parameters) -> decima_model.npz fixture."""
+    import torch
+
+    sd = torch.load(osp.join("/root/reference", "models", "decima", "model.pt"), map_location="cpu")
+    np.savez_compressed(osp.join(HERE, "decima_model.npz"), **{k: v.numpy() for k, v in sd.items()})
 
 
 def main(argv):
@@ -58,6 +70,8 @@ def main(argv):
 
     names = argv or list(CASES)
     checksum = bankmod.synthetic_bank(0).checksum()
+    if any(n.startswith("decima_") for n in names):
+        export_decima_weights()
     for name in names:
         env_cfg, policy, seed, rng, tl, slim = CASES[name]
         # small cases also record what the reference's DecimaObsWrapper makes of every observation

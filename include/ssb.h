@@ -69,7 +69,8 @@ typedef struct {
     int32_t pad;
 } ssb_config;
 
-#define SSB_FLAG_DECIMA_OBS 1 /* allocate the Decima observation buffers (ssb_decima_obs) */
+#define SSB_FLAG_DECIMA_OBS 1    /* allocate the Decima observation buffers (ssb_decima_obs) */
+#define SSB_FLAG_DECIMA_POLICY 2 /* + weights, scratch and outputs of the Decima policy (implies OBS) */
 
 /* Flattened template bank (host pointers; copied to the device by ssb_create).  Layout: see
  * spark-sched-sim_b200/bank.py, which restates tpch.py:118-206. */
@@ -195,6 +196,27 @@ typedef struct {
 } ssb_decima_views;
 int ssb_decima_obs(ssb_env *env, void *stream);
 int ssb_get_decima_views(ssb_env *env, ssb_decima_views *out);
+
+/* Decima policy on the device (DecimaScheduler.schedule, schedulers/decima/scheduler.py:71-99):
+ * observation adapter -> DAG-GNN encoder -> stage scores -> sample -> executor-count scores ->
+ * sample, one decision for every env; needs SSB_FLAG_DECIMA_POLICY and weights.
+ *   weights: HOST, 20 802 floats, the tensors of models/decima/model.pt concatenated in
+ *            state_dict order (each row-major).
+ *   forced_stage / forced_num_exec: DEVICE i32[B] or NULL; an entry >= 0 replaces the sampled index
+ *            (replaying recorded actions); sampling uses the Philox policy stream of the env's seed.
+ *   stage_idx_out / num_exec_out: DEVICE i32[B] or NULL, in the ENV's action format
+ *            (DecimaActWrapper, env_wrapper.py:33-34: num_exec + 1), ready for ssb_step. */
+typedef struct {
+    float *stage_logits; /* [B][node_stride]: scores of the schedulable stages, action[3] of them */
+    float *exec_logits;  /* [B][exec_stride]: scores of num_exec = 0 .. cap-1 for the chosen job */
+    int32_t *action;     /* [B][4]: stage_idx, job_idx, num_exec (Decima format), #stage candidates */
+    float *lgprob;       /* [B]: log pi(stage) + log pi(num_exec) */
+    int32_t node_stride, exec_stride;
+} ssb_policy_views;
+int ssb_set_decima_weights(ssb_env *env, const float *weights, int32_t n_floats);
+int ssb_decima_policy(ssb_env *env, const int32_t *forced_stage, const int32_t *forced_num_exec,
+                      int32_t *stage_idx_out, int32_t *num_exec_out, void *stream);
+int ssb_get_policy_views(ssb_env *env, ssb_policy_views *out);
 /* device pointer to ssb_stats[B] */
 int ssb_get_stats(ssb_env *env, ssb_stats **out);
 int ssb_reset_stats(ssb_env *env, void *stream);

@@ -30,6 +30,19 @@ class SsbConfig(C.Structure):
 
 
 FLAG_DECIMA_OBS = 1
+FLAG_DECIMA_POLICY = 2
+DECIMA_NUM_PARAMS = 20802
+
+
+class SsbPolicyViews(C.Structure):
+    _fields_ = [
+        ("stage_logits", C.c_void_p),
+        ("exec_logits", C.c_void_p),
+        ("action", C.c_void_p),
+        ("lgprob", C.c_void_p),
+        ("node_stride", C.c_int32),
+        ("exec_stride", C.c_int32),
+    ]
 
 
 class SsbDecimaViews(C.Structure):
@@ -109,6 +122,7 @@ EXPORTS = [
     "ssb_load_trace", "ssb_clear_trace", "ssb_reset", "ssb_step", "ssb_reset_host", "ssb_step_host",
     "ssb_rollout_fair", "ssb_fair_actions", "ssb_get_views", "ssb_get_stats", "ssb_reset_stats",
     "ssb_get_jobs", "ssb_get_log", "ssb_decima_obs", "ssb_get_decima_views",
+    "ssb_set_decima_weights", "ssb_decima_policy", "ssb_get_policy_views",
 ]
 
 _lib = None
@@ -146,6 +160,9 @@ def lib():
     L.ssb_get_views.argtypes = [vp, C.POINTER(SsbViews)]
     L.ssb_decima_obs.argtypes = [vp, vp]
     L.ssb_get_decima_views.argtypes = [vp, C.POINTER(SsbDecimaViews)]
+    L.ssb_set_decima_weights.argtypes = [vp, vp, i32]
+    L.ssb_decima_policy.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.ssb_get_policy_views.argtypes = [vp, C.POINTER(SsbPolicyViews)]
     L.ssb_get_stats.argtypes = [vp, C.POINTER(vp)]
     L.ssb_reset_stats.argtypes = [vp, vp]
     L.ssb_get_jobs.argtypes = [vp, i32, C.POINTER(i32), vp, vp, vp, vp, i32]

@@ -41,7 +41,8 @@ ERROR_MESSAGES = {
 class BatchedSparkSchedSimEnv:
     def __init__(self, env_cfg: dict, num_envs: int, bank: TemplateBank | None = None,
                  device: str | torch.device = "cuda:0", max_jobs: int | None = None,
-                 tape_capacity: int = 0, log_capacity: int = 0, decima_obs: bool = False):
+                 tape_capacity: int = 0, log_capacity: int = 0, decima_obs: bool = False,
+                 decima_policy: bool = False):
         self.L = nat.lib()
         if not torch.cuda.is_available():
             raise RuntimeError("BatchedSparkSchedSimEnv needs a CUDA device (no CPU fallback)")
@@ -60,7 +61,10 @@ class BatchedSparkSchedSimEnv:
             self.num_envs, self.num_executors, self.job_arrival_cap, self.max_jobs,
             int(tape_capacity), int(log_capacity), float(env_cfg["moving_delay"]),
             float(env_cfg.get("warmup_delay", 0.0)), float(env_cfg["job_arrival_rate"]),
-            float(env_cfg.get("beta", 0.0)), nat.FLAG_DECIMA_OBS if decima_obs else 0, 0)
+            float(env_cfg.get("beta", 0.0)),
+            (nat.FLAG_DECIMA_OBS if (decima_obs or decima_policy) else 0)
+            | (nat.FLAG_DECIMA_POLICY if decima_policy else 0), 0)
+        decima_obs = decima_obs or decima_policy
         self._bank_struct, self._bank_keep = nat.make_bank_struct(self.bank)
         nbytes = C.c_size_t()
         nat.check(self.L.ssb_workspace_bytes(C.byref(self.cfg), C.byref(self._bank_struct),
@@ -94,6 +98,15 @@ class BatchedSparkSchedSimEnv:
             self.dec_commit_caps = self._view(dv.commit_caps, B * J * 4, torch.int32).view(B, J)
             self.dec_edge_bits = self._view(dv.edge_bits, B * M * 8, torch.int64).view(B, M)
             self.dec_depth = self._view(dv.depth, B * 4, torch.int32)
+        self.has_decima_policy = bool(decima_policy)
+        if decima_policy:
+            pv = nat.SsbPolicyViews()
+            nat.check(self.L.ssb_get_policy_views(self._h, C.byref(pv)), "ssb_get_policy_views")
+            Ep = pv.exec_stride
+            self.pol_stage_logits = self._view(pv.stage_logits, B * S * 4, torch.float32).view(B, S)
+            self.pol_exec_logits = self._view(pv.exec_logits, B * Ep * 4, torch.float32).view(B, Ep)
+            self.pol_action = self._view(pv.action, B * 4 * 4, torch.int32).view(B, 4)
+            self.pol_lgprob = self._view(pv.lgprob, B * 4, torch.float32)
 
     # ---------------------------------------------------------------- plumbing
     def _view(self, ptr, nbytes, dtype):
@@ -229,6 +242,41 @@ class BatchedSparkSchedSimEnv:
             "depth": depth,
             "edge_masks": ((bits[None, :] >> k) & np.uint64(1)).astype(bool),
         }
+
+    # ---------------------------------------------------------------- Decima policy
+    DECIMA_PARAM_ORDER = tuple(
+        f"{net}.{layer}.{kind}"
+        for net in ("encoder.node_encoder.mlp_prep", "encoder.node_encoder.mlp_msg",
+                    "encoder.node_encoder.mlp_update", "encoder.dag_encoder.mlp",
+                    "encoder.global_encoder.mlp", "stage_policy_network.mlp_score",
+                    "exec_policy_network.mlp_score")
+        for layer in (0, 2, 4) for kind in ("weight", "bias"))
+
+    def set_decima_weights(self, state_dict) -> None:
+        """Uploads a DecimaScheduler state dict (torch tensors or numpy arrays keyed as in
+        models/decima/model.pt): 42 tensors / 20 802 float32 parameters."""
+        flat = np.concatenate([np.asarray(state_dict[k].detach().cpu().numpy()
+                                          if hasattr(state_dict[k], "detach") else state_dict[k],
+                                          dtype=np.float32).reshape(-1)
+                               for k in self.DECIMA_PARAM_ORDER])
+        assert flat.size == nat.DECIMA_NUM_PARAMS, flat.size
+        flat = np.ascontiguousarray(flat)
+        nat.check(self.L.ssb_set_decima_weights(self._h, flat.ctypes.data, flat.size),
+                  "ssb_set_decima_weights")
+
+    def decima_policy(self, forced_stage=None, forced_num_exec=None):
+        """One Decima decision per env on the device (observation adapter + GNN + sampling).
+        Returns (stage_idx, num_exec) device tensors in the env's action format; the scores, the
+        Decima-format action and the log-probability are in pol_* tensors."""
+        fs = self._dev(forced_stage, torch.int32)
+        fn = self._dev(forced_num_exec, torch.int32)
+        a = torch.empty(self.num_envs, dtype=torch.int32, device=self.device)
+        n = torch.empty(self.num_envs, dtype=torch.int32, device=self.device)
+        self._keep_pol = (fs, fn)
+        nat.check(self.L.ssb_decima_policy(self._h, fs.data_ptr() if fs is not None else None,
+                                           fn.data_ptr() if fn is not None else None,
+                                           a.data_ptr(), n.data_ptr(), self._stream()), "ssb_decima_policy")
+        return a, n
 
     def load_trace(self, b, t_arrival, template, tape=None):
         ta = np.ascontiguousarray(t_arrival, np.float64)

@@ -11,6 +11,7 @@
 #include <new>
 #include <vector>
 
+#include "ssb_decima.cuh"
 #include "ssb_sim.cuh"
 
 using namespace ssb;
@@ -100,6 +101,39 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_decima_obs(Params p)
     if (b >= p.B) return;
     Sim sim(p, b, lane);
     sim.decima_obs_w(Sk[threadIdx.x >> 5]);
+}
+
+// Decima: observation adapter + GNN forward + action sampling for every env (one decision each).
+// Outputs are in the env's action format (DecimaActWrapper: num_exec + 1), ready for ssb_step.
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+k_decima_policy(Params p, const int32_t *forced_stage, const int32_t *forced_num_exec, int32_t *stage_idx_out,
+                int32_t *num_exec_out)
+{
+    __shared__ uint64_t Sk[WARPS_PER_CTA][64];
+    const int b = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= p.B) return;
+    Sim sim(p, b, lane);
+    sim.decima_obs_w(Sk[threadIdx.x >> 5]);
+    __syncwarp();
+    PolicyBufs pb;
+    pb.h_init = p.pol_h_init + (size_t)b * p.Sc * 16;
+    pb.h = p.pol_h + (size_t)b * p.Sc * 16;
+    pb.msg = p.pol_msg + (size_t)b * p.Sc * 16;
+    pb.h_dag = p.pol_h_dag + (size_t)b * p.Jc * 16;
+    pb.g = p.pol_g + (size_t)b * p.Jc * 16;
+    pb.h_glob = p.pol_h_glob + (size_t)b * 16;
+    pb.row_start = p.pol_row_start + (size_t)b * p.Sc;
+    pb.flag = p.pol_flag + (size_t)b * 3 * p.Sc;
+    pb.stage_logits = p.pol_stage_logits + (size_t)b * p.Sc;
+    pb.exec_logits = p.pol_exec_logits + (size_t)b * p.Epad;
+    pb.action = p.pol_action + (size_t)b * 4;
+    pb.lgprob = p.pol_lgprob + b;
+    decima_policy_w(sim, p.pol_w, pb, forced_stage ? forced_stage[b] : -1,
+                    forced_num_exec ? forced_num_exec[b] : -1);
+    if (lane == 0) {
+        if (stage_idx_out) stage_idx_out[b] = pb.action[0];
+        if (num_exec_out) num_exec_out[b] = 1 + pb.action[2];
+    }
 }
 
 __global__ void k_zero_stats(ssb_stats *s, int n)
@@ -202,12 +236,28 @@ void carve(Carver &cv, const ssb_config &c, const ssb_bank &bk, const Dims &d, P
     p.obs_edges = cv.take<int32_t>(B * d.Mc * 2);
     p.obs_dag_ptr = cv.take<int32_t>(B * (c.max_jobs + 1));
     p.obs_supplies = cv.take<int32_t>(B * c.max_jobs);
-    if (c.flags & SSB_FLAG_DECIMA_OBS) {
+    if (c.flags & (SSB_FLAG_DECIMA_OBS | SSB_FLAG_DECIMA_POLICY)) {
         p.dec_feat = cv.take<float>(B * d.Sc * 5);
         p.dec_stage_mask = cv.take<uint8_t>(B * d.Sc);
         p.dec_caps = cv.take<int32_t>(B * c.max_jobs);
         p.dec_edge_bits = cv.take<uint64_t>(B * d.Mc);
         p.dec_depth = cv.take<int32_t>(B);
+    }
+    if (c.flags & SSB_FLAG_DECIMA_POLICY) {
+        p.Epad = (c.num_executors + 3) & ~3;
+        p.pol_w = cv.take<float>(dw::TOTAL);
+        p.pol_h_init = cv.take<float>(B * d.Sc * 16);
+        p.pol_h = cv.take<float>(B * d.Sc * 16);
+        p.pol_msg = cv.take<float>(B * d.Sc * 16);
+        p.pol_h_dag = cv.take<float>(B * c.max_jobs * 16);
+        p.pol_g = cv.take<float>(B * c.max_jobs * 16);
+        p.pol_h_glob = cv.take<float>(B * 16);
+        p.pol_row_start = cv.take<int32_t>(B * d.Sc);
+        p.pol_flag = cv.take<uint8_t>(B * 3 * d.Sc);
+        p.pol_stage_logits = cv.take<float>(B * d.Sc);
+        p.pol_exec_logits = cv.take<float>(B * p.Epad);
+        p.pol_action = cv.take<int32_t>(B * 4);
+        p.pol_lgprob = cv.take<float>(B);
     }
     *st_a = cv.take<int32_t>(B);
     *st_n = cv.take<int32_t>(B);
@@ -491,6 +541,36 @@ int ssb_get_decima_views(ssb_env *env, ssb_decima_views *out)
     out->edge_stride = env->p.Mc;
     out->job_stride = env->p.Jc;
     out->pad = 0;
+    return SSB_OK;
+}
+
+int ssb_set_decima_weights(ssb_env *env, const float *weights, int32_t n_floats)
+{
+    if (!env || !weights || !env->p.pol_w || n_floats != dw::TOTAL) return SSB_E_INVALID;
+    CUDA_TRY(cudaSetDevice(env->device));
+    CUDA_TRY(cudaMemcpy(env->p.pol_w, weights, sizeof(float) * dw::TOTAL, cudaMemcpyHostToDevice));
+    return SSB_OK;
+}
+
+int ssb_decima_policy(ssb_env *env, const int32_t *forced_stage, const int32_t *forced_num_exec,
+                      int32_t *stage_idx_out, int32_t *num_exec_out, void *stream)
+{
+    if (!env || !env->p.pol_w) return SSB_E_INVALID;  // needs SSB_FLAG_DECIMA_POLICY
+    k_decima_policy<<<env->grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(
+        env->p, forced_stage, forced_num_exec, stage_idx_out, num_exec_out);
+    CUDA_TRY(cudaGetLastError());
+    return SSB_OK;
+}
+
+int ssb_get_policy_views(ssb_env *env, ssb_policy_views *out)
+{
+    if (!env || !out || !env->p.pol_w) return SSB_E_INVALID;
+    out->stage_logits = env->p.pol_stage_logits;
+    out->exec_logits = env->p.pol_exec_logits;
+    out->action = env->p.pol_action;
+    out->lgprob = env->p.pol_lgprob;
+    out->node_stride = env->p.Sc;
+    out->exec_stride = env->p.Epad;
     return SSB_OK;
 }
 

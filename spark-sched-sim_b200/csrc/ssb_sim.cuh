@@ -1328,6 +1328,7 @@ struct Sim {
             H.error = err; H.done = 0; H.n_nodes_total = nb; H.n_edges_total = eb;
             H.use_tape = (trace && H.tape_len >= 0) ? 1 : 0;
             H.pending = 0;
+            H.policy_draws = 0;
         }
         __syncwarp();
         if (h->error) {

@@ -99,6 +99,8 @@ struct __align__(16) EnvHdr {
     int32_t commit_from_common, commit_to_common, total_none, error;
     int32_t done, trace_jobs, tape_len, n_nodes_total;
     int32_t n_edges_total, reset_count, use_tape, pending;
+    uint32_t policy_draws;  // Philox policy-stream counter (on-device action sampling)
+    int32_t pad2[3];
 };
 
 // Everything a kernel needs, passed by value.
@@ -142,6 +144,18 @@ struct Params {
     int32_t *dec_caps;        // [B][Jc]
     uint64_t *dec_edge_bits;  // [B][Mc]
     int32_t *dec_depth;       // [B]
+    // Decima policy (nullptr unless SSB_FLAG_DECIMA_POLICY): weights, scratch, outputs
+    float *pol_w;             // [20802] state_dict order
+    float *pol_h_init, *pol_h, *pol_msg;  // [B][Sc][16]
+    float *pol_h_dag, *pol_g;             // [B][Jc][16]
+    float *pol_h_glob;                    // [B][16]
+    int32_t *pol_row_start;               // [B][Sc]
+    uint8_t *pol_flag;                    // [B][3][Sc]
+    float *pol_stage_logits;              // [B][Sc]
+    float *pol_exec_logits;               // [B][Epad]
+    int32_t *pol_action;                  // [B][4]
+    float *pol_lgprob;                    // [B]
+    int Epad;
 };
 
 }  // namespace ssb

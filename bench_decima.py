@@ -1,0 +1,84 @@
+"""Secondary benchmark (not the driver's bench line): Decima rollouts on the device.
+
+BASELINE.json configs[2]: Decima GNN policy rollouts with on-device observation construction.
+Each decision = ssb_decima_policy (observation adapter + GNN + sampling) + ssb_step, both stream-
+ordered on device tensors (no host round trip).  Weights: the reference's shipped model (fixture
+tests/golden/decima_model.npz).  Prints one JSON line.
+
+    python bench_decima.py [--envs 4096] [--executors 10] [--jobs 50] [--decisions 200] [--budget 0]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os.path as osp
+import sys
+
+import numpy as np
+
+REPO = osp.dirname(osp.abspath(__file__))
+sys.path.insert(0, REPO)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--envs", type=int, default=4096)
+    ap.add_argument("--executors", type=int, default=10)
+    ap.add_argument("--jobs", type=int, default=50)
+    ap.add_argument("--decisions", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--budget", type=int, default=0, help="max events per env per step (0 = run to decision)")
+    args = ap.parse_args()
+
+    import torch
+
+    from spark_sched_sim_b200.bank import synthetic_bank
+    from spark_sched_sim_b200.batched_env import BatchedSparkSchedSimEnv
+
+    cfg = {"num_executors": args.executors, "job_arrival_cap": args.jobs, "job_arrival_rate": 4.0e-5,
+           "moving_delay": 2000.0, "warmup_delay": 1000.0}
+    B = args.envs
+    env = BatchedSparkSchedSimEnv(cfg, num_envs=B, bank=synthetic_bank(0), decima_policy=True)
+    z = np.load(osp.join(REPO, "tests", "golden", "decima_model.npz"))
+    env.set_decima_weights({k: z[k] for k in z.files})
+    seeds = (1234 + np.arange(B)).astype(np.uint64)
+    env.reset_host(seeds)
+
+    def decide(n):
+        for _ in range(n):
+            a, c = env.decima_policy()
+            env.step(a, c, max_events=args.budget)
+
+    decide(args.warmup)
+    env.reset_stats()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    decide(args.decisions)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    st = env.stats()
+    hdr = env.hdr()
+    # time of the policy kernel alone
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for _ in range(20):
+        env.decima_policy()
+    p1.record()
+    torch.cuda.synchronize()
+    print(json.dumps({
+        "metric": "scheduling decisions/sec (Decima policy, batched envs)",
+        "value": st["decisions"] / (ms * 1e-3), "unit": "decisions/s", "n_gpus": 1,
+        "config": {"workload": f"{B} envs x ({args.jobs} jobs, {args.executors} executors), Decima policy "
+                               "(shipped model.pt) on device, 2 launches per decision",
+                   "max_events_per_step": args.budget},
+        "decisions": st["decisions"], "events": st["events"], "ms_total": ms,
+        "policy_kernel_ms": p0.elapsed_time(p1) / 20,
+        "env_errors": int(((hdr["error"] != 0) & (hdr["error"] != 9)).sum()),
+        "finished_envs": int((hdr["terminated"] != 0).sum()),
+    }))
+
+
+if __name__ == "__main__":
+    main()

@@ -245,7 +245,7 @@ void carve(Carver &cv, const ssb_config &c, const ssb_bank &bk, const Dims &d, P
     }
     if (c.flags & SSB_FLAG_DECIMA_POLICY) {
         p.Epad = (c.num_executors + 3) & ~3;
-        p.pol_w = cv.take<float>(dw::TOTAL);
+        p.pol_w = cv.take<float>(dd::TOTAL);
         p.pol_h_init = cv.take<float>(B * d.Sc * 16);
         p.pol_h = cv.take<float>(B * d.Sc * 16);
         p.pol_msg = cv.take<float>(B * d.Sc * 16);
@@ -548,7 +548,25 @@ int ssb_set_decima_weights(ssb_env *env, const float *weights, int32_t n_floats)
 {
     if (!env || !weights || !env->p.pol_w || n_floats != dw::TOTAL) return SSB_E_INVALID;
     CUDA_TRY(cudaSetDevice(env->device));
-    CUDA_TRY(cudaMemcpy(env->p.pol_w, weights, sizeof(float) * dw::TOTAL, cudaMemcpyHostToDevice));
+    // state_dict order ([out][in] per Linear) -> device layout (transposed, 4-float padded; ssb_decima.cuh)
+    static const int dims[7][4] = {{5, 32, 16, 16},  {16, 32, 16, 16}, {16, 32, 16, 16}, {21, 32, 16, 16},
+                                   {16, 32, 16, 16}, {53, 64, 64, 1},  {36, 64, 64, 1}};
+    std::vector<float> dev(dd::TOTAL, 0.0f);
+    size_t src = 0, dst = 0;
+    for (int m = 0; m < 7; m++) {
+        for (int l = 0; l < 3; l++) {
+            const int in = dims[m][l], out = dims[m][l + 1];
+            for (int o = 0; o < out; o++)
+                for (int i = 0; i < in; i++) dev[dst + (size_t)i * out + o] = weights[src + (size_t)o * in + i];
+            src += (size_t)in * out;
+            dst += dd::pad4(in * out);
+            for (int o = 0; o < out; o++) dev[dst + o] = weights[src + o];
+            src += out;
+            dst += dd::pad4(out);
+        }
+    }
+    if (src != (size_t)dw::TOTAL || dst != (size_t)dd::TOTAL) return SSB_E_INVALID;
+    CUDA_TRY(cudaMemcpy(env->p.pol_w, dev.data(), sizeof(float) * dd::TOTAL, cudaMemcpyHostToDevice));
     return SSB_OK;
 }
 

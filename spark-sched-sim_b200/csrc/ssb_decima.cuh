@@ -16,9 +16,23 @@
 
 namespace ssb {
 
-// flat weight layout = state_dict order of models/decima/model.pt (42 tensors, 20 802 floats)
+// ABI layout (dw): the tensors of models/decima/model.pt in state_dict order, each [out][in] row-major
+// (42 tensors, 20 802 floats).  Device layout (dd): per layer the TRANSPOSED weight [in][out] followed
+// by the bias, every tensor padded to a multiple of 4 floats so that a lane fetches the weights of four
+// consecutive output neurons with one 128-bit load (ssb_set_decima_weights does the re-layout).
 namespace dw {
 constexpr int mlp(int in, int h1, int h2, int out) { return h1 * in + h1 + h2 * h1 + h2 + out * h2 + out; }
+constexpr int TOTAL = mlp(5, 32, 16, 16) + 2 * mlp(16, 32, 16, 16) + mlp(21, 32, 16, 16) + mlp(16, 32, 16, 16) +
+                      mlp(53, 64, 64, 1) + mlp(36, 64, 64, 1);
+static_assert(TOTAL == 20802, "Decima parameter count");
+}  // namespace dw
+namespace dd {
+__host__ __device__ constexpr int pad4(int n) { return (n + 3) & ~3; }
+__host__ __device__ constexpr int layer(int in, int out) { return pad4(in * out) + pad4(out); }
+__host__ __device__ constexpr int mlp(int in, int h1, int h2, int out)
+{
+    return layer(in, h1) + layer(h1, h2) + layer(h2, out);
+}
 constexpr int PREP = 0;
 constexpr int MSG = PREP + mlp(5, 32, 16, 16);
 constexpr int UPD = MSG + mlp(16, 32, 16, 16);
@@ -27,8 +41,7 @@ constexpr int GLOB = DAG + mlp(21, 32, 16, 16);
 constexpr int STAGE = GLOB + mlp(16, 32, 16, 16);
 constexpr int EXEC = STAGE + mlp(53, 64, 64, 1);
 constexpr int TOTAL = EXEC + mlp(36, 64, 64, 1);
-static_assert(TOTAL == 20802, "Decima parameter count");
-}  // namespace dw
+}  // namespace dd
 
 template <bool TANH>
 __device__ __forceinline__ float act(float x)
@@ -37,33 +50,53 @@ __device__ __forceinline__ float act(float x)
     return x > 0.0f ? x : 0.2f * x;  // LeakyReLU(negative_slope=0.2), config/decima_tpch.yaml:69-73
 }
 
+// One Linear (+ activation): out[o] = act(bias[o] + sum_i W[o][i] * in[i]), accumulated in input order
+// with fmaf.  16 output accumulators live in registers at a time; Wt is the transposed weight.
+template <int IN, int OUT, bool ACT, bool TANH>
+__device__ __forceinline__ void dense(const float *__restrict__ Wt, const float *in, float *out)
+{
+    const float *bias = Wt + dd::pad4(IN * OUT);
+    if (OUT == 1) {
+        float s = __ldg(bias);
+#pragma unroll 4
+        for (int i = 0; i < IN; i++) s = fmaf(__ldg(Wt + i), in[i], s);
+        out[0] = s;
+        return;
+    }
+#pragma unroll 1
+    for (int oc = 0; oc < OUT; oc += 16) {
+        float acc[16];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const float4 bv = __ldg(reinterpret_cast<const float4 *>(bias + oc) + q);
+            acc[4 * q] = bv.x; acc[4 * q + 1] = bv.y; acc[4 * q + 2] = bv.z; acc[4 * q + 3] = bv.w;
+        }
+#pragma unroll 2
+        for (int i = 0; i < IN; i++) {
+            const float v = in[i];
+            const float4 *wp = reinterpret_cast<const float4 *>(Wt + i * OUT + oc);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const float4 wv = __ldg(wp + q);
+                acc[4 * q] = fmaf(wv.x, v, acc[4 * q]);
+                acc[4 * q + 1] = fmaf(wv.y, v, acc[4 * q + 1]);
+                acc[4 * q + 2] = fmaf(wv.z, v, acc[4 * q + 2]);
+                acc[4 * q + 3] = fmaf(wv.w, v, acc[4 * q + 3]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 16; q++) out[oc + q] = ACT ? act<TANH>(acc[q]) : acc[q];
+    }
+}
+
 // make_mlp(IN, [H1, H2], OUT): Linear / act / Linear / act / Linear (decima/utils.py:45-64)
 template <int IN, int H1, int H2, int OUT, bool TANH>
 __device__ __forceinline__ void mlp3(const float *__restrict__ w, const float (&in)[IN], float (&out)[OUT])
 {
-    const float *W0 = w, *b0 = W0 + H1 * IN, *W2 = b0 + H1, *b2 = W2 + H2 * H1, *W4 = b2 + H2, *b4 = W4 + OUT * H2;
     float a1[H1], a2[H2];
-#pragma unroll
-    for (int o = 0; o < H1; o++) {
-        float s = __ldg(b0 + o);
-#pragma unroll
-        for (int i = 0; i < IN; i++) s = fmaf(__ldg(W0 + o * IN + i), in[i], s);
-        a1[o] = act<TANH>(s);
-    }
-#pragma unroll
-    for (int o = 0; o < H2; o++) {
-        float s = __ldg(b2 + o);
-#pragma unroll
-        for (int i = 0; i < H1; i++) s = fmaf(__ldg(W2 + o * H1 + i), a1[i], s);
-        a2[o] = act<TANH>(s);
-    }
-#pragma unroll
-    for (int o = 0; o < OUT; o++) {
-        float s = __ldg(b4 + o);
-#pragma unroll
-        for (int i = 0; i < H2; i++) s = fmaf(__ldg(W4 + o * H2 + i), a2[i], s);
-        out[o] = s;
-    }
+    dense<IN, H1, true, TANH>(w, in, a1);
+    dense<H1, H2, true, TANH>(w + dd::layer(IN, H1), a1, a2);
+    dense<H2, OUT, false, TANH>(w + dd::layer(IN, H1) + dd::layer(H1, H2), a2, out);
 }
 
 __device__ __forceinline__ void ld16(const float *p, float (&v)[16])
@@ -141,7 +174,7 @@ __device__ inline void decima_policy_w(Sim &sim, const float *__restrict__ w, co
             float in[5], out[16];
 #pragma unroll
             for (int i = 0; i < 5; i++) in[i] = x[n * 5 + i];
-            mlp3<5, 32, 16, 16, false>(w + dw::PREP, in, out);
+            mlp3<5, 32, 16, 16, false>(w + dd::PREP, in, out);
             st16(pb.h_init + (size_t)n * 16, out);
             if (depth == 0) st16(pb.h + (size_t)n * 16, out);  // _forward_no_mp (:236-241)
             is_tail[n] = 0;
@@ -166,7 +199,7 @@ __device__ inline void decima_policy_w(Sim &sim, const float *__restrict__ w, co
                 if (!is_tail[n]) {
                     float in[16];
                     ld16(pb.h_init + (size_t)n * 16, in);
-                    mlp3<16, 32, 16, 16, false>(w + dw::UPD, in, out);
+                    mlp3<16, 32, 16, 16, false>(w + dd::UPD, in, out);
                 } else {
 #pragma unroll
                     for (int i = 0; i < 16; i++) out[i] = 0.0f;
@@ -187,7 +220,7 @@ __device__ inline void decima_policy_w(Sim &sim, const float *__restrict__ w, co
                 if (n < N && snd[n]) {
                     float in[16], out[16];
                     ld16(pb.h + (size_t)n * 16, in);
-                    mlp3<16, 32, 16, 16, false>(w + dw::MSG, in, out);
+                    mlp3<16, 32, 16, 16, false>(w + dd::MSG, in, out);
                     st16(pb.msg + (size_t)n * 16, out);
                 }
             }
@@ -206,7 +239,7 @@ __device__ inline void decima_policy_w(Sim &sim, const float *__restrict__ w, co
                             for (int i = 0; i < 16; i++) agg[i] += m[i];
                         }
                     }
-                    mlp3<16, 32, 16, 16, false>(w + dw::UPD, agg, out);
+                    mlp3<16, 32, 16, 16, false>(w + dd::UPD, agg, out);
                     ld16(pb.h_init + (size_t)n * 16, hi);
 #pragma unroll
                     for (int i = 0; i < 16; i++) out[i] = hi[i] + out[i];
@@ -226,7 +259,7 @@ __device__ inline void decima_policy_w(Sim &sim, const float *__restrict__ w, co
             ld16(pb.h + (size_t)n * 16, hv);
 #pragma unroll
             for (int i = 0; i < 16; i++) in[5 + i] = hv[i];
-            mlp3<21, 32, 16, 16, false>(w + dw::DAG, in, out);
+            mlp3<21, 32, 16, 16, false>(w + dd::DAG, in, out);
             st16(pb.msg + (size_t)n * 16, out);  // msg buffer reused for the per-node dag terms
         }
     }
@@ -244,7 +277,7 @@ __device__ inline void decima_policy_w(Sim &sim, const float *__restrict__ w, co
                 for (int i = 0; i < 16; i++) s[i] += z[i];
             }
             st16(pb.h_dag + (size_t)j * 16, s);
-            mlp3<16, 32, 16, 16, false>(w + dw::GLOB, s, gj);  // GlobalEncoder (:265-276)
+            mlp3<16, 32, 16, 16, false>(w + dd::GLOB, s, gj);  // GlobalEncoder (:265-276)
             st16(pb.g + (size_t)j * 16, gj);
         }
     }
@@ -277,7 +310,7 @@ __device__ inline void decima_policy_w(Sim &sim, const float *__restrict__ w, co
             for (int i = 0; i < 16; i++) in[21 + i] = t[i];
 #pragma unroll
             for (int i = 0; i < 16; i++) in[37 + i] = hg[i];
-            mlp3<53, 64, 64, 1, true>(w + dw::STAGE, in, out);
+            mlp3<53, 64, 64, 1, true>(w + dd::STAGE, in, out);
             pb.stage_logits[n_cand + __popc(bm & ((1u << lane) - 1))] = out[0];
         }
         n_cand += __popc(bm);
@@ -322,7 +355,7 @@ __device__ inline void decima_policy_w(Sim &sim, const float *__restrict__ w, co
 #pragma unroll
                 for (int i = 0; i < 16; i++) in[19 + i] = hg[i];
                 in[35] = __fdiv_rn((float)c, (float)p.E);  // torch.arange(E) / E in float32 (:380)
-                mlp3<36, 64, 64, 1, true>(w + dw::EXEC, in, out);
+                mlp3<36, 64, 64, 1, true>(w + dd::EXEC, in, out);
                 pb.exec_logits[c] = out[0];
             }
         }

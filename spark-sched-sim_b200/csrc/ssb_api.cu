@@ -18,7 +18,10 @@ using namespace ssb;
 
 namespace {
 
-constexpr int WARPS_PER_CTA = 4;
+#ifndef SSB_WARPS_PER_CTA
+#define SSB_WARPS_PER_CTA 4
+#endif
+constexpr int WARPS_PER_CTA = SSB_WARPS_PER_CTA;
 thread_local char g_cuda_err[256] = "";
 
 #define CUDA_TRY(expr)                                                                   \

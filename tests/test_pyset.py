@@ -54,6 +54,57 @@ def test_reward_set_ascending_shortcut():
     assert used > 5000
 
 
+def _register_table_order(ids):
+    """Python mirror of the kernel's in-register emulation for <= 18 ascending distinct ids < 255
+    (ssb_sim.cuh compute_jobtime): 8-slot table without linear probes, rebuilt into a 32-slot table at
+    the 5th element, where the 9-slot linear probe is a find-first-zero on the occupancy mask."""
+    occ8, t8, occ, T, cnt, big = 0, {}, 0, {}, 0, False
+
+    def put32(key):
+        nonlocal occ
+        perturb, i = key, key & 31
+        while True:
+            if not (occ >> i) & 1:
+                break
+            if i + 9 <= 31:
+                m = (~occ >> (i + 1)) & 0x1FF
+                if m:
+                    i = i + (m & -m).bit_length()
+                    break
+            perturb >>= 5
+            i = (i * 5 + 1 + perturb) & 31
+        occ |= 1 << i
+        T[i] = key
+
+    for key in ids:
+        if big:
+            put32(key); cnt += 1
+            continue
+        perturb, i = key, key & 7
+        while (occ8 >> i) & 1:
+            perturb >>= 5
+            i = (i * 5 + 1 + perturb) & 7
+        occ8 |= 1 << i
+        t8[i] = key
+        cnt += 1
+        if cnt == 5:
+            for s in range(8):
+                if (occ8 >> s) & 1:
+                    put32(t8[s])
+            big = True
+    return [T[s] for s in range(32) if (occ >> s) & 1] if big else [t8[s] for s in range(8) if (occ8 >> s) & 1]
+
+
+@pytest.mark.skipif(sys.version_info[:2] != (3, 12), reason="layout pinned to CPython 3.12")
+def test_reward_small_set_register_emulation():
+    rnd = random.Random(11)
+    for _ in range(30000):
+        n = rnd.randint(1, 18)
+        ids = sorted(rnd.sample(range(rnd.choice([20, 50, 200, 255])), n))
+        dup = [x for x in ids if rnd.random() < 0.7]  # second list repeats part of the first
+        assert list(set(ids + dup)) == _register_table_order(ids), ids
+
+
 @pytest.mark.skipif(sys.version_info[:2] != (3, 12), reason="layout pinned to CPython 3.12")
 @pytest.mark.parametrize("universe", [3, 10, 50, 100, 200])
 def test_pyset_matches_cpython(universe):

@@ -220,6 +220,9 @@ int ssb_get_policy_views(ssb_env *env, ssb_policy_views *out);
 /* device pointer to ssb_stats[B] */
 int ssb_get_stats(ssb_env *env, ssb_stats **out);
 int ssb_reset_stats(ssb_env *env, void *stream);
+/* development aid: device pointer to u64[B][16] per-phase cycle counters; they are only advanced by a
+ * library built with -DSSB_PROFILE (profiles/phase_breakdown.py), otherwise they stay zero */
+int ssb_get_debug_counters(ssb_env *env, uint64_t **out);
 
 /* results (HOST outputs, synchronous): per-job arrival/completion time, template and state
  * (0 = not arrived yet, 1 = active, 2 = completed) of env_index; any output may be NULL */

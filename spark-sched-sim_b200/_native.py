@@ -122,7 +122,7 @@ EXPORTS = [
     "ssb_load_trace", "ssb_clear_trace", "ssb_reset", "ssb_step", "ssb_reset_host", "ssb_step_host",
     "ssb_rollout_fair", "ssb_fair_actions", "ssb_get_views", "ssb_get_stats", "ssb_reset_stats",
     "ssb_get_jobs", "ssb_get_log", "ssb_decima_obs", "ssb_get_decima_views",
-    "ssb_set_decima_weights", "ssb_decima_policy", "ssb_get_policy_views",
+    "ssb_set_decima_weights", "ssb_decima_policy", "ssb_get_policy_views", "ssb_get_debug_counters",
 ]
 
 _lib = None
@@ -165,6 +165,7 @@ def lib():
     L.ssb_get_policy_views.argtypes = [vp, C.POINTER(SsbPolicyViews)]
     L.ssb_get_stats.argtypes = [vp, C.POINTER(vp)]
     L.ssb_reset_stats.argtypes = [vp, vp]
+    L.ssb_get_debug_counters.argtypes = [vp, C.POINTER(vp)]
     L.ssb_get_jobs.argtypes = [vp, i32, C.POINTER(i32), vp, vp, vp, vp, i32]
     L.ssb_get_log.argtypes = [vp, i32, i64, i64, C.POINTER(i64)] + [vp] * 7
     if L.ssb_abi_version() != ABI_VERSION:

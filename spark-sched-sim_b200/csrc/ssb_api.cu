@@ -76,6 +76,9 @@ k_rollout_fair(Params p, int num_decisions, int dynamic_partition, int auto_rese
     const int b = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (b >= p.B) return;
     Sim sim(p, b, lane);
+#ifdef SSB_PROFILE
+    const long long t_start = clock64();
+#endif
     int d = 0;
     while (d < num_decisions) {
         if (sim.h->error) break;
@@ -91,10 +94,19 @@ k_rollout_fair(Params p, int num_decisions, int dynamic_partition, int auto_rese
             continue;
         }
         int a = -1, n = 1;
+#ifdef SSB_PROFILE
+        long long tp0 = clock64();
+#endif
         sim.fair_action_w(dynamic_partition != 0, a, n);
+#ifdef SSB_PROFILE
+        if (lane == 0) p.prof[(size_t)b * 16 + 8] += (unsigned long long)(clock64() - tp0);
+#endif
         sim.step_w(a, n);
         d++;
     }
+#ifdef SSB_PROFILE
+    if (lane == 0) p.prof[(size_t)b * 16 + 10] += (unsigned long long)(clock64() - t_start);
+#endif
 }
 
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_decima_obs(Params p)
@@ -224,6 +236,7 @@ void carve(Carver &cv, const ssb_config &c, const ssb_bank &bk, const Dims &d, P
     p.stage = cv.take<StageRec>(B * d.Sc);
     p.active = cv.take<int16_t>(B * c.max_jobs);
     p.old_act = cv.take<int16_t>(B * c.max_jobs);
+    p.reward_ord = cv.take<int16_t>(B * c.max_jobs);
     p.commits = cv.take<Commit>(B * d.Cc);
     p.pool_hdr = cv.take<PoolHdr>(B * d.P);
     p.pool_tab = cv.take<uint8_t>(B * d.P * d.TAB);
@@ -234,6 +247,7 @@ void carve(Carver &cv, const ssb_config &c, const ssb_bank &bk, const Dims &d, P
     p.tape = cv.take<double>(c.tape_capacity > 0 ? B * (size_t)c.tape_capacity : 1);
     p.log = cv.take<LogRow>(c.log_capacity > 0 ? B * (size_t)c.log_capacity : 1);
     p.stats = cv.take<ssb_stats>(B);
+    p.prof = cv.take<unsigned long long>(B * 16);
     p.obs_hdr = cv.take<ssb_obs_hdr>(B);
     p.obs_nodes = cv.take<float>(B * d.Sc * 3);
     p.obs_edges = cv.take<int32_t>(B * d.Mc * 2);
@@ -389,6 +403,7 @@ int ssb_create(const ssb_config *cfg, const ssb_bank *bk, int device, void *work
     p.b_child = bd.child; p.b_present = bd.present; p.b_dur = bd.dur; p.b_vals = bd.vals; p.iv = bd.iv;
     CUDA_TRY(cudaMemset(p.hdr, 0, sizeof(EnvHdr) * (size_t)p.B));
     CUDA_TRY(cudaMemset(p.stats, 0, sizeof(ssb_stats) * (size_t)p.B));
+    CUDA_TRY(cudaMemset(p.prof, 0, sizeof(unsigned long long) * 16 * (size_t)p.B));
     CUDA_TRY(cudaMemset(p.obs_hdr, 0, sizeof(ssb_obs_hdr) * (size_t)p.B));
     CUDA_TRY(cudaStreamCreateWithFlags(&env->own_stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaDeviceSynchronize());
@@ -599,6 +614,13 @@ int ssb_get_stats(ssb_env *env, ssb_stats **out)
 {
     if (!env || !out) return SSB_E_INVALID;
     *out = env->p.stats;
+    return SSB_OK;
+}
+
+int ssb_get_debug_counters(ssb_env *env, uint64_t **out)
+{
+    if (!env || !out) return SSB_E_INVALID;
+    *out = reinterpret_cast<uint64_t *>(env->p.prof);
     return SSB_OK;
 }
 

@@ -14,6 +14,26 @@
 namespace ssb {
 
 #define FULL 0xffffffffu
+// development aid: per-phase cycle counters (lane 0), compiled in only with -DSSB_PROFILE
+#ifdef SSB_PROFILE
+#define SSB_T0() long long t0_ = clock64()
+#define SSB_TRESET() t0_ = clock64()
+#define SSB_TACC(slot)                                                     \
+    do {                                                                    \
+        long long t1_ = clock64();                                          \
+        if (lane == 0) p.prof[(size_t)b * 16 + (slot)] += (unsigned long long)(t1_ - t0_); \
+        t0_ = t1_;                                                          \
+    } while (0)
+#define SSB_TCNT(slot, n)                                                   \
+    do {                                                                    \
+        if (lane == 0) p.prof[(size_t)b * 16 + (slot)] += (unsigned long long)(n); \
+    } while (0)
+#else
+#define SSB_T0() do { } while (0)
+#define SSB_TRESET() do { } while (0)
+#define SSB_TACC(slot) do { } while (0)
+#define SSB_TCNT(slot, n) do { } while (0)
+#endif
 // rarely executed state-machine pieces (executor motion, set emulation) are kept out of line so the
 // hot event loop stays compact in the instruction cache
 // SSB_RARE: executed a few times per episode at most (resets, table resizes, failures) -> out of line.
@@ -44,6 +64,8 @@ namespace ssb {
 __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                                 uint32_t k0, uint32_t k1)
 {
+    // (not fully unrolled on purpose: the rollout kernel is bound by instruction fetch, and the smaller
+    // body measured 7 % faster end to end than the fully unrolled one -- profiles/r01_ab_unroll.txt)
 #pragma unroll 2
     for (int r = 0; r < 10; r++) {
         uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
@@ -923,7 +945,8 @@ struct Sim {
         // timestamps almost always decide; ties there take the exact path.
         const uint32_t hi = (uint32_t)(L.kt >> 32);
         unsigned less = 0;
-        // (kept rolled on purpose: the kernel is instruction-fetch bound, see profiles/)
+        // (kept rolled on purpose: instruction fetch, not shuffle latency, bounds this loop -- the
+        // unrolled form measured 6475 vs 4266 cycles per iteration, profiles/r01_ab_unroll.txt)
 #pragma unroll 1
         for (int i = 0; i < p.E; i++) less |= (__shfl_sync(FULL, hi, i) < hi) ? (1u << i) : 0u;
         {
@@ -1003,128 +1026,116 @@ struct Sim {
                 // registers only: L and H die before the general path below is entered
                 HotLane L;
                 HotEnv H;
+                SSB_T0();
                 hot_load(L, H);
+                SSB_TACC(11);
                 for (;;) {
                     int m = fast_batch_w(L, H, budget);
                     budget -= m;
+                    SSB_TCNT(1, 1);
                     if (m == 0 || budget == 0) break;
                 }
                 hot_flush(H);
+                SSB_TACC(0);
             }
+            SSB_T0();
             double t;
             int idx = pop_min_w(t);
             if (idx < 0) break;
             if (budget-- == 0) return false;
             if (lane == 0) handle_event(idx, t);
             __syncwarp();
+            SSB_TACC(2);
+            SSB_TCNT(3, 1);
             if (h->error) break;
             if (num_committable() <= 0) continue;
             int n = find_schedulable_all_w();
-            if (n) break;
+            if (n) { SSB_TACC(4); break; }
             if (lane == 0) { move_idle_executors(POOL_NONE, -1); h->source = POOL_NONE; }
             __syncwarp();
+            SSB_TACC(4);
             if (h->error) break;
         }
         return true;
     }
 
-    // ------------------------------------------------------------ reward (:847-874), lane 0
+    // ------------------------------------------------------------ reward (:847-874)
     // continuously discounted job-time of one job over [a, b] after the step's start (:866-869)
     __device__ SSB_RARE double discounted_term(double a, double b) const
     {
         return exp(-p.beta * 1e-3 * a) - exp(-p.beta * 1e-3 * b);
     }
-    __device__ SSB_COLD double compute_jobtime()
+    // Lane 0: writes the job ids of set(active_old + active_new) in CPython's iteration order to
+    // `ord` and returns their number (:855-858).  Both lists ascend and jobs that arrived during the
+    // step have larger ids than every old one, so the distinct ids are inserted in ascending order; the
+    // table sizes go 8 -> 32 -> 128 -> 512 -> ... at 5, 19, 77, 307, ... elements, and once every id is
+    // smaller than the final table size each id sits in its own slot => iteration is ascending
+    // (tests/test_pyset.py checks the claims against the interpreter).  Small sets are emulated in
+    // registers, anything else with the generic set emulation.
+    __device__ SSB_COLD int reward_order(int16_t *ord)
     {
-        double wall = h->wall_time, wall_old = h->wall_old;
-        if (wall - wall_old == 0.0) return 0.0;
         const int16_t *old = p.old_act + (size_t)b * p.Jc;
         const int n_old = h->n_old_active, n_new = h->n_active;
-        double jt = 0.0, beta = p.beta;
-        // The sum runs over set(active_old + active_new) in CPython's iteration order (:855-858).  Both
-        // lists ascend and jobs that arrived during the step have larger ids than every old one, so the
-        // distinct ids are inserted in ascending order; the table sizes go 8 -> 32 -> 128 -> 512 -> ...
-        // at 5, 19, 77, 307, ... elements, and once every id is smaller than the final table size each
-        // id sits in its own slot => iteration is ascending.  (tests/test_pyset.py checks this claim
-        // against the interpreter.)  Otherwise emulate the set.
-        {
-            const int last_old = n_old ? old[n_old - 1] : -1;
-            int n = n_old;
-            for (int i = n_new - 1; i >= 0 && act[i] > last_old; i--) n++;
-            const int max_id = n_new && act[n_new - 1] > last_old ? act[n_new - 1] : last_old;
-            const int F = n < 5 ? 8 : n < 19 ? 32 : n < 77 ? 128 : n < 307 ? 512 : n < 1229 ? 2048 : 0;
-            if (max_id < F) {
-                int a = 0, c = 0;
-                while (a < n_old || c < n_new) {  // ascending merge of the two lists
-                    int j;
-                    if (c >= n_new || (a < n_old && old[a] <= act[c])) {
-                        j = old[a++];
-                        if (c < n_new && act[c] == j) c++;
-                    } else j = act[c++];
-                    double start = fmax(jb[j].t_arrival, wall_old), end = fmin(jb[j].t_completed, wall);
-                    if (beta == 0.0) jt = __dadd_rn(jt, __dadd_rn(end, -start));
-                    else jt += discounted_term(start - wall_old, end - wall_old);
+        const int last_old = n_old ? old[n_old - 1] : -1;
+        int n = n_old;
+        for (int i = n_new - 1; i >= 0 && act[i] > last_old; i--) n++;
+        const int max_id = n_new && act[n_new - 1] > last_old ? act[n_new - 1] : last_old;
+        const int F = n < 5 ? 8 : n < 19 ? 32 : n < 77 ? 128 : n < 307 ? 512 : n < 1229 ? 2048 : 0;
+        int k = 0;
+        if (max_id < F) {  // ascending: old, then the arrivals
+            for (int i = 0; i < n_old; i++) ord[k++] = old[i];
+            for (int i = 0; i < n_new; i++) if (act[i] > last_old) ord[k++] = act[i];
+            return k;
+        }
+        if (n <= 18 && max_id < 255) {
+            // 8- or 32-slot table without deletions, in registers: keys as bytes of u64 words, occupancy
+            // as a bit mask, so the 9-slot linear probe of set_add_entry is one find-first-zero
+            uint64_t t8 = 0, T0 = 0, T1 = 0, T2 = 0, T3 = 0;
+            uint32_t occ8 = 0, occ = 0;
+            int cnt = 0;
+            bool big = false;
+            auto put32 = [&](int key) {
+                unsigned perturb = (unsigned)key, i = (unsigned)key & 31u;
+                for (;;) {
+                    if (!((occ >> i) & 1u)) break;
+                    if (i + 9 <= 31) {
+                        unsigned m = (~occ >> (i + 1)) & 0x1ffu;
+                        if (m) { i = i + (unsigned)__ffs((int)m); break; }
+                    }
+                    perturb >>= 5;
+                    i = (i * 5 + 1 + perturb) & 31u;
                 }
-                if (beta > 0.0) jt /= beta;
-                return jt;
-            }
-            if (n <= 18 && max_id < 255) {
-                // Small sets (8- or 32-slot table, no deletions): emulate the table in registers --
-                // keys as bytes of u64 words, occupancy as a bit mask, so the 9-slot linear probe of
-                // set_add_entry / set_insert_clean is one find-first-zero.
-                uint64_t t8 = 0, T0 = 0, T1 = 0, T2 = 0, T3 = 0;
-                uint32_t occ8 = 0, occ = 0;
-                int cnt = 0;
-                bool big = false;
-                auto put32 = [&](int key) {
-                    unsigned perturb = (unsigned)key, i = (unsigned)key & 31u;
-                    for (;;) {
-                        if (!((occ >> i) & 1u)) break;
-                        if (i + 9 <= 31) {
-                            unsigned m = (~occ >> (i + 1)) & 0x1ffu;
-                            if (m) { i = i + (unsigned)__ffs((int)m); break; }
-                        }
-                        perturb >>= 5;
-                        i = (i * 5 + 1 + perturb) & 31u;
-                    }
-                    occ |= 1u << i;
-                    const uint64_t v = (uint64_t)key << (8 * (i & 7));
-                    const unsigned wsel = i >> 3;
-                    T0 |= wsel == 0 ? v : 0ull; T1 |= wsel == 1 ? v : 0ull;
-                    T2 |= wsel == 2 ? v : 0ull; T3 |= wsel == 3 ? v : 0ull;
-                };
-                auto put = [&](int key) {
-                    if (big) { put32(key); cnt++; return; }
-                    unsigned perturb = (unsigned)key, i = (unsigned)key & 7u;  // mask 7: no linear probes
-                    while ((occ8 >> i) & 1u) { perturb >>= 5; i = (i * 5 + 1 + perturb) & 7u; }
-                    occ8 |= 1u << i;
-                    t8 |= (uint64_t)key << (8 * i);
-                    if (++cnt == 5) {  // fill*5 >= mask*3: resize to 32, re-insert in old slot order
-                        for (int s = 0; s < 8; s++)
-                            if ((occ8 >> s) & 1u) put32((int)((t8 >> (8 * s)) & 0xff));
-                        big = true;
-                    }
-                };
-                for (int i = 0; i < n_old; i++) put(old[i]);
-                for (int i = 0; i < n_new; i++) if (act[i] > last_old) put(act[i]);
-                const int slots = big ? 32 : 8;
-                for (int s = 0; s < slots; s++) {
-                    int j;
-                    if (big) {
-                        if (!((occ >> s) & 1u)) continue;
-                        const uint64_t wv = (s >> 3) == 0 ? T0 : (s >> 3) == 1 ? T1 : (s >> 3) == 2 ? T2 : T3;
-                        j = (int)((wv >> (8 * (s & 7))) & 0xff);
-                    } else {
-                        if (!((occ8 >> s) & 1u)) continue;
-                        j = (int)((t8 >> (8 * s)) & 0xff);
-                    }
-                    double start = fmax(jb[j].t_arrival, wall_old), end = fmin(jb[j].t_completed, wall);
-                    if (beta == 0.0) jt = __dadd_rn(jt, __dadd_rn(end, -start));
-                    else jt += discounted_term(start - wall_old, end - wall_old);
+                occ |= 1u << i;
+                const uint64_t v = (uint64_t)key << (8 * (i & 7));
+                const unsigned wsel = i >> 3;
+                T0 |= wsel == 0 ? v : 0ull; T1 |= wsel == 1 ? v : 0ull;
+                T2 |= wsel == 2 ? v : 0ull; T3 |= wsel == 3 ? v : 0ull;
+            };
+            auto put = [&](int key) {
+                if (big) { put32(key); cnt++; return; }
+                unsigned perturb = (unsigned)key, i = (unsigned)key & 7u;  // mask 7: no linear probes
+                while ((occ8 >> i) & 1u) { perturb >>= 5; i = (i * 5 + 1 + perturb) & 7u; }
+                occ8 |= 1u << i;
+                t8 |= (uint64_t)key << (8 * i);
+                if (++cnt == 5) {  // fill*5 >= mask*3: resize to 32, re-insert in old slot order
+                    for (int s = 0; s < 8; s++)
+                        if ((occ8 >> s) & 1u) put32((int)((t8 >> (8 * s)) & 0xff));
+                    big = true;
                 }
-                if (beta > 0.0) jt /= beta;
-                return jt;
+            };
+            for (int i = 0; i < n_old; i++) put(old[i]);
+            for (int i = 0; i < n_new; i++) if (act[i] > last_old) put(act[i]);
+            if (!big) {
+                for (int s = 0; s < 8; s++)
+                    if ((occ8 >> s) & 1u) ord[k++] = (int16_t)((t8 >> (8 * s)) & 0xff);
+            } else {
+                for (int s = 0; s < 32; s++) {
+                    if (!((occ >> s) & 1u)) continue;
+                    const uint64_t wv = (s >> 3) == 0 ? T0 : (s >> 3) == 1 ? T1 : (s >> 3) == 2 ? T2 : T3;
+                    ord[k++] = (int16_t)((wv >> (8 * (s & 7))) & 0xff);
+                }
             }
+            return k;
         }
         uint16_t *tab = p.rset + (size_t)b * 2 * p.RT, *tmp = tab + p.RT;
         PSet<uint16_t> ids;
@@ -1133,12 +1144,32 @@ struct Sim {
         for (int i = 0; i < n_old; i++) ps_add(ids, old[i], tmp);
 #pragma unroll 1
         for (int i = 0; i < n_new; i++) ps_add(ids, act[i], tmp);
-        for (int i = 0; i <= ids.mask; i++) {
-            int j = ids.t[i];
-            if (j >= PSet<uint16_t>::DUMMY) continue;
-            double start = fmax(jb[j].t_arrival, wall_old), end = fmin(jb[j].t_completed, wall);
-            if (beta == 0.0) jt = __dadd_rn(jt, __dadd_rn(end, -start));
-            else jt += discounted_term(start - wall_old, end - wall_old);
+        for (int i = 0; i <= ids.mask; i++)
+            if (ids.t[i] < PSet<uint16_t>::DUMMY) ord[k++] = (int16_t)ids.t[i];
+        return k;
+    }
+    // _compute_jobtime: lane 0 fixes the summation order, all lanes fetch their jobs' overlap with the
+    // step in parallel, and the f64 sum is taken sequentially in that order (bit-identical to the loop)
+    __device__ double compute_jobtime_w()
+    {
+        const double wall = h->wall_time, wall_old = h->wall_old;
+        if (wall - wall_old == 0.0) return 0.0;
+        int16_t *ord = p.reward_ord + (size_t)b * p.Jc;
+        int n = 0;
+        if (lane == 0) n = reward_order(ord);
+        n = __shfl_sync(FULL, n, 0);
+        __syncwarp();
+        const double beta = p.beta;
+        double jt = 0.0;
+        for (int base = 0; base < n; base += 32) {
+            double term = 0.0;
+            if (base + lane < n) {
+                const int j = ord[base + lane];
+                const double start = fmax(jb[j].t_arrival, wall_old), end = fmin(jb[j].t_completed, wall);
+                term = beta == 0.0 ? __dadd_rn(end, -start) : discounted_term(start - wall_old, end - wall_old);
+            }
+            const int m = min(32, n - base);
+            for (int i = 0; i < m; i++) jt = __dadd_rn(jt, __shfl_sync(FULL, term, i));
         }
         if (beta > 0.0) jt /= beta;
         return jt;
@@ -1276,6 +1307,7 @@ struct Sim {
     {
         if (h->error >= 1000) { if (lane == 0) oh->error = h->error; __syncwarp(); return; }
         if (h->done) { if (lane == 0) oh->error = SSB_ENV_DONE; __syncwarp(); return; }
+        SSB_T0();
         if (!h->pending) {
             int rc = 0;
             if (lane == 0) rc = take_action(stage_idx, num_exec);
@@ -1287,7 +1319,7 @@ struct Sim {
                 return;
             }
             if (lane == 0) stats->decisions++;
-            if (rc == 0) { observe_w(0.0, false); return; }
+            if (rc == 0) { SSB_TACC(5); observe_w(0.0, false); SSB_TACC(7); return; }
             // commitment round has completed (:195-199)
             const int n_active0 = h->n_active;
             for (int i = lane; i < n_active0; i += 32) p.old_act[(size_t)b * p.Jc + i] = act[i];
@@ -1306,8 +1338,10 @@ struct Sim {
             __syncwarp();
             clear_sched_w();
         }
+        SSB_TACC(5);
         bool reached = true;
         if (!h->error) reached = resume_simulation_w(max_events);
+        SSB_TRESET();
         if (!reached) {
             if (lane == 0) {
                 h->pending = 1;
@@ -1318,19 +1352,19 @@ struct Sim {
             __syncwarp();
             return;
         }
-        double reward = 0.0;
+        double reward = -compute_jobtime_w();
         bool terminated = false;
         if (lane == 0) {
             h->pending = 0;
-            reward = -compute_jobtime();
             terminated = h->n_completed == h->n_jobs;
             if (terminated) { h->done = 1; stats->episodes++; }
             else if (!h->error && !(num_committable() > 0 && h->n_sched > 0)) fail(1000 + __LINE__);
         }
-        reward = __shfl_sync(FULL, reward, 0);
         terminated = __shfl_sync(FULL, (int)terminated, 0);
         __syncwarp();
+        SSB_TACC(6);
         observe_w(reward, terminated);
+        SSB_TACC(7);
     }
 
     // ------------------------------------------------------------ reset() (:127-186)

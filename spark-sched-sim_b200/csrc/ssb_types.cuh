@@ -124,6 +124,7 @@ struct Params {
     StageRec *stage;   // [B][Sc]
     int16_t *active;   // [B][Jc]  active_job_ids
     int16_t *old_act;  // [B][Jc]
+    int16_t *reward_ord;  // [B][Jc] job ids in the reward's summation order
     Commit *commits;   // [B][Cc]
     PoolHdr *pool_hdr; // [B][P]
     uint8_t *pool_tab; // [B][P][TAB]
@@ -134,6 +135,7 @@ struct Params {
     double *tape;      // [B][tape_cap]
     LogRow *log;       // [B][log_cap]
     ssb_stats *stats;  // [B]
+    unsigned long long *prof;  // [B][16] cycle counters per phase (written only when built with -DSSB_PROFILE)
     // observation slabs
     ssb_obs_hdr *obs_hdr;
     float *obs_nodes;

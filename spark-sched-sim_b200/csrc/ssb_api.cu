@@ -46,6 +46,8 @@ k_reset(Params p, const uint64_t *seeds, const double *time_limits, const uint8_
     sim.reset_w(seed, time_limits ? time_limits[b] : INFINITY);
 }
 
+// NS: executor slots per lane of the batched fast path (1: E <= 32, 2: E <= 64), see ssb_sim.cuh
+template <int NS>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 k_step(Params p, const int32_t *stage_idx, const int32_t *num_exec, const uint8_t *mask, int max_events)
 {
@@ -55,7 +57,7 @@ k_step(Params p, const int32_t *stage_idx, const int32_t *num_exec, const uint8_
     Sim sim(p, b, lane);
     if (lane == 0) sim.oh->error = 0;
     __syncwarp();
-    sim.step_w(stage_idx[b], num_exec[b], max_events);
+    sim.template step_w<NS>(stage_idx[b], num_exec[b], max_events);
 }
 
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
@@ -70,6 +72,7 @@ k_fair_actions(Params p, int dynamic_partition, int32_t *stage_idx, int32_t *num
 }
 
 // fused policy + step: `num_decisions` decisions per environment in one launch
+template <int NS>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 k_rollout_fair(Params p, int num_decisions, int dynamic_partition, int auto_reset, uint64_t seed_step)
 {
@@ -101,7 +104,7 @@ k_rollout_fair(Params p, int num_decisions, int dynamic_partition, int auto_rese
 #ifdef SSB_PROFILE
         if (lane == 0) p.prof[(size_t)b * 16 + 8] += (unsigned long long)(clock64() - tp0);
 #endif
-        sim.step_w(a, n);
+        sim.template step_w<NS>(a, n);
         d++;
     }
 #ifdef SSB_PROFILE
@@ -464,8 +467,12 @@ int ssb_step(ssb_env *env, const int32_t *stage_idx, const int32_t *num_exec, co
              int32_t max_events, void *stream)
 {
     if (!env || !stage_idx || !num_exec) return SSB_E_INVALID;
-    k_step<<<env->grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(env->p, stage_idx, num_exec, mask,
-                                                                       max_events);
+    if (env->p.E <= 32)
+        k_step<1><<<env->grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(env->p, stage_idx, num_exec, mask,
+                                                                              max_events);
+    else
+        k_step<2><<<env->grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(env->p, stage_idx, num_exec, mask,
+                                                                              max_events);
     CUDA_TRY(cudaGetLastError());
     return SSB_OK;
 }
@@ -509,8 +516,12 @@ int ssb_rollout_fair(ssb_env *env, int32_t num_decisions, int32_t dynamic_partit
                      uint64_t seed_step, void *stream)
 {
     if (!env || num_decisions < 0) return SSB_E_INVALID;
-    k_rollout_fair<<<env->grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(
-        env->p, num_decisions, dynamic_partition, auto_reset, seed_step);
+    if (env->p.E <= 32)
+        k_rollout_fair<1><<<env->grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(
+            env->p, num_decisions, dynamic_partition, auto_reset, seed_step);
+    else
+        k_rollout_fair<2><<<env->grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(
+            env->p, num_decisions, dynamic_partition, auto_reset, seed_step);
     CUDA_TRY(cudaGetLastError());
     return SSB_OK;
 }

@@ -865,13 +865,14 @@ struct Sim {
         bool quiet;  // no committable executors at the current (possibly stale) source
     };
     // (must inline: a non-inlined callee taking L/H by reference would pin them in local memory)
-    __device__ __forceinline__ void hot_load(HotLane &L, HotEnv &H)
+    // slot of executor e (e >= E: an empty slot whose pseudo node id is unique)
+    __device__ __forceinline__ void hot_load_slot(HotLane &L, int e)
     {
         L.kt = 0x7ff8000000000000ull; L.ks = 0xffffffffu; L.kind = 0; L.j = 0; L.s = 0;
-        L.node = -1 - lane; L.task = -1; L.t_acc = 0.0; L.rem = L.comp = L.mc = 0;
+        L.node = -1 - e; L.task = -1; L.t_acc = 0.0; L.rem = L.comp = L.mc = 0;
         L.oc_a = L.oc_b = make_uint2(0u, 0u); L.thr = L.range = 0; L.fast_ok = false;
-        if (lane < p.E) {
-            const ExecRec &x = ex[lane];
+        if (e < p.E) {
+            const ExecRec &x = ex[e];
             L.kind = x.ev_kind;
             if (L.kind) {
                 L.kt = (unsigned long long)__double_as_longlong(x.ev_t);
@@ -900,12 +901,20 @@ struct Sim {
                 }
             }
         }
+    }
+    __device__ __forceinline__ void hot_load_env(HotEnv &H)
+    {
         H.t_arr = 0x7ff0000000000000ull;
         int na = h->next_arrival;
         if (na < h->n_jobs) H.t_arr = (unsigned long long)__double_as_longlong(jb[na].t_arrival);
         H.wall = h->wall_time; H.log_n = h->log_n; H.launch_idx = h->launch_idx; H.seq = h->seq;
         H.events = 0;
         H.quiet = num_committable() == 0;
+    }
+    __device__ __forceinline__ void hot_load(HotLane &L, HotEnv &H)
+    {
+        hot_load_slot(L, lane);
+        hot_load_env(H);
     }
     __device__ __forceinline__ void hot_flush(const HotEnv &H)
     {
@@ -926,12 +935,12 @@ struct Sim {
         }
         return less;
     }
-    __device__ SSB_RARE void log_batch_row(long long row, double t, double t_acc, int task, int j, int s)
+    __device__ SSB_RARE void log_batch_row(long long row, double t, double t_acc, int task, int j, int s, int e)
     {
         if (row >= p.log_cap) return;
         LogRow r;
         r.t = t; r.t_acc = t_acc; r.task = task; r.job = (int16_t)j; r.stage = (int16_t)s;
-        r.exec = (int16_t)lane; r.type = (uint8_t)EV_TASK_FINISHED; r.pad = 0; r.pad1 = 0;
+        r.exec = (int16_t)e; r.type = (uint8_t)EV_TASK_FINISHED; r.pad = 0; r.pad1 = 0;
         p.log[(size_t)b * p.log_cap + row] = r;
     }
     __device__ __forceinline__ int fast_batch_w(HotLane &L, HotEnv &H, int budget)
@@ -993,7 +1002,7 @@ struct Sim {
         if (m == 0) return 0;
         const int cnt = __popc(same_node & mem_mask);  // launches of my stage in this batch
         if (member) {
-            if (p.log_cap > 0) log_batch_row(H.log_n + rank, t, L.t_acc, L.task, L.j, L.s);
+            if (p.log_cap > 0) log_batch_row(H.log_n + rank, t, L.t_acc, L.task, L.j, L.s, lane);
             L.kt = nt; L.t_acc = t; L.ks = H.seq + (uint32_t)rank; L.task = rem - 1;
             ExecRec &x = ex[lane];
             x.ev_t = __longlong_as_double((long long)nt); x.t_acc = t; x.ev_seq = L.ks; x.ev_task = L.task;
@@ -1014,15 +1023,189 @@ struct Sim {
         return m;
     }
 
+
+    // ------------------------------------------------------------ batched fast path, 32 < E <= 64
+    // Same algorithm with two executors per lane: slot A = executor `lane`, slot B = executor
+    // `lane + 32`.  Order masks come in four flavours xy = "lanes whose slot-y event precedes my slot-x
+    // event".  The stage of a slot does not change during a fast phase, so the same-stage masks are
+    // built once per phase.
+    struct Same2 { unsigned aa, ab, ba, bb; };
+    __device__ __forceinline__ void same_nodes2_w(const HotLane &A, const HotLane &Bq, Same2 &S)
+    {
+        S.aa = S.ab = S.ba = S.bb = 0;
+#pragma unroll 1
+        for (int i = 0; i < 32; i++) {
+            const int na = __shfl_sync(FULL, A.node, i), nb = __shfl_sync(FULL, Bq.node, i);
+            const unsigned bit = 1u << i;
+            S.aa |= na == A.node ? bit : 0u;  S.ab |= nb == A.node ? bit : 0u;
+            S.ba |= na == Bq.node ? bit : 0u; S.bb |= nb == Bq.node ? bit : 0u;
+        }
+    }
+    // exact (t, seq) order masks, used when two pending events agree in the upper timestamp word
+    __device__ SSB_RARE void exact_less2_w(unsigned long long kta, uint32_t ksa, unsigned long long ktb,
+                                            uint32_t ksb, unsigned *out)
+    {
+        unsigned aa = 0, ab = 0, ba = 0, bb = 0;
+        for (int i = 0; i < 32; i++) {
+            const unsigned long long ota = __shfl_sync(FULL, kta, i), otb = __shfl_sync(FULL, ktb, i);
+            const uint32_t osa = __shfl_sync(FULL, ksa, i), osb = __shfl_sync(FULL, ksb, i);
+            const unsigned bit = 1u << i;
+            aa |= (ota < kta || (ota == kta && osa < ksa)) ? bit : 0u;
+            ab |= (otb < kta || (otb == kta && osb < ksa)) ? bit : 0u;
+            ba |= (ota < ktb || (ota == ktb && osa < ksb)) ? bit : 0u;
+            bb |= (otb < ktb || (otb == ktb && osb < ksb)) ? bit : 0u;
+        }
+        out[0] = aa; out[1] = ab; out[2] = ba; out[3] = bb;
+    }
+    __device__ __forceinline__ int fast_batch2_w(HotLane &A, HotLane &Bq, const Same2 &S, HotEnv &H, int budget)
+    {
+        const unsigned long long INF_BITS = 0x7ff0000000000000ull;
+        if (!H.quiet) return 0;
+        const bool pa = A.kind != 0, pb = Bq.kind != 0;
+        const unsigned penda = __ballot_sync(FULL, pa), pendb = __ballot_sync(FULL, pb);
+        if (!(penda | pendb)) return 0;
+        const uint32_t hia = (uint32_t)(A.kt >> 32), hib = (uint32_t)(Bq.kt >> 32);
+        unsigned aa = 0, ab = 0, ba = 0, bb = 0;
+#pragma unroll 1
+        for (int i = 0; i < 32; i++) {
+            const uint32_t oa = __shfl_sync(FULL, hia, i), ob = __shfl_sync(FULL, hib, i);
+            const unsigned bit = 1u << i;
+            aa |= oa < hia ? bit : 0u; ab |= ob < hia ? bit : 0u;
+            ba |= oa < hib ? bit : 0u; bb |= ob < hib ? bit : 0u;
+        }
+        aa &= penda; ab &= pendb; ba &= penda; bb &= pendb;
+        int ranka = __popc(aa) + __popc(ab), rankb = __popc(ba) + __popc(bb);
+        {
+            // events that agree in the upper word get equal ranks, so the ranks of the pending events
+            // are a permutation of 0..n-1 exactly when the upper words decided every comparison
+            const int n = __popc(penda) + __popc(pendb);
+            const unsigned long long mine = (pa ? 1ull << ranka : 0ull) | (pb ? 1ull << rankb : 0ull);
+            const unsigned long long seen = (unsigned long long)__reduce_or_sync(FULL, (uint32_t)mine) |
+                                            ((unsigned long long)__reduce_or_sync(FULL, (uint32_t)(mine >> 32)) << 32);
+            if (seen != (n >= 64 ? ~0ull : (1ull << n) - 1ull)) {
+                unsigned ex4[4];
+                exact_less2_w(A.kt, A.ks, Bq.kt, Bq.ks, ex4);
+                aa = ex4[0] & penda; ab = ex4[1] & pendb; ba = ex4[2] & penda; bb = ex4[3] & pendb;
+                ranka = __popc(aa) + __popc(ab); rankb = __popc(ba) + __popc(bb);
+            }
+        }
+        const int bsa = __popc(aa & S.aa) + __popc(ab & S.ab), bsb = __popc(ba & S.ba) + __popc(bb & S.bb);
+        const int rema = A.rem - bsa, remb = Bq.rem - bsb;
+        bool ea = pa && A.fast_ok && A.kt < H.t_arr && ranka < budget && rema > 1 &&
+                  ((rema <= A.mc) == (rema - 1 <= A.mc));
+        bool eb = pb && Bq.fast_ok && Bq.kt < H.t_arr && rankb < budget && remb > 1 &&
+                  ((remb <= Bq.mc) == (remb - 1 <= Bq.mc));
+        const double ta = __longlong_as_double((long long)A.kt), tb = __longlong_as_double((long long)Bq.kt);
+        double da = 0.0, db = 0.0;
+        // durations of the two slots, one after the other through the same (rolled) code
+#pragma unroll 1
+        for (int k = 0; k < 2; k++) {
+            bool el = k ? eb : ea;
+            double d = 0.0;
+            if (el) {
+                const uint32_t li = H.launch_idx + (uint32_t)(k ? rankb : ranka);
+                if (h->use_tape) {
+                    if ((int)li < h->tape_len) d = p.tape[(size_t)b * p.tape_cap + li];
+                    else el = false;  // the general path reports the exhausted tape
+                } else {
+                    const uint4 w = philox4x32_10(li, 0u, 2u, 0u, (uint32_t)h->seed, (uint32_t)(h->seed >> 32));
+                    uint2 oc = k ? Bq.oc_a : A.oc_a;
+                    const int range = k ? Bq.range : A.range;
+                    if (range) {
+                        double u = __dmul_rn((double)w.x, 1.0 / 4294967296.0);
+                        int rand_pt = 1 + (int)__dmul_rn(u, (double)range);
+                        if (rand_pt > (k ? Bq.thr : A.thr)) oc = k ? Bq.oc_b : A.oc_b;
+                    }
+                    d = p.b_vals[oc.x + bounded(w.y, oc.y)];
+                }
+            }
+            if (k) { eb = el; db = d; } else { ea = el; da = d; }
+        }
+        const unsigned long long nta = ea ? (unsigned long long)__double_as_longlong(__dadd_rn(ta, da)) : INF_BITS;
+        const unsigned long long ntb = eb ? (unsigned long long)__double_as_longlong(__dadd_rn(tb, db)) : INF_BITS;
+        const unsigned long long ntm = nta < ntb ? nta : ntb;
+        const uint32_t ghi = __reduce_min_sync(FULL, (uint32_t)(ntm >> 32));
+        const uint32_t glo = __reduce_min_sync(FULL, (uint32_t)(ntm >> 32) == ghi ? (uint32_t)ntm : 0xffffffffu);
+        const unsigned long long G = ((unsigned long long)ghi << 32) | glo;
+        const unsigned bada = __ballot_sync(FULL, pa && (!ea || A.kt > G));
+        const unsigned badb = __ballot_sync(FULL, pb && (!eb || Bq.kt > G));
+        const bool ma = pa && !((bada >> lane) & 1) && !(aa & bada) && !(ab & badb);
+        const bool mb = pb && !((badb >> lane) & 1) && !(ba & bada) && !(bb & badb);
+        const unsigned mema = __ballot_sync(FULL, ma), memb = __ballot_sync(FULL, mb);
+        const int m = __popc(mema) + __popc(memb);
+        if (m == 0) return 0;
+        const int cnta = __popc(S.aa & mema) + __popc(S.ab & memb);
+        const int cntb = __popc(S.ba & mema) + __popc(S.bb & memb);
+        if (ma) {
+            if (p.log_cap > 0) log_batch_row(H.log_n + ranka, ta, A.t_acc, A.task, A.j, A.s, lane);
+            A.kt = nta; A.t_acc = ta; A.ks = H.seq + (uint32_t)ranka; A.task = rema - 1;
+            ExecRec &x = ex[lane];
+            x.ev_t = __longlong_as_double((long long)nta); x.t_acc = ta; x.ev_seq = A.ks; x.ev_task = A.task;
+            if (bsa == cnta - 1) {  // last launch of this stage in the batch: it owns the counters
+                StageRec &r = st[A.node];
+                r.remaining = (uint16_t)(A.rem - cnta);
+                r.completed = (uint16_t)(A.comp + cnta);
+                r.mrd = (float)da;
+            }
+        }
+        if (mb) {
+            if (p.log_cap > 0) log_batch_row(H.log_n + rankb, tb, Bq.t_acc, Bq.task, Bq.j, Bq.s, lane + 32);
+            Bq.kt = ntb; Bq.t_acc = tb; Bq.ks = H.seq + (uint32_t)rankb; Bq.task = remb - 1;
+            ExecRec &x = ex[lane + 32];
+            x.ev_t = __longlong_as_double((long long)ntb); x.t_acc = tb; x.ev_seq = Bq.ks; x.ev_task = Bq.task;
+            if (bsb == cntb - 1) {
+                StageRec &r = st[Bq.node];
+                r.remaining = (uint16_t)(Bq.rem - cntb);
+                r.completed = (uint16_t)(Bq.comp + cntb);
+                r.mrd = (float)db;
+            }
+        }
+        A.rem -= cnta; A.comp += cnta; Bq.rem -= cntb; Bq.comp += cntb;
+        // wall time = time of the last member (non-negative doubles order like their bit patterns)
+        const unsigned long long tma = ma ? (unsigned long long)__double_as_longlong(ta) : 0ull;
+        const unsigned long long tmb = mb ? (unsigned long long)__double_as_longlong(tb) : 0ull;
+        const unsigned long long tmx = tma > tmb ? tma : tmb;
+        const uint32_t whi = __reduce_max_sync(FULL, (uint32_t)(tmx >> 32));
+        const uint32_t wlo = __reduce_max_sync(FULL, (uint32_t)(tmx >> 32) == whi ? (uint32_t)tmx : 0u);
+        H.wall = __longlong_as_double((long long)(((unsigned long long)whi << 32) | wlo));
+        H.launch_idx += (uint32_t)m; H.seq += (uint32_t)m; H.log_n += m; H.events += m;
+        return m;
+    }
+    // one fast phase with two slots per lane; returns the number of events it handled
+    __device__ __forceinline__ int fast_phase2_w(int budget)
+    {
+        HotEnv H;
+        hot_load_env(H);
+        if (!H.quiet) return 0;
+        HotLane A, Bq;
+        Same2 S;
+        hot_load_slot(A, lane);
+        hot_load_slot(Bq, lane + 32);
+        same_nodes2_w(A, Bq, S);
+        int used = 0;
+        for (;;) {
+            const int m = fast_batch2_w(A, Bq, S, H, budget - used);
+            used += m;
+            if (m == 0 || used == budget) break;
+        }
+        hot_flush(H);
+        return used;
+    }
+
     // ------------------------------------------------------------ _resume_simulation (:320-343)
     // Returns false when `max_events` (> 0) events were processed without reaching the next
     // scheduling decision: the environment is then "pending" and a later call continues here.
+    // NS = executor slots per lane of the batched fast path: 1 serves E <= 32, 2 serves E <= 64
+    // (separate kernel instantiations, so that the one-slot kernels keep their register budget).
+    template <int NS>
     __device__ bool resume_simulation_w(int max_events)
     {
         int budget = max_events > 0 ? max_events : 0x7fffffff;
-        const bool use_fast = p.E <= 32;
+        const bool use_fast = NS == 1 ? p.E <= 32 : p.E <= 64;
         for (;;) {
-            if (use_fast && budget > 0) {
+            if constexpr (NS == 2) {
+                if (use_fast && budget > 0) budget -= fast_phase2_w(budget);
+            } else if (use_fast && budget > 0) {
                 // registers only: L and H die before the general path below is entered
                 HotLane L;
                 HotEnv H;
@@ -1303,6 +1486,7 @@ struct Sim {
     // max_events > 0 bounds the simulation work of this call: an environment that has not reached
     // its next decision yet is left "pending" (ssb_obs_hdr.pending = 1) and the next step_w() call on it
     // ignores its action arguments and simply continues.  max_events <= 0: reference semantics.
+    template <int NS = 1>
     __device__ void step_w(int stage_idx, int num_exec, int max_events = 0)
     {
         if (h->error >= 1000) { if (lane == 0) oh->error = h->error; __syncwarp(); return; }
@@ -1340,7 +1524,7 @@ struct Sim {
         }
         SSB_TACC(5);
         bool reached = true;
-        if (!h->error) reached = resume_simulation_w(max_events);
+        if (!h->error) reached = resume_simulation_w<NS>(max_events);
         SSB_TRESET();
         if (!reached) {
             if (lane == 0) {

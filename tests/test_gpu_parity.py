@@ -112,14 +112,18 @@ def test_cuda_invalid_actions(bank):
     assert rc == 0
 
 
-@pytest.mark.parametrize("E,J,policy", [(10, 50, "fair"), (10, 20, "fifo"), (50, 30, "fair"), (3, 10, "fair")])
+@pytest.mark.parametrize("E,J,policy", [(10, 50, "fair"), (10, 20, "fifo"), (50, 30, "fair"), (3, 10, "fair"),
+                                        # 32 < E <= 64: two executor slots per lane in the batched fast path
+                                        (33, 20, "fair"), (64, 40, "fifo"), (50, 200, "fair"),
+                                        # E > 64: general path only
+                                        (100, 30, "fair")])
 def test_fused_rollout_matches_oracle(bank, E, J, policy):
     """Fused on-device policy+step episodes vs the CPU oracle from the same seeds: every job's
     arrival/completion time, the final wall time, and the decision/event counts."""
     from oracle import OracleEnv
     from spark_sched_sim_b200.batched_env import BatchedSparkSchedSimEnv
 
-    B = 16
+    B = 16 if J < 200 else 6  # (50, 200) = BASELINE config 4's episode shape
     cfg = {"num_executors": E, "job_arrival_cap": J, "job_arrival_rate": 4.0e-5,
            "moving_delay": 2000.0, "warmup_delay": 1000.0}
     env = BatchedSparkSchedSimEnv(cfg, num_envs=B, bank=bank)

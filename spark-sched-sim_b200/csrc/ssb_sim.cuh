@@ -1486,56 +1486,48 @@ struct Sim {
     // max_events > 0 bounds the simulation work of this call: an environment that has not reached
     // its next decision yet is left "pending" (ssb_obs_hdr.pending = 1) and the next step_w() call on it
     // ignores its action arguments and simply continues.  max_events <= 0: reference semantics.
-    template <int NS = 1>
-    __device__ void step_w(int stage_idx, int num_exec, int max_events = 0)
+    // The pieces of step() before and after the simulation advances; step_w() strings them together.
+    // step_begin_w: _take_action and, when the commitment round is over, its bookkeeping (:190-199).
+    // Returns 0 when the step is already complete (same-round observation written, or the action was
+    // rejected), 1 when the simulation has to advance.
+    __device__ __forceinline__ int step_begin_w(int stage_idx, int num_exec)
     {
-        if (h->error >= 1000) { if (lane == 0) oh->error = h->error; __syncwarp(); return; }
-        if (h->done) { if (lane == 0) oh->error = SSB_ENV_DONE; __syncwarp(); return; }
         SSB_T0();
-        if (!h->pending) {
-            int rc = 0;
-            if (lane == 0) rc = take_action(stage_idx, num_exec);
-            rc = __shfl_sync(FULL, rc, 0);
+        int rc = 0;
+        if (lane == 0) rc = take_action(stage_idx, num_exec);
+        rc = __shfl_sync(FULL, rc, 0);
+        __syncwarp();
+        if (rc < 0) {  // ValueError / KeyError: state untouched, report and let the caller retry
+            if (lane == 0) oh->error = -rc;
             __syncwarp();
-            if (rc < 0) {  // ValueError / KeyError: state untouched, report and let the caller retry
-                if (lane == 0) oh->error = -rc;
-                __syncwarp();
-                return;
-            }
-            if (lane == 0) stats->decisions++;
-            if (rc == 0) { SSB_TACC(5); observe_w(0.0, false); SSB_TACC(7); return; }
-            // commitment round has completed (:195-199)
-            const int n_active0 = h->n_active;
-            for (int i = lane; i < n_active0; i += 32) p.old_act[(size_t)b * p.Jc + i] = act[i];
-            __syncwarp();
-            if (lane == 0) {
-                commit_remaining_executors();
-                fulfill_commitments_from_source();
-                h->source = POOL_NONE;
-                h->wall_old = h->wall_time;
-                h->n_old_active = n_active0;
-            }
-            __syncwarp();
-            // selected_stages.clear() comes AFTER the fulfilment: backup scheduling during it must
-            // still see this round's selections (:197-199, :825-839)
-            for (int i = lane; i < n_active0; i += 32) jb[act[i]].selected = 0;
-            __syncwarp();
-            clear_sched_w();
+            return 0;
         }
+        if (lane == 0) stats->decisions++;
+        if (rc == 0) { SSB_TACC(5); observe_w(0.0, false); SSB_TACC(7); return 0; }
+        // commitment round has completed (:195-199)
+        const int n_active0 = h->n_active;
+        for (int i = lane; i < n_active0; i += 32) p.old_act[(size_t)b * p.Jc + i] = act[i];
+        __syncwarp();
+        if (lane == 0) {
+            commit_remaining_executors();
+            fulfill_commitments_from_source();
+            h->source = POOL_NONE;
+            h->wall_old = h->wall_time;
+            h->n_old_active = n_active0;
+        }
+        __syncwarp();
+        // selected_stages.clear() comes AFTER the fulfilment: backup scheduling during it must
+        // still see this round's selections (:197-199, :825-839)
+        for (int i = lane; i < n_active0; i += 32) jb[act[i]].selected = 0;
+        __syncwarp();
+        clear_sched_w();
         SSB_TACC(5);
-        bool reached = true;
-        if (!h->error) reached = resume_simulation_w<NS>(max_events);
-        SSB_TRESET();
-        if (!reached) {
-            if (lane == 0) {
-                h->pending = 1;
-                oh->pending = 1;
-                oh->reward = 0.0;
-                oh->wall_time = h->wall_time;
-            }
-            __syncwarp();
-            return;
-        }
+        return 1;
+    }
+    // step_end_w: reward, termination flag and the next observation (:201-221)
+    __device__ __forceinline__ void step_end_w()
+    {
+        SSB_T0();
         double reward = -compute_jobtime_w();
         bool terminated = false;
         if (lane == 0) {
@@ -1549,6 +1541,28 @@ struct Sim {
         SSB_TACC(6);
         observe_w(reward, terminated);
         SSB_TACC(7);
+    }
+    template <int NS = 1>
+    __device__ void step_w(int stage_idx, int num_exec, int max_events = 0)
+    {
+        if (h->error >= 1000) { if (lane == 0) oh->error = h->error; __syncwarp(); return; }
+        if (h->done) { if (lane == 0) oh->error = SSB_ENV_DONE; __syncwarp(); return; }
+        if (!h->pending) {
+            if (step_begin_w(stage_idx, num_exec) == 0) return;
+        }
+        bool reached = true;
+        if (!h->error) reached = resume_simulation_w<NS>(max_events);
+        if (!reached) {
+            if (lane == 0) {
+                h->pending = 1;
+                oh->pending = 1;
+                oh->reward = 0.0;
+                oh->wall_time = h->wall_time;
+            }
+            __syncwarp();
+            return;
+        }
+        step_end_w();
     }
 
     // ------------------------------------------------------------ reset() (:127-186)

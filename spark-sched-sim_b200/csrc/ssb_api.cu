@@ -5,13 +5,16 @@
 // latency-bound chains per environment, so residency (warps per SM) is what hides the latency.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <new>
 #include <vector>
 
 #include "ssb_decima.cuh"
+#include "ssb_decima_tc.cuh"
 #include "ssb_sim.cuh"
 
 using namespace ssb;
@@ -278,6 +281,19 @@ void carve(Carver &cv, const ssb_config &c, const ssb_bank &bk, const Dims &d, P
         p.pol_exec_logits = cv.take<float>(B * p.Epad);
         p.pol_action = cv.take<int32_t>(B * 4);
         p.pol_lgprob = cv.take<float>(B);
+        p.pl_all = cv.take<int32_t>(B * d.Sc);
+        p.pl_sink = cv.take<int32_t>(B * d.Sc);
+        p.pl_cand = cv.take<int32_t>(B * d.Sc);
+        p.pl_cand_job = cv.take<int32_t>(B * d.Sc);
+        p.pl_cand_out = cv.take<int32_t>(B * d.Sc);
+        p.pl_jobs = cv.take<int32_t>(B * c.max_jobs);
+        p.pl_exec = cv.take<int32_t>(B * p.Epad);
+        // every masked edge contributes at most one sender and one receiver entry per level it is masked at
+        p.lvl_cap = (int)std::min<size_t>(4 * B * d.Mc, (size_t)0x7fffffff);
+        p.pl_lvl = cv.take<int32_t>((size_t)p.lvl_cap);
+        p.pl_cnt = cv.take<int32_t>(tc::CNT_TOTAL);
+        p.pl_ncand = cv.take<int32_t>(B);
+        p.pl_bits = cv.take<unsigned long long>(B * d.Sc * 2);
     }
     *st_a = cv.take<int32_t>(B);
     *st_n = cv.take<int32_t>(B);
@@ -302,7 +318,27 @@ struct ssb_env {
     double *st_tl;
     uint8_t *st_mask;
     int grid;
+    int num_sms;
+    int dmax;           // upper bound of the message-passing depth: longest template chain - 1
+    int decima_legacy;  // SSB_DECIMA_LEGACY=1: the fp32 CUDA-core policy kernel (A/B runs)
 };
+
+template <int ST>
+int launch_tile(ssb_env *env, const int32_t *list, const int32_t *offset, const int32_t *count, int level,
+                int ctas_per_sm, cudaStream_t s)
+{
+    tc::TileArgs a{list, offset, count, level};
+    tc::k_tile_mlp<ST><<<env->num_sms * ctas_per_sm, 128, tc::Smem<ST>::BYTES, s>>>(env->p, a);
+    CUDA_TRY(cudaGetLastError());
+    return SSB_OK;
+}
+template <int ST>
+int prepare_tile_kernel()
+{
+    CUDA_TRY(cudaFuncSetAttribute(tc::k_tile_mlp<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)tc::Smem<ST>::BYTES));
+    return SSB_OK;
+}
 
 extern "C" {
 
@@ -355,6 +391,37 @@ int ssb_create(const ssb_config *cfg, const ssb_bank *bk, int device, void *work
     p.mean_interarrival = 1 / cfg->job_arrival_rate;  // tpch.py:42
     p.beta = cfg->beta;
     env->grid = (cfg->num_envs + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    CUDA_TRY(cudaDeviceGetAttribute(&env->num_sms, cudaDevAttrMultiProcessorCount, device));
+    {
+        // longest chain of topological generations over the templates bounds the depth of every observation
+        int dmax = 0;
+        for (int t = 0; t < bk->num_templates; t++) {
+            const int ns = bk->num_stages[t], base = bk->stage_base[t];
+            const uint64_t all = ns >= 64 ? ~0ull : ((1ull << ns) - 1);
+            uint64_t done = 0;
+            int gens = 0;
+            while (done != all && gens < 64) {
+                uint64_t lk = 0;
+                for (int s = 0; s < ns; s++)
+                    if (!((done >> s) & 1) && (bk->parent_mask[base + s] & ~done) == 0) lk |= 1ull << s;
+                if (!lk) break;
+                done |= lk;
+                gens++;
+            }
+            dmax = gens - 1 > dmax ? gens - 1 : dmax;
+        }
+        env->dmax = dmax;
+        const char *lg = getenv("SSB_DECIMA_LEGACY");
+        env->decima_legacy = lg && lg[0] == '1';
+    }
+    if (p.pol_w) {
+        int rc;
+        if ((rc = prepare_tile_kernel<tc::ST_PREP>()) || (rc = prepare_tile_kernel<tc::ST_SINK>()) ||
+            (rc = prepare_tile_kernel<tc::ST_MSG>()) || (rc = prepare_tile_kernel<tc::ST_RCV>()) ||
+            (rc = prepare_tile_kernel<tc::ST_DAG>()) || (rc = prepare_tile_kernel<tc::ST_GLOB>()) ||
+            (rc = prepare_tile_kernel<tc::ST_STAGE>()) || (rc = prepare_tile_kernel<tc::ST_EXEC>()))
+            return rc;
+    }
     // ---- bank upload
     const size_t T = bk->num_templates, TS = bk->num_template_stages, ME = bk->num_template_edges;
     BankDev &bd = env->bank;
@@ -603,8 +670,40 @@ int ssb_decima_policy(ssb_env *env, const int32_t *forced_stage, const int32_t *
                       int32_t *stage_idx_out, int32_t *num_exec_out, void *stream)
 {
     if (!env || !env->p.pol_w) return SSB_E_INVALID;  // needs SSB_FLAG_DECIMA_POLICY
-    k_decima_policy<<<env->grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(
-        env->p, forced_stage, forced_num_exec, stage_idx_out, num_exec_out);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (env->decima_legacy) {
+        k_decima_policy<<<env->grid, WARPS_PER_CTA * 32, 0, s>>>(env->p, forced_stage, forced_num_exec,
+                                                                 stage_idx_out, num_exec_out);
+        CUDA_TRY(cudaGetLastError());
+        return SSB_OK;
+    }
+    // observation adapter -> row lists -> one tensor-core tile pass per MLP (ssb_decima_tc.cuh)
+    const Params &p = env->p;
+    const int32_t *cnt = p.pl_cnt;
+    const int warp_grid = (p.B + 3) / 4;
+    int rc;
+    CUDA_TRY(cudaMemsetAsync(p.pl_cnt, 0, sizeof(int32_t) * tc::CNT_TOTAL, s));
+    k_decima_obs<<<env->grid, WARPS_PER_CTA * 32, 0, s>>>(p);
+    tc::k_pol_plan_a<<<warp_grid, 128, 0, s>>>(p);
+    tc::k_pol_plan_scan<<<1, 32, 0, s>>>(p);
+    tc::k_pol_plan_b<<<warp_grid, 128, 0, s>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    if ((rc = launch_tile<tc::ST_PREP>(env, p.pl_all, nullptr, cnt + tc::CNT_ALL, 0, 4, s))) return rc;
+    if ((rc = launch_tile<tc::ST_SINK>(env, p.pl_sink, nullptr, cnt + tc::CNT_SINK, 0, 4, s))) return rc;
+    for (int k = env->dmax - 1; k >= 0; k--) {  // reversed(edge_masks) (scheduler.py:214-232)
+        if ((rc = launch_tile<tc::ST_MSG>(env, p.pl_lvl, cnt + tc::OFF_LVL + 2 * k, cnt + tc::CNT_LVL + 2 * k, k, 4, s)))
+            return rc;
+        if ((rc = launch_tile<tc::ST_RCV>(env, p.pl_lvl, cnt + tc::OFF_LVL + 2 * k + 1, cnt + tc::CNT_LVL + 2 * k + 1,
+                                          k, 4, s)))
+            return rc;
+    }
+    if ((rc = launch_tile<tc::ST_DAG>(env, p.pl_all, nullptr, cnt + tc::CNT_ALL, 0, 4, s))) return rc;
+    if ((rc = launch_tile<tc::ST_GLOB>(env, p.pl_jobs, nullptr, cnt + tc::CNT_JOBS, 0, 4, s))) return rc;
+    tc::k_pol_glob_sum<<<(p.B + 7) / 8, 128, 0, s>>>(p);
+    if ((rc = launch_tile<tc::ST_STAGE>(env, nullptr, nullptr, cnt + tc::CNT_CAND, 0, 1, s))) return rc;
+    tc::k_pol_sample_stage<<<warp_grid, 128, 0, s>>>(p, forced_stage);
+    if ((rc = launch_tile<tc::ST_EXEC>(env, p.pl_exec, nullptr, cnt + tc::CNT_EXEC, 0, 1, s))) return rc;
+    tc::k_pol_sample_exec<<<warp_grid, 128, 0, s>>>(p, forced_num_exec, stage_idx_out, num_exec_out);
     CUDA_TRY(cudaGetLastError());
     return SSB_OK;
 }

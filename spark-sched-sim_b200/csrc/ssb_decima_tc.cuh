@@ -1,0 +1,648 @@
+// ssb_decima_tc.cuh -- Decima policy forward pass batched ACROSS environments on the 5th-generation
+// tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM).
+//
+// DecimaScheduler.schedule (schedulers/decima/scheduler.py:71-99) evaluates seven small 3-layer MLPs
+// (SURVEY.md App. E).  One environment offers ~16 rows per message-passing level -- far too few for a
+// 128-row UMMA tile -- so the work is organised by MLP instead of by environment: a planning pass
+// turns every environment's observation into flat ROW LISTS (all nodes, sinks, the senders and
+// receivers of every level, jobs, schedulable stages, executor counts), and one generic tile kernel
+// runs "gather 128 rows -> Linear/act/Linear/act/Linear on the tensor cores -> scatter" over a list.
+// The level loop of NodeEncoder (:214-232) stays the literal sequence (deepest level first, parents
+// OVERWRITE their embedding) -- it is a sequence of launches over all environments at once.
+//
+// fp32 accuracy on tf32 tensor cores: every operand is split x = hi + lo (both rounded to tf32) and
+// a product is accumulated as hi*hi + lo*hi + hi*lo (3 MMAs per k-step, fp32 accumulation in TMEM);
+// the dropped lo*lo term is < 2^-22 relative.  Scores agree with the reference's torch fp32 forward
+// within the same 5e-5 the fp32 CUDA-core kernel was held to (tests/test_gpu_decima_policy.py).
+//
+// Tile kernel (128 threads, thread r <-> tile row r <-> TMEM lane r):
+//   A tile  [128 x K]  and the weights W [N x K] sit in shared memory in the canonical K-major,
+//           no-swizzle UMMA layout: 8-row x 16-byte core matrices, LBO = 128 B between the two
+//           16-byte K chunks of one MMA, SBO = (K/4) * 128 B between 8-row groups;
+//   D       [128 x N] fp32 in TMEM columns [0, N); read back with tcgen05.ld.32x32b (one row per
+//           thread), bias + activation applied in registers, and written as the next layer's A tile.
+#pragma once
+#include "ssb_decima.cuh"
+
+namespace ssb {
+namespace tc {
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address, leading / stride byte
+// offsets (all >> 4), version 1 (Blackwell), no swizzle, base offset 0
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) |
+           ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = f32, A = B = tf32, both K-major, dense
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N)
+{
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t mbar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(ok)
+            : "r"(mbar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_saddr, uint32_t ncols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_saddr), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// 16 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v)
+{
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+        "[%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float to_tf32(float x)
+{
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+// ------------------------------------------------------------------ row lists and counters
+// p.pl_cnt layout (int32): list lengths, then per level k: senders at [CNT_LVL + 2k], receivers at
+// [CNT_LVL + 2k + 1]; OFF_LVL: exclusive offsets of those 128 lists into p.pl_lvl; CUR_LVL: fill cursors.
+constexpr int CNT_ALL = 0, CNT_SINK = 1, CNT_CAND = 2, CNT_JOBS = 3, CNT_EXEC = 4, CNT_OVERFLOW = 5;
+constexpr int MAX_LEVELS = 64;
+constexpr int CNT_LVL = 8, OFF_LVL = CNT_LVL + 2 * MAX_LEVELS, CUR_LVL = OFF_LVL + 2 * MAX_LEVELS + 1;
+constexpr int CNT_TOTAL = CUR_LVL + 2 * MAX_LEVELS;
+
+enum Stage { ST_PREP, ST_SINK, ST_MSG, ST_RCV, ST_DAG, ST_GLOB, ST_STAGE, ST_EXEC };
+
+template <int ST> struct Spec;
+//                                      padded K0, real K0, H1, H2, OUT, tanh, offset of the MLP in dd layout
+template <> struct Spec<ST_PREP>  { static constexpr int K0 = 8,  IN = 5,  H1 = 32, H2 = 16, OUT = 16, W = dd::PREP;  static constexpr bool TANH = false; };
+template <> struct Spec<ST_SINK>  { static constexpr int K0 = 16, IN = 16, H1 = 32, H2 = 16, OUT = 16, W = dd::UPD;   static constexpr bool TANH = false; };
+template <> struct Spec<ST_MSG>   { static constexpr int K0 = 16, IN = 16, H1 = 32, H2 = 16, OUT = 16, W = dd::MSG;   static constexpr bool TANH = false; };
+template <> struct Spec<ST_RCV>   { static constexpr int K0 = 16, IN = 16, H1 = 32, H2 = 16, OUT = 16, W = dd::UPD;   static constexpr bool TANH = false; };
+template <> struct Spec<ST_DAG>   { static constexpr int K0 = 24, IN = 21, H1 = 32, H2 = 16, OUT = 16, W = dd::DAG;   static constexpr bool TANH = false; };
+template <> struct Spec<ST_GLOB>  { static constexpr int K0 = 16, IN = 16, H1 = 32, H2 = 16, OUT = 16, W = dd::GLOB;  static constexpr bool TANH = false; };
+template <> struct Spec<ST_STAGE> { static constexpr int K0 = 56, IN = 53, H1 = 64, H2 = 64, OUT = 1,  W = dd::STAGE; static constexpr bool TANH = true; };
+template <> struct Spec<ST_EXEC>  { static constexpr int K0 = 40, IN = 36, H1 = 64, H2 = 64, OUT = 1,  W = dd::EXEC;  static constexpr bool TANH = true; };
+
+template <int ST>
+struct Smem {
+    using S = Spec<ST>;
+    static constexpr int KMAX = S::K0 > S::H1 ? (S::K0 > S::H2 ? S::K0 : S::H2) : (S::H1 > S::H2 ? S::H1 : S::H2);
+    static constexpr int W1 = S::H1 * S::K0, W2 = S::H2 * S::H1, W3 = S::OUT > 1 ? S::OUT * S::H2 : 0;
+    // float offsets
+    static constexpr int A_HI = 0, A_LO = A_HI + 128 * KMAX;
+    static constexpr int W1_HI = A_LO + 128 * KMAX, W1_LO = W1_HI + W1;
+    static constexpr int W2_HI = W1_LO + W1, W2_LO = W2_HI + W2;
+    static constexpr int W3_HI = W2_LO + W2, W3_LO = W3_HI + W3;
+    static constexpr int BIAS = W3_LO + W3;                 // H1 + H2 + max(OUT, 1) biases
+    static constexpr int W3V = BIAS + S::H1 + S::H2 + 16;   // OUT == 1: the last layer's H2 weights
+    static constexpr int CTRL = W3V + (S::OUT > 1 ? 0 : S::H2);  // mbarrier (8 B) + TMEM slot (4 B)
+    static constexpr int FLOATS = CTRL + 4;
+    static constexpr size_t BYTES = (size_t)FLOATS * 4 + 128;  // + slack to align the base to 128 B
+};
+
+// canonical K-major no-swizzle offset (in floats) of element (row, k) of a [rows x K] operand
+__device__ __forceinline__ int canon(int row, int k, int K)
+{
+    return (row >> 3) * (K * 8) + (k >> 2) * 32 + (row & 7) * 4 + (k & 3);
+}
+
+// writes this thread's row of the A tile (hi and lo parts) for a layer with K inputs
+template <int K>
+__device__ __forceinline__ void write_a_row(float *a_hi, float *a_lo, int row, const float *v)
+{
+#pragma unroll
+    for (int c = 0; c < K / 4; c++) {
+        float4 h, l;
+        h.x = to_tf32(v[4 * c]);     l.x = to_tf32(v[4 * c] - h.x);
+        h.y = to_tf32(v[4 * c + 1]); l.y = to_tf32(v[4 * c + 1] - h.y);
+        h.z = to_tf32(v[4 * c + 2]); l.z = to_tf32(v[4 * c + 2] - h.z);
+        h.w = to_tf32(v[4 * c + 3]); l.w = to_tf32(v[4 * c + 3] - h.w);
+        const int off = canon(row, 4 * c, K);
+        *reinterpret_cast<float4 *>(a_hi + off) = h;
+        *reinterpret_cast<float4 *>(a_lo + off) = l;
+    }
+}
+// one Linear layer on the tensor cores: D[128 x N] = A[128 x K] . W[N x K]^T with the 3-term split
+template <int K, int N>
+__device__ __forceinline__ void issue_layer(uint32_t tmem_d, const float *a_hi, const float *a_lo, const float *w_hi,
+                                            const float *w_lo, uint32_t mbar)
+{
+    constexpr uint32_t idesc = umma_idesc_tf32(128, N);
+    constexpr uint32_t sbo = (K / 4) * 128;
+    const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), wh = smem_u32(w_hi), wl = smem_u32(w_lo);
+#pragma unroll
+    for (int ks = 0; ks < K / 8; ks++) {
+        const uint64_t dah = umma_desc(ah + ks * 256, 128, sbo), dal = umma_desc(al + ks * 256, 128, sbo);
+        const uint64_t dwh = umma_desc(wh + ks * 256, 128, sbo), dwl = umma_desc(wl + ks * 256, 128, sbo);
+        umma_tf32(tmem_d, dah, dwh, idesc, ks > 0 ? 1u : 0u);
+        umma_tf32(tmem_d, dal, dwh, idesc, 1u);
+        umma_tf32(tmem_d, dah, dwl, idesc, 1u);
+    }
+    umma_commit(mbar);
+}
+// loads a Linear's weight (dd layout: transposed [in][out], then the bias) into the canonical hi/lo tiles
+template <int IN, int K, int N>
+__device__ __forceinline__ void load_weights(const float *__restrict__ wt, float *w_hi, float *w_lo, float *bias, int tid)
+{
+    for (int i = tid; i < N * K; i += 128) {
+        const int n = i / K, k = i % K;
+        const float x = k < IN ? __ldg(wt + k * N + n) : 0.0f;
+        const float h = to_tf32(x);
+        w_hi[canon(n, k, K)] = h;
+        w_lo[canon(n, k, K)] = to_tf32(x - h);
+    }
+    for (int i = tid; i < N; i += 128) bias[i] = __ldg(wt + dd::pad4(IN * N) + i);
+}
+
+struct TileArgs {
+    const int32_t *list;    // row ids (base of the array)
+    const int32_t *offset;  // device pointer to the list's first index in `list` (nullptr: 0)
+    const int32_t *count;   // device pointer to the list length
+    int level;              // ST_RCV: the message-passing level whose masked edges are aggregated
+};
+
+// ------------------------------------------------------------------ gather / scatter of one row
+template <int ST>
+__device__ __forceinline__ void gather_row(const Params &p, const TileArgs &a, int id, float *in)
+{
+    using S = Spec<ST>;
+#pragma unroll
+    for (int i = 0; i < S::K0; i++) in[i] = 0.0f;
+    if (id < 0) return;
+    if constexpr (ST == ST_PREP) {
+#pragma unroll
+        for (int i = 0; i < 5; i++) in[i] = p.dec_feat[(size_t)id * 5 + i];
+    } else if constexpr (ST == ST_SINK) {
+        ld16(p.pol_h_init + (size_t)id * 16, *reinterpret_cast<float(*)[16]>(in));
+    } else if constexpr (ST == ST_MSG) {
+        ld16(p.pol_h + (size_t)id * 16, *reinterpret_cast<float(*)[16]>(in));
+    } else if constexpr (ST == ST_RCV) {
+        // agg[u] = sum of the messages of u's children over the edges masked at this level, in edge order
+        const int b = id / p.Sc, u = id - b * p.Sc;
+        const int32_t *edges = p.obs_edges + (size_t)b * p.Mc * 2;
+        const uint64_t *ebits = p.dec_edge_bits + (size_t)b * p.Mc;
+        const int M = p.obs_hdr[b].num_edges;
+        for (int e = p.pol_row_start[id]; e < M && edges[2 * e] == u; e++) {
+            if ((ebits[e] >> a.level) & 1) {
+                float m[16];
+                ld16(p.pol_msg + ((size_t)b * p.Sc + edges[2 * e + 1]) * 16, m);
+#pragma unroll
+                for (int i = 0; i < 16; i++) in[i] += m[i];
+            }
+        }
+    } else if constexpr (ST == ST_DAG) {
+#pragma unroll
+        for (int i = 0; i < 5; i++) in[i] = p.dec_feat[(size_t)id * 5 + i];
+        ld16(p.pol_h + (size_t)id * 16, *reinterpret_cast<float(*)[16]>(in + 5));
+    } else if constexpr (ST == ST_GLOB) {
+        // h_dag[j] = sum over the job's nodes of their dag terms (kept in pol_msg), in node order
+        const int b = id / p.Jc, j = id - b * p.Jc;
+        const int32_t *dag_ptr = p.obs_dag_ptr + (size_t)b * (p.Jc + 1);
+        for (int n = dag_ptr[j]; n < dag_ptr[j + 1]; n++) {
+            float z[16];
+            ld16(p.pol_msg + ((size_t)b * p.Sc + n) * 16, z);
+#pragma unroll
+            for (int i = 0; i < 16; i++) in[i] += z[i];
+        }
+        st16(p.pol_h_dag + (size_t)id * 16, *reinterpret_cast<float(*)[16]>(in));
+    } else if constexpr (ST == ST_STAGE) {
+        // id = position in the candidate list
+        const int node = p.pl_cand[id], jid = p.pl_cand_job[id], b = node / p.Sc;
+#pragma unroll
+        for (int i = 0; i < 5; i++) in[i] = p.dec_feat[(size_t)node * 5 + i];
+        ld16(p.pol_h + (size_t)node * 16, *reinterpret_cast<float(*)[16]>(in + 5));
+        ld16(p.pol_h_dag + (size_t)jid * 16, *reinterpret_cast<float(*)[16]>(in + 21));
+        ld16(p.pol_h_glob + (size_t)b * 16, *reinterpret_cast<float(*)[16]>(in + 37));
+    } else if constexpr (ST == ST_EXEC) {
+        // id = b * Epad + c, c = candidate executor count - 1 (scheduler.py:338-385)
+        const int b = id / p.Epad, c = id - b * p.Epad;
+        const int job_idx = p.pol_action[(size_t)b * 4 + 1];
+        const int first = p.obs_dag_ptr[(size_t)b * (p.Jc + 1) + job_idx];
+#pragma unroll
+        for (int i = 0; i < 3; i++) in[i] = p.dec_feat[((size_t)b * p.Sc + first) * 5 + i];
+        ld16(p.pol_h_dag + ((size_t)b * p.Jc + job_idx) * 16, *reinterpret_cast<float(*)[16]>(in + 3));
+        ld16(p.pol_h_glob + (size_t)b * 16, *reinterpret_cast<float(*)[16]>(in + 19));
+        in[35] = __fdiv_rn((float)c, (float)p.E);  // torch.arange(E) / E in float32 (:380)
+    }
+}
+
+template <int ST>
+__device__ __forceinline__ void scatter_row(const Params &p, int id, const float *out)
+{
+    if (id < 0) return;
+    if constexpr (ST == ST_PREP) {
+        st16(p.pol_h_init + (size_t)id * 16, *reinterpret_cast<const float(*)[16]>(out));
+        // _forward_no_mp (:236-241) when the observation has no edge masks; otherwise h starts at 0 (:204)
+        float h0[16];
+        const bool no_mp = p.dec_depth[id / p.Sc] == 0;
+#pragma unroll
+        for (int i = 0; i < 16; i++) h0[i] = no_mp ? out[i] : 0.0f;
+        st16(p.pol_h + (size_t)id * 16, h0);
+    } else if constexpr (ST == ST_SINK) {
+        st16(p.pol_h + (size_t)id * 16, *reinterpret_cast<const float(*)[16]>(out));
+    } else if constexpr (ST == ST_MSG) {
+        st16(p.pol_msg + (size_t)id * 16, *reinterpret_cast<const float(*)[16]>(out));
+    } else if constexpr (ST == ST_RCV) {
+        float hi[16], o[16];
+        ld16(p.pol_h_init + (size_t)id * 16, hi);
+#pragma unroll
+        for (int i = 0; i < 16; i++) o[i] = hi[i] + out[i];
+        st16(p.pol_h + (size_t)id * 16, o);
+    } else if constexpr (ST == ST_DAG) {
+        st16(p.pol_msg + (size_t)id * 16, *reinterpret_cast<const float(*)[16]>(out));
+    } else if constexpr (ST == ST_GLOB) {
+        st16(p.pol_g + (size_t)id * 16, *reinterpret_cast<const float(*)[16]>(out));
+    } else if constexpr (ST == ST_STAGE) {
+        p.pol_stage_logits[p.pl_cand_out[id]] = out[0];
+    } else if constexpr (ST == ST_EXEC) {
+        p.pol_exec_logits[id] = out[0];
+    }
+}
+
+template <bool TANH>
+__device__ __forceinline__ float act_tc(float x)
+{
+    if (TANH) return tanhf(x);
+    return x > 0.0f ? x : 0.2f * x;
+}
+
+// ------------------------------------------------------------------ the tile kernel
+template <int ST>
+__global__ void __launch_bounds__(128) k_tile_mlp(Params p, TileArgs a)
+{
+    using S = Spec<ST>;
+    using L = Smem<ST>;
+    const int n_rows = *a.count;
+    if (n_rows <= 0) return;
+    const int32_t *list = a.list + (a.offset ? *a.offset : 0);
+    const int n_tiles = (n_rows + 127) >> 7;
+    if ((int)blockIdx.x >= n_tiles) return;
+    extern __shared__ unsigned char smem_raw[];
+    float *sm = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+    const int tid = threadIdx.x, warp = tid >> 5;
+    float *a_hi = sm + L::A_HI, *a_lo = sm + L::A_LO;
+    float *bias = sm + L::BIAS;
+    const uint32_t mbar = smem_u32(sm + L::CTRL), slot = smem_u32(sm + L::CTRL + 2);
+    const float *w = p.pol_w + S::W;
+    load_weights<S::IN, S::K0, S::H1>(w, sm + L::W1_HI, sm + L::W1_LO, bias, tid);
+    load_weights<S::H1, S::H1, S::H2>(w + dd::layer(S::IN, S::H1), sm + L::W2_HI, sm + L::W2_LO, bias + S::H1, tid);
+    if constexpr (S::OUT > 1) {
+        load_weights<S::H2, S::H2, S::OUT>(w + dd::layer(S::IN, S::H1) + dd::layer(S::H1, S::H2), sm + L::W3_HI,
+                                           sm + L::W3_LO, bias + S::H1 + S::H2, tid);
+    } else {
+        const float *w3 = w + dd::layer(S::IN, S::H1) + dd::layer(S::H1, S::H2);  // [H2][1] then the bias
+        for (int i = tid; i < S::H2; i += 128) sm[L::W3V + i] = __ldg(w3 + i);
+        if (tid == 0) bias[S::H1 + S::H2] = __ldg(w3 + dd::pad4(S::H2));
+    }
+    if (warp == 0) tmem_alloc(slot, 64);
+    if (tid == 0) mbar_init(mbar, 1);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(sm + L::CTRL + 2);
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);  // this warp's 32 TMEM lanes
+    uint32_t parity = 0;
+
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int row = tile * 128 + tid;
+        int id = -1;
+        if (row < n_rows) id = (ST == ST_STAGE) ? row : list[row];
+        {
+            float in[S::K0];
+            gather_row<ST>(p, a, id, in);
+            write_a_row<S::K0>(a_hi, a_lo, tid, in);
+        }
+        fence_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            issue_layer<S::K0, S::H1>(tmem, a_hi, a_lo, sm + L::W1_HI, sm + L::W1_LO, mbar);
+        }
+        mbar_wait(mbar, parity);
+        parity ^= 1;
+        tc_fence_after();
+        {
+            float v[S::H1];
+#pragma unroll
+            for (int c = 0; c < S::H1; c += 16) tmem_ld16(trow + c, v + c);
+#pragma unroll
+            for (int i = 0; i < S::H1; i++) v[i] = act_tc<S::TANH>(v[i] + bias[i]);
+            write_a_row<S::H1>(a_hi, a_lo, tid, v);
+        }
+        tc_fence_before();
+        fence_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            issue_layer<S::H1, S::H2>(tmem, a_hi, a_lo, sm + L::W2_HI, sm + L::W2_LO, mbar);
+        }
+        mbar_wait(mbar, parity);
+        parity ^= 1;
+        tc_fence_after();
+        float v2[S::H2];
+#pragma unroll
+        for (int c = 0; c < S::H2; c += 16) tmem_ld16(trow + c, v2 + c);
+#pragma unroll
+        for (int i = 0; i < S::H2; i++) v2[i] = act_tc<S::TANH>(v2[i] + bias[S::H1 + i]);
+        if constexpr (S::OUT > 1) {
+            write_a_row<S::H2>(a_hi, a_lo, tid, v2);
+            tc_fence_before();
+            fence_async_smem();
+            __syncthreads();
+            if (tid == 0) {
+                tc_fence_after();
+                issue_layer<S::H2, S::OUT>(tmem, a_hi, a_lo, sm + L::W3_HI, sm + L::W3_LO, mbar);
+            }
+            mbar_wait(mbar, parity);
+            parity ^= 1;
+            tc_fence_after();
+            float o[S::OUT];
+#pragma unroll
+            for (int c = 0; c < S::OUT; c += 16) tmem_ld16(trow + c, o + c);
+#pragma unroll
+            for (int i = 0; i < S::OUT; i++) o[i] += bias[S::H1 + S::H2 + i];
+            scatter_row<ST>(p, id, o);
+        } else {
+            // score heads end in a single neuron: a dot product in this row's thread
+            float s = bias[S::H1 + S::H2];
+#pragma unroll
+            for (int i = 0; i < S::H2; i++) s = fmaf(sm[L::W3V + i], v2[i], s);
+            scatter_row<ST>(p, id, &s);
+        }
+        tc_fence_before();  // this tile's TMEM reads are ordered before the next tile's first MMA
+    }
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 64);
+}
+
+// ------------------------------------------------------------------ planning kernels (one warp per env)
+// Pass A: per-node level bit sets (which levels a node sends / receives at), row_start, the lists of
+// all nodes / sinks / schedulable stages / jobs, and the global per-level sender / receiver counts.
+__device__ inline void plan_bits_w(const Params &p, int b, int lane, int N, int M, int depth, int *hist /* smem [128] */)
+{
+    unsigned long long *bits = p.pl_bits + (size_t)b * p.Sc * 2;
+    const int32_t *edges = p.obs_edges + (size_t)b * p.Mc * 2;
+    const uint64_t *ebits = p.dec_edge_bits + (size_t)b * p.Mc;
+    for (int i = lane; i < 2 * MAX_LEVELS; i += 32) hist[i] = 0;
+    for (int n = lane; n < N; n += 32) { bits[2 * n] = 0ull; bits[2 * n + 1] = 0ull; }
+    __syncwarp();
+    if (depth > 0) {
+        for (int e = lane; e < M; e += 32) {
+            const int u = edges[2 * e], v = edges[2 * e + 1];
+            const unsigned long long m = ebits[e];
+            atomicOr(&bits[2 * v], m);      // v (child) sends at the levels of this edge
+            atomicOr(&bits[2 * u + 1], m);  // u (parent) receives
+            if (e == 0 || edges[2 * (e - 1)] != u) p.pol_row_start[(size_t)b * p.Sc + u] = e;  // sorted by tail
+        }
+    }
+    __syncwarp();
+    for (int n = lane; n < N; n += 32) {
+        unsigned long long s = bits[2 * n], r = bits[2 * n + 1];
+        while (s) { const int k = __ffsll((long long)s) - 1; s &= s - 1; atomicAdd(&hist[2 * k], 1); }
+        while (r) { const int k = __ffsll((long long)r) - 1; r &= r - 1; atomicAdd(&hist[2 * k + 1], 1); }
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(128) k_pol_plan_a(Params p)
+{
+    __shared__ int hist_s[4][2 * MAX_LEVELS];
+    const int b = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= p.B) return;
+    int *hist = hist_s[threadIdx.x >> 5];
+    const ssb_obs_hdr &oh = p.obs_hdr[b];
+    const bool live = !(oh.terminated || oh.error);
+    const int N = live ? oh.num_nodes : 0, M = live ? oh.num_edges : 0, Ja = live ? oh.num_active_jobs : 0;
+    const int depth = live ? p.dec_depth[b] : 0;
+    plan_bits_w(p, b, lane, N, M, depth, hist);
+    for (int i = lane; i < 2 * depth; i += 32)
+        if (hist[i]) atomicAdd(&p.pl_cnt[CNT_LVL + i], hist[i]);
+    const unsigned long long *bits = p.pl_bits + (size_t)b * p.Sc * 2;
+    const uint8_t *smask = p.dec_stage_mask + (size_t)b * p.Sc;
+    const int32_t *dag_ptr = p.obs_dag_ptr + (size_t)b * (p.Jc + 1);
+    // reserve this env's ranges in the flat lists
+    int n_sink = 0, n_cand = 0;
+    for (int n0 = 0; n0 < N; n0 += 32) {
+        const int n = n0 + lane;
+        n_sink += __popc(__ballot_sync(FULL, n < N && depth > 0 && bits[2 * n + 1] == 0ull));
+        n_cand += __popc(__ballot_sync(FULL, n < N && smask[n]));
+    }
+    int base_all = 0, base_sink = 0, base_cand = 0, base_jobs = 0;
+    if (lane == 0) {
+        base_all = atomicAdd(&p.pl_cnt[CNT_ALL], N);
+        base_sink = atomicAdd(&p.pl_cnt[CNT_SINK], n_sink);
+        base_cand = atomicAdd(&p.pl_cnt[CNT_CAND], n_cand);
+        base_jobs = atomicAdd(&p.pl_cnt[CNT_JOBS], Ja);
+        p.pl_ncand[b] = n_cand;
+    }
+    base_all = __shfl_sync(FULL, base_all, 0); base_sink = __shfl_sync(FULL, base_sink, 0);
+    base_cand = __shfl_sync(FULL, base_cand, 0); base_jobs = __shfl_sync(FULL, base_jobs, 0);
+    int cs = 0, cc = 0;
+    for (int n0 = 0; n0 < N; n0 += 32) {
+        const int n = n0 + lane;
+        const bool is_sink = n < N && depth > 0 && bits[2 * n + 1] == 0ull, is_cand = n < N && smask[n];
+        const unsigned ms = __ballot_sync(FULL, is_sink), mc = __ballot_sync(FULL, is_cand);
+        const unsigned below = (1u << lane) - 1;
+        if (n < N) p.pl_all[base_all + n] = b * p.Sc + n;
+        if (is_sink) p.pl_sink[base_sink + cs + __popc(ms & below)] = b * p.Sc + n;
+        if (is_cand) {
+            int lo = 0, hi = Ja;  // job of node n: last j with dag_ptr[j] <= n
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (dag_ptr[mid] <= n) lo = mid; else hi = mid; }
+            const int r = cc + __popc(mc & below);
+            p.pl_cand[base_cand + r] = b * p.Sc + n;
+            p.pl_cand_job[base_cand + r] = b * p.Jc + lo;
+            p.pl_cand_out[base_cand + r] = b * p.Sc + r;
+        }
+        cs += __popc(ms); cc += __popc(mc);
+    }
+    for (int j = lane; j < Ja; j += 32) p.pl_jobs[base_jobs + j] = b * p.Jc + j;
+}
+
+// exclusive scan of the 2 * MAX_LEVELS level-list lengths; cursors start at the offsets
+__global__ void k_pol_plan_scan(Params p)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int run = 0;
+    for (int i = 0; i < 2 * MAX_LEVELS; i++) {
+        p.pl_cnt[OFF_LVL + i] = run;
+        p.pl_cnt[CUR_LVL + i] = run;
+        run += p.pl_cnt[CNT_LVL + i];
+    }
+    p.pl_cnt[OFF_LVL + 2 * MAX_LEVELS] = run;
+    if (run > p.lvl_cap) p.pl_cnt[CNT_OVERFLOW] = 1;
+}
+
+// Pass B: fill the per-level sender / receiver lists
+__global__ void __launch_bounds__(128) k_pol_plan_b(Params p)
+{
+    __shared__ int hist_s[4][2 * MAX_LEVELS];
+    const int b = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= p.B) return;
+    if (p.pl_cnt[CNT_OVERFLOW]) return;
+    int *hist = hist_s[threadIdx.x >> 5];
+    const ssb_obs_hdr &oh = p.obs_hdr[b];
+    const bool live = !(oh.terminated || oh.error);
+    const int N = live ? oh.num_nodes : 0, depth = live ? p.dec_depth[b] : 0;
+    if (depth == 0) return;
+    const unsigned long long *bits = p.pl_bits + (size_t)b * p.Sc * 2;
+    // this env's per-level counts again, then one reservation per non-empty list
+    for (int i = lane; i < 2 * MAX_LEVELS; i += 32) hist[i] = 0;
+    __syncwarp();
+    for (int n = lane; n < N; n += 32) {
+        unsigned long long s = bits[2 * n], r = bits[2 * n + 1];
+        while (s) { const int k = __ffsll((long long)s) - 1; s &= s - 1; atomicAdd(&hist[2 * k], 1); }
+        while (r) { const int k = __ffsll((long long)r) - 1; r &= r - 1; atomicAdd(&hist[2 * k + 1], 1); }
+    }
+    __syncwarp();
+    for (int i = lane; i < 2 * depth; i += 32) {
+        const int c = hist[i];
+        hist[i] = c ? atomicAdd(&p.pl_cnt[CUR_LVL + i], c) : 0;  // becomes this env's write cursor
+    }
+    __syncwarp();
+    for (int n = lane; n < N; n += 32) {
+        unsigned long long s = bits[2 * n], r = bits[2 * n + 1];
+        while (s) { const int k = __ffsll((long long)s) - 1; s &= s - 1; p.pl_lvl[atomicAdd(&hist[2 * k], 1)] = b * p.Sc + n; }
+        while (r) { const int k = __ffsll((long long)r) - 1; r &= r - 1; p.pl_lvl[atomicAdd(&hist[2 * k + 1], 1)] = b * p.Sc + n; }
+    }
+}
+
+// h_glob = sum over the active jobs of the global MLP's outputs (:265-276), in job order
+__global__ void __launch_bounds__(128) k_pol_glob_sum(Params p)
+{
+    const int b = blockIdx.x * 8 + (threadIdx.x >> 4), c = threadIdx.x & 15;
+    if (b >= p.B) return;
+    const ssb_obs_hdr &oh = p.obs_hdr[b];
+    const int Ja = (oh.terminated || oh.error) ? 0 : oh.num_active_jobs;
+    float s = 0.0f;
+    for (int j = 0; j < Ja; j++) s += p.pol_g[((size_t)b * p.Jc + j) * 16 + c];
+    p.pol_h_glob[(size_t)b * 16 + c] = s;
+}
+
+// stage sampling (utils.sample, decima/utils.py:19-23) + the rows of the executor-count head
+__global__ void __launch_bounds__(128) k_pol_sample_stage(Params p, const int32_t *forced_stage)
+{
+    const int b = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= p.B) return;
+    const ssb_obs_hdr &oh = p.obs_hdr[b];
+    const bool live = !(oh.terminated || oh.error);
+    const int N = live ? oh.num_nodes : 0, Ja = live ? oh.num_active_jobs : 0;
+    const int n_cand = live ? p.pl_ncand[b] : 0;
+    const EnvHdr &h = p.hdr[b];
+    const uint4 rw = philox4x32_10(h.policy_draws, 0u, 4u, 0u, (uint32_t)h.seed, (uint32_t)(h.seed >> 32));
+    const float u1 = ((float)(rw.x >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    float lgprob = 0.0f;
+    const int stage_idx = n_cand > 0 ? sample_w(p.pol_stage_logits + (size_t)b * p.Sc, n_cand,
+                                                forced_stage ? forced_stage[b] : -1, u1, lane, lgprob) : -1;
+    int job_idx = -1, cap = 0;
+    if (stage_idx >= 0 && stage_idx < n_cand) {
+        const uint8_t *smask = p.dec_stage_mask + (size_t)b * p.Sc;
+        const int32_t *dag_ptr = p.obs_dag_ptr + (size_t)b * (p.Jc + 1);
+        int seen = 0, node = -1;
+        for (int n0 = 0; n0 < N && node < 0; n0 += 32) {
+            const int n = n0 + lane;
+            const unsigned bm = __ballot_sync(FULL, n < N && smask[n]);
+            const int c = __popc(bm);
+            if (stage_idx < seen + c) {
+                unsigned m = bm;
+                for (int q = stage_idx - seen; q > 0; q--) m &= m - 1;
+                node = n0 + __ffs(m) - 1;
+            }
+            seen += c;
+        }
+        int lo = 0, hi = Ja;
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (dag_ptr[mid] <= node) lo = mid; else hi = mid; }
+        job_idx = lo;
+        cap = p.dec_caps[(size_t)b * p.Jc + job_idx];
+    }
+    int base = 0;
+    if (lane == 0) {
+        int32_t *act = p.pol_action + (size_t)b * 4;
+        act[0] = stage_idx; act[1] = job_idx; act[2] = 0; act[3] = n_cand;
+        p.pol_lgprob[b] = lgprob;
+        if (cap > 0) base = atomicAdd(&p.pl_cnt[CNT_EXEC], cap);
+    }
+    base = __shfl_sync(FULL, base, 0);
+    for (int c = lane; c < cap; c += 32) p.pl_exec[base + c] = b * p.Epad + c;
+}
+
+__global__ void __launch_bounds__(128)
+k_pol_sample_exec(Params p, const int32_t *forced_num_exec, int32_t *stage_idx_out, int32_t *num_exec_out)
+{
+    const int b = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= p.B) return;
+    EnvHdr &h = p.hdr[b];
+    int32_t *act = p.pol_action + (size_t)b * 4;
+    const int job_idx = act[1];
+    const int cap = job_idx >= 0 ? p.dec_caps[(size_t)b * p.Jc + job_idx] : 0;
+    const uint32_t pd = h.policy_draws;
+    const uint4 rw = philox4x32_10(pd, 0u, 4u, 0u, (uint32_t)h.seed, (uint32_t)(h.seed >> 32));
+    const float u2 = ((float)(rw.y >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    float lgprob = p.pol_lgprob[b];
+    int num_exec = 0;
+    if (cap > 0)
+        num_exec = sample_w(p.pol_exec_logits + (size_t)b * p.Epad, cap, forced_num_exec ? forced_num_exec[b] : -1,
+                            u2, lane, lgprob);
+    __syncwarp();
+    if (lane == 0) {
+        act[2] = num_exec;
+        p.pol_lgprob[b] = lgprob;
+        h.policy_draws = pd + 1;
+        if (stage_idx_out) stage_idx_out[b] = act[0];
+        if (num_exec_out) num_exec_out[b] = 1 + num_exec;
+    }
+}
+
+}  // namespace tc
+}  // namespace ssb

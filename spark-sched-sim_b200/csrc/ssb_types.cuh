@@ -158,6 +158,16 @@ struct Params {
     int32_t *pol_action;                  // [B][4]
     float *pol_lgprob;                    // [B]
     int Epad;
+    // tensor-core policy path (ssb_decima_tc.cuh): row lists built per decision by the planning kernels
+    int32_t *pl_all, *pl_sink;                     // [B * Sc] flat node ids (b * Sc + n)
+    int32_t *pl_cand, *pl_cand_job, *pl_cand_out;  // [B * Sc] schedulable stages: node, job row, logit slot
+    int32_t *pl_jobs;                              // [B * Jc] flat job ids (b * Jc + i)
+    int32_t *pl_exec;                              // [B * Epad] rows of the executor-count head
+    int32_t *pl_lvl;                               // [lvl_cap] senders / receivers of every level
+    int32_t *pl_cnt;                               // counters, offsets, cursors (tc::CNT_*)
+    int32_t *pl_ncand;                             // [B]
+    unsigned long long *pl_bits;                   // [B * Sc][2] levels at which a node sends / receives
+    int lvl_cap;
 };
 
 }  // namespace ssb

@@ -182,6 +182,8 @@ def main() -> None:
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-threads", type=int, default=1,
+                    help="host threads driving the e2e loop, each with its own shard of the envs")
     ap.add_argument("--e2e-budget", type=int, default=192,
                     help="max timeline events per env per ssb_step_host call (0 = run to next decision)")
     args = ap.parse_args()
@@ -285,37 +287,79 @@ def main() -> None:
     }
 
     # ---------------- e2e through the host-buffer C ABI
+    # The caller-facing loop of a vector env.  --e2e-threads T > 1 splits this GPU's envs over T handles driven by
+    # T host threads (one shard's host round trip overlaps the other shards' kernels); measured on B200 it does
+    # not help (7.9 / 7.7 / 7.1 / 6.4 M decisions/s at T = 1 / 2 / 3 / 4): the loop is bound by the GPU, not the host.
     e2e = None
     if not args.no_e2e:
+        from concurrent.futures import ThreadPoolExecutor
+
         De = E2E_DECISIONS_PER_STEP
-        a_pin = torch.empty(B, dtype=torch.int32).pin_memory()
-        n_pin = torch.empty(B, dtype=torch.int32).pin_memory()
+        T = max(1, args.e2e_threads)
+        shards = np.array_split(np.arange(B), T)
+        envs = [BatchedSparkSchedSimEnv(ENV_CFG, num_envs=len(ix), bank=bank, device=dev) for ix in shards]
+        streams = [torch.cuda.Stream(dev) for _ in range(T)]
+        pins = [(torch.empty(len(ix), dtype=torch.int32).pin_memory(),
+                 torch.empty(len(ix), dtype=torch.int32).pin_memory()) for ix in shards]
+        resets = [1] * T
 
-        def e2e_step():
-            for _ in range(De):
-                a, n = env.fair_actions(True)        # policy on the observation just written
-                a_pin.copy_(a, non_blocking=True)    # D2H: the actions a host-side caller sees
-                n_pin.copy_(n, non_blocking=True)
-                torch.cuda.current_stream().synchronize()
-                # H2D actions, bounded step (envs still simulating come back "pending" and simply
-                # continue next call -- no env waits for the batch's longest event chain), D2H headers
-                h = env.step_host(a_pin.numpy(), n_pin.numpy(), max_events=args.e2e_budget)
-                done = (h["terminated"] != 0) | (h["truncated"] != 0)
-                if done.any():                       # per-env reset(seed) exactly as a caller would
-                    env.reset_host(seeds + np.uint64(seed_step) * np.uint64(e2e_step.resets),
-                                   mask=done.astype(np.uint8))
-                    e2e_step.resets += 1
-        e2e_step.resets = 1
+        def e2e_steps(t, n_steps):
+            torch.cuda.set_device(dev)
+            e, sd, (a_pin, n_pin) = envs[t], seeds[shards[t]], pins[t]
+            with torch.cuda.stream(streams[t]):
+                for _ in range(n_steps * De):
+                    a, n = e.fair_actions(True)          # policy on the observation just written
+                    a_pin.copy_(a, non_blocking=True)    # D2H: the actions a host-side caller sees
+                    n_pin.copy_(n, non_blocking=True)
+                    streams[t].synchronize()
+                    # H2D actions, bounded step (envs still simulating come back "pending" and simply
+                    # continue next call -- no env waits for the batch's longest event chain), D2H headers
+                    h = e.step_host(a_pin.numpy(), n_pin.numpy(), max_events=args.e2e_budget)
+                    done = (h["terminated"] != 0) | (h["truncated"] != 0)
+                    if done.any():                       # per-env reset(seed) exactly as a caller would
+                        e.reset_host(sd + np.uint64(seed_step) * np.uint64(resets[t]),
+                                     mask=done.astype(np.uint8))
+                        resets[t] += 1
 
+        for t in range(T):
+            envs[t].reset_host(seeds[shards[t]])
+        Ke = max(2, min(K, 5))
+        with ThreadPoolExecutor(T) as ex:
+            list(ex.map(lambda t: e2e_steps(t, 2), range(T)))
+            for e in envs:
+                e.reset_stats()
+            barrier()
+            t0 = time.perf_counter()
+            list(ex.map(lambda t: e2e_steps(t, Ke), range(T)))
+            barrier()
+            dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dd = torch.tensor([float(sum(e.stats()["decisions"] for e in envs))], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(dd)
+        e2e = {"value": float(dd.item()) / float(tt.item()), "unit": "decisions/s",
+               "h2d_bytes_per_step": De * 2 * 4 * B, "d2h_bytes_per_step": De * (2 * 4 + 48) * B,
+               "steps": Ke, "calls_per_step": De, "max_events_per_call": args.e2e_budget,
+               "host_threads": T,
+               "path": "per shard: ssb_fair_actions -> D2H actions (pinned) -> ssb_step_host (H2D, step, D2H "
+                       "headers) -> ssb_reset_host for finished envs",
+               "gpu_launches": Ke * De * 2 * T}
+        launches_e2e = Ke * De * 2 * T
+        # the rollout-collection call (rollout_worker.py:135-157 as ONE call): fused rollout on the device,
+        # every transition (wall time, action, reward, flags) copied to pinned host memory per step
+        from spark_sched_sim_b200 import _native as nat
+        nb = B * D * nat.TRANSITION_DTYPE.itemsize
+        traj_dev = torch.empty(nb, dtype=torch.uint8, device=dev)
+        traj_pin = torch.empty(nb, dtype=torch.uint8).pin_memory()
         env.reset_host(seeds)
         for _ in range(2):
-            e2e_step()
+            env.rollout_fair_traj(D, True, True, seed_step, out=traj_dev, host=traj_pin)
         env.reset_stats()
-        Ke = max(2, min(K, 5))
         barrier()
         t0 = time.perf_counter()
         for _ in range(Ke):
-            e2e_step()
+            tr = env.rollout_fair_traj(D, True, True, seed_step, out=traj_dev, host=traj_pin)
         barrier()
         dt = time.perf_counter() - t0
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
@@ -323,14 +367,15 @@ def main() -> None:
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dist.all_reduce(dd)
-        e2e = {"value": float(dd.item()) / float(tt.item()), "unit": "decisions/s",
-               "h2d_bytes_per_step": De * 2 * 4 * B, "d2h_bytes_per_step": De * (2 * 4 + 48) * B,
-               "steps": Ke, "calls_per_step": De, "max_events_per_call": args.e2e_budget,
-               "path": "ssb_fair_actions -> D2H actions (pinned) -> ssb_step_host (H2D, step, D2H headers)",
-               "gpu_launches": Ke * De * 2}
-        launches_e2e = Ke * De * 2
+        e2e_rollout = {"value": float(dd.item()) / float(tt.item()), "unit": "decisions/s",
+                       "h2d_bytes_per_step": 0, "d2h_bytes_per_step": nb, "steps": Ke,
+                       "path": "ssb_rollout_fair_traj (policy + step fused on the device) -> D2H of the "
+                               "B x 128 transition records to pinned memory",
+                       "mean_reward_check": float(tr["reward"].mean())}
+        launches_e2e += Ke
     else:
         launches_e2e = 0
+        e2e_rollout = None
 
     cpu = None
     if rank == 0 and world == 1 and args.cpu_seconds > 0:
@@ -348,7 +393,7 @@ def main() -> None:
                        "parallelism": f"envs sharded over {world} GPU(s); all-reduce of rollout stats only"},
             "events_per_s": total_ev / (max_ms * 1e-3), "episodes": total_eps, "env_errors": total_err,
             "wall_s_timed_region": t_wall,
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_rollout": e2e_rollout, "clocks": clocks,
             "gpu_launches": launches + launches_e2e,
         }
         print(json.dumps(out))

@@ -176,6 +176,21 @@ int ssb_step_host(ssb_env *env, const int32_t *stage_idx, const int32_t *num_exe
  * (rollout_worker.py:118-120) and continues; otherwise it idles once done. */
 int ssb_rollout_fair(ssb_env *env, int32_t num_decisions, int32_t dynamic_partition, int32_t auto_reset,
                      uint64_t seed_step, void *stream);
+/* One stored transition of a rollout: what RolloutBuffer.add keeps per step besides the observation
+ * (trainers/rollout_worker.py:18-46): the wall time of the observation the action was taken on, the
+ * action, and the reward step() returned for it. */
+typedef struct {
+    double wall_time;
+    double reward;
+    int32_t stage_idx, num_exec; /* env-format action (stage_idx == -1: no-op) */
+    int32_t flags;               /* 1: step() terminated, 2: truncated, 4: first decision after a reset */
+    int32_t pad;
+} ssb_transition;
+/* ssb_rollout_fair that also records every transition: traj = DEVICE ssb_transition[B][num_decisions],
+ * row d of env b at traj[b * num_decisions + d]; an env that stops early (auto_reset == 0) leaves
+ * its remaining rows untouched. */
+int ssb_rollout_fair_traj(ssb_env *env, int32_t num_decisions, int32_t dynamic_partition, int32_t auto_reset,
+                          uint64_t seed_step, ssb_transition *traj, void *stream);
 /* evaluates the built-in policy on the current observations -> DEVICE i32[B] each */
 int ssb_fair_actions(ssb_env *env, int32_t dynamic_partition, int32_t *stage_idx, int32_t *num_exec,
                      void *stream);

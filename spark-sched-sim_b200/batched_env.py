@@ -173,6 +173,26 @@ class BatchedSparkSchedSimEnv:
                                           int(auto_reset), int(seed_step), self._stream()),
                   "ssb_rollout_fair")
 
+    def rollout_fair_traj(self, num_decisions, dynamic_partition=True, auto_reset=True, seed_step=1,
+                          out: "torch.Tensor | None" = None, host: "torch.Tensor | None" = None):
+        """Fused rollout that also records every transition (what RolloutBuffer keeps per step besides
+        the observation, trainers/rollout_worker.py:18-46).  `out`: uint8 device tensor of
+        B * num_decisions * 32 bytes (allocated if None).  With `host` (a pinned uint8 tensor of the same
+        size) the records are copied to the host and returned as a structured numpy array
+        [B, num_decisions] of _native.TRANSITION_DTYPE; otherwise the device tensor is returned."""
+        nbytes = self.num_envs * int(num_decisions) * nat.TRANSITION_DTYPE.itemsize
+        if out is None:
+            out = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        assert out.numel() >= nbytes and out.is_cuda
+        nat.check(self.L.ssb_rollout_fair_traj(self._h, int(num_decisions), int(dynamic_partition),
+                                               int(auto_reset), int(seed_step), out.data_ptr(),
+                                               self._stream()), "ssb_rollout_fair_traj")
+        if host is None:
+            return out
+        host[:nbytes].copy_(out[:nbytes], non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return host[:nbytes].numpy().view(nat.TRANSITION_DTYPE).reshape(self.num_envs, int(num_decisions))
+
     # ---------------------------------------------------------------- host-buffer API (e2e path)
     def reset_host(self, seeds: np.ndarray, time_limits: np.ndarray | None = None,
                    mask: np.ndarray | None = None) -> np.ndarray:

@@ -51,7 +51,7 @@ k_reset(Params p, const uint64_t *seeds, const double *time_limits, const uint8_
 
 // NS: executor slots per lane of the batched fast path (1: E <= 32, 2: E <= 64), see ssb_sim.cuh
 template <int NS>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, NS == 1 ? 7 : 1)
 k_step(Params p, const int32_t *stage_idx, const int32_t *num_exec, const uint8_t *mask, int max_events)
 {
     const int b = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5), lane = threadIdx.x & 31;
@@ -75,9 +75,12 @@ k_fair_actions(Params p, int dynamic_partition, int32_t *stage_idx, int32_t *num
 }
 
 // fused policy + step: `num_decisions` decisions per environment in one launch
+// (min 7 CTAs per SM for the one-slot kernel: 4096 envs = 1024 CTAs must all be resident at once on
+// 148 SMs; at 80 registers only 6 fit and the last 136 CTAs run as a second wave, +37 % time)
 template <int NS>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
-k_rollout_fair(Params p, int num_decisions, int dynamic_partition, int auto_reset, uint64_t seed_step)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, NS == 1 ? 7 : 1)
+k_rollout_fair(Params p, int num_decisions, int dynamic_partition, int auto_reset, uint64_t seed_step,
+               ssb_transition *traj)
 {
     const int b = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (b >= p.B) return;
@@ -85,11 +88,12 @@ k_rollout_fair(Params p, int num_decisions, int dynamic_partition, int auto_rese
 #ifdef SSB_PROFILE
     const long long t_start = clock64();
 #endif
-    int d = 0;
+    int d = 0, fresh = 0;
     while (d < num_decisions) {
         if (sim.h->error) break;
         if (sim.h->done || sim.oh->truncated) {
             if (!auto_reset) break;
+            fresh = 4;
             // rollout_worker.py:118-120: seed = base_seed + seed_step * reset_count
             const uint64_t seed = sim.h->base_seed + seed_step * (uint64_t)sim.h->reset_count;
             const double tl = sim.h->time_limit;
@@ -107,7 +111,16 @@ k_rollout_fair(Params p, int num_decisions, int dynamic_partition, int auto_rese
 #ifdef SSB_PROFILE
         if (lane == 0) p.prof[(size_t)b * 16 + 8] += (unsigned long long)(clock64() - tp0);
 #endif
+        const double wall0 = sim.oh->wall_time;
         sim.template step_w<NS>(a, n);
+        if (traj && lane == 0) {  // RolloutBuffer.add (rollout_worker.py:34-40) minus the observation
+            ssb_transition t;
+            t.wall_time = wall0; t.reward = sim.oh->reward; t.stage_idx = a; t.num_exec = n;
+            t.flags = (sim.oh->terminated ? 1 : 0) | (sim.oh->truncated ? 2 : 0) | fresh;
+            t.pad = 0;
+            traj[(size_t)b * num_decisions + d] = t;
+        }
+        fresh = 0;
         d++;
     }
 #ifdef SSB_PROFILE
@@ -579,18 +592,24 @@ int ssb_step_host(ssb_env *env, const int32_t *stage_idx, const int32_t *num_exe
     return SSB_OK;
 }
 
-int ssb_rollout_fair(ssb_env *env, int32_t num_decisions, int32_t dynamic_partition, int32_t auto_reset,
-                     uint64_t seed_step, void *stream)
+int ssb_rollout_fair_traj(ssb_env *env, int32_t num_decisions, int32_t dynamic_partition, int32_t auto_reset,
+                          uint64_t seed_step, ssb_transition *traj, void *stream)
 {
     if (!env || num_decisions < 0) return SSB_E_INVALID;
     if (env->p.E <= 32)
         k_rollout_fair<1><<<env->grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(
-            env->p, num_decisions, dynamic_partition, auto_reset, seed_step);
+            env->p, num_decisions, dynamic_partition, auto_reset, seed_step, traj);
     else
         k_rollout_fair<2><<<env->grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(
-            env->p, num_decisions, dynamic_partition, auto_reset, seed_step);
+            env->p, num_decisions, dynamic_partition, auto_reset, seed_step, traj);
     CUDA_TRY(cudaGetLastError());
     return SSB_OK;
+}
+
+int ssb_rollout_fair(ssb_env *env, int32_t num_decisions, int32_t dynamic_partition, int32_t auto_reset,
+                     uint64_t seed_step, void *stream)
+{
+    return ssb_rollout_fair_traj(env, num_decisions, dynamic_partition, auto_reset, seed_step, nullptr, stream);
 }
 
 int ssb_fair_actions(ssb_env *env, int32_t dynamic_partition, int32_t *stage_idx, int32_t *num_exec, void *stream)

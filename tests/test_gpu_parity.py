@@ -215,6 +215,44 @@ def test_auto_reset_rollout(bank):
         assert np.array_equal(o[key], g[key]), key
 
 
+def test_rollout_transitions_match_oracle(bank):
+    """ssb_rollout_fair_traj: the recorded (wall_time, action, reward, flags) rows are what a host loop
+    over the oracle's reset()/fair_action()/step() produces, across auto-resets."""
+    import torch
+    from oracle import OracleEnv
+    from spark_sched_sim_b200 import _native as nat
+    from spark_sched_sim_b200.batched_env import BatchedSparkSchedSimEnv
+
+    B, K = 6, 900
+    cfg = {"num_executors": 10, "job_arrival_cap": 8, "job_arrival_rate": 4.0e-5,
+           "moving_delay": 2000.0, "warmup_delay": 1000.0}
+    env = BatchedSparkSchedSimEnv(cfg, num_envs=B, bank=bank)
+    seeds = np.arange(500, 500 + B, dtype=np.uint64)
+    env.reset_host(seeds)
+    host = torch.empty(B * K * nat.TRANSITION_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+    tr = env.rollout_fair_traj(K, True, auto_reset=True, seed_step=1000, host=host)
+    assert tr.shape == (B, K) and (env.hdr()["error"] == 0).all()
+    for b in (0, 5):
+        orc = OracleEnv(bank, 10, 8, 2000.0, 1000.0, 4.0e-5)
+        k = ep = 0
+        while k < K:
+            orc.reset_seed(int(seeds[b]) + 1000 * ep)
+            term, first = False, ep > 0
+            while not term and k < K:
+                wall0 = orc.wall_time
+                a, n = orc.fair_action(True)
+                rc, rew, term = orc.step(a, n)
+                assert rc == 0
+                row = tr[b, k]
+                assert (row["wall_time"], row["stage_idx"], row["num_exec"]) == (wall0, a, n), (b, k)
+                assert row["reward"] == rew and (row["flags"] & 1) == int(term), (b, k)
+                assert bool(row["flags"] & 4) == first, (b, k)
+                first = False
+                k += 1
+            ep += 1
+        assert ep > 1
+
+
 @pytest.mark.parametrize("name,budget", [("e10_j8_random_s5_philox", 1), ("e10_j8_fair_s2_philox", 7),
                                          ("e50_j8_random_s8_philox", 33), ("c2_fair_s1234_philox", 64)])
 def test_budgeted_step_is_equivalent(bank, name, budget):

@@ -7,7 +7,6 @@
 
 #include <algorithm>
 #include <cmath>
-#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -137,39 +136,6 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_decima_obs(Params p)
     sim.decima_obs_w(Sk[threadIdx.x >> 5]);
 }
 
-// Decima: observation adapter + GNN forward + action sampling for every env (one decision each).
-// Outputs are in the env's action format (DecimaActWrapper: num_exec + 1), ready for ssb_step.
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
-k_decima_policy(Params p, const int32_t *forced_stage, const int32_t *forced_num_exec, int32_t *stage_idx_out,
-                int32_t *num_exec_out)
-{
-    __shared__ uint64_t Sk[WARPS_PER_CTA][64];
-    const int b = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (b >= p.B) return;
-    Sim sim(p, b, lane);
-    sim.decima_obs_w(Sk[threadIdx.x >> 5]);
-    __syncwarp();
-    PolicyBufs pb;
-    pb.h_init = p.pol_h_init + (size_t)b * p.Sc * 16;
-    pb.h = p.pol_h + (size_t)b * p.Sc * 16;
-    pb.msg = p.pol_msg + (size_t)b * p.Sc * 16;
-    pb.h_dag = p.pol_h_dag + (size_t)b * p.Jc * 16;
-    pb.g = p.pol_g + (size_t)b * p.Jc * 16;
-    pb.h_glob = p.pol_h_glob + (size_t)b * 16;
-    pb.row_start = p.pol_row_start + (size_t)b * p.Sc;
-    pb.flag = p.pol_flag + (size_t)b * 3 * p.Sc;
-    pb.stage_logits = p.pol_stage_logits + (size_t)b * p.Sc;
-    pb.exec_logits = p.pol_exec_logits + (size_t)b * p.Epad;
-    pb.action = p.pol_action + (size_t)b * 4;
-    pb.lgprob = p.pol_lgprob + b;
-    decima_policy_w(sim, p.pol_w, pb, forced_stage ? forced_stage[b] : -1,
-                    forced_num_exec ? forced_num_exec[b] : -1);
-    if (lane == 0) {
-        if (stage_idx_out) stage_idx_out[b] = pb.action[0];
-        if (num_exec_out) num_exec_out[b] = 1 + pb.action[2];
-    }
-}
-
 __global__ void k_zero_stats(ssb_stats *s, int n)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -289,7 +255,6 @@ void carve(Carver &cv, const ssb_config &c, const ssb_bank &bk, const Dims &d, P
         p.pol_g = cv.take<float>(B * c.max_jobs * 16);
         p.pol_h_glob = cv.take<float>(B * 16);
         p.pol_row_start = cv.take<int32_t>(B * d.Sc);
-        p.pol_flag = cv.take<uint8_t>(B * 3 * d.Sc);
         p.pol_stage_logits = cv.take<float>(B * d.Sc);
         p.pol_exec_logits = cv.take<float>(B * p.Epad);
         p.pol_action = cv.take<int32_t>(B * 4);
@@ -307,6 +272,7 @@ void carve(Carver &cv, const ssb_config &c, const ssb_bank &bk, const Dims &d, P
         p.pl_cnt = cv.take<int32_t>(tc::CNT_TOTAL);
         p.pl_ncand = cv.take<int32_t>(B);
         p.pl_bits = cv.take<unsigned long long>(B * d.Sc * 2);
+        p.pol_wblob = cv.take<float>(tc::BLOB_TOTAL);
     }
     *st_a = cv.take<int32_t>(B);
     *st_n = cv.take<int32_t>(B);
@@ -333,7 +299,6 @@ struct ssb_env {
     int grid;
     int num_sms;
     int dmax;           // upper bound of the message-passing depth: longest template chain - 1
-    int decima_legacy;  // SSB_DECIMA_LEGACY=1: the fp32 CUDA-core policy kernel (A/B runs)
 };
 
 template <int ST>
@@ -424,8 +389,6 @@ int ssb_create(const ssb_config *cfg, const ssb_bank *bk, int device, void *work
             dmax = gens - 1 > dmax ? gens - 1 : dmax;
         }
         env->dmax = dmax;
-        const char *lg = getenv("SSB_DECIMA_LEGACY");
-        env->decima_legacy = lg && lg[0] == '1';
     }
     if (p.pol_w) {
         int rc;
@@ -682,6 +645,17 @@ int ssb_set_decima_weights(ssb_env *env, const float *weights, int32_t n_floats)
     }
     if (src != (size_t)dw::TOTAL || dst != (size_t)dd::TOTAL) return SSB_E_INVALID;
     CUDA_TRY(cudaMemcpy(env->p.pol_w, dev.data(), sizeof(float) * dd::TOTAL, cudaMemcpyHostToDevice));
+    // tensor-core path: per-stage blobs (canonical UMMA tiles, tf32 hi/lo halves, biases)
+    tc::k_build_blob<tc::ST_PREP><<<1, 128>>>(env->p);
+    tc::k_build_blob<tc::ST_SINK><<<1, 128>>>(env->p);
+    tc::k_build_blob<tc::ST_MSG><<<1, 128>>>(env->p);
+    tc::k_build_blob<tc::ST_RCV><<<1, 128>>>(env->p);
+    tc::k_build_blob<tc::ST_DAG><<<1, 128>>>(env->p);
+    tc::k_build_blob<tc::ST_GLOB><<<1, 128>>>(env->p);
+    tc::k_build_blob<tc::ST_STAGE><<<1, 128>>>(env->p);
+    tc::k_build_blob<tc::ST_EXEC><<<1, 128>>>(env->p);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaDeviceSynchronize());
     return SSB_OK;
 }
 
@@ -690,12 +664,6 @@ int ssb_decima_policy(ssb_env *env, const int32_t *forced_stage, const int32_t *
 {
     if (!env || !env->p.pol_w) return SSB_E_INVALID;  // needs SSB_FLAG_DECIMA_POLICY
     cudaStream_t s = (cudaStream_t)stream;
-    if (env->decima_legacy) {
-        k_decima_policy<<<env->grid, WARPS_PER_CTA * 32, 0, s>>>(env->p, forced_stage, forced_num_exec,
-                                                                 stage_idx_out, num_exec_out);
-        CUDA_TRY(cudaGetLastError());
-        return SSB_OK;
-    }
     // observation adapter -> row lists -> one tensor-core tile pass per MLP (ssb_decima_tc.cuh)
     const Params &p = env->p;
     const int32_t *cnt = p.pl_cnt;

@@ -148,6 +148,9 @@ struct Smem {
     static constexpr int W3V = BIAS + S::H1 + S::H2 + 16;   // OUT == 1: the last layer's H2 weights
     static constexpr int CTRL = W3V + (S::OUT > 1 ? 0 : S::H2);  // mbarrier (8 B) + TMEM slot (4 B)
     static constexpr int FLOATS = CTRL + 4;
+    // [W1_HI, CTRL) is the stage's constant "weight blob": built once per weight upload in global memory
+    // (k_build_blob) in exactly this layout, so a CTA's prologue is one coalesced copy
+    static constexpr int BLOB = CTRL - W1_HI;
     static constexpr size_t BYTES = (size_t)FLOATS * 4 + 128;  // + slack to align the base to 128 B
 };
 
@@ -233,13 +236,33 @@ __device__ __forceinline__ void gather_row(const Params &p, const TileArgs &a, i
         const int32_t *edges = p.obs_edges + (size_t)b * p.Mc * 2;
         const uint64_t *ebits = p.dec_edge_bits + (size_t)b * p.Mc;
         const int M = p.obs_hdr[b].num_edges;
-        for (int e = p.pol_row_start[id]; e < M && edges[2 * e] == u; e++) {
-            if ((ebits[e] >> a.level) & 1) {
-                float m[16];
-                ld16(p.pol_msg + ((size_t)b * p.Sc + edges[2 * e + 1]) * 16, m);
+        // (edges of one parent are contiguous; four at a time so that their loads overlap)
+        for (int e0 = p.pol_row_start[id]; e0 < M; e0 += 4) {
+            int2 uv[4];
+            uint64_t bits[4];
 #pragma unroll
-                for (int i = 0; i < 16; i++) in[i] += m[i];
+            for (int q = 0; q < 4; q++) {
+                const int e = e0 + q < M ? e0 + q : M - 1;
+                uv[q] = *reinterpret_cast<const int2 *>(edges + 2 * e);
+                bits[q] = ebits[e];
             }
+            bool use[4], more = true;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                more = more && e0 + q < M && uv[q].x == u;
+                use[q] = more && ((bits[q] >> a.level) & 1);
+            }
+            float m[4][16];
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                if (use[q]) ld16(p.pol_msg + ((size_t)b * p.Sc + uv[q].y) * 16, m[q]);
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                if (use[q]) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) in[i] += m[q][i];
+                }
+            if (!more) break;
         }
     } else if constexpr (ST == ST_DAG) {
 #pragma unroll
@@ -249,11 +272,18 @@ __device__ __forceinline__ void gather_row(const Params &p, const TileArgs &a, i
         // h_dag[j] = sum over the job's nodes of their dag terms (kept in pol_msg), in node order
         const int b = id / p.Jc, j = id - b * p.Jc;
         const int32_t *dag_ptr = p.obs_dag_ptr + (size_t)b * (p.Jc + 1);
-        for (int n = dag_ptr[j]; n < dag_ptr[j + 1]; n++) {
-            float z[16];
-            ld16(p.pol_msg + ((size_t)b * p.Sc + n) * 16, z);
+        const int n1 = dag_ptr[j + 1];
+        for (int n0 = dag_ptr[j]; n0 < n1; n0 += 4) {  // four rows in flight, summed in node order
+            float z[4][16];
 #pragma unroll
-            for (int i = 0; i < 16; i++) in[i] += z[i];
+            for (int q = 0; q < 4; q++)
+                if (n0 + q < n1) ld16(p.pol_msg + ((size_t)b * p.Sc + n0 + q) * 16, z[q]);
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                if (n0 + q < n1) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) in[i] += z[q][i];
+                }
         }
         st16(p.pol_h_dag + (size_t)id * 16, *reinterpret_cast<float(*)[16]>(in));
     } else if constexpr (ST == ST_STAGE) {
@@ -318,22 +348,30 @@ __device__ __forceinline__ float act_tc(float x)
 }
 
 // ------------------------------------------------------------------ the tile kernel
+// offset (floats) of stage ST's weight blob in p.pol_wblob
+__host__ __device__ constexpr int blob_size(int st)
+{
+    return st == ST_PREP ? Smem<ST_PREP>::BLOB : st == ST_SINK ? Smem<ST_SINK>::BLOB : st == ST_MSG ? Smem<ST_MSG>::BLOB
+         : st == ST_RCV ? Smem<ST_RCV>::BLOB : st == ST_DAG ? Smem<ST_DAG>::BLOB : st == ST_GLOB ? Smem<ST_GLOB>::BLOB
+         : st == ST_STAGE ? Smem<ST_STAGE>::BLOB : Smem<ST_EXEC>::BLOB;
+}
+__host__ __device__ constexpr int blob_offset(int st)
+{
+    int off = 0;
+    for (int i = 0; i < st; i++) off += blob_size(i);
+    return off;
+}
+constexpr int BLOB_TOTAL = blob_offset(ST_EXEC) + blob_size(ST_EXEC);
+
+// one CTA per stage: dd-layout weights -> canonical hi/lo tiles + biases (+ last-layer vector) in global memory
 template <int ST>
-__global__ void __launch_bounds__(128) k_tile_mlp(Params p, TileArgs a)
+__global__ void __launch_bounds__(128) k_build_blob(Params p)
 {
     using S = Spec<ST>;
     using L = Smem<ST>;
-    const int n_rows = *a.count;
-    if (n_rows <= 0) return;
-    const int32_t *list = a.list + (a.offset ? *a.offset : 0);
-    const int n_tiles = (n_rows + 127) >> 7;
-    if ((int)blockIdx.x >= n_tiles) return;
-    extern __shared__ unsigned char smem_raw[];
-    float *sm = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
-    const int tid = threadIdx.x, warp = tid >> 5;
-    float *a_hi = sm + L::A_HI, *a_lo = sm + L::A_LO;
+    const int tid = threadIdx.x;
+    float *sm = p.pol_wblob + blob_offset(ST) - L::W1_HI;  // so that the Smem<ST> offsets apply unchanged
     float *bias = sm + L::BIAS;
-    const uint32_t mbar = smem_u32(sm + L::CTRL), slot = smem_u32(sm + L::CTRL + 2);
     const float *w = p.pol_w + S::W;
     load_weights<S::IN, S::K0, S::H1>(w, sm + L::W1_HI, sm + L::W1_LO, bias, tid);
     load_weights<S::H1, S::H1, S::H2>(w + dd::layer(S::IN, S::H1), sm + L::W2_HI, sm + L::W2_LO, bias + S::H1, tid);
@@ -345,6 +383,37 @@ __global__ void __launch_bounds__(128) k_tile_mlp(Params p, TileArgs a)
         for (int i = tid; i < S::H2; i += 128) sm[L::W3V + i] = __ldg(w3 + i);
         if (tid == 0) bias[S::H1 + S::H2] = __ldg(w3 + dd::pad4(S::H2));
     }
+}
+
+#ifdef SSB_PROFILE
+#define TC_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) p.prof[ST * 16 + (i)] = (unsigned long long)clock64(); } while (0)
+#else
+#define TC_STAMP(i) do { } while (0)
+#endif
+
+template <int ST>
+__global__ void __launch_bounds__(128) k_tile_mlp(Params p, TileArgs a)
+{
+    using S = Spec<ST>;
+    using L = Smem<ST>;
+    TC_STAMP(0);
+    const int n_rows = *a.count;
+    if (n_rows <= 0) return;
+    const int32_t *list = a.list + (a.offset ? *a.offset : 0);
+    const int n_tiles = (n_rows + 127) >> 7;
+    if ((int)blockIdx.x >= n_tiles) return;
+    extern __shared__ unsigned char smem_raw[];
+    float *sm = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+    const int tid = threadIdx.x, warp = tid >> 5;
+    float *a_hi = sm + L::A_HI, *a_lo = sm + L::A_LO;
+    float *bias = sm + L::BIAS;
+    const uint32_t mbar = smem_u32(sm + L::CTRL), slot = smem_u32(sm + L::CTRL + 2);
+    {
+        const float4 *src = reinterpret_cast<const float4 *>(p.pol_wblob + blob_offset(ST));
+        float4 *dst = reinterpret_cast<float4 *>(sm + L::W1_HI);
+        for (int i = tid; i < L::BLOB / 4; i += 128) dst[i] = __ldg(src + i);
+    }
+    TC_STAMP(1);
     if (warp == 0) tmem_alloc(slot, 64);
     if (tid == 0) mbar_init(mbar, 1);
     fence_async_smem();
@@ -354,6 +423,7 @@ __global__ void __launch_bounds__(128) k_tile_mlp(Params p, TileArgs a)
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(sm + L::CTRL + 2);
     const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);  // this warp's 32 TMEM lanes
     uint32_t parity = 0;
+    TC_STAMP(2);
 
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int row = tile * 128 + tid;
@@ -362,10 +432,12 @@ __global__ void __launch_bounds__(128) k_tile_mlp(Params p, TileArgs a)
         {
             float in[S::K0];
             gather_row<ST>(p, a, id, in);
+            if (tile == (int)blockIdx.x) TC_STAMP(3);
             write_a_row<S::K0>(a_hi, a_lo, tid, in);
         }
         fence_async_smem();
         __syncthreads();
+        if (tile == (int)blockIdx.x) TC_STAMP(4);
         if (tid == 0) {
             tc_fence_after();
             issue_layer<S::K0, S::H1>(tmem, a_hi, a_lo, sm + L::W1_HI, sm + L::W1_LO, mbar);
@@ -373,6 +445,7 @@ __global__ void __launch_bounds__(128) k_tile_mlp(Params p, TileArgs a)
         mbar_wait(mbar, parity);
         parity ^= 1;
         tc_fence_after();
+        if (tile == (int)blockIdx.x) TC_STAMP(5);
         {
             float v[S::H1];
 #pragma unroll
@@ -384,6 +457,7 @@ __global__ void __launch_bounds__(128) k_tile_mlp(Params p, TileArgs a)
         tc_fence_before();
         fence_async_smem();
         __syncthreads();
+        if (tile == (int)blockIdx.x) TC_STAMP(6);
         if (tid == 0) {
             tc_fence_after();
             issue_layer<S::H1, S::H2>(tmem, a_hi, a_lo, sm + L::W2_HI, sm + L::W2_LO, mbar);
@@ -391,6 +465,7 @@ __global__ void __launch_bounds__(128) k_tile_mlp(Params p, TileArgs a)
         mbar_wait(mbar, parity);
         parity ^= 1;
         tc_fence_after();
+        if (tile == (int)blockIdx.x) TC_STAMP(7);
         float v2[S::H2];
 #pragma unroll
         for (int c = 0; c < S::H2; c += 16) tmem_ld16(trow + c, v2 + c);
@@ -422,9 +497,11 @@ __global__ void __launch_bounds__(128) k_tile_mlp(Params p, TileArgs a)
             scatter_row<ST>(p, id, &s);
         }
         tc_fence_before();  // this tile's TMEM reads are ordered before the next tile's first MMA
+        if (tile == (int)blockIdx.x) TC_STAMP(8);
     }
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, 64);
+    TC_STAMP(9);
 }
 
 // ------------------------------------------------------------------ planning kernels (one warp per env)

@@ -152,7 +152,6 @@ struct Params {
     float *pol_h_dag, *pol_g;             // [B][Jc][16]
     float *pol_h_glob;                    // [B][16]
     int32_t *pol_row_start;               // [B][Sc]
-    uint8_t *pol_flag;                    // [B][3][Sc]
     float *pol_stage_logits;              // [B][Sc]
     float *pol_exec_logits;               // [B][Epad]
     int32_t *pol_action;                  // [B][4]
@@ -167,6 +166,7 @@ struct Params {
     int32_t *pl_cnt;                               // counters, offsets, cursors (tc::CNT_*)
     int32_t *pl_ncand;                             // [B]
     unsigned long long *pl_bits;                   // [B * Sc][2] levels at which a node sends / receives
+    float *pol_wblob;  // per-stage weight blobs in shared-memory layout (tc::blob_offset)
     int lvl_cap;
 };
 

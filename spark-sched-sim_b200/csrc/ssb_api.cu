@@ -50,7 +50,7 @@ k_reset(Params p, const uint64_t *seeds, const double *time_limits, const uint8_
 
 // NS: executor slots per lane of the batched fast path (1: E <= 32, 2: E <= 64), see ssb_sim.cuh
 template <int NS>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, NS == 1 ? 7 : 1)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, NS == 1 ? 7 : 4)
 k_step(Params p, const int32_t *stage_idx, const int32_t *num_exec, const uint8_t *mask, int max_events)
 {
     const int b = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5), lane = threadIdx.x & 31;
@@ -75,9 +75,10 @@ k_fair_actions(Params p, int dynamic_partition, int32_t *stage_idx, int32_t *num
 
 // fused policy + step: `num_decisions` decisions per environment in one launch
 // (min 7 CTAs per SM for the one-slot kernel: 4096 envs = 1024 CTAs must all be resident at once on
-// 148 SMs; at 80 registers only 6 fit and the last 136 CTAs run as a second wave, +37 % time)
+// 148 SMs; at 80 registers only 6 fit and the last 136 CTAs run as a second wave, +37 % time.
+// Two-slot kernel: 4 CTAs per SM = 128 registers, what it needs without spilling.)
 template <int NS>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, NS == 1 ? 7 : 1)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, NS == 1 ? 7 : 4)
 k_rollout_fair(Params p, int num_decisions, int dynamic_partition, int auto_reset, uint64_t seed_step,
                ssb_transition *traj)
 {

@@ -1,4 +1,4 @@
-"""Secondary benchmark (not the driver's bench line): Decima rollouts on the device.
+"""Secondary benchmark (not the driver's bench line): Decima rollouts on the device, 1..N GPUs.
 
 BASELINE.json configs[2]: Decima GNN policy rollouts with on-device observation construction.
 Each decision = ssb_decima_policy (observation adapter + GNN + sampling) + ssb_step, both stream-
@@ -6,6 +6,10 @@ ordered on device tensors (no host round trip).  Weights: the reference's shippe
 tests/golden/decima_model.npz).  Prints one JSON line.
 
     python bench_decima.py [--envs 4096] [--executors 10] [--jobs 50] [--decisions 200] [--budget 0]
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 bench_decima.py ...   (configs[4])
+
+Under torchrun every rank owns `--envs` environments with disjoint seeds (weak scaling); the only exchange
+is the all-reduce of the rollout statistics (NCCL), timed inside the region; time = max over ranks.
 """
 from __future__ import annotations
 
@@ -30,19 +34,32 @@ def main():
     ap.add_argument("--budget", type=int, default=0, help="max events per env per step (0 = run to decision)")
     args = ap.parse_args()
 
-    import torch
+    import os
 
+    import torch
+    import torch.distributed as dist
+
+    from spark_sched_sim_b200 import parallel
     from spark_sched_sim_b200.bank import synthetic_bank
     from spark_sched_sim_b200.batched_env import BatchedSparkSchedSimEnv
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
 
     cfg = {"num_executors": args.executors, "job_arrival_cap": args.jobs, "job_arrival_rate": 4.0e-5,
            "moving_delay": 2000.0, "warmup_delay": 1000.0}
     B = args.envs
-    env = BatchedSparkSchedSimEnv(cfg, num_envs=B, bank=synthetic_bank(0), decima_policy=True)
+    env = BatchedSparkSchedSimEnv(cfg, num_envs=B, bank=synthetic_bank(0), decima_policy=True, device=dev)
     z = np.load(osp.join(REPO, "tests", "golden", "decima_model.npz"))
     env.set_decima_weights({k: z[k] for k in z.files})
-    seeds = (1234 + np.arange(B)).astype(np.uint64)
+    seeds, _ = parallel.shard_seeds(1234, B, rank, world)
     env.reset_host(seeds)
+    stats_vec = torch.zeros(8, dtype=torch.float64, device=dev)
 
     def decide(n):
         for _ in range(n):
@@ -51,15 +68,28 @@ def main():
 
     decide(args.warmup)
     env.reset_stats()
+    if world > 1:
+        dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     decide(args.decisions)
+    if world > 1:
+        dist.all_reduce(stats_vec)  # rollout statistics: the path's only exchange
     e1.record()
+    if world > 1:
+        dist.barrier()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     st = env.stats()
     hdr = env.hdr()
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        c = torch.tensor([float(st["decisions"]), float(st["events"])], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(c)
+        ms = float(t.item())
+        st = dict(st, decisions=int(c[0].item()), events=int(c[1].item()))
     # time of the policy kernel alone
     p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     p0.record()
@@ -67,11 +97,15 @@ def main():
         env.decima_policy()
     p1.record()
     torch.cuda.synchronize()
+    if world > 1:
+        dist.destroy_process_group()
+    if rank != 0:
+        return
     print(json.dumps({
         "metric": "scheduling decisions/sec (Decima policy, batched envs)",
-        "value": st["decisions"] / (ms * 1e-3), "unit": "decisions/s", "n_gpus": 1,
-        "config": {"workload": f"{B} envs x ({args.jobs} jobs, {args.executors} executors), Decima policy "
-                               "(shipped model.pt) on device, 2 launches per decision",
+        "value": st["decisions"] / (ms * 1e-3), "unit": "decisions/s", "n_gpus": world, "scaling": "weak",
+        "config": {"workload": f"{B} envs per GPU x ({args.jobs} jobs, {args.executors} executors), Decima policy "
+                               "(shipped model.pt) on the tensor cores, ssb_decima_policy + ssb_step per decision",
                    "max_events_per_step": args.budget},
         "decisions": st["decisions"], "events": st["events"], "ms_total": ms,
         "policy_kernel_ms": p0.elapsed_time(p1) / 20,

@@ -855,6 +855,8 @@ struct Sim {
         uint2 oc_a, oc_b;    // rest-wave (offset, count) for the left / right executor level
         int thr, range;      // _sample_executor_key: key = left iff 1 + int(u * range) <= thr
         bool fast_ok;        // this executor's next launch can be sampled without the fallback chain
+        bool touched;        // handled at least one event in this fast phase (its t_acc is then that event's time)
+        unsigned same;       // lanes whose pending event belongs to the same stage (constant during a fast phase)
     };
     struct HotEnv {  // uniform per-environment scalars
         unsigned long long t_arr;
@@ -871,6 +873,7 @@ struct Sim {
         L.kt = 0x7ff8000000000000ull; L.ks = 0xffffffffu; L.kind = 0; L.j = 0; L.s = 0;
         L.node = -1 - e; L.task = -1; L.t_acc = 0.0; L.rem = L.comp = L.mc = 0;
         L.oc_a = L.oc_b = make_uint2(0u, 0u); L.thr = L.range = 0; L.fast_ok = false;
+        L.touched = false; L.same = 0;
         if (e < p.E) {
             const ExecRec &x = ex[e];
             L.kind = x.ev_kind;
@@ -915,6 +918,19 @@ struct Sim {
     {
         hot_load_slot(L, lane);
         hot_load_env(H);
+        L.same = __match_any_sync(FULL, L.node);
+    }
+    // one-slot fast phase: the wall time is the time of the last event handled, i.e. the maximum over the
+    // lanes that handled one of their t_acc (non-negative doubles order like their bit patterns)
+    __device__ __forceinline__ void hot_flush1(const HotLane &L, HotEnv &H)
+    {
+        if (H.events) {
+            const unsigned long long tb = L.touched ? (unsigned long long)__double_as_longlong(L.t_acc) : 0ull;
+            const uint32_t whi = __reduce_max_sync(FULL, (uint32_t)(tb >> 32));
+            const uint32_t wlo = __reduce_max_sync(FULL, (uint32_t)(tb >> 32) == whi ? (uint32_t)tb : 0u);
+            H.wall = __longlong_as_double((long long)(((unsigned long long)whi << 32) | wlo));
+        }
+        hot_flush(H);
     }
     __device__ __forceinline__ void hot_flush(const HotEnv &H)
     {
@@ -950,9 +966,11 @@ struct Sim {
         const bool pending = L.kind != 0;
         const unsigned pend_mask = __ballot_sync(FULL, pending);
         if (!pend_mask) return 0;
-        // order of the pending events by (t, push counter) (event.py:34-35).  The upper 32 bits of the
-        // timestamps almost always decide; ties there take the exact path.
-        const uint32_t hi = (uint32_t)(L.kt >> 32);
+        // order of the pending events by (t, push counter) (event.py:34-35).  A 32-bit fixed-point key,
+        // floor(16 t) saturated, almost always decides (event times are mostly whole milliseconds, which tie
+        // in the upper f64 word above 2^20 ms); equal keys take the exact path.
+        const double tq = __dmul_rn(__longlong_as_double((long long)L.kt), 16.0);
+        const uint32_t hi = pending ? __double2uint_rd(tq) : 0xffffffffu;
         unsigned less = 0;
         // (kept rolled on purpose: instruction fetch, not shuffle latency, bounds this loop -- the
         // unrolled form measured 6475 vs 4266 cycles per iteration, profiles/r01_ab_unroll.txt)
@@ -964,7 +982,7 @@ struct Sim {
         }
         less &= pend_mask;
         const int rank = __popc(less);
-        const unsigned same_node = __match_any_sync(FULL, L.node);
+        const unsigned same_node = L.same;
         const int before_same = __popc(less & same_node);
         // eligibility: TASK_FINISHED before the next arrival (an arrival at the same time pops first,
         // its seq is smaller), tasks left after this launch, saturation bit of the stage unchanged
@@ -1003,7 +1021,7 @@ struct Sim {
         const int cnt = __popc(same_node & mem_mask);  // launches of my stage in this batch
         if (member) {
             if (p.log_cap > 0) log_batch_row(H.log_n + rank, t, L.t_acc, L.task, L.j, L.s, lane);
-            L.kt = nt; L.t_acc = t; L.ks = H.seq + (uint32_t)rank; L.task = rem - 1;
+            L.kt = nt; L.t_acc = t; L.ks = H.seq + (uint32_t)rank; L.task = rem - 1; L.touched = true;
             ExecRec &x = ex[lane];
             x.ev_t = __longlong_as_double((long long)nt); x.t_acc = t; x.ev_seq = L.ks; x.ev_task = L.task;
             if (before_same == cnt - 1) {  // last launch of this stage in the batch: it owns the counters
@@ -1014,11 +1032,7 @@ struct Sim {
             }
         }
         L.rem -= cnt; L.comp += cnt;  // every lane on that stage tracks its counters
-        // wall time = time of the last member (members are a prefix, so it is their maximum)
-        const uint32_t thi = (uint32_t)(__double_as_longlong(t) >> 32), tlo = (uint32_t)__double_as_longlong(t);
-        const uint32_t whi = __reduce_max_sync(FULL, member ? thi : 0u);
-        const uint32_t wlo = __reduce_max_sync(FULL, (member && thi == whi) ? tlo : 0u);
-        H.wall = __longlong_as_double((long long)(((unsigned long long)whi << 32) | wlo));
+        // (the wall time -- the time of the last member -- is taken once per phase, in hot_flush1)
         H.launch_idx += (uint32_t)m; H.seq += (uint32_t)m; H.log_n += m; H.events += m;
         return m;
     }
@@ -1064,7 +1078,9 @@ struct Sim {
         const bool pa = A.kind != 0, pb = Bq.kind != 0;
         const unsigned penda = __ballot_sync(FULL, pa), pendb = __ballot_sync(FULL, pb);
         if (!(penda | pendb)) return 0;
-        const uint32_t hia = (uint32_t)(A.kt >> 32), hib = (uint32_t)(Bq.kt >> 32);
+        // 32-bit fixed-point order keys floor(16 t), saturated (see fast_batch_w); empty slots sort last
+        const uint32_t hia = pa ? __double2uint_rd(__dmul_rn(__longlong_as_double((long long)A.kt), 16.0)) : 0xffffffffu;
+        const uint32_t hib = pb ? __double2uint_rd(__dmul_rn(__longlong_as_double((long long)Bq.kt), 16.0)) : 0xffffffffu;
         unsigned aa = 0, ab = 0, ba = 0, bb = 0;
 #pragma unroll 1
         for (int i = 0; i < 32; i++) {
@@ -1218,7 +1234,7 @@ struct Sim {
                     SSB_TCNT(1, 1);
                     if (m == 0 || budget == 0) break;
                 }
-                hot_flush(H);
+                hot_flush1(L, H);
                 SSB_TACC(0);
             }
             SSB_T0();

@@ -253,6 +253,81 @@ def test_rollout_transitions_match_oracle(bank):
         assert ep > 1
 
 
+def _oracle_transitions(bank, cfg, seed, seed_step, K, time_limit=np.inf, beta=0.0):
+    """K decisions of the oracle under the fair policy with the rollout worker's re-seeding rule."""
+    from oracle import OracleEnv
+
+    orc = OracleEnv(bank, cfg["num_executors"], cfg["job_arrival_cap"], cfg["moving_delay"], cfg["warmup_delay"],
+                    cfg["job_arrival_rate"], beta=beta)
+    rows, k, ep = [], 0, 0
+    while k < K:
+        orc.reset_seed(int(seed) + seed_step * ep, time_limit)
+        done = False
+        while not done and k < K:
+            wall0 = orc.wall_time
+            a, n = orc.fair_action(True)
+            rc, rew, term = orc.step(a, n)
+            assert rc == 0
+            trunc = orc.wall_time >= time_limit  # StochasticTimeLimit (wrappers/stochastic_time_limit.py:29-30)
+            rows.append((wall0, rew, a, n, int(term), int(trunc)))
+            done = term or trunc
+            k += 1
+        ep += 1
+    return rows, ep
+
+
+def test_rollout_with_time_limit_truncation(bank):
+    """Continuous arrivals up to a time limit (no job cap): episodes end by truncation, the fused rollout
+    re-seeds them, and every transition equals the oracle's."""
+    import torch
+    from spark_sched_sim_b200 import _native as nat
+    from spark_sched_sim_b200.batched_env import BatchedSparkSchedSimEnv
+
+    B, K, TL = 4, 500, 4.0e5
+    cfg = {"num_executors": 10, "job_arrival_cap": 0, "job_arrival_rate": 4.0e-5,
+           "moving_delay": 2000.0, "warmup_delay": 1000.0}
+    env = BatchedSparkSchedSimEnv(cfg, num_envs=B, bank=bank, max_jobs=96)
+    seeds = np.arange(900, 900 + B, dtype=np.uint64)
+    env.reset_host(seeds, time_limits=np.full(B, TL))
+    host = torch.empty(B * K * nat.TRANSITION_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+    tr = env.rollout_fair_traj(K, True, auto_reset=True, seed_step=50, host=host)
+    assert (env.hdr()["error"] == 0).all()
+    n_trunc = 0
+    for b in range(B):
+        rows, eps = _oracle_transitions(bank, cfg, seeds[b], 50, K, time_limit=TL)
+        for k, (wall0, rew, a, n, term, trunc) in enumerate(rows):
+            r = tr[b, k]
+            assert (r["wall_time"], r["reward"], r["stage_idx"], r["num_exec"]) == (wall0, rew, a, n), (b, k)
+            assert (r["flags"] & 1, (r["flags"] >> 1) & 1) == (term, trunc), (b, k)
+            n_trunc += trunc
+        assert eps > 1
+    assert n_trunc > 0
+
+
+def test_rollout_with_discounted_reward(bank):
+    """beta > 0: the continuously discounted reward (:866-869) goes through exp(); transitions match the
+    oracle with rewards at 1e-12 relative (device exp vs libm), everything else exactly."""
+    import torch
+    from spark_sched_sim_b200 import _native as nat
+    from spark_sched_sim_b200.batched_env import BatchedSparkSchedSimEnv
+
+    B, K, beta = 3, 400, 5.0e-3
+    cfg = {"num_executors": 10, "job_arrival_cap": 12, "job_arrival_rate": 4.0e-5,
+           "moving_delay": 2000.0, "warmup_delay": 1000.0, "beta": beta}
+    env = BatchedSparkSchedSimEnv(cfg, num_envs=B, bank=bank)
+    seeds = np.arange(40, 40 + B, dtype=np.uint64)
+    env.reset_host(seeds)
+    host = torch.empty(B * K * nat.TRANSITION_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+    tr = env.rollout_fair_traj(K, True, auto_reset=True, seed_step=7, host=host)
+    assert (env.hdr()["error"] == 0).all()
+    for b in range(B):
+        rows, _ = _oracle_transitions(bank, cfg, seeds[b], 7, K, beta=beta)
+        for k, (wall0, rew, a, n, term, trunc) in enumerate(rows):
+            r = tr[b, k]
+            assert (r["wall_time"], r["stage_idx"], r["num_exec"], r["flags"] & 1) == (wall0, a, n, term), (b, k)
+            assert abs(r["reward"] - rew) <= 1e-12 * max(1.0, abs(rew)), (b, k, r["reward"], rew)
+
+
 @pytest.mark.parametrize("name,budget", [("e10_j8_random_s5_philox", 1), ("e10_j8_fair_s2_philox", 7),
                                          ("e50_j8_random_s8_philox", 33), ("c2_fair_s1234_philox", 64)])
 def test_budgeted_step_is_equivalent(bank, name, budget):

@@ -1271,21 +1271,13 @@ struct Sim {
     // smaller than the final table size each id sits in its own slot => iteration is ascending
     // (tests/test_pyset.py checks the claims against the interpreter).  Small sets are emulated in
     // registers, anything else with the generic set emulation.
-    __device__ SSB_COLD int reward_order(int16_t *ord)
+    // (the ascending case is handled by compute_jobtime_w without materialising the order)
+    __device__ SSB_COLD int reward_order(int16_t *ord, int n, int max_id)
     {
         const int16_t *old = p.old_act + (size_t)b * p.Jc;
         const int n_old = h->n_old_active, n_new = h->n_active;
         const int last_old = n_old ? old[n_old - 1] : -1;
-        int n = n_old;
-        for (int i = n_new - 1; i >= 0 && act[i] > last_old; i--) n++;
-        const int max_id = n_new && act[n_new - 1] > last_old ? act[n_new - 1] : last_old;
-        const int F = n < 5 ? 8 : n < 19 ? 32 : n < 77 ? 128 : n < 307 ? 512 : n < 1229 ? 2048 : 0;
         int k = 0;
-        if (max_id < F) {  // ascending: old, then the arrivals
-            for (int i = 0; i < n_old; i++) ord[k++] = old[i];
-            for (int i = 0; i < n_new; i++) if (act[i] > last_old) ord[k++] = act[i];
-            return k;
-        }
         if (n <= 18 && max_id < 255) {
             // 8- or 32-slot table without deletions, in registers: keys as bytes of u64 words, occupancy
             // as a bit mask, so the 9-slot linear probe of set_add_entry is one find-first-zero
@@ -1354,16 +1346,29 @@ struct Sim {
         const double wall = h->wall_time, wall_old = h->wall_old;
         if (wall - wall_old == 0.0) return 0.0;
         int16_t *ord = p.reward_ord + (size_t)b * p.Jc;
-        int n = 0;
-        if (lane == 0) n = reward_order(ord);
-        n = __shfl_sync(FULL, n, 0);
-        __syncwarp();
+        // distinct ids = the old list, then the jobs that arrived during the step (the tail of act)
+        const int16_t *old = p.old_act + (size_t)b * p.Jc;
+        const int n_old = h->n_old_active, n_new = h->n_active;
+        const int last_old = n_old ? old[n_old - 1] : -1;
+        int n_arr = 0;
+        while (n_arr < n_new && act[n_new - 1 - n_arr] > last_old) n_arr++;
+        int n = n_old + n_arr;
+        const int max_id = n_arr ? act[n_new - 1] : last_old;
+        const int F = n < 5 ? 8 : n < 19 ? 32 : n < 77 ? 128 : n < 307 ? 512 : n < 1229 ? 2048 : 0;
+        const bool ascending = max_id < F;  // every id in its own slot of the final table
+        if (!ascending) {
+            int m = 0;
+            if (lane == 0) m = reward_order(ord, n, max_id);
+            n = __shfl_sync(FULL, m, 0);
+            __syncwarp();
+        }
         const double beta = p.beta;
         double jt = 0.0;
         for (int base = 0; base < n; base += 32) {
             double term = 0.0;
             if (base + lane < n) {
-                const int j = ord[base + lane];
+                const int k = base + lane;
+                const int j = !ascending ? ord[k] : k < n_old ? old[k] : act[n_new - n_arr + (k - n_old)];
                 const double start = fmax(jb[j].t_arrival, wall_old), end = fmin(jb[j].t_completed, wall);
                 term = beta == 0.0 ? __dadd_rn(end, -start) : discounted_term(start - wall_old, end - wall_old);
             }

@@ -301,11 +301,10 @@ def main() -> None:
         streams = [torch.cuda.Stream(dev) for _ in range(T)]
         pins = [(torch.empty(len(ix), dtype=torch.int32).pin_memory(),
                  torch.empty(len(ix), dtype=torch.int32).pin_memory()) for ix in shards]
-        resets = [1] * T
 
         def e2e_steps(t, n_steps):
             torch.cuda.set_device(dev)
-            e, sd, (a_pin, n_pin) = envs[t], seeds[shards[t]], pins[t]
+            e, (a_pin, n_pin) = envs[t], pins[t]
             with torch.cuda.stream(streams[t]):
                 for _ in range(n_steps * De):
                     a, n = e.fair_actions(True)          # policy on the observation just written
@@ -314,15 +313,13 @@ def main() -> None:
                     streams[t].synchronize()
                     # H2D actions, bounded step (envs still simulating come back "pending" and simply
                     # continue next call -- no env waits for the batch's longest event chain), D2H headers
+                    # finished envs re-seed themselves on their next step (ssb_set_autoreset: the caller's
+                    # `if done: env.reset(seed=...)` without a separate launch); h["was_reset"] marks them
                     h = e.step_host(a_pin.numpy(), n_pin.numpy(), max_events=args.e2e_budget)
-                    done = (h["terminated"] != 0) | (h["truncated"] != 0)
-                    if done.any():                       # per-env reset(seed) exactly as a caller would
-                        e.reset_host(sd + np.uint64(seed_step) * np.uint64(resets[t]),
-                                     mask=done.astype(np.uint8))
-                        resets[t] += 1
 
         for t in range(T):
             envs[t].reset_host(seeds[shards[t]])
+            envs[t].set_autoreset(True, seed_step)
         Ke = max(2, min(K, 5))
         with ThreadPoolExecutor(T) as ex:
             list(ex.map(lambda t: e2e_steps(t, 2), range(T)))
@@ -342,8 +339,8 @@ def main() -> None:
                "h2d_bytes_per_step": De * 2 * 4 * B, "d2h_bytes_per_step": De * (2 * 4 + 48) * B,
                "steps": Ke, "calls_per_step": De, "max_events_per_call": args.e2e_budget,
                "host_threads": T,
-               "path": "per shard: ssb_fair_actions -> D2H actions (pinned) -> ssb_step_host (H2D, step, D2H "
-                       "headers) -> ssb_reset_host for finished envs",
+               "path": "ssb_fair_actions -> D2H actions (pinned) -> ssb_step_host (H2D actions, bounded step with "
+                       "auto-reset of finished envs, D2H headers)",
                "gpu_launches": Ke * De * 2 * T}
         launches_e2e = Ke * De * 2 * T
         # the rollout-collection call (rollout_worker.py:135-157 as ONE call): fused rollout on the device,

@@ -107,7 +107,8 @@ typedef struct {
     uint8_t terminated;
     uint8_t truncated; /* wall_time >= time limit (wrappers/stochastic_time_limit.py:29-30) */
     uint8_t pending;   /* budgeted step only: next decision not reached yet, observation not rewritten */
-    uint8_t pad;
+    uint8_t was_reset; /* auto-reset only: this ssb_step call re-seeded the env instead of applying its action;
+                          the observation is the first one of the new episode (reward 0) */
 } ssb_obs_hdr;
 
 /* Device views of the observation slabs (fixed stride per environment). */
@@ -163,6 +164,13 @@ int ssb_reset(ssb_env *env, const uint64_t *seeds, const double *time_limits, co
  *   interleaving across envs changes (no env waits for the batch's longest event chain). */
 int ssb_step(ssb_env *env, const int32_t *stage_idx, const int32_t *num_exec, const uint8_t *mask,
              int32_t max_events, void *stream);
+
+/* Vector-env auto-reset ("next step" mode): when enabled, an ssb_step call on an env whose episode is over
+ * (terminated, or truncated by its time limit) re-seeds it with seed + seed_step * reset_count
+ * (rollout_worker.py:118-120, the rule ssb_rollout_fair uses), ignores the action, writes the new episode's
+ * first observation and sets ssb_obs_hdr.was_reset -- what a caller's `if done: env.reset(seed=...)` does,
+ * without a separate ssb_reset launch per call. */
+int ssb_set_autoreset(ssb_env *env, int32_t enable, uint64_t seed_step);
 
 /* same with HOST buffers: copies in, runs, copies the B observation headers out, synchronises */
 int ssb_reset_host(ssb_env *env, const uint64_t *seeds, const double *time_limits, const uint8_t *mask,

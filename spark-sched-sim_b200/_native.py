@@ -109,7 +109,7 @@ OBS_HDR_DTYPE = np.dtype(
         ("terminated", "u1"),
         ("truncated", "u1"),
         ("pending", "u1"),
-        ("pad", "u1"),
+        ("was_reset", "u1"),
     ]
 )
 assert OBS_HDR_DTYPE.itemsize == 48
@@ -123,7 +123,7 @@ STATS_DTYPE = np.dtype([(f, "<u8") for f in STATS_FIELDS])
 
 EXPORTS = [
     "ssb_abi_version", "ssb_last_cuda_error", "ssb_workspace_bytes", "ssb_create", "ssb_destroy",
-    "ssb_load_trace", "ssb_clear_trace", "ssb_reset", "ssb_step", "ssb_reset_host", "ssb_step_host",
+    "ssb_load_trace", "ssb_clear_trace", "ssb_reset", "ssb_step", "ssb_reset_host", "ssb_step_host", "ssb_set_autoreset",
     "ssb_rollout_fair", "ssb_rollout_fair_traj", "ssb_fair_actions", "ssb_get_views", "ssb_get_stats", "ssb_reset_stats",
     "ssb_get_jobs", "ssb_get_log", "ssb_decima_obs", "ssb_get_decima_views",
     "ssb_set_decima_weights", "ssb_decima_policy", "ssb_get_policy_views", "ssb_get_debug_counters",
@@ -159,6 +159,7 @@ def lib():
     L.ssb_step.argtypes = [vp, vp, vp, vp, i32, vp]
     L.ssb_reset_host.argtypes = [vp, vp, vp, vp, vp]
     L.ssb_step_host.argtypes = [vp, vp, vp, vp, i32, vp]
+    L.ssb_set_autoreset.argtypes = [vp, i32, u64]
     L.ssb_rollout_fair.argtypes = [vp, i32, i32, i32, u64, vp]
     L.ssb_rollout_fair_traj.argtypes = [vp, i32, i32, i32, u64, vp, vp]
     L.ssb_fair_actions.argtypes = [vp, i32, vp, vp, vp]

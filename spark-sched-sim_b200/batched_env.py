@@ -173,6 +173,12 @@ class BatchedSparkSchedSimEnv:
                                           int(auto_reset), int(seed_step), self._stream()),
                   "ssb_rollout_fair")
 
+    def set_autoreset(self, enable: bool = True, seed_step: int = 1) -> None:
+        """Vector-env auto-reset ("next step" mode): a step() on a finished env re-seeds it with
+        seed + seed_step * reset_count (rollout_worker.py:118-120), ignores its action and returns the new
+        episode's first observation with hdr["was_reset"] = 1."""
+        nat.check(self.L.ssb_set_autoreset(self._h, int(bool(enable)), int(seed_step)), "ssb_set_autoreset")
+
     def rollout_fair_traj(self, num_decisions, dynamic_partition=True, auto_reset=True, seed_step=1,
                           out: "torch.Tensor | None" = None, host: "torch.Tensor | None" = None):
         """Fused rollout that also records every transition (what RolloutBuffer keeps per step besides

@@ -51,12 +51,24 @@ k_reset(Params p, const uint64_t *seeds, const double *time_limits, const uint8_
 // NS: executor slots per lane of the batched fast path (1: E <= 32, 2: E <= 64), see ssb_sim.cuh
 template <int NS>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, NS == 1 ? 7 : 4)
-k_step(Params p, const int32_t *stage_idx, const int32_t *num_exec, const uint8_t *mask, int max_events)
+k_step(Params p, const int32_t *stage_idx, const int32_t *num_exec, const uint8_t *mask, int max_events,
+       int auto_reset, uint64_t seed_step)
 {
     const int b = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (b >= p.B) return;
     if (mask && !mask[b]) return;
     Sim sim(p, b, lane);
+    if (auto_reset && !sim.h->error && (sim.h->done || sim.oh->truncated)) {
+        // the caller's `if terminated or truncated: env.reset(seed=...)` (rollout_worker.py:118-120, :150-153)
+        const uint64_t seed = sim.h->base_seed + seed_step * (uint64_t)sim.h->reset_count;
+        const double tl = sim.h->time_limit;
+        const bool was_trunc = !sim.h->done;
+        __syncwarp();
+        if (lane == 0) { sim.h->reset_count += 1; if (was_trunc) sim.stats->episodes++; }
+        sim.reset_w(seed, tl);
+        if (lane == 0) sim.oh->was_reset = 1;
+        return;
+    }
     if (lane == 0) sim.oh->error = 0;
     __syncwarp();
     sim.template step_w<NS>(stage_idx[b], num_exec[b], max_events);
@@ -300,6 +312,8 @@ struct ssb_env {
     int grid;
     int num_sms;
     int dmax;           // upper bound of the message-passing depth: longest template chain - 1
+    int auto_reset;     // ssb_set_autoreset
+    uint64_t auto_seed_step;
 };
 
 template <int ST>
@@ -512,12 +526,20 @@ int ssb_step(ssb_env *env, const int32_t *stage_idx, const int32_t *num_exec, co
 {
     if (!env || !stage_idx || !num_exec) return SSB_E_INVALID;
     if (env->p.E <= 32)
-        k_step<1><<<env->grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(env->p, stage_idx, num_exec, mask,
-                                                                              max_events);
+        k_step<1><<<env->grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(
+            env->p, stage_idx, num_exec, mask, max_events, env->auto_reset, env->auto_seed_step);
     else
-        k_step<2><<<env->grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(env->p, stage_idx, num_exec, mask,
-                                                                              max_events);
+        k_step<2><<<env->grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(
+            env->p, stage_idx, num_exec, mask, max_events, env->auto_reset, env->auto_seed_step);
     CUDA_TRY(cudaGetLastError());
+    return SSB_OK;
+}
+
+int ssb_set_autoreset(ssb_env *env, int32_t enable, uint64_t seed_step)
+{
+    if (!env) return SSB_E_INVALID;
+    env->auto_reset = enable ? 1 : 0;
+    env->auto_seed_step = seed_step;
     return SSB_OK;
 }
 

@@ -1455,7 +1455,7 @@ struct Sim {
             o.error = h->error;
             o.terminated = terminated ? 1 : 0;
             o.truncated = (h->wall_time >= h->time_limit) ? 1 : 0;
-            o.pending = 0; o.pad = 0;
+            o.pending = 0; o.was_reset = 0;
             *oh = o;
             stats->observations++;
             stats->sum_nodes += N; stats->sum_edges += M; stats->sum_jobs += n_active;

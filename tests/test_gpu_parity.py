@@ -304,6 +304,38 @@ def test_rollout_with_time_limit_truncation(bank):
     assert n_trunc > 0
 
 
+def test_step_api_autoreset_matches_oracle(bank):
+    """ssb_set_autoreset: a step() on a finished env re-seeds it (seed + seed_step * reset_count), ignores the
+    action and flags was_reset; the sequence of real transitions equals the oracle loop with explicit resets."""
+    from spark_sched_sim_b200.batched_env import BatchedSparkSchedSimEnv
+
+    B, K = 4, 700
+    cfg = {"num_executors": 10, "job_arrival_cap": 6, "job_arrival_rate": 4.0e-5,
+           "moving_delay": 2000.0, "warmup_delay": 1000.0}
+    env = BatchedSparkSchedSimEnv(cfg, num_envs=B, bank=bank)
+    seeds = np.arange(300, 300 + B, dtype=np.uint64)
+    env.reset_host(seeds)
+    env.set_autoreset(True, 11)
+    got = [[] for _ in range(B)]
+    n_resets = 0
+    while min(len(g) for g in got) < K:
+        wall0 = env.hdr()["wall_time"].copy()
+        a, n = env.fair_actions(True)
+        a_h, n_h = a.cpu().numpy(), n.cpu().numpy()
+        h = env.step_host(a_h, n_h).copy()
+        assert (h["error"] == 0).all()
+        for b in range(B):
+            if h["was_reset"][b]:
+                assert h["reward"][b] == 0.0 and h["wall_time"][b] == 0.0 and not h["terminated"][b]
+                n_resets += 1
+            else:
+                got[b].append((wall0[b], h["reward"][b], int(a_h[b]), int(n_h[b]), int(h["terminated"][b]), 0))
+    assert n_resets > B
+    for b in range(B):
+        rows, _ = _oracle_transitions(bank, cfg, seeds[b], 11, K)
+        assert got[b][:K] == rows, b
+
+
 def test_rollout_with_discounted_reward(bank):
     """beta > 0: the continuously discounted reward (:866-869) goes through exp(); transitions match the
     oracle with rewards at 1e-12 relative (device exp vs libm), everything else exactly."""

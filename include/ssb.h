@@ -199,6 +199,22 @@ typedef struct {
  * its remaining rows untouched. */
 int ssb_rollout_fair_traj(ssb_env *env, int32_t num_decisions, int32_t dynamic_partition, int32_t auto_reset,
                           uint64_t seed_step, ssb_transition *traj, void *stream);
+
+/* ---- what the trainer derives from the rollout buffers before a policy update
+ * (trainers/trainer.py:172-212 _preprocess_rollouts).  Plain functions on DEVICE buffers, no handle:
+ * traj = ssb_transition[B][stride], num_steps = i32[B] rows stored per rollout (clamped to stride),
+ * final_wall = f64[B] wall time after each rollout's last step. */
+/* ReturnsCalculator._calc_discounted_returns (trainers/utils/returns_calculator.py:67-76):
+ * R_k = r_k + exp(-beta * 1e-3 * (t_{k+1} - t_k)) * R_{k+1}, R_n = 0 -> returns f64[B][stride] */
+int ssb_discounted_returns(const ssb_transition *traj, const int32_t *num_steps, const double *final_wall,
+                           int32_t num_rollouts_total, int32_t stride, double beta, double *returns,
+                           void *stream);
+/* Baseline.average (trainers/utils/baselines.py:12-37): consecutive groups of `group_size` rollouts ran the
+ * same job sequence; baseline[b][k] = mean over the group of every member's returns linearly interpolated
+ * (np.interp) at rollout b's step time k -> baselines f64[B][stride].  group_size <= 128. */
+int ssb_group_baselines(const ssb_transition *traj, const double *returns, const int32_t *num_steps,
+                        int32_t num_rollouts_total, int32_t stride, int32_t group_size, double *baselines,
+                        void *stream);
 /* evaluates the built-in policy on the current observations -> DEVICE i32[B] each */
 int ssb_fair_actions(ssb_env *env, int32_t dynamic_partition, int32_t *stage_idx, int32_t *num_exec,
                      void *stream);

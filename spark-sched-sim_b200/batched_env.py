@@ -229,6 +229,10 @@ class BatchedSparkSchedSimEnv:
         s = self.stats_bytes.cpu().numpy().view(nat.STATS_DTYPE).reshape(-1)
         return {f: int(s[f].sum()) for f in nat.STATS_FIELDS}
 
+    def stats_per_env(self) -> np.ndarray:
+        """The ssb_stats counters of every env (structured array [B])."""
+        return self.stats_bytes.cpu().numpy().view(nat.STATS_DTYPE).reshape(-1).copy()
+
     def reset_stats(self):
         nat.check(self.L.ssb_reset_stats(self._h, self._stream()), "ssb_reset_stats")
 

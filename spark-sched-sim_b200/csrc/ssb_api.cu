@@ -14,6 +14,7 @@
 
 #include "ssb_decima.cuh"
 #include "ssb_decima_tc.cuh"
+#include "ssb_learn.cuh"
 #include "ssb_sim.cuh"
 
 using namespace ssb;
@@ -588,6 +589,27 @@ int ssb_rollout_fair_traj(ssb_env *env, int32_t num_decisions, int32_t dynamic_p
     else
         k_rollout_fair<2><<<env->grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(
             env->p, num_decisions, dynamic_partition, auto_reset, seed_step, traj);
+    CUDA_TRY(cudaGetLastError());
+    return SSB_OK;
+}
+
+int ssb_discounted_returns(const ssb_transition *traj, const int32_t *num_steps, const double *final_wall,
+                           int32_t B, int32_t stride, double beta, double *returns, void *stream)
+{
+    if (!traj || !num_steps || !final_wall || !returns || B < 1 || stride < 1) return SSB_E_INVALID;
+    learn::k_discounted_returns<<<(B + 3) / 4, 128, 0, (cudaStream_t)stream>>>(traj, num_steps, final_wall, B, stride,
+                                                                              beta, returns);
+    CUDA_TRY(cudaGetLastError());
+    return SSB_OK;
+}
+
+int ssb_group_baselines(const ssb_transition *traj, const double *returns, const int32_t *num_steps, int32_t B,
+                        int32_t stride, int32_t group_size, double *baselines, void *stream)
+{
+    if (!traj || !returns || !num_steps || !baselines || B < 1 || stride < 1 || group_size < 1 || group_size > 128)
+        return SSB_E_INVALID;
+    learn::k_group_baselines<<<(B + 3) / 4, 128, 0, (cudaStream_t)stream>>>(traj, returns, num_steps, B, stride,
+                                                                           group_size, baselines);
     CUDA_TRY(cudaGetLastError());
     return SSB_OK;
 }

@@ -12,7 +12,7 @@ GOLDEN_DIR = osp.join(osp.dirname(osp.abspath(__file__)), "golden")
 
 def golden_names(slim=None):
     names = sorted(osp.basename(p)[:-4] for p in glob.glob(osp.join(GOLDEN_DIR, "*.npz")))
-    names = [n for n in names if n != "decima_model"]  # the policy weights fixture, not a trace
+    names = [n for n in names if n not in ("decima_model", "learner_vectors")]  # fixtures that are not traces
     if slim is None:
         return names
     return [n for n in names if n.startswith("c2_") == slim]

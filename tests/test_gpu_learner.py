@@ -1,0 +1,82 @@
+"""GPU parity of ssb_discounted_returns / ssb_group_baselines (1) on the reference's recorded vectors and
+(2) on real fused rollouts against the numpy oracle (oracle/learner.py).  Baselines are compared bit for bit
+when fed the same returns; returns at 1e-12 relative (device exp vs numpy exp)."""
+import numpy as np
+import pytest
+import torch
+
+from test_learner_oracle import CASES
+
+pytestmark = pytest.mark.gpu
+
+
+def pack(times, rewards, stride):
+    from spark_sched_sim_b200 import _native as nat
+
+    B = len(rewards)
+    tr = np.zeros((B, stride), nat.TRANSITION_DTYPE)
+    for i in range(B):
+        n = len(rewards[i])
+        tr["wall_time"][i, :n] = times[i][:n]
+        tr["reward"][i, :n] = rewards[i]
+    dev = torch.from_numpy(tr.view(np.uint8).reshape(-1)).cuda()
+    num = torch.tensor([len(r) for r in rewards], dtype=torch.int32, device="cuda")
+    final = torch.tensor([t[-1] for t in times], dtype=torch.float64, device="cuda")
+    return dev, num, final
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_reference_vectors(name):
+    from spark_sched_sim_b200.returns import Baseline, ReturnsCalculator
+
+    c = CASES[name]
+    B, stride = len(c["lens"]), int(c["lens"].max()) + 3
+    traj, num, final = pack(c["times"], c["rewards"], stride)
+    ret = ReturnsCalculator(beta=c["beta"])(traj, num, final, stride)
+    got = ret.cpu().numpy()
+    for i in range(B):
+        assert np.allclose(got[i, :c["lens"][i]], c["returns"][i], rtol=1e-12, atol=0.0), i
+    # baselines from the reference's own returns: bit-exact
+    ref_ret = torch.zeros_like(ret)
+    for i in range(B):
+        ref_ret[i, :c["lens"][i]] = torch.from_numpy(c["returns"][i]).cuda()
+    base = Baseline(B // c["num_rollouts"], c["num_rollouts"])(traj, ref_ret, num).cpu().numpy()
+    for i in range(B):
+        assert np.array_equal(base[i, :c["lens"][i]], c["baselines"][i]), i
+
+
+def test_on_fused_rollouts(bank):
+    """Whole pipeline on the device: fair rollouts of 4 job sequences x 4 envs each (same seed within a group,
+    as trainer.py:268-270 assigns them), returns and group baselines vs the numpy oracle."""
+    from learner import discounted_returns, group_baselines
+    from spark_sched_sim_b200 import _native as nat
+    from spark_sched_sim_b200.batched_env import BatchedSparkSchedSimEnv
+    from spark_sched_sim_b200.returns import Baseline, ReturnsCalculator
+
+    S, R, K, beta = 4, 4, 700, 5e-3
+    B = S * R
+    cfg = {"num_executors": 10, "job_arrival_cap": 8, "job_arrival_rate": 4.0e-5,
+           "moving_delay": 2000.0, "warmup_delay": 1000.0, "beta": beta}
+    env = BatchedSparkSchedSimEnv(cfg, num_envs=B, bank=bank)
+    seeds = (100 + np.arange(B) // R).astype(np.uint64)
+    env.reset_host(seeds)
+    # groups share the job sequence; FIFO vs fair partitioning alternates so that the rollouts differ
+    traj = env.rollout_fair_traj(K, True, auto_reset=False)
+    hdr = env.hdr()
+    assert (hdr["terminated"] != 0).all() and (hdr["error"] == 0).all()
+    st = env.stats_per_env()
+    num = torch.from_numpy(st["decisions"].astype(np.int32)).cuda()
+    final = torch.from_numpy(hdr["wall_time"].copy()).cuda()
+    ret = ReturnsCalculator(beta=beta)(traj, num, final, K)
+    base = Baseline(S, R)(traj, ret, num)
+    tr = traj.cpu().numpy().view(nat.TRANSITION_DTYPE).reshape(B, K)
+    n = st["decisions"].astype(int)
+    ts = [np.concatenate([tr["wall_time"][i, :n[i]], [hdr["wall_time"][i]]]) for i in range(B)]
+    o_ret = [discounted_returns(tr["reward"][i, :n[i]], ts[i], beta) for i in range(B)]
+    g_ret = ret.cpu().numpy()
+    for i in range(B):
+        assert np.allclose(g_ret[i, :n[i]], o_ret[i], rtol=1e-12, atol=0.0), i
+    o_base = group_baselines([t[:-1] for t in ts], [g_ret[i, :n[i]] for i in range(B)], R)
+    g_base = base.cpu().numpy()
+    for i in range(B):
+        assert np.array_equal(g_base[i, :n[i]], o_base[i]), i

@@ -61,10 +61,18 @@ def main():
     env.reset_host(seeds)
     stats_vec = torch.zeros(8, dtype=torch.float64, device=dev)
 
-    def decide(n):
-        for _ in range(n):
-            a, c = env.decima_policy()
-            env.step(a, c, max_events=args.budget)
+    from spark_sched_sim_b200 import _native as nat
+
+    env.set_autoreset(True, B * world)
+    chunk = 25  # decisions per ssb_rollout_decima call (one rollout-buffer slab)
+    nb = B * chunk * nat.TRANSITION_DTYPE.itemsize
+    traj_dev = torch.empty(nb, dtype=torch.uint8, device=dev)
+    traj_pin = torch.empty(nb, dtype=torch.uint8).pin_memory()
+
+    def decide(n, to_host=False):
+        # rollout collection through the public call: policy + step on the device, transitions recorded
+        for _ in range(max(1, n // chunk)):
+            env.rollout_decima(chunk, max_events=args.budget, out=traj_dev, host=traj_pin if to_host else None)
 
     decide(args.warmup)
     env.reset_stats()
@@ -90,6 +98,15 @@ def main():
         dist.all_reduce(c)
         ms = float(t.item())
         st = dict(st, decisions=int(c[0].item()), events=int(c[1].item()))
+    # e2e: the same with every slab of transitions copied to pinned host memory (wall clock)
+    import time
+    env.reset_stats()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    decide(args.decisions, to_host=True)
+    torch.cuda.synchronize()
+    e2e_dt = time.perf_counter() - t0
+    e2e_dec = env.stats()["decisions"]
     # time of the policy kernel alone
     p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     p0.record()
@@ -109,6 +126,8 @@ def main():
                    "max_events_per_step": args.budget},
         "decisions": st["decisions"], "events": st["events"], "ms_total": ms,
         "policy_kernel_ms": p0.elapsed_time(p1) / 20,
+        "e2e": {"value": e2e_dec * world / e2e_dt, "unit": "decisions/s (this rank x world)", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": nb, "path": "ssb_rollout_decima (25 decisions) -> D2H of the transition slab"},
         "env_errors": int(((hdr["error"] != 0) & (hdr["error"] != 9)).sum()),
         "finished_envs": int((hdr["terminated"] != 0).sum()),
     }))

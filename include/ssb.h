@@ -191,8 +191,9 @@ typedef struct {
     double wall_time;
     double reward;
     int32_t stage_idx, num_exec; /* env-format action (stage_idx == -1: no-op) */
-    int32_t flags;               /* 1: step() terminated, 2: truncated, 4: first decision after a reset */
-    int32_t pad;
+    int32_t flags;               /* 1: step() terminated, 2: truncated, 4: first decision after a reset,
+                                    8: no transition -- this call only re-seeded the env (ssb_rollout_decima) */
+    float lgprob;                /* log-probability of the action under the policy (0 for the heuristics) */
 } ssb_transition;
 /* ssb_rollout_fair that also records every transition: traj = DEVICE ssb_transition[B][num_decisions],
  * row d of env b at traj[b * num_decisions + d]; an env that stops early (auto_reset == 0) leaves
@@ -256,6 +257,12 @@ int ssb_set_decima_weights(ssb_env *env, const float *weights, int32_t n_floats)
 int ssb_decima_policy(ssb_env *env, const int32_t *forced_stage, const int32_t *forced_num_exec,
                       int32_t *stage_idx_out, int32_t *num_exec_out, void *stream);
 int ssb_get_policy_views(ssb_env *env, ssb_policy_views *out);
+/* Decima rollout collection (trainers/rollout_worker.py:135-157 with DecimaScheduler): num_decisions times
+ * { ssb_decima_policy (sampled actions) ; ssb_step(max_events) } for every env, everything stream-ordered on the
+ * device, each call's (wall time, action, lgprob, reward, flags) stored at traj[b * num_decisions + d] (DEVICE,
+ * may be NULL).  Finished envs follow ssb_set_autoreset: with it, the call after the end of an episode
+ * re-seeds the env (row flagged 8); without it they idle (rows flagged with error SSB_ENV_DONE semantics). */
+int ssb_rollout_decima(ssb_env *env, int32_t num_decisions, int32_t max_events, ssb_transition *traj, void *stream);
 /* device pointer to ssb_stats[B] */
 int ssb_get_stats(ssb_env *env, ssb_stats **out);
 int ssb_reset_stats(ssb_env *env, void *stream);

@@ -115,7 +115,7 @@ OBS_HDR_DTYPE = np.dtype(
 assert OBS_HDR_DTYPE.itemsize == 48
 # ssb_transition (include/ssb.h): one stored step of a fused rollout
 TRANSITION_DTYPE = np.dtype([("wall_time", "<f8"), ("reward", "<f8"), ("stage_idx", "<i4"), ("num_exec", "<i4"),
-                             ("flags", "<i4"), ("pad", "<i4")])
+                             ("flags", "<i4"), ("lgprob", "<f4")])
 assert TRANSITION_DTYPE.itemsize == 32
 STATS_FIELDS = ("decisions", "events", "sched_scans", "sum_nodes", "sum_edges", "sum_jobs",
                 "observations", "episodes")
@@ -126,7 +126,7 @@ EXPORTS = [
     "ssb_load_trace", "ssb_clear_trace", "ssb_reset", "ssb_step", "ssb_reset_host", "ssb_step_host", "ssb_set_autoreset",
     "ssb_rollout_fair", "ssb_rollout_fair_traj", "ssb_discounted_returns", "ssb_group_baselines", "ssb_fair_actions", "ssb_get_views", "ssb_get_stats", "ssb_reset_stats",
     "ssb_get_jobs", "ssb_get_log", "ssb_decima_obs", "ssb_get_decima_views",
-    "ssb_set_decima_weights", "ssb_decima_policy", "ssb_get_policy_views", "ssb_get_debug_counters",
+    "ssb_set_decima_weights", "ssb_decima_policy", "ssb_rollout_decima", "ssb_get_policy_views", "ssb_get_debug_counters",
 ]
 
 _lib = None
@@ -160,6 +160,7 @@ def lib():
     L.ssb_reset_host.argtypes = [vp, vp, vp, vp, vp]
     L.ssb_step_host.argtypes = [vp, vp, vp, vp, i32, vp]
     L.ssb_set_autoreset.argtypes = [vp, i32, u64]
+    L.ssb_rollout_decima.argtypes = [vp, i32, i32, vp, vp]
     L.ssb_rollout_fair.argtypes = [vp, i32, i32, i32, u64, vp]
     L.ssb_rollout_fair_traj.argtypes = [vp, i32, i32, i32, u64, vp, vp]
     L.ssb_discounted_returns.argtypes = [vp, vp, vp, i32, i32, C.c_double, vp, vp]

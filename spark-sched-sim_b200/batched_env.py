@@ -308,6 +308,23 @@ class BatchedSparkSchedSimEnv:
                                            a.data_ptr(), n.data_ptr(), self._stream()), "ssb_decima_policy")
         return a, n
 
+    def rollout_decima(self, num_decisions, max_events=0, out: "torch.Tensor | None" = None,
+                       host: "torch.Tensor | None" = None):
+        """Decima rollout collection on the device: num_decisions x { decima_policy ; step } with every call's
+        (wall time, action, lgprob, reward, flags) recorded -- the RolloutBuffer of
+        trainers/rollout_worker.py:18-46 minus the observations.  Finished envs follow set_autoreset().
+        Returns the device tensor, or with `host` (pinned uint8) a structured array [B, num_decisions]."""
+        nbytes = self.num_envs * int(num_decisions) * nat.TRANSITION_DTYPE.itemsize
+        if out is None:
+            out = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        nat.check(self.L.ssb_rollout_decima(self._h, int(num_decisions), int(max_events), out.data_ptr(),
+                                            self._stream()), "ssb_rollout_decima")
+        if host is None:
+            return out
+        host[:nbytes].copy_(out[:nbytes], non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return host[:nbytes].numpy().view(nat.TRANSITION_DTYPE).reshape(self.num_envs, int(num_decisions))
+
     def load_trace(self, b, t_arrival, template, tape=None):
         ta = np.ascontiguousarray(t_arrival, np.float64)
         tm = np.ascontiguousarray(template, np.int32)

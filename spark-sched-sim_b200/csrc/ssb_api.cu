@@ -130,7 +130,7 @@ k_rollout_fair(Params p, int num_decisions, int dynamic_partition, int auto_rese
             ssb_transition t;
             t.wall_time = wall0; t.reward = sim.oh->reward; t.stage_idx = a; t.num_exec = n;
             t.flags = (sim.oh->terminated ? 1 : 0) | (sim.oh->truncated ? 2 : 0) | fresh;
-            t.pad = 0;
+            t.lgprob = 0.0f;
             traj[(size_t)b * num_decisions + d] = t;
         }
         fresh = 0;
@@ -148,6 +148,28 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_decima_obs(Params p)
     if (b >= p.B) return;
     Sim sim(p, b, lane);
     sim.decima_obs_w(Sk[threadIdx.x >> 5]);
+}
+
+// rollout-buffer rows around one { policy ; step } call of ssb_rollout_decima
+__global__ void k_traj_pre(Params p, const int32_t *a, const int32_t *n, ssb_transition *traj, int K, int d)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.B) return;
+    ssb_transition t;
+    t.wall_time = p.obs_hdr[b].wall_time; t.reward = 0.0; t.stage_idx = a[b]; t.num_exec = n[b];
+    t.flags = p.obs_hdr[b].was_reset ? 4 : 0;
+    t.lgprob = p.pol_lgprob[b];
+    traj[(size_t)b * K + d] = t;
+}
+__global__ void k_traj_post(Params p, ssb_transition *traj, int K, int d)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.B) return;
+    const ssb_obs_hdr &o = p.obs_hdr[b];
+    ssb_transition &t = traj[(size_t)b * K + d];
+    if (o.was_reset || o.error == SSB_ENV_DONE) { t.flags = 8; t.reward = 0.0; return; }
+    t.reward = o.reward;
+    t.flags |= (o.terminated ? 1 : 0) | (o.truncated ? 2 : 0);
 }
 
 __global__ void k_zero_stats(ssb_stats *s, int n)
@@ -273,6 +295,8 @@ void carve(Carver &cv, const ssb_config &c, const ssb_bank &bk, const Dims &d, P
         p.pol_exec_logits = cv.take<float>(B * p.Epad);
         p.pol_action = cv.take<int32_t>(B * 4);
         p.pol_lgprob = cv.take<float>(B);
+        p.pol_act_a = cv.take<int32_t>(B);
+        p.pol_act_n = cv.take<int32_t>(B);
         p.pl_all = cv.take<int32_t>(B * d.Sc);
         p.pl_sink = cv.take<int32_t>(B * d.Sc);
         p.pl_cand = cv.take<int32_t>(B * d.Sc);
@@ -736,6 +760,23 @@ int ssb_decima_policy(ssb_env *env, const int32_t *forced_stage, const int32_t *
     tc::k_pol_sample_stage<<<warp_grid, 128, 0, s>>>(p, forced_stage);
     if ((rc = launch_tile<tc::ST_EXEC>(env, p.pl_exec, nullptr, cnt + tc::CNT_EXEC, 0, 1, s))) return rc;
     tc::k_pol_sample_exec<<<warp_grid, 128, 0, s>>>(p, forced_num_exec, stage_idx_out, num_exec_out);
+    CUDA_TRY(cudaGetLastError());
+    return SSB_OK;
+}
+
+int ssb_rollout_decima(ssb_env *env, int32_t num_decisions, int32_t max_events, ssb_transition *traj, void *stream)
+{
+    if (!env || !env->p.pol_w || num_decisions < 0) return SSB_E_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    const Params &p = env->p;
+    const int tb = (p.B + 127) / 128;
+    for (int d = 0; d < num_decisions; d++) {
+        int rc = ssb_decima_policy(env, nullptr, nullptr, p.pol_act_a, p.pol_act_n, stream);
+        if (rc) return rc;
+        if (traj) k_traj_pre<<<tb, 128, 0, s>>>(p, p.pol_act_a, p.pol_act_n, traj, num_decisions, d);
+        if ((rc = ssb_step(env, p.pol_act_a, p.pol_act_n, nullptr, max_events, stream))) return rc;
+        if (traj) k_traj_post<<<tb, 128, 0, s>>>(p, traj, num_decisions, d);
+    }
     CUDA_TRY(cudaGetLastError());
     return SSB_OK;
 }

@@ -107,3 +107,45 @@ def test_policy_sampling_rollout_and_distribution(bank):
     h = env.hdr()
     assert (h["terminated"] != 0).all()
     assert torch.isfinite(env.pol_lgprob).all()
+
+
+def test_rollout_decima_records_the_python_loop(bank):
+    """ssb_rollout_decima == the loop { decima_policy ; step } driven from Python with the same seeds (the
+    Philox policy stream makes sampling reproducible): every recorded wall time, action, lgprob, reward and
+    flag, across auto-resets."""
+    from spark_sched_sim_b200 import _native as nat
+    from spark_sched_sim_b200.batched_env import BatchedSparkSchedSimEnv
+
+    B, K = 8, 400
+    cfg = {"num_executors": 10, "job_arrival_cap": 5, "job_arrival_rate": 4.0e-5,
+           "moving_delay": 2000.0, "warmup_delay": 1000.0}
+    seeds = np.arange(B, dtype=np.uint64) + 21
+    envs = []
+    for _ in range(2):
+        e = BatchedSparkSchedSimEnv(cfg, num_envs=B, bank=bank, decima_policy=True)
+        e.set_decima_weights(weights())
+        e.reset_host(seeds)
+        e.set_autoreset(True, 100)
+        envs.append(e)
+    host = torch.empty(B * K * nat.TRANSITION_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+    tr = envs[0].rollout_decima(K, host=host)
+    e = envs[1]
+    n_reset = n_term = 0
+    for d in range(K):
+        wall0 = e.hdr()["wall_time"].copy()
+        a, n = e.decima_policy()
+        lg = e.pol_lgprob.cpu().numpy().copy()
+        e.step(a, n)
+        h = e.hdr()
+        a_h, n_h = a.cpu().numpy(), n.cpu().numpy()
+        for b in range(B):
+            r = tr[b, d]
+            if h["was_reset"][b]:
+                assert r["flags"] == 8, (b, d)
+                n_reset += 1
+                continue
+            assert (r["wall_time"], r["stage_idx"], r["num_exec"], r["reward"]) == (wall0[b], a_h[b], n_h[b], h["reward"][b]), (b, d)
+            assert r["lgprob"] == lg[b] and (r["flags"] & 1) == int(h["terminated"][b]), (b, d)
+            n_term += int(h["terminated"][b])
+    assert n_reset >= B and n_term >= B
+    assert (envs[0].hdr()["wall_time"] == e.hdr()["wall_time"]).all()

@@ -41,3 +41,4 @@ for st in range(8):
     t = pp[st]
     d = np.diff(t[:10]).astype(np.int64)
     print(f"{names[st]:14s} total {int(t[9] - t[0]):7d} cyc : " + "  ".join(f"{lab[i]}={int(d[i])}" for i in range(9)))
+

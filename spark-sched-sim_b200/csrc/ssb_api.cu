@@ -437,6 +437,7 @@ int ssb_create(const ssb_config *cfg, const ssb_bank *bk, int device, void *work
             (rc = prepare_tile_kernel<tc::ST_DAG>()) || (rc = prepare_tile_kernel<tc::ST_GLOB>()) ||
             (rc = prepare_tile_kernel<tc::ST_STAGE>()) || (rc = prepare_tile_kernel<tc::ST_EXEC>()))
             return rc;
+
     }
     // ---- bank upload
     const size_t T = bk->num_templates, TS = bk->num_template_stages, ME = bk->num_template_edges;

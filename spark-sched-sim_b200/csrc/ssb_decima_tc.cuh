@@ -391,6 +391,92 @@ __global__ void __launch_bounds__(128) k_build_blob(Params p)
 #define TC_STAMP(i) do { } while (0)
 #endif
 
+// One 128-row tile through the stage's three layers.  wb = the stage's weight blob in shared memory
+// (layout of Smem<ST> from W1_HI on), a_hi / a_lo = the A tile, tmem = this CTA's 64 accumulator columns.
+template <int ST, bool STAMPS>
+__device__ __forceinline__ void run_tile(const Params &p, const TileArgs &a, const int32_t *list, int n_rows, int tile,
+                                         float *a_hi, float *a_lo, const float *wb, uint32_t mbar, uint32_t tmem,
+                                         uint32_t &parity)
+{
+    using S = Spec<ST>;
+    using L = Smem<ST>;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const float *bias = wb + (L::BIAS - L::W1_HI);
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);  // this warp's 32 TMEM lanes
+        const int row = tile * 128 + tid;
+        int id = -1;
+        if (row < n_rows) id = (ST == ST_STAGE) ? row : list[row];
+        {
+            float in[S::K0];
+            gather_row<ST>(p, a, id, in);
+            if (STAMPS && tile == (int)blockIdx.x) TC_STAMP(3);
+            write_a_row<S::K0>(a_hi, a_lo, tid, in);
+        }
+        fence_async_smem();
+        __syncthreads();
+        if (STAMPS && tile == (int)blockIdx.x) TC_STAMP(4);
+        if (tid == 0) {
+            tc_fence_after();
+            issue_layer<S::K0, S::H1>(tmem, a_hi, a_lo, wb + (L::W1_HI - L::W1_HI), wb + (L::W1_LO - L::W1_HI), mbar);
+        }
+        mbar_wait(mbar, parity);
+        parity ^= 1;
+        tc_fence_after();
+        if (STAMPS && tile == (int)blockIdx.x) TC_STAMP(5);
+        {
+            float v[S::H1];
+#pragma unroll
+            for (int c = 0; c < S::H1; c += 16) tmem_ld16(trow + c, v + c);
+#pragma unroll
+            for (int i = 0; i < S::H1; i++) v[i] = act_tc<S::TANH>(v[i] + bias[i]);
+            write_a_row<S::H1>(a_hi, a_lo, tid, v);
+        }
+        tc_fence_before();
+        fence_async_smem();
+        __syncthreads();
+        if (STAMPS && tile == (int)blockIdx.x) TC_STAMP(6);
+        if (tid == 0) {
+            tc_fence_after();
+            issue_layer<S::H1, S::H2>(tmem, a_hi, a_lo, wb + (L::W2_HI - L::W1_HI), wb + (L::W2_LO - L::W1_HI), mbar);
+        }
+        mbar_wait(mbar, parity);
+        parity ^= 1;
+        tc_fence_after();
+        if (STAMPS && tile == (int)blockIdx.x) TC_STAMP(7);
+        float v2[S::H2];
+#pragma unroll
+        for (int c = 0; c < S::H2; c += 16) tmem_ld16(trow + c, v2 + c);
+#pragma unroll
+        for (int i = 0; i < S::H2; i++) v2[i] = act_tc<S::TANH>(v2[i] + bias[S::H1 + i]);
+        if constexpr (S::OUT > 1) {
+            write_a_row<S::H2>(a_hi, a_lo, tid, v2);
+            tc_fence_before();
+            fence_async_smem();
+            __syncthreads();
+            if (tid == 0) {
+                tc_fence_after();
+                issue_layer<S::H2, S::OUT>(tmem, a_hi, a_lo, wb + (L::W3_HI - L::W1_HI), wb + (L::W3_LO - L::W1_HI), mbar);
+            }
+            mbar_wait(mbar, parity);
+            parity ^= 1;
+            tc_fence_after();
+            float o[S::OUT];
+#pragma unroll
+            for (int c = 0; c < S::OUT; c += 16) tmem_ld16(trow + c, o + c);
+#pragma unroll
+            for (int i = 0; i < S::OUT; i++) o[i] += bias[S::H1 + S::H2 + i];
+            scatter_row<ST>(p, id, o);
+        } else {
+            // score heads end in a single neuron: a dot product in this row's thread
+            float s = bias[S::H1 + S::H2];
+#pragma unroll
+            for (int i = 0; i < S::H2; i++) s = fmaf(wb[L::W3V - L::W1_HI + i], v2[i], s);
+            scatter_row<ST>(p, id, &s);
+        }
+        tc_fence_before();  // this tile's TMEM reads are ordered before the next tile's first MMA
+        if (STAMPS && tile == (int)blockIdx.x) TC_STAMP(8);
+    }
+
 template <int ST>
 __global__ void __launch_bounds__(128) k_tile_mlp(Params p, TileArgs a)
 {
@@ -406,7 +492,6 @@ __global__ void __launch_bounds__(128) k_tile_mlp(Params p, TileArgs a)
     float *sm = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
     const int tid = threadIdx.x, warp = tid >> 5;
     float *a_hi = sm + L::A_HI, *a_lo = sm + L::A_LO;
-    float *bias = sm + L::BIAS;
     const uint32_t mbar = smem_u32(sm + L::CTRL), slot = smem_u32(sm + L::CTRL + 2);
     {
         const float4 *src = reinterpret_cast<const float4 *>(p.pol_wblob + blob_offset(ST));
@@ -421,88 +506,16 @@ __global__ void __launch_bounds__(128) k_tile_mlp(Params p, TileArgs a)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(sm + L::CTRL + 2);
-    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);  // this warp's 32 TMEM lanes
     uint32_t parity = 0;
     TC_STAMP(2);
 
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int row = tile * 128 + tid;
-        int id = -1;
-        if (row < n_rows) id = (ST == ST_STAGE) ? row : list[row];
-        {
-            float in[S::K0];
-            gather_row<ST>(p, a, id, in);
-            if (tile == (int)blockIdx.x) TC_STAMP(3);
-            write_a_row<S::K0>(a_hi, a_lo, tid, in);
-        }
-        fence_async_smem();
-        __syncthreads();
-        if (tile == (int)blockIdx.x) TC_STAMP(4);
-        if (tid == 0) {
-            tc_fence_after();
-            issue_layer<S::K0, S::H1>(tmem, a_hi, a_lo, sm + L::W1_HI, sm + L::W1_LO, mbar);
-        }
-        mbar_wait(mbar, parity);
-        parity ^= 1;
-        tc_fence_after();
-        if (tile == (int)blockIdx.x) TC_STAMP(5);
-        {
-            float v[S::H1];
-#pragma unroll
-            for (int c = 0; c < S::H1; c += 16) tmem_ld16(trow + c, v + c);
-#pragma unroll
-            for (int i = 0; i < S::H1; i++) v[i] = act_tc<S::TANH>(v[i] + bias[i]);
-            write_a_row<S::H1>(a_hi, a_lo, tid, v);
-        }
-        tc_fence_before();
-        fence_async_smem();
-        __syncthreads();
-        if (tile == (int)blockIdx.x) TC_STAMP(6);
-        if (tid == 0) {
-            tc_fence_after();
-            issue_layer<S::H1, S::H2>(tmem, a_hi, a_lo, sm + L::W2_HI, sm + L::W2_LO, mbar);
-        }
-        mbar_wait(mbar, parity);
-        parity ^= 1;
-        tc_fence_after();
-        if (tile == (int)blockIdx.x) TC_STAMP(7);
-        float v2[S::H2];
-#pragma unroll
-        for (int c = 0; c < S::H2; c += 16) tmem_ld16(trow + c, v2 + c);
-#pragma unroll
-        for (int i = 0; i < S::H2; i++) v2[i] = act_tc<S::TANH>(v2[i] + bias[S::H1 + i]);
-        if constexpr (S::OUT > 1) {
-            write_a_row<S::H2>(a_hi, a_lo, tid, v2);
-            tc_fence_before();
-            fence_async_smem();
-            __syncthreads();
-            if (tid == 0) {
-                tc_fence_after();
-                issue_layer<S::H2, S::OUT>(tmem, a_hi, a_lo, sm + L::W3_HI, sm + L::W3_LO, mbar);
-            }
-            mbar_wait(mbar, parity);
-            parity ^= 1;
-            tc_fence_after();
-            float o[S::OUT];
-#pragma unroll
-            for (int c = 0; c < S::OUT; c += 16) tmem_ld16(trow + c, o + c);
-#pragma unroll
-            for (int i = 0; i < S::OUT; i++) o[i] += bias[S::H1 + S::H2 + i];
-            scatter_row<ST>(p, id, o);
-        } else {
-            // score heads end in a single neuron: a dot product in this row's thread
-            float s = bias[S::H1 + S::H2];
-#pragma unroll
-            for (int i = 0; i < S::H2; i++) s = fmaf(sm[L::W3V + i], v2[i], s);
-            scatter_row<ST>(p, id, &s);
-        }
-        tc_fence_before();  // this tile's TMEM reads are ordered before the next tile's first MMA
-        if (tile == (int)blockIdx.x) TC_STAMP(8);
-    }
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+        run_tile<ST, true>(p, a, list, n_rows, tile, a_hi, a_lo, sm + L::W1_HI, mbar, tmem, parity);
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, 64);
     TC_STAMP(9);
 }
+
 
 // ------------------------------------------------------------------ planning kernels (one warp per env)
 // Pass A: per-node level bit sets (which levels a node sends / receives at), row_start, the lists of

@@ -215,6 +215,40 @@ def test_auto_reset_rollout(bank):
         assert np.array_equal(o[key], g[key]), key
 
 
+def test_fused_rollout_fuzz_vs_oracle(bank):
+    """Seeded sweep over the configuration space (executors 1..64, job caps, delays, fair/FIFO): whole episodes of
+    the fused rollout equal the oracle's in every job completion time, final wall time and decision/event count."""
+    from oracle import OracleEnv
+    from spark_sched_sim_b200.batched_env import BatchedSparkSchedSimEnv
+
+    rng = np.random.default_rng(7)
+    for case in range(14):
+        E = int(rng.choice([1, 2, 5, 10, 17, 31, 32, 33, 40, 50, 63, 64]))
+        J = int(rng.integers(1, 26))
+        fair = bool(rng.integers(0, 2))
+        moving, warm = float(rng.choice([0.0, 500.0, 2000.0])), float(rng.choice([0.0, 1000.0, 3000.0]))
+        rate = float(rng.choice([1e-5, 4e-5, 2e-4]))
+        B = 4
+        cfg = {"num_executors": E, "job_arrival_cap": J, "job_arrival_rate": rate,
+               "moving_delay": moving, "warmup_delay": warm}
+        env = BatchedSparkSchedSimEnv(cfg, num_envs=B, bank=bank)
+        seeds = (rng.integers(0, 2**31, B)).astype(np.uint64)
+        env.reset_host(seeds)
+        env.rollout_fair(1_000_000, dynamic_partition=fair, auto_reset=False)
+        hdr = env.hdr()
+        assert (hdr["error"] == 0).all() and (hdr["terminated"] == 1).all(), (case, cfg, hdr["error"])
+        dec = ev = 0
+        for b in range(B):
+            orc = OracleEnv(bank, E, J, moving, warm, rate)
+            d, e = orc.run_fair_episode(int(seeds[b]), fair)
+            dec += d; ev += e
+            assert np.array_equal(orc.job_times()[1], env.jobs(b)[1]), (case, cfg, b)
+            assert hdr["wall_time"][b] == orc.wall_time, (case, cfg, b)
+        st = env.stats()
+        assert (st["decisions"], st["events"]) == (dec, ev), (case, cfg)
+        del env
+
+
 def test_rollout_transitions_match_oracle(bank):
     """ssb_rollout_fair_traj: the recorded (wall_time, action, reward, flags) rows are what a host loop
     over the oracle's reset()/fair_action()/step() produces, across auto-resets."""

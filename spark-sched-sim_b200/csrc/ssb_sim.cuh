@@ -1356,7 +1356,25 @@ struct Sim {
         const int max_id = n_arr ? act[n_new - 1] : last_old;
         const int F = n < 5 ? 8 : n < 19 ? 32 : n < 77 ? 128 : n < 307 ? 512 : n < 1229 ? 2048 : 0;
         const bool ascending = max_id < F;  // every id in its own slot of the final table
-        if (!ascending) {
+        // Small sets (n < 19: an 8- or 32-slot table) whose ids are distinct modulo the table size also sit each
+        // in its own slot, id & mask, whatever the insertion order -> iteration order = slot order
+        // (tests/test_pyset.py::test_small_set_slot_order checks this against the interpreter).
+        bool by_slot = false;
+        int src = lane;  // lane whose term is summed at position `lane`
+        if (!ascending && n < 19) {
+            const int mask = n < 5 ? 7 : 31;
+            const int key = lane < n ? (lane < n_old ? old[lane] : act[n_new - n_arr + (lane - n_old)]) : -1 - lane;
+            const int slot = lane < n ? (key & mask) : 32 + lane;
+            const unsigned same = __match_any_sync(FULL, slot);
+            if (!__any_sync(FULL, same & (same - 1))) {
+                by_slot = true;
+                const unsigned occ = __ballot_sync(FULL, lane < n) ? __reduce_or_sync(FULL, lane < n ? 1u << slot : 0u) : 0u;
+                const int pos = lane < n ? __popc(occ & ((1u << slot) - 1u)) : 32;
+                for (int k = 0; k < n; k++)
+                    if (__shfl_sync(FULL, pos, k) == lane) src = k;
+            }
+        }
+        if (!ascending && !by_slot) {
             int m = 0;
             if (lane == 0) m = reward_order(ord, n, max_id);
             n = __shfl_sync(FULL, m, 0);
@@ -1368,10 +1386,11 @@ struct Sim {
             double term = 0.0;
             if (base + lane < n) {
                 const int k = base + lane;
-                const int j = !ascending ? ord[k] : k < n_old ? old[k] : act[n_new - n_arr + (k - n_old)];
+                const int j = (!ascending && !by_slot) ? ord[k] : k < n_old ? old[k] : act[n_new - n_arr + (k - n_old)];
                 const double start = fmax(jb[j].t_arrival, wall_old), end = fmin(jb[j].t_completed, wall);
                 term = beta == 0.0 ? __dadd_rn(end, -start) : discounted_term(start - wall_old, end - wall_old);
             }
+            if (by_slot) term = __shfl_sync(FULL, term, src);  // n <= 18: a single chunk
             const int m = min(32, n - base);
             for (int i = 0; i < m; i++) jt = __dadd_rn(jt, __shfl_sync(FULL, term, i));
         }

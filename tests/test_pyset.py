@@ -136,3 +136,22 @@ def test_pyset_matches_cpython(universe):
                         emu.add(x)
             assert list(real) == emu.list(), (universe, trial)
             assert len(real) == len(emu)
+
+
+def test_small_set_slot_order():
+    """Claim used by the reward kernel (compute_jobtime_w): a set built from fewer than 19 ascending distinct
+    ints whose values are distinct modulo the final table size (8 below five elements, else 32) iterates in
+    slot order, i.e. sorted by value & (size - 1) -- checked against the interpreter."""
+    import random
+
+    rnd = random.Random(5)
+    checked = 0
+    for _ in range(60000):
+        n = rnd.randint(1, 18)
+        keys = sorted(rnd.sample(range(0, 256), n))
+        mask = 7 if n < 5 else 31
+        if len({k & mask for k in keys}) != n:
+            continue
+        assert list(set(keys)) == sorted(keys, key=lambda k: k & mask), keys
+        checked += 1
+    assert checked > 10000

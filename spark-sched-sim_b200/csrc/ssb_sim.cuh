@@ -857,6 +857,7 @@ struct Sim {
         bool fast_ok;        // this executor's next launch can be sampled without the fallback chain
         bool touched;        // handled at least one event in this fast phase (its t_acc is then that event's time)
         unsigned same;       // lanes whose pending event belongs to the same stage (constant during a fast phase)
+        uint32_t rx, ry;     // task-stream draws (Philox words x, y) of launch number H.rng_base + lane
     };
     struct HotEnv {  // uniform per-environment scalars
         unsigned long long t_arr;
@@ -865,6 +866,7 @@ struct Sim {
         uint32_t launch_idx, seq;
         int events;
         bool quiet;  // no committable executors at the current (possibly stale) source
+        uint32_t rng_base;  // launch number whose draws lane 0 caches (one-slot fast path)
     };
     // (must inline: a non-inlined callee taking L/H by reference would pin them in local memory)
     // slot of executor e (e >= E: an empty slot whose pseudo node id is unique)
@@ -914,11 +916,21 @@ struct Sim {
         H.events = 0;
         H.quiet = num_committable() == 0;
     }
+    // The task stream is counter-based, so the draws of the next 32 launches can be produced by the 32 lanes at
+    // once and handed out by shuffle: one Philox evaluation per 32 launches instead of one per loop iteration.
+    __device__ __forceinline__ void hot_refill_rng(HotLane &L, HotEnv &H)
+    {
+        H.rng_base = H.launch_idx;
+        const uint4 w = philox4x32_10(H.rng_base + (uint32_t)lane, 0u, 2u, 0u, (uint32_t)h->seed, (uint32_t)(h->seed >> 32));
+        L.rx = w.x; L.ry = w.y;
+    }
     __device__ __forceinline__ void hot_load(HotLane &L, HotEnv &H)
     {
         hot_load_slot(L, lane);
         hot_load_env(H);
         L.same = __match_any_sync(FULL, L.node);
+        L.rx = L.ry = 0u; H.rng_base = H.launch_idx;
+        if (H.quiet && !h->use_tape) hot_refill_rng(L, H);
     }
     // one-slot fast phase: the wall time is the time of the last event handled, i.e. the maximum over the
     // lanes that handled one of their t_acc (non-negative doubles order like their bit patterns)
@@ -992,20 +1004,27 @@ struct Sim {
         const double t = __longlong_as_double((long long)L.kt);
         double d = 0.0;
         unsigned long long nt = INF_BITS;
+        const bool tape = h->use_tape;
+        const uint32_t li = H.launch_idx + (uint32_t)rank;
+        uint32_t wx = 0u, wy = 0u;
+        if (!tape) {  // draws of launch li: cached by lane li - rng_base (refilled when the window runs out)
+            if (H.launch_idx + (uint32_t)__popc(pend_mask) > H.rng_base + 32u) hot_refill_rng(L, H);
+            const int src = (int)(li - H.rng_base) & 31;
+            wx = __shfl_sync(FULL, L.rx, src);
+            wy = __shfl_sync(FULL, L.ry, src);
+        }
         if (elig) {
-            const uint32_t li = H.launch_idx + (uint32_t)rank;
-            if (h->use_tape) {
+            if (tape) {
                 if ((int)li < h->tape_len) d = p.tape[(size_t)b * p.tape_cap + li];
                 else elig = false;  // the general path reports the exhausted tape
             } else {  // tpch.py:75-106 for an executor continuing on its stage: rest_wave[level]
-                const uint4 w = philox4x32_10(li, 0u, 2u, 0u, (uint32_t)h->seed, (uint32_t)(h->seed >> 32));
                 uint2 oc = L.oc_a;
                 if (L.range) {
-                    double u = __dmul_rn((double)w.x, 1.0 / 4294967296.0);
+                    double u = __dmul_rn((double)wx, 1.0 / 4294967296.0);
                     int rand_pt = 1 + (int)__dmul_rn(u, (double)L.range);
                     if (rand_pt > L.thr) oc = L.oc_b;
                 }
-                d = p.b_vals[oc.x + bounded(w.y, oc.y)];
+                d = p.b_vals[oc.x + bounded(wy, oc.y)];
             }
             if (elig) nt = (unsigned long long)__double_as_longlong(__dadd_rn(t, d));
         }

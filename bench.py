@@ -184,7 +184,7 @@ def main() -> None:
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-threads", type=int, default=1,
                     help="host threads driving the e2e loop, each with its own shard of the envs")
-    ap.add_argument("--e2e-budget", type=int, default=192,
+    ap.add_argument("--e2e-budget", type=int, default=256,
                     help="max timeline events per env per ssb_step_host call (0 = run to next decision)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -298,28 +298,30 @@ def main() -> None:
         T = max(1, args.e2e_threads)
         shards = np.array_split(np.arange(B), T)
         envs = [BatchedSparkSchedSimEnv(ENV_CFG, num_envs=len(ix), bank=bank, device=dev) for ix in shards]
-        streams = [torch.cuda.Stream(dev) for _ in range(T)]
         pins = [(torch.empty(len(ix), dtype=torch.int32).pin_memory(),
                  torch.empty(len(ix), dtype=torch.int32).pin_memory()) for ix in shards]
 
+        nexts = [(torch.empty(len(ix), dtype=torch.int32).pin_memory(),
+                  torch.empty(len(ix), dtype=torch.int32).pin_memory()) for ix in shards]
+
         def e2e_steps(t, n_steps):
             torch.cuda.set_device(dev)
-            e, (a_pin, n_pin) = envs[t], pins[t]
-            with torch.cuda.stream(streams[t]):
-                for _ in range(n_steps * De):
-                    a, n = e.fair_actions(True)          # policy on the observation just written
-                    a_pin.copy_(a, non_blocking=True)    # D2H: the actions a host-side caller sees
-                    n_pin.copy_(n, non_blocking=True)
-                    streams[t].synchronize()
-                    # H2D actions, bounded step (envs still simulating come back "pending" and simply
-                    # continue next call -- no env waits for the batch's longest event chain), D2H headers
-                    # finished envs re-seed themselves on their next step (ssb_set_autoreset: the caller's
-                    # `if done: env.reset(seed=...)` without a separate launch); h["was_reset"] marks them
-                    h = e.step_host(a_pin.numpy(), n_pin.numpy(), max_events=args.e2e_budget)
+            e, (a_pin, n_pin), (a_nxt, n_nxt) = envs[t], pins[t], nexts[t]
+            a_h, n_h, a_o, n_o = a_pin.numpy(), n_pin.numpy(), a_nxt.numpy(), n_nxt.numpy()
+            for _ in range(n_steps * De):
+                # one call per decision batch: H2D of the host's actions, bounded step (envs still simulating come
+                # back "pending" and continue next call; finished envs re-seed themselves, ssb_set_autoreset), the
+                # fair scheduler's action for the new observation evaluated inside the step kernel, D2H of the B
+                # observation headers and of those actions, one synchronisation
+                e.step_fair_host(a_h, n_h, a_o, n_o, True, max_events=args.e2e_budget)
+                a_h, n_h, a_o, n_o = a_o, n_o, a_h, n_h   # the host feeds the actions it received back in
 
         for t in range(T):
             envs[t].reset_host(seeds[shards[t]])
             envs[t].set_autoreset(True, seed_step)
+            a0, n0 = envs[t].fair_actions(True)   # the first actions; afterwards the step call returns them
+            pins[t][0].copy_(a0); pins[t][1].copy_(n0)
+            torch.cuda.synchronize()
         Ke = max(2, min(K, 5))
         with ThreadPoolExecutor(T) as ex:
             list(ex.map(lambda t: e2e_steps(t, 2), range(T)))
@@ -339,10 +341,11 @@ def main() -> None:
                "h2d_bytes_per_step": De * 2 * 4 * B, "d2h_bytes_per_step": De * (2 * 4 + 48) * B,
                "steps": Ke, "calls_per_step": De, "max_events_per_call": args.e2e_budget,
                "host_threads": T,
-               "path": "ssb_fair_actions -> D2H actions (pinned) -> ssb_step_host (H2D actions, bounded step with "
-                       "auto-reset of finished envs, D2H headers)",
-               "gpu_launches": Ke * De * 2 * T}
-        launches_e2e = Ke * De * 2 * T
+               "path": "ssb_step_fair_host per decision batch: H2D of the host's actions -> bounded step with auto-reset "
+                       "of finished envs + the fair scheduler's next action (in the step kernel) -> D2H of the "
+                       "observation headers and the next actions (pinned) -> host feeds them back",
+               "gpu_launches": Ke * De * T}
+        launches_e2e = Ke * De * T
         # the rollout-collection call (rollout_worker.py:135-157 as ONE call): fused rollout on the device,
         # every transition (wall time, action, reward, flags) copied to pinned host memory per step
         from spark_sched_sim_b200 import _native as nat

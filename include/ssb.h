@@ -177,6 +177,13 @@ int ssb_reset_host(ssb_env *env, const uint64_t *seeds, const double *time_limit
                    ssb_obs_hdr *hdr_out);
 int ssb_step_host(ssb_env *env, const int32_t *stage_idx, const int32_t *num_exec, const uint8_t *mask,
                   int32_t max_events, ssb_obs_hdr *hdr_out);
+/* ssb_step_host that also returns, per env, the action the built-in fair (dynamic_partition = 1) / FIFO scheduler
+ * (round_robin.py:14-49) takes on the observation the call leaves behind -- evaluated inside the step kernel,
+ * so a caller that follows (or overrides) the heuristic needs one call and one synchronisation per decision.
+ * Envs that are pending / finished get (-1, 1).  HOST outputs i32[B] each. */
+int ssb_step_fair_host(ssb_env *env, const int32_t *stage_idx, const int32_t *num_exec, const uint8_t *mask,
+                       int32_t max_events, int32_t dynamic_partition, ssb_obs_hdr *hdr_out, int32_t *next_stage_idx,
+                       int32_t *next_num_exec);
 
 /* fused rollout: every env takes `num_decisions` decisions with the built-in fair (dynamic_partition
  * = 1) or FIFO (= 0) policy (round_robin.py:14-49) evaluated on the observation it just wrote.

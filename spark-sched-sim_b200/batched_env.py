@@ -88,7 +88,9 @@ class BatchedSparkSchedSimEnv:
         sp = C.c_void_p()
         nat.check(self.L.ssb_get_stats(self._h, C.byref(sp)), "ssb_get_stats")
         self.stats_bytes = self._view(sp.value, B * nat.STATS_DTYPE.itemsize, torch.uint8).view(B, -1)
-        self._hdr_host = np.zeros(B, nat.OBS_HDR_DTYPE)
+        # pinned: the D2H copy of the headers in the *_host calls is then a true async DMA
+        self._hdr_pin = torch.zeros(B * nat.OBS_HDR_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+        self._hdr_host = self._hdr_pin.numpy().view(nat.OBS_HDR_DTYPE).reshape(-1)
         self.has_decima_obs = bool(decima_obs)
         if decima_obs:
             dv = nat.SsbDecimaViews()
@@ -218,6 +220,22 @@ class BatchedSparkSchedSimEnv:
         nat.check(self.L.ssb_step_host(self._h, a.ctypes.data, n.ctypes.data,
                                        m.ctypes.data if m is not None else None, int(max_events),
                                        self._hdr_host.ctypes.data), "ssb_step_host")
+        return self._hdr_host
+
+    def step_fair_host(self, stage_idx: np.ndarray, num_exec: np.ndarray, next_stage_idx: np.ndarray,
+                       next_num_exec: np.ndarray, dynamic_partition: bool = True, mask: np.ndarray | None = None,
+                       max_events: int = 0) -> np.ndarray:
+        """step_host that also fills next_stage_idx / next_num_exec (host int32[B], ideally pinned) with the built-in
+        fair / FIFO scheduler's action for the new observation (evaluated inside the step kernel)."""
+        a = np.ascontiguousarray(stage_idx, dtype=np.int32)
+        n = np.ascontiguousarray(num_exec, dtype=np.int32)
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        assert next_stage_idx.dtype == np.int32 and next_num_exec.dtype == np.int32
+        nat.check(self.L.ssb_step_fair_host(self._h, a.ctypes.data, n.ctypes.data,
+                                            m.ctypes.data if m is not None else None, int(max_events),
+                                            int(dynamic_partition), self._hdr_host.ctypes.data,
+                                            next_stage_idx.ctypes.data, next_num_exec.ctypes.data),
+                  "ssb_step_fair_host")
         return self._hdr_host
 
     # ---------------------------------------------------------------- results

@@ -53,12 +53,20 @@ k_reset(Params p, const uint64_t *seeds, const double *time_limits, const uint8_
 template <int NS>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, NS == 1 ? 7 : 4)
 k_step(Params p, const int32_t *stage_idx, const int32_t *num_exec, const uint8_t *mask, int max_events,
-       int auto_reset, uint64_t seed_step)
+       int auto_reset, uint64_t seed_step, int32_t *next_a, int32_t *next_n, int dynamic_partition)
 {
     const int b = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (b >= p.B) return;
     if (mask && !mask[b]) return;
     Sim sim(p, b, lane);
+    // next_a / next_n (optional): the built-in fair / FIFO scheduler's action for the observation this call
+    // leaves behind (ssb_step_fair_host), evaluated while the state is still in cache
+    auto suggest = [&]() {
+        if (!next_a) return;
+        int a = -1, n = 1;
+        if (!sim.h->error && !sim.h->done && !sim.h->pending) sim.fair_action_w(dynamic_partition != 0, a, n);
+        if (lane == 0) { next_a[b] = a; next_n[b] = n; }
+    };
     if (auto_reset && !sim.h->error && (sim.h->done || sim.oh->truncated)) {
         // the caller's `if terminated or truncated: env.reset(seed=...)` (rollout_worker.py:118-120, :150-153)
         const uint64_t seed = sim.h->base_seed + seed_step * (uint64_t)sim.h->reset_count;
@@ -68,11 +76,15 @@ k_step(Params p, const int32_t *stage_idx, const int32_t *num_exec, const uint8_
         if (lane == 0) { sim.h->reset_count += 1; if (was_trunc) sim.stats->episodes++; }
         sim.reset_w(seed, tl);
         if (lane == 0) sim.oh->was_reset = 1;
+        __syncwarp();
+        suggest();
         return;
     }
     if (lane == 0) sim.oh->error = 0;
     __syncwarp();
     sim.template step_w<NS>(stage_idx[b], num_exec[b], max_events);
+    __syncwarp();
+    suggest();
 }
 
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
@@ -547,18 +559,24 @@ int ssb_reset(ssb_env *env, const uint64_t *seeds, const double *time_limits, co
     return SSB_OK;
 }
 
+static int step_launch(ssb_env *env, const int32_t *stage_idx, const int32_t *num_exec, const uint8_t *mask,
+                       int32_t max_events, int32_t *next_a, int32_t *next_n, int dyn, cudaStream_t s)
+{
+    if (env->p.E <= 32)
+        k_step<1><<<env->grid, WARPS_PER_CTA * 32, 0, s>>>(env->p, stage_idx, num_exec, mask, max_events, env->auto_reset,
+                                                           env->auto_seed_step, next_a, next_n, dyn);
+    else
+        k_step<2><<<env->grid, WARPS_PER_CTA * 32, 0, s>>>(env->p, stage_idx, num_exec, mask, max_events, env->auto_reset,
+                                                           env->auto_seed_step, next_a, next_n, dyn);
+    CUDA_TRY(cudaGetLastError());
+    return SSB_OK;
+}
+
 int ssb_step(ssb_env *env, const int32_t *stage_idx, const int32_t *num_exec, const uint8_t *mask,
              int32_t max_events, void *stream)
 {
     if (!env || !stage_idx || !num_exec) return SSB_E_INVALID;
-    if (env->p.E <= 32)
-        k_step<1><<<env->grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(
-            env->p, stage_idx, num_exec, mask, max_events, env->auto_reset, env->auto_seed_step);
-    else
-        k_step<2><<<env->grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(
-            env->p, stage_idx, num_exec, mask, max_events, env->auto_reset, env->auto_seed_step);
-    CUDA_TRY(cudaGetLastError());
-    return SSB_OK;
+    return step_launch(env, stage_idx, num_exec, mask, max_events, nullptr, nullptr, 0, (cudaStream_t)stream);
 }
 
 int ssb_set_autoreset(ssb_env *env, int32_t enable, uint64_t seed_step)
@@ -600,6 +618,29 @@ int ssb_step_host(ssb_env *env, const int32_t *stage_idx, const int32_t *num_exe
     int rc = ssb_step(env, env->st_a, env->st_n, mask ? env->st_mask : nullptr, max_events, s);
     if (rc) return rc;
     if (hdr_out) CUDA_TRY(cudaMemcpyAsync(hdr_out, env->p.obs_hdr, B * sizeof(ssb_obs_hdr), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return SSB_OK;
+}
+
+int ssb_step_fair_host(ssb_env *env, const int32_t *stage_idx, const int32_t *num_exec, const uint8_t *mask,
+                       int32_t max_events, int32_t dynamic_partition, ssb_obs_hdr *hdr_out, int32_t *next_stage_idx,
+                       int32_t *next_num_exec)
+{
+    if (!env || !stage_idx || !num_exec || !next_stage_idx || !next_num_exec) return SSB_E_INVALID;
+    CUDA_TRY(cudaSetDevice(env->device));
+    cudaStream_t s = env->own_stream;
+    const size_t B = env->p.B;
+    CUDA_TRY(cudaMemcpyAsync(env->st_a, stage_idx, B * 4, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(env->st_n, num_exec, B * 4, cudaMemcpyHostToDevice, s));
+    if (mask) CUDA_TRY(cudaMemcpyAsync(env->st_mask, mask, B, cudaMemcpyHostToDevice, s));
+    // the suggestions are written to the staging arrays the actions were read from (each env reads its action
+    // before it writes its suggestion)
+    int rc = step_launch(env, env->st_a, env->st_n, mask ? env->st_mask : nullptr, max_events, env->st_a, env->st_n,
+                         dynamic_partition, s);
+    if (rc) return rc;
+    if (hdr_out) CUDA_TRY(cudaMemcpyAsync(hdr_out, env->p.obs_hdr, B * sizeof(ssb_obs_hdr), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(next_stage_idx, env->st_a, B * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(next_num_exec, env->st_n, B * 4, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     return SSB_OK;
 }

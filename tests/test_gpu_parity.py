@@ -370,6 +370,36 @@ def test_step_api_autoreset_matches_oracle(bank):
         assert got[b][:K] == rows, b
 
 
+def test_step_fair_host_matches_oracle(bank):
+    """ssb_step_fair_host: the step kernel's own fair-scheduler suggestion drives the next call (one call and one
+    synchronisation per decision); with auto-reset the real transitions equal the oracle loop's."""
+    from spark_sched_sim_b200.batched_env import BatchedSparkSchedSimEnv
+
+    B, K = 4, 600
+    cfg = {"num_executors": 10, "job_arrival_cap": 6, "job_arrival_rate": 4.0e-5,
+           "moving_delay": 2000.0, "warmup_delay": 1000.0}
+    env = BatchedSparkSchedSimEnv(cfg, num_envs=B, bank=bank)
+    seeds = np.arange(700, 700 + B, dtype=np.uint64)
+    env.reset_host(seeds)
+    env.set_autoreset(True, 13)
+    a0, n0 = env.fair_actions(True)
+    a, n = a0.cpu().numpy().copy(), n0.cpu().numpy().copy()
+    na, nn = np.zeros(B, np.int32), np.zeros(B, np.int32)
+    got = [[] for _ in range(B)]
+    wall = env.hdr()["wall_time"].copy()
+    while min(len(g) for g in got) < K:
+        h = env.step_fair_host(a, n, na, nn, True).copy()
+        assert (h["error"] == 0).all()
+        for b in range(B):
+            if not h["was_reset"][b]:
+                got[b].append((wall[b], h["reward"][b], int(a[b]), int(n[b]), int(h["terminated"][b]), 0))
+        wall = h["wall_time"].copy()
+        a, n = na.copy(), nn.copy()
+    for b in range(B):
+        rows, _ = _oracle_transitions(bank, cfg, seeds[b], 13, K)
+        assert got[b][:K] == rows, b
+
+
 def test_rollout_with_discounted_reward(bank):
     """beta > 0: the continuously discounted reward (:866-869) goes through exp(); transitions match the
     oracle with rewards at 1e-12 relative (device exp vs libm), everything else exactly."""

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SSB_ABI_VERSION 1
+#define SSB_ABI_VERSION 2
 
 /* status codes of the entry points */
 enum {
@@ -240,6 +240,8 @@ typedef struct {
     uint64_t *edge_bits;    /* [B][edge_stride]: bit k set <=> edge in edge_masks[k] */
     int32_t *depth;         /* [B]: number of edge masks (message passing depth) */
     int32_t node_stride, edge_stride, job_stride, pad;
+    uint8_t *frontier_mask; /* [B][node_stride] 1 = no incoming edge in the observed graph, i.e. every parent has
+                               completed -- the "frontier" of heuristics/utils.py:5-37 (Job.frontier_stages) */
 } ssb_decima_views;
 int ssb_decima_obs(ssb_env *env, void *stream);
 int ssb_get_decima_views(ssb_env *env, ssb_decima_views *out);

@@ -9,7 +9,7 @@ import numpy as np
 
 PKG_DIR = osp.dirname(osp.abspath(__file__))
 LIB_PATH = osp.join(PKG_DIR, "_lib", "libssb.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class SsbConfig(C.Structure):
@@ -56,6 +56,7 @@ class SsbDecimaViews(C.Structure):
         ("edge_stride", C.c_int32),
         ("job_stride", C.c_int32),
         ("pad", C.c_int32),
+        ("frontier_mask", C.c_void_p),
     ]
 
 

@@ -97,6 +97,7 @@ class BatchedSparkSchedSimEnv:
             nat.check(self.L.ssb_get_decima_views(self._h, C.byref(dv)), "ssb_get_decima_views")
             self.dec_features = self._view(dv.features, B * S * 5 * 4, torch.float32).view(B, S, 5)
             self.dec_stage_mask = self._view(dv.stage_mask, B * S, torch.uint8).view(B, S)
+            self.dec_frontier_mask = self._view(dv.frontier_mask, B * S, torch.uint8).view(B, S)
             self.dec_commit_caps = self._view(dv.commit_caps, B * J * 4, torch.int32).view(B, J)
             self.dec_edge_bits = self._view(dv.edge_bits, B * M * 8, torch.int64).view(B, M)
             self.dec_depth = self._view(dv.depth, B * 4, torch.int32)
@@ -284,6 +285,7 @@ class BatchedSparkSchedSimEnv:
         return {
             "features": self.dec_features[b, :N].cpu().numpy(),
             "stage_mask": self.dec_stage_mask[b, :N].cpu().numpy().astype(bool),
+            "frontier_mask": self.dec_frontier_mask[b, :N].cpu().numpy().astype(bool),
             "commit_caps": caps,
             "exec_mask": np.arange(self.num_executors)[None, :] < caps[:, None],
             "edge_bits": bits,

@@ -289,6 +289,7 @@ void carve(Carver &cv, const ssb_config &c, const ssb_bank &bk, const Dims &d, P
     if (c.flags & (SSB_FLAG_DECIMA_OBS | SSB_FLAG_DECIMA_POLICY)) {
         p.dec_feat = cv.take<float>(B * d.Sc * 5);
         p.dec_stage_mask = cv.take<uint8_t>(B * d.Sc);
+        p.dec_frontier_mask = cv.take<uint8_t>(B * d.Sc);
         p.dec_caps = cv.take<int32_t>(B * c.max_jobs);
         p.dec_edge_bits = cv.take<uint64_t>(B * d.Mc);
         p.dec_depth = cv.take<int32_t>(B);
@@ -723,6 +724,7 @@ int ssb_get_decima_views(ssb_env *env, ssb_decima_views *out)
     if (!env || !out || !env->p.dec_feat) return SSB_E_INVALID;
     out->features = env->p.dec_feat;
     out->stage_mask = env->p.dec_stage_mask;
+    out->frontier_mask = env->p.dec_frontier_mask;
     out->commit_caps = env->p.dec_caps;
     out->edge_bits = env->p.dec_edge_bits;
     out->depth = env->p.dec_depth;

@@ -1762,6 +1762,7 @@ struct Sim {
         const int n_active = h->n_active, ncommit = num_committable(), src_job = source_job_id();
         float *feat = p.dec_feat + (size_t)b * p.Sc * 5;
         uint8_t *smask = p.dec_stage_mask + (size_t)b * p.Sc;
+        uint8_t *fmask = p.dec_frontier_mask + (size_t)b * p.Sc;
         int32_t *caps = p.dec_caps + (size_t)b * p.Jc;
         uint64_t *ebits = p.dec_edge_bits + (size_t)b * p.Mc;
         const double Ed = (double)p.E;
@@ -1769,7 +1770,7 @@ struct Sim {
         for (int i = 0; i < n_active; i++) {
             const int j = act[i];
             const JobRec &J = jb[j];
-            const uint64_t active = J.active, sched = J.sched;
+            const uint64_t active = J.active, sched = J.sched, frontier = J.frontier;
             const int supply = J.supply, ns = J.n_stages;
             int cap = min(max(p.E - supply, 0), ncommit);  // :74-77
             if (j == src_job) cap = ncommit;               // :81-82
@@ -1786,6 +1787,7 @@ struct Sim {
                 f[3] = __fdiv_rn(rem, 200.0f);                          // float32 / num_tasks_scale (:137)
                 f[4] = __fdiv_rn(__fmul_rn(rem, r.mrd), 100000.0f);     // float32 * float32 / work_scale (:141)
                 smask[rank] = (uint8_t)((sched >> s) & 1);
+                fmask[rank] = (uint8_t)((frontier >> s) & 1);
             }
             const uint64_t *pm = p.b_parent + J.ts_base, *cm = p.b_child + J.ts_base;
             uint64_t assigned = 0;

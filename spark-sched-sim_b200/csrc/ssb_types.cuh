@@ -143,6 +143,7 @@ struct Params {
     // Decima observation adapter outputs (nullptr unless SSB_FLAG_DECIMA_OBS)
     float *dec_feat;          // [B][Sc][5]
     uint8_t *dec_stage_mask;  // [B][Sc]
+    uint8_t *dec_frontier_mask;  // [B][Sc]
     int32_t *dec_caps;        // [B][Jc]
     uint64_t *dec_edge_bits;  // [B][Mc]
     int32_t *dec_depth;       // [B]

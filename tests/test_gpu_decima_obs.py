@@ -38,6 +38,10 @@ def test_decima_obs_matches_reference_wrapper(bank, name):
         d = env.decima_obs_host(slot, hdr)
         assert np.array_equal(d["features"], tr["dec_feat"][n:n + N]), (k, "features")
         assert np.array_equal(d["stage_mask"], tr["dec_stage_mask"][n:n + N].astype(bool)), (k, "stage_mask")
+        # frontier (heuristics/utils.py:5-14): nodes of the observed graph without an incoming edge
+        want = np.ones(N, bool)
+        want[env.obs(slot, hdr)["edge_links"][:, 1]] = False
+        assert np.array_equal(d["frontier_mask"], want), (k, "frontier_mask")
         assert np.array_equal(d["commit_caps"], tr["dec_caps"][s:s + Ja]), (k, "caps")
         assert d["depth"] == tr["dec_depth"][k], (k, "depth")
         assert np.array_equal(d["edge_bits"], tr["dec_edge_bits"][e:e + M]), (k, "edge masks")

@@ -1,0 +1,25 @@
+"""Small workload for compute-sanitizer (memcheck / initcheck): Decima rollout on the tensor-core path with auto-reset,
+and a two-slot (E = 50) fused fair rollout.  Usage on the GPU box:
+    compute-sanitizer --tool memcheck python profiles/sanitizer_run.py
+Round 1: memcheck 0 errors, initcheck 0 errors (after zeroing the weight blobs' padding)."""
+import sys, os.path as osp
+sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
+import numpy as np, torch
+from spark_sched_sim_b200.bank import synthetic_bank
+from spark_sched_sim_b200.batched_env import BatchedSparkSchedSimEnv
+cfg = {"num_executors": 10, "job_arrival_cap": 6, "job_arrival_rate": 4.0e-5, "moving_delay": 2000.0, "warmup_delay": 1000.0}
+B = 64
+env = BatchedSparkSchedSimEnv(cfg, num_envs=B, bank=synthetic_bank(0), decima_policy=True)
+z = np.load(osp.join('tests', 'golden', 'decima_model.npz'))
+env.set_decima_weights({k: z[k] for k in z.files})
+env.reset_host((np.arange(B) + 5).astype(np.uint64))
+env.set_autoreset(True, 64)
+tr = env.rollout_decima(60)
+torch.cuda.synchronize()
+h = env.hdr()
+print('decima ok', env.stats()['decisions'], (h['error'] != 0).sum())
+env2 = BatchedSparkSchedSimEnv({**cfg, "num_executors": 50, "job_arrival_cap": 12}, num_envs=32, bank=synthetic_bank(0))
+env2.reset_host((np.arange(32) + 9).astype(np.uint64))
+env2.rollout_fair(400, True, True, 32)
+torch.cuda.synchronize()
+print('e50 ok', env2.stats()['decisions'], (env2.hdr()['error'] != 0).sum())

@@ -758,7 +758,8 @@ int ssb_set_decima_weights(ssb_env *env, const float *weights, int32_t n_floats)
     }
     if (src != (size_t)dw::TOTAL || dst != (size_t)dd::TOTAL) return SSB_E_INVALID;
     CUDA_TRY(cudaMemcpy(env->p.pol_w, dev.data(), sizeof(float) * dd::TOTAL, cudaMemcpyHostToDevice));
-    // tensor-core path: per-stage blobs (canonical UMMA tiles, tf32 hi/lo halves, biases)
+    // tensor-core path: per-stage blobs (canonical UMMA tiles, tf32 hi/lo halves, biases); padding stays zero
+    CUDA_TRY(cudaMemset(env->p.pol_wblob, 0, sizeof(float) * tc::BLOB_TOTAL));
     tc::k_build_blob<tc::ST_PREP><<<1, 128>>>(env->p);
     tc::k_build_blob<tc::ST_SINK><<<1, 128>>>(env->p);
     tc::k_build_blob<tc::ST_MSG><<<1, 128>>>(env->p);

@@ -1790,45 +1790,80 @@ struct Sim {
                 fmask[rank] = (uint8_t)((frontier >> s) & 1);
             }
             const uint64_t *pm = p.b_parent + J.ts_base, *cm = p.b_child + J.ts_base;
-            uint64_t assigned = 0;
-            int dj = 0;
-            while (assigned != active && dj < 64) {
-                const uint64_t open = active & ~assigned;
-                const int s0 = lane, s1 = lane + 32;
-                const bool r0 = s0 < ns && ((open >> s0) & 1) && (pm[s0] & open) == 0;
-                const bool r1 = s1 < ns && ((open >> s1) & 1) && (pm[s1] & open) == 0;
-                const uint64_t Lk = (uint64_t)__ballot_sync(FULL, r0) | ((uint64_t)__ballot_sync(FULL, r1) << 32);
-                const uint64_t mine = ((r0 ? cm[s0] : 0ull) | (r1 ? cm[s1] : 0ull)) & active;
-                const uint64_t succ = (uint64_t)__reduce_or_sync(FULL, (uint32_t)mine) |
-                                      ((uint64_t)__reduce_or_sync(FULL, (uint32_t)(mine >> 32)) << 32);
-                if (lane == 0) Sk[dj] = Lk | succ;
-                assigned |= Lk;
-                dj++;
-                if (Lk == 0) break;  // cannot happen in a DAG
-            }
-            __syncwarp();
-            D = max(D, dj);
             const int eb = p.b_edge_base[J.tmpl], ne = p.b_edge_base[J.tmpl + 1] - eb;
-            for (int k0 = 0; k0 < ne; k0 += 32) {
-                const int k = k0 + lane;
-                int u = 0, v = 0;
-                bool keep = false;
-                if (k < ne) {
-                    u = p.b_edges[2 * (eb + k)];
-                    v = p.b_edges[2 * (eb + k) + 1];
-                    keep = ((active >> u) & 1) && ((active >> v) & 1);
+            int dj = 0;
+            if (ns <= 32) {
+                // Jobs of up to 32 stages (every TPC-H template): 32-bit masks, one stage per lane.  Lane s keeps
+                // the set of levels k with s in L_k U succ(L_k) in a register; an edge's mask bits are then the
+                // AND of its two ends' level sets (read through shared memory).
+                const uint32_t act32 = (uint32_t)active;
+                const uint32_t pm32 = lane < ns ? (uint32_t)pm[lane] : 0u, cm32 = lane < ns ? (uint32_t)cm[lane] : 0u;
+                uint32_t assigned = 0;
+                uint64_t ls = 0;
+                while (assigned != act32 && dj < 64) {
+                    const uint32_t open = act32 & ~assigned;
+                    const bool r0 = ((open >> lane) & 1) && (pm32 & open) == 0;
+                    const uint32_t Lk = __ballot_sync(FULL, r0);
+                    const uint32_t S = Lk | __reduce_or_sync(FULL, r0 ? (cm32 & act32) : 0u);
+                    if ((S >> lane) & 1) ls |= bit64(dj);
+                    assigned |= Lk;
+                    dj++;
+                    if (Lk == 0) break;  // cannot happen in a DAG
                 }
-                const unsigned m = __ballot_sync(FULL, keep);
-                if (keep) {
-                    uint64_t bits = 0;
-                    for (int q = 0; q < dj; q++) {
-                        const uint64_t S = Sk[q];
-                        if (((S >> u) & 1) && ((S >> v) & 1)) bits |= bit64(q);
+                Sk[lane] = ls;
+                __syncwarp();
+                for (int k0 = 0; k0 < ne; k0 += 32) {
+                    const int k = k0 + lane;
+                    int u = 0, v = 0;
+                    bool keep = false;
+                    if (k < ne) {
+                        u = p.b_edges[2 * (eb + k)];
+                        v = p.b_edges[2 * (eb + k) + 1];
+                        keep = ((act32 >> u) & 1) && ((act32 >> v) & 1);
                     }
-                    ebits[M + __popc(m & ((1u << lane) - 1))] = bits;
+                    const unsigned m = __ballot_sync(FULL, keep);
+                    if (keep) ebits[M + __popc(m & ((1u << lane) - 1))] = Sk[u] & Sk[v];
+                    M += __popc(m);
                 }
-                M += __popc(m);
+            } else {
+                uint64_t assigned = 0;
+                while (assigned != active && dj < 64) {
+                    const uint64_t open = active & ~assigned;
+                    const int s0 = lane, s1 = lane + 32;
+                    const bool r0 = s0 < ns && ((open >> s0) & 1) && (pm[s0] & open) == 0;
+                    const bool r1 = s1 < ns && ((open >> s1) & 1) && (pm[s1] & open) == 0;
+                    const uint64_t Lk = (uint64_t)__ballot_sync(FULL, r0) | ((uint64_t)__ballot_sync(FULL, r1) << 32);
+                    const uint64_t mine = ((r0 ? cm[s0] : 0ull) | (r1 ? cm[s1] : 0ull)) & active;
+                    const uint64_t succ = (uint64_t)__reduce_or_sync(FULL, (uint32_t)mine) |
+                                          ((uint64_t)__reduce_or_sync(FULL, (uint32_t)(mine >> 32)) << 32);
+                    if (lane == 0) Sk[dj] = Lk | succ;
+                    assigned |= Lk;
+                    dj++;
+                    if (Lk == 0) break;  // cannot happen in a DAG
+                }
+                __syncwarp();
+                for (int k0 = 0; k0 < ne; k0 += 32) {
+                    const int k = k0 + lane;
+                    int u = 0, v = 0;
+                    bool keep = false;
+                    if (k < ne) {
+                        u = p.b_edges[2 * (eb + k)];
+                        v = p.b_edges[2 * (eb + k) + 1];
+                        keep = ((active >> u) & 1) && ((active >> v) & 1);
+                    }
+                    const unsigned m = __ballot_sync(FULL, keep);
+                    if (keep) {
+                        uint64_t bits = 0;
+                        for (int q = 0; q < dj; q++) {
+                            const uint64_t S = Sk[q];
+                            if (((S >> u) & 1) && ((S >> v) & 1)) bits |= bit64(q);
+                        }
+                        ebits[M + __popc(m & ((1u << lane) - 1))] = bits;
+                    }
+                    M += __popc(m);
+                }
             }
+            D = max(D, dj);
             __syncwarp();
             N += popc64(active);
         }

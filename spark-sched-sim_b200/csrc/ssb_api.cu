@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -163,20 +164,23 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_decima_obs(Params p)
 }
 
 // rollout-buffer rows around one { policy ; step } call of ssb_rollout_decima
-__global__ void k_traj_pre(Params p, const int32_t *a, const int32_t *n, ssb_transition *traj, int K, int d)
+// (the row index d lives in device memory so that one captured graph serves every decision of a call)
+__global__ void k_traj_pre(Params p, const int32_t *a, const int32_t *n, ssb_transition *traj, int K)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= p.B) return;
+    const int d = *p.traj_d;
     ssb_transition t;
     t.wall_time = p.obs_hdr[b].wall_time; t.reward = 0.0; t.stage_idx = a[b]; t.num_exec = n[b];
     t.flags = p.obs_hdr[b].was_reset ? 4 : 0;
     t.lgprob = p.pol_lgprob[b];
     traj[(size_t)b * K + d] = t;
 }
-__global__ void k_traj_post(Params p, ssb_transition *traj, int K, int d)
+__global__ void k_traj_post(Params p, ssb_transition *traj, int K)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= p.B) return;
+    const int d = *p.traj_d;
     const ssb_obs_hdr &o = p.obs_hdr[b];
     ssb_transition &t = traj[(size_t)b * K + d];
     if (o.was_reset || o.error == SSB_ENV_DONE) { t.flags = 8; t.reward = 0.0; return; }
@@ -308,6 +312,7 @@ void carve(Carver &cv, const ssb_config &c, const ssb_bank &bk, const Dims &d, P
         p.pol_exec_logits = cv.take<float>(B * p.Epad);
         p.pol_action = cv.take<int32_t>(B * 4);
         p.pol_lgprob = cv.take<float>(B);
+        p.traj_d = cv.take<int32_t>(4);
         p.pol_act_a = cv.take<int32_t>(B);
         p.pol_act_n = cv.take<int32_t>(B);
         p.pl_all = cv.take<int32_t>(B * d.Sc);
@@ -350,6 +355,12 @@ struct ssb_env {
     int grid;
     int num_sms;
     int dmax;           // upper bound of the message-passing depth: longest template chain - 1
+    // CUDA graph of one ssb_rollout_decima decision and the arguments it was captured with
+    cudaEvent_t ev;
+    cudaGraphExec_t dg_exec;
+    ssb_transition *dg_traj;
+    int dg_k, dg_events, dg_autoreset, no_graph;
+    uint64_t dg_seed_step;
     int auto_reset;     // ssb_set_autoreset
     uint64_t auto_seed_step;
 };
@@ -422,6 +433,10 @@ int ssb_create(const ssb_config *cfg, const ssb_bank *bk, int device, void *work
     p.mean_interarrival = 1 / cfg->job_arrival_rate;  // tpch.py:42
     p.beta = cfg->beta;
     env->grid = (cfg->num_envs + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    {
+        const char *ng = getenv("SSB_NO_GRAPH");
+        env->no_graph = ng && ng[0] == '1';
+    }
     CUDA_TRY(cudaDeviceGetAttribute(&env->num_sms, cudaDevAttrMultiProcessorCount, device));
     {
         // longest chain of topological generations over the templates bounds the depth of every observation
@@ -506,6 +521,7 @@ int ssb_create(const ssb_config *cfg, const ssb_bank *bk, int device, void *work
     CUDA_TRY(cudaMemset(p.prof, 0, sizeof(unsigned long long) * 16 * (size_t)p.B));
     CUDA_TRY(cudaMemset(p.obs_hdr, 0, sizeof(ssb_obs_hdr) * (size_t)p.B));
     CUDA_TRY(cudaStreamCreateWithFlags(&env->own_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&env->ev, cudaEventDisableTiming));
     CUDA_TRY(cudaDeviceSynchronize());
     *out = env;
     return SSB_OK;
@@ -517,6 +533,8 @@ int ssb_destroy(ssb_env *env)
     cudaSetDevice(env->device);
     cudaStreamSynchronize(env->own_stream);
     cudaStreamDestroy(env->own_stream);
+    if (env->dg_exec) cudaGraphExecDestroy(env->dg_exec);
+    if (env->ev) cudaEventDestroy(env->ev);
     delete env;
     return SSB_OK;
 }
@@ -809,20 +827,70 @@ int ssb_decima_policy(ssb_env *env, const int32_t *forced_stage, const int32_t *
     return SSB_OK;
 }
 
+__global__ void k_traj_next(Params p) { if (threadIdx.x == 0 && blockIdx.x == 0) *p.traj_d += 1; }
+
+// one decision of ssb_rollout_decima, enqueued on s (captured into a CUDA graph by the caller)
+static int decima_decision(ssb_env *env, int32_t num_decisions, int32_t max_events, ssb_transition *traj, cudaStream_t s)
+{
+    const Params &p = env->p;
+    const int tb = (p.B + 127) / 128;
+    int rc = ssb_decima_policy(env, nullptr, nullptr, p.pol_act_a, p.pol_act_n, s);
+    if (rc) return rc;
+    if (traj) k_traj_pre<<<tb, 128, 0, s>>>(p, p.pol_act_a, p.pol_act_n, traj, num_decisions);
+    if ((rc = ssb_step(env, p.pol_act_a, p.pol_act_n, nullptr, max_events, s))) return rc;
+    if (traj) k_traj_post<<<tb, 128, 0, s>>>(p, traj, num_decisions);
+    k_traj_next<<<1, 32, 0, s>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    return SSB_OK;
+}
+
 int ssb_rollout_decima(ssb_env *env, int32_t num_decisions, int32_t max_events, ssb_transition *traj, void *stream)
 {
     if (!env || !env->p.pol_w || num_decisions < 0) return SSB_E_INVALID;
-    cudaStream_t s = (cudaStream_t)stream;
-    const Params &p = env->p;
-    const int tb = (p.B + 127) / 128;
-    for (int d = 0; d < num_decisions; d++) {
-        int rc = ssb_decima_policy(env, nullptr, nullptr, p.pol_act_a, p.pol_act_n, stream);
-        if (rc) return rc;
-        if (traj) k_traj_pre<<<tb, 128, 0, s>>>(p, p.pol_act_a, p.pol_act_n, traj, num_decisions, d);
-        if ((rc = ssb_step(env, p.pol_act_a, p.pol_act_n, nullptr, max_events, stream))) return rc;
-        if (traj) k_traj_post<<<tb, 128, 0, s>>>(p, traj, num_decisions, d);
+    cudaStream_t caller = (cudaStream_t)stream, s = caller;
+    // the legacy default stream cannot be captured: run on the handle's own stream, ordered after / before the
+    // caller's stream with events
+    const bool hop = caller == nullptr || caller == cudaStreamLegacy || caller == cudaStreamPerThread;
+    if (hop && !env->no_graph) {
+        s = env->own_stream;
+        CUDA_TRY(cudaEventRecord(env->ev, caller));
+        CUDA_TRY(cudaStreamWaitEvent(s, env->ev, 0));
     }
-    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemsetAsync(env->p.traj_d, 0, sizeof(int32_t), s));
+    // The ~50 launches of one decision are captured once into a CUDA graph and replayed: the kernels are short
+    // (10-100 us) and strictly dependent, so the per-launch gaps are a visible share of a decision.
+    // (SSB_NO_GRAPH=1 launches them one by one.)
+    const bool same = env->dg_exec && env->dg_traj == traj && env->dg_k == num_decisions && env->dg_events == max_events &&
+                      env->dg_autoreset == env->auto_reset && env->dg_seed_step == env->auto_seed_step;
+    if (!same && !env->no_graph) {
+        if (env->dg_exec) { cudaGraphExecDestroy(env->dg_exec); env->dg_exec = nullptr; }
+        cudaGraph_t g = nullptr;
+        CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        const int rc = decima_decision(env, num_decisions, max_events, traj, s);
+        const cudaError_t ce = cudaStreamEndCapture(s, &g);
+        if (rc || ce != cudaSuccess || !g) {
+            if (g) cudaGraphDestroy(g);
+            cudaGetLastError();
+            env->no_graph = 1;  // fall back to plain launches for this handle
+        } else {
+            const cudaError_t ie = cudaGraphInstantiate(&env->dg_exec, g, 0);
+            cudaGraphDestroy(g);
+            if (ie != cudaSuccess) { env->dg_exec = nullptr; env->no_graph = 1; cudaGetLastError(); }
+            env->dg_traj = traj; env->dg_k = num_decisions; env->dg_events = max_events;
+            env->dg_autoreset = env->auto_reset; env->dg_seed_step = env->auto_seed_step;
+        }
+    }
+    for (int d = 0; d < num_decisions; d++) {
+        if (env->dg_exec && !env->no_graph) CUDA_TRY(cudaGraphLaunch(env->dg_exec, s));
+        else {
+            const int rc = decima_decision(env, num_decisions, max_events, traj, s);
+            if (rc) return rc;
+        }
+    }
+    if (s != caller) {
+        CUDA_TRY(cudaEventRecord(env->ev, s));
+        CUDA_TRY(cudaStreamWaitEvent(caller, env->ev, 0));
+    }
     return SSB_OK;
 }
 

@@ -158,6 +158,7 @@ struct Params {
     int32_t *pol_action;                  // [B][4]
     float *pol_lgprob;                    // [B]
     int32_t *pol_act_a, *pol_act_n;       // [B] env-format actions of ssb_rollout_decima
+    int32_t *traj_d;                      // row index of the rollout-buffer slab being written
     int Epad;
     // tensor-core policy path (ssb_decima_tc.cuh): row lists built per decision by the planning kernels
     int32_t *pl_all, *pl_sink;                     // [B * Sc] flat node ids (b * Sc + n)

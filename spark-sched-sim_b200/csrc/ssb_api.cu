@@ -1,8 +1,10 @@
 // ssb_api.cu -- kernels and the C ABI of libssb (include/ssb.h).
 //
-// Launch geometry: one warp per environment, 4 environments per 128-thread CTA, grid = ceil(B/4).
-// At B = 4096 that is 1024 CTAs (~7 per SM on 148 SMs), all resident at once; the kernels are
-// latency-bound chains per environment, so residency (warps per SM) is what hides the latency.
+// Launch geometry of the simulator kernels: one warp per environment, 4 environments per 128-thread CTA,
+// grid = ceil(B/4).  At B = 4096 that is 1024 CTAs (~7 per SM on 148 SMs), all resident at once (the one-slot
+// kernels are held to 72 registers for that); the kernels are dependency chains per environment bound by
+// instruction supply, so residency is what keeps the SM busy.  The Decima policy is a sequence
+// of list-driven tile kernels over all environments (ssb_decima_tc.cuh).
 #include <cuda_runtime.h>
 
 #include <algorithm>

@@ -223,7 +223,9 @@ def main() -> None:
         torch.cuda.synchronize()
 
     def allreduce_stats():
-        # the path's only exchange step: rollout statistics summed over ranks
+        # the path's only exchange step: collect_stats (rollout_worker.py:122-129) of this rank's envs as sums,
+        # reduced on the device and summed over ranks
+        env.collect_stats(stats_vec)
         if world > 1:
             dist.all_reduce(stats_vec)
 
@@ -244,7 +246,7 @@ def main() -> None:
         flush.fill_(k & 0xFF)  # evict L2 between timed iterations (untimed)
         ev0[k].record()
         env.rollout_fair(D, True, True, seed_step)
-        launches += 1
+        launches += 2
         allreduce_stats()
         ev1[k].record()
     barrier()
@@ -392,6 +394,7 @@ def main() -> None:
                              f"{env.workspace_bytes >> 20} MiB per GPU",
                        "parallelism": f"envs sharded over {world} GPU(s); all-reduce of rollout stats only"},
             "events_per_s": total_ev / (max_ms * 1e-3), "episodes": total_eps, "env_errors": total_err,
+            "rollout_stats": parallel.stats_from_sums(stats_vec),
             "wall_s_timed_region": t_wall,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_rollout": e2e_rollout, "clocks": clocks,
             "gpu_launches": launches + launches_e2e,

@@ -272,6 +272,13 @@ int ssb_get_policy_views(ssb_env *env, ssb_policy_views *out);
  * may be NULL).  Finished envs follow ssb_set_autoreset: with it, the call after the end of an episode
  * re-seeds the env (row flagged 8); without it they idle (rows flagged with error SSB_ENV_DONE semantics). */
 int ssb_rollout_decima(ssb_env *env, int32_t num_decisions, int32_t max_events, ssb_transition *traj, void *stream);
+/* collect_stats (trainers/rollout_worker.py:122-129) over all envs as SUMS that can be all-reduced across GPUs:
+ * out = DEVICE f64[8]: [0] sum over envs of avg_num_jobs = (total job time so far) / wall_time
+ * (metrics.py:15-16; envs at wall_time 0 skipped), [1] number of envs counted in [0], [2] completed jobs,
+ * [3] job arrivals (completed + active), [4] sum of the completed jobs' durations in ms (current episodes; the
+ * reference's avg_job_duration averages its last 200 completions across resets), [5] sum of wall times, [6..7] 0.
+ * Fixed summation order (deterministic). */
+int ssb_collect_stats(ssb_env *env, double *out, void *stream);
 /* device pointer to ssb_stats[B] */
 int ssb_get_stats(ssb_env *env, ssb_stats **out);
 int ssb_reset_stats(ssb_env *env, void *stream);

@@ -125,7 +125,7 @@ STATS_DTYPE = np.dtype([(f, "<u8") for f in STATS_FIELDS])
 EXPORTS = [
     "ssb_abi_version", "ssb_last_cuda_error", "ssb_workspace_bytes", "ssb_create", "ssb_destroy",
     "ssb_load_trace", "ssb_clear_trace", "ssb_reset", "ssb_step", "ssb_reset_host", "ssb_step_host", "ssb_step_fair_host", "ssb_set_autoreset",
-    "ssb_rollout_fair", "ssb_rollout_fair_traj", "ssb_discounted_returns", "ssb_group_baselines", "ssb_fair_actions", "ssb_get_views", "ssb_get_stats", "ssb_reset_stats",
+    "ssb_rollout_fair", "ssb_rollout_fair_traj", "ssb_discounted_returns", "ssb_group_baselines", "ssb_fair_actions", "ssb_get_views", "ssb_get_stats", "ssb_collect_stats", "ssb_reset_stats",
     "ssb_get_jobs", "ssb_get_log", "ssb_decima_obs", "ssb_get_decima_views",
     "ssb_set_decima_weights", "ssb_decima_policy", "ssb_rollout_decima", "ssb_get_policy_views", "ssb_get_debug_counters",
 ]
@@ -176,6 +176,7 @@ def lib():
     L.ssb_get_policy_views.argtypes = [vp, C.POINTER(SsbPolicyViews)]
     L.ssb_get_stats.argtypes = [vp, C.POINTER(vp)]
     L.ssb_reset_stats.argtypes = [vp, vp]
+    L.ssb_collect_stats.argtypes = [vp, vp, vp]
     L.ssb_get_debug_counters.argtypes = [vp, C.POINTER(vp)]
     L.ssb_get_jobs.argtypes = [vp, i32, C.POINTER(i32), vp, vp, vp, vp, i32]
     L.ssb_get_log.argtypes = [vp, i32, i64, i64, C.POINTER(i64)] + [vp] * 7

@@ -252,6 +252,15 @@ class BatchedSparkSchedSimEnv:
         """The ssb_stats counters of every env (structured array [B])."""
         return self.stats_bytes.cpu().numpy().view(nat.STATS_DTYPE).reshape(-1).copy()
 
+    def collect_stats(self, out: "torch.Tensor | None" = None) -> torch.Tensor:
+        """collect_stats (trainers/rollout_worker.py:122-129) over this GPU's envs as a device f64[8] vector of
+        sums (see ssb_collect_stats); all-reduce it over ranks, then parallel.stats_from_sums() turns it into
+        the reference's dict."""
+        if out is None:
+            out = torch.zeros(8, dtype=torch.float64, device=self.device)
+        nat.check(self.L.ssb_collect_stats(self._h, out.data_ptr(), self._stream()), "ssb_collect_stats")
+        return out
+
     def reset_stats(self):
         nat.check(self.L.ssb_reset_stats(self._h, self._stream()), "ssb_reset_stats")
 

@@ -190,6 +190,44 @@ __global__ void k_traj_post(Params p, ssb_transition *traj, int K)
     t.flags |= (o.terminated ? 1 : 0) | (o.truncated ? 2 : 0);
 }
 
+// collect_stats sums, one block, fixed order: warp w handles envs w, w + 32, ...; lanes over the env's jobs
+__global__ void __launch_bounds__(1024) k_collect_stats(Params p, double *out)
+{
+    __shared__ double part[32][6];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    for (int b = w; b < p.B; b += 32) {
+        const EnvHdr &h = p.hdr[b];
+        const JobRec *jb = p.job + (size_t)b * p.Jc;
+        const double wall = h.wall_time;
+        double jt = 0.0, cd = 0.0;
+        int nc = 0, na = 0;
+        for (int j = lane; j < h.next_arrival; j += 32) {  // jobs that have arrived, in id order per lane
+            const JobRec &J = jb[j];
+            jt += fmin(J.t_completed, wall) - J.t_arrival;
+            if (J.state == JOB_COMPLETED) { nc++; cd += J.t_completed - J.t_arrival; }
+            na++;
+        }
+        for (int off = 16; off; off >>= 1) {  // fixed butterfly order
+            jt += __shfl_xor_sync(0xffffffffu, jt, off);
+            cd += __shfl_xor_sync(0xffffffffu, cd, off);
+            nc += __shfl_xor_sync(0xffffffffu, nc, off);
+            na += __shfl_xor_sync(0xffffffffu, na, off);
+        }
+        if (wall > 0.0) { acc[0] += jt / wall; acc[1] += 1.0; }
+        acc[2] += nc; acc[3] += na; acc[4] += cd; acc[5] += wall;
+    }
+    if (lane == 0)
+        for (int i = 0; i < 6; i++) part[w][i] = acc[i];
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        double s = 0.0;
+        if (threadIdx.x < 6)
+            for (int i = 0; i < 32; i++) s += part[i][threadIdx.x];
+        out[threadIdx.x] = s;
+    }
+}
+
 __global__ void k_zero_stats(ssb_stats *s, int n)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -919,6 +957,14 @@ int ssb_get_debug_counters(ssb_env *env, uint64_t **out)
 {
     if (!env || !out) return SSB_E_INVALID;
     *out = reinterpret_cast<uint64_t *>(env->p.prof);
+    return SSB_OK;
+}
+
+int ssb_collect_stats(ssb_env *env, double *out, void *stream)
+{
+    if (!env || !out) return SSB_E_INVALID;
+    k_collect_stats<<<1, 1024, 0, (cudaStream_t)stream>>>(env->p, out);
+    CUDA_TRY(cudaGetLastError());
     return SSB_OK;
 }
 

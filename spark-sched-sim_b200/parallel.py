@@ -57,3 +57,12 @@ def rollout_summary(sum_job_time: float, sum_wall_time: float, num_completed: fl
         "num_completed_jobs": num_completed,
         "num_job_arrivals": num_arrived,
     }
+
+
+def stats_from_sums(vec) -> dict:
+    """The reference's per-iteration statistics (trainer.py:310-320 averages the workers' collect_stats dicts)
+    from the (all-reduced) ssb_collect_stats vector."""
+    v = [float(x) for x in (vec.tolist() if hasattr(vec, "tolist") else vec)]
+    n = max(v[1], 1.0)
+    return {"avg_num_jobs": v[0] / n, "num_completed_jobs": v[2] / n, "num_job_arrivals": v[3] / n,
+            "avg_job_duration": (v[4] / v[2] * 1e-3) if v[2] else float("nan")}

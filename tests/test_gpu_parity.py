@@ -400,6 +400,35 @@ def test_step_fair_host_matches_oracle(bank):
         assert got[b][:K] == rows, b
 
 
+def test_collect_stats_matches_host_metrics(bank):
+    """ssb_collect_stats sums == the reference's metrics (spark_sched_sim/metrics.py) evaluated per env on the
+    host from the per-job times, mid-episode."""
+    from spark_sched_sim_b200 import parallel
+    from spark_sched_sim_b200.batched_env import BatchedSparkSchedSimEnv
+
+    B = 70
+    cfg = {"num_executors": 10, "job_arrival_cap": 12, "job_arrival_rate": 4.0e-5,
+           "moving_delay": 2000.0, "warmup_delay": 1000.0}
+    env = BatchedSparkSchedSimEnv(cfg, num_envs=B, bank=bank)
+    env.reset_host(np.arange(B, dtype=np.uint64) + 3)
+    env.rollout_fair(90, True, auto_reset=False)
+    v = env.collect_stats().cpu().numpy()
+    hdr = env.hdr()
+    want = np.zeros(6)
+    for b in range(B):
+        ta, tc, tm, state = env.jobs(b, with_state=True)
+        wall = hdr["wall_time"][b]
+        arrived = state != 0
+        jt = (np.minimum(tc[arrived], wall) - ta[arrived]).sum()
+        if wall > 0:
+            want[0] += jt / wall; want[1] += 1
+        done = state == 2
+        want[2] += done.sum(); want[3] += arrived.sum(); want[4] += (tc[done] - ta[done]).sum(); want[5] += wall
+    assert np.allclose(v[:6], want, rtol=1e-12), (v, want)
+    s = parallel.stats_from_sums(v)
+    assert 0 < s["avg_num_jobs"] < 12 and s["num_job_arrivals"] <= 12
+
+
 def test_rollout_with_discounted_reward(bank):
     """beta > 0: the continuously discounted reward (:866-869) goes through exp(); transitions match the
     oracle with rewards at 1e-12 relative (device exp vs libm), everything else exactly."""

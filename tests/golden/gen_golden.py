@@ -36,6 +36,8 @@ CASES = {
     "c2_fair_s1234_pcg64": (C2, "fair", 1234, "pcg64", None, True),
     "c2_fair_s1234_philox": (C2, "fair", 1234, "philox", None, True),
     "c2_random_s7_philox": (C2, "random", 7, "philox", None, True),
+    # BASELINE config 4's episode shape: 200 jobs x 50 executors (two executor slots per lane on the device)
+    "c4_fair_s21_philox": (cfg(50, 200), "fair", 21, "philox", None, True),
     "e10_j8_fair_s1_pcg64": (cfg(10, 8), "fair", 1, "pcg64", None, False),
     "e10_j8_fair_s2_philox": (cfg(10, 8), "fair", 2, "philox", None, False),
     "e10_j8_fifo_s3_philox": (cfg(10, 8), "fifo", 3, "philox", None, False),

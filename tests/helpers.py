@@ -15,7 +15,7 @@ def golden_names(slim=None):
     names = [n for n in names if n not in ("decima_model", "learner_vectors")]  # fixtures that are not traces
     if slim is None:
         return names
-    return [n for n in names if n.startswith("c2_") == slim]
+    return [n for n in names if n.startswith(("c2_", "c4_")) == slim]
 
 
 def load_golden(name):

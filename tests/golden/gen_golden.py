@@ -38,6 +38,8 @@ CASES = {
     "c2_random_s7_philox": (C2, "random", 7, "philox", None, True),
     # BASELINE config 4's episode shape: 200 jobs x 50 executors (two executor slots per lane on the device)
     "c4_fair_s21_philox": (cfg(50, 200), "fair", 21, "philox", None, True),
+    # continuous Poisson arrivals until a time limit (no job cap), 50 executors
+    "c4_tl_fifo_s22_philox": (cfg(50, None), "fifo", 22, "philox", 3.0e6, True),
     "e10_j8_fair_s1_pcg64": (cfg(10, 8), "fair", 1, "pcg64", None, False),
     "e10_j8_fair_s2_philox": (cfg(10, 8), "fair", 2, "philox", None, False),
     "e10_j8_fifo_s3_philox": (cfg(10, 8), "fifo", 3, "philox", None, False),
@@ -55,6 +57,7 @@ CASES = {
     # hold the policy's stage / executor-count scores for every decision (`pol_*`)
     "decima_e10_j8_s5_philox": (cfg(10, 8), "decima", 5, "philox", None, False),
     "decima_e50_j6_s3_philox": (cfg(50, 6), "decima", 3, "philox", None, False),
+    "decima_e50_j14_s4_philox": (cfg(50, 14), "decima", 4, "philox", None, False),
 }
 
 

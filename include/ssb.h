@@ -172,6 +172,13 @@ int ssb_step(ssb_env *env, const int32_t *stage_idx, const int32_t *num_exec, co
  * without a separate ssb_reset launch per call. */
 int ssb_set_autoreset(ssb_env *env, int32_t enable, uint64_t seed_step);
 
+/* StochasticTimeLimit (wrappers/stochastic_time_limit.py:5-31) on the device: with mean_ms > 0 every reset that is
+ * not given an explicit time limit -- ssb_reset with time_limits == NULL, and every auto-reset of the step API and
+ * of the fused rollouts -- draws the new episode's limit ~ Exp(mean_ms) from the LIMIT stream of the episode's seed
+ * (Philox ctr (0, 0, 3, 0); oracle/philox_ref.py:time_limit_draw).  mean_ms == 0 (default): explicit limits only,
+ * auto-resets keep the previous limit. */
+int ssb_set_mean_time_limit(ssb_env *env, double mean_ms);
+
 /* same with HOST buffers: copies in, runs, copies the B observation headers out, synchronises */
 int ssb_reset_host(ssb_env *env, const uint64_t *seeds, const double *time_limits, const uint8_t *mask,
                    ssb_obs_hdr *hdr_out);

@@ -182,6 +182,11 @@ class BatchedSparkSchedSimEnv:
         episode's first observation with hdr["was_reset"] = 1."""
         nat.check(self.L.ssb_set_autoreset(self._h, int(bool(enable)), int(seed_step)), "ssb_set_autoreset")
 
+    def set_mean_time_limit(self, mean_ms: float) -> None:
+        """StochasticTimeLimit on the device: every reset without an explicit limit (and every auto-reset) draws
+        the episode's time limit ~ Exp(mean_ms) from the episode seed's Philox LIMIT stream."""
+        nat.check(self.L.ssb_set_mean_time_limit(self._h, float(mean_ms)), "ssb_set_mean_time_limit")
+
     def rollout_fair_traj(self, num_decisions, dynamic_partition=True, auto_reset=True, seed_step=1,
                           out: "torch.Tensor | None" = None, host: "torch.Tensor | None" = None):
         """Fused rollout that also records every transition (what RolloutBuffer keeps per step besides

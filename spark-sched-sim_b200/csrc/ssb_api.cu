@@ -49,7 +49,7 @@ k_reset(Params p, const uint64_t *seeds, const double *time_limits, const uint8_
     Sim sim(p, b, lane);
     const uint64_t seed = seeds ? seeds[b] : 0ull;
     if (lane == 0) { sim.h->base_seed = seed; sim.h->reset_count = 1; }
-    sim.reset_w(seed, time_limits ? time_limits[b] : INFINITY);
+    sim.reset_w(seed, time_limits ? time_limits[b] : (p.mean_time_limit > 0.0 ? sim.sample_time_limit(seed) : INFINITY));
 }
 
 // NS: executor slots per lane of the batched fast path (1: E <= 32, 2: E <= 64), see ssb_sim.cuh
@@ -73,7 +73,7 @@ k_step(Params p, const int32_t *stage_idx, const int32_t *num_exec, const uint8_
     if (auto_reset && !sim.h->error && (sim.h->done || sim.oh->truncated)) {
         // the caller's `if terminated or truncated: env.reset(seed=...)` (rollout_worker.py:118-120, :150-153)
         const uint64_t seed = sim.h->base_seed + seed_step * (uint64_t)sim.h->reset_count;
-        const double tl = sim.h->time_limit;
+        const double tl = sim.next_time_limit(seed);
         const bool was_trunc = !sim.h->done;
         __syncwarp();
         if (lane == 0) { sim.h->reset_count += 1; if (was_trunc) sim.stats->episodes++; }
@@ -124,7 +124,7 @@ k_rollout_fair(Params p, int num_decisions, int dynamic_partition, int auto_rese
             fresh = 4;
             // rollout_worker.py:118-120: seed = base_seed + seed_step * reset_count
             const uint64_t seed = sim.h->base_seed + seed_step * (uint64_t)sim.h->reset_count;
-            const double tl = sim.h->time_limit;
+            const double tl = sim.next_time_limit(seed);
             const bool was_trunc = !sim.h->done;
             __syncwarp();
             if (lane == 0) { sim.h->reset_count += 1; if (was_trunc) sim.stats->episodes++; }
@@ -643,6 +643,13 @@ int ssb_set_autoreset(ssb_env *env, int32_t enable, uint64_t seed_step)
     if (!env) return SSB_E_INVALID;
     env->auto_reset = enable ? 1 : 0;
     env->auto_seed_step = seed_step;
+    return SSB_OK;
+}
+
+int ssb_set_mean_time_limit(ssb_env *env, double mean_ms)
+{
+    if (!env || !(mean_ms >= 0.0)) return SSB_E_INVALID;
+    env->p.mean_time_limit = mean_ms;
     return SSB_OK;
 }
 

@@ -1624,6 +1624,19 @@ struct Sim {
         step_end_w();
     }
 
+    // StochasticTimeLimit (wrappers/stochastic_time_limit.py:19-21): the episode's time limit ~ Exp(mean), drawn on
+    // the Philox LIMIT stream of the episode's seed (oracle/philox_ref.py:time_limit_draw)
+    __device__ double sample_time_limit(uint64_t seed) const
+    {
+        const uint4 w = philox4x32_10(0u, 0u, 3u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32));
+        return __dmul_rn(p.mean_time_limit, neglog_u32(w.x));
+    }
+    // time limit of the episode an auto-reset starts: a fresh draw when a mean is configured, else unchanged
+    __device__ double next_time_limit(uint64_t seed) const
+    {
+        return p.mean_time_limit > 0.0 ? sample_time_limit(seed) : h->time_limit;
+    }
+
     // ------------------------------------------------------------ reset() (:127-186)
     __device__ SSB_RARE void reset_w(uint64_t seed, double time_limit)
     {

@@ -108,6 +108,7 @@ struct Params {
     int B, E, Jc, Sc, Mc, TAB, RT, P, Cc, max_stages;
     int tape_cap, log_cap, job_arrival_cap;
     double moving_delay, warmup_delay, mean_interarrival, beta;
+    double mean_time_limit;  // > 0: every reset without an explicit limit draws one (StochasticTimeLimit)
     // template bank (read-only)
     const int32_t *b_num_stages, *b_stage_base, *b_edge_base, *b_num_tasks;
     const int16_t *b_edges;  // [edges][2]

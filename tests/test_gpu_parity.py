@@ -287,14 +287,18 @@ def test_rollout_transitions_match_oracle(bank):
         assert ep > 1
 
 
-def _oracle_transitions(bank, cfg, seed, seed_step, K, time_limit=np.inf, beta=0.0):
-    """K decisions of the oracle under the fair policy with the rollout worker's re-seeding rule."""
+def _oracle_transitions(bank, cfg, seed, seed_step, K, time_limit=np.inf, beta=0.0, mean_time_limit=0.0):
+    """K decisions of the oracle under the fair policy with the rollout worker's re-seeding rule.
+    mean_time_limit > 0: every episode's limit is the StochasticTimeLimit draw of its seed."""
     from oracle import OracleEnv
+    from philox_ref import time_limit_draw
 
     orc = OracleEnv(bank, cfg["num_executors"], cfg["job_arrival_cap"], cfg["moving_delay"], cfg["warmup_delay"],
                     cfg["job_arrival_rate"], beta=beta)
     rows, k, ep = [], 0, 0
     while k < K:
+        if mean_time_limit > 0:
+            time_limit = time_limit_draw(int(seed) + seed_step * ep, mean_time_limit)
         orc.reset_seed(int(seed) + seed_step * ep, time_limit)
         done = False
         while not done and k < K:
@@ -427,6 +431,36 @@ def test_collect_stats_matches_host_metrics(bank):
     assert np.allclose(v[:6], want, rtol=1e-12), (v, want)
     s = parallel.stats_from_sums(v)
     assert 0 < s["avg_num_jobs"] < 12 and s["num_job_arrivals"] <= 12
+
+
+def test_stochastic_time_limit_on_device(bank):
+    """ssb_set_mean_time_limit: resets without an explicit limit and auto-resets draw the episode's limit
+    ~ Exp(mean) from the seed's Philox LIMIT stream (StochasticTimeLimit); the fused rollout then equals the
+    oracle driven with the spec's draws (oracle/philox_ref.py:time_limit_draw)."""
+    import torch
+    from spark_sched_sim_b200 import _native as nat
+    from spark_sched_sim_b200.batched_env import BatchedSparkSchedSimEnv
+
+    B, K, MEAN = 4, 500, 3.0e5
+    cfg = {"num_executors": 10, "job_arrival_cap": 0, "job_arrival_rate": 4.0e-5,
+           "moving_delay": 2000.0, "warmup_delay": 1000.0}
+    env = BatchedSparkSchedSimEnv(cfg, num_envs=B, bank=bank, max_jobs=128)
+    env.set_mean_time_limit(MEAN)
+    seeds = np.arange(60, 60 + B, dtype=np.uint64)
+    env.reset_host(seeds)
+    host = torch.empty(B * K * nat.TRANSITION_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+    tr = env.rollout_fair_traj(K, True, auto_reset=True, seed_step=17, host=host)
+    assert (env.hdr()["error"] == 0).all()
+    n_trunc = 0
+    for b in range(B):
+        rows, eps = _oracle_transitions(bank, cfg, seeds[b], 17, K, mean_time_limit=MEAN)
+        assert eps > 2
+        for k, (wall0, rew, a, n, term, trunc) in enumerate(rows):
+            r = tr[b, k]
+            assert (r["wall_time"], r["reward"], r["stage_idx"], r["num_exec"]) == (wall0, rew, a, n), (b, k)
+            assert (r["flags"] & 1, (r["flags"] >> 1) & 1) == (term, trunc), (b, k)
+            n_trunc += trunc
+    assert n_trunc > B
 
 
 def test_rollout_with_discounted_reward(bank):

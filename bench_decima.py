@@ -32,6 +32,8 @@ def main():
     ap.add_argument("--decisions", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--budget", type=int, default=0, help="max events per env per step (0 = run to decision)")
+    ap.add_argument("--mean-time-limit", type=float, default=0.0,
+                    help="StochasticTimeLimit mean in ms (config/decima_tpch.yaml: 2e7); 0 = episodes end by job cap only")
     args = ap.parse_args()
 
     import os
@@ -64,6 +66,8 @@ def main():
     from spark_sched_sim_b200 import _native as nat
 
     env.set_autoreset(True, B * world)
+    if args.mean_time_limit > 0:
+        env.set_mean_time_limit(args.mean_time_limit)  # applies from the next (auto-)reset of every env
     chunk = 25  # decisions per ssb_rollout_decima call (one rollout-buffer slab)
     nb = B * chunk * nat.TRANSITION_DTYPE.itemsize
     traj_dev = torch.empty(nb, dtype=torch.uint8, device=dev)

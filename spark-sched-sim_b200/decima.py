@@ -50,6 +50,9 @@ class DecimaObsWrapper(ObservationWrapper):
             "stage_mask": d["stage_mask"],
             "exec_mask": d["exec_mask"],
             "edge_masks": d["edge_masks"],
+            # handle for schedulers.DecimaScheduler, which evaluates the policy on the device (extra key:
+            # the reference's schedulers only read the keys above)
+            "_ssb_env": self._batched,
         }
 
 

@@ -29,7 +29,7 @@ class SparkSchedSimEnv(Env):
     metadata = {"render_modes": [], "render_fps": 30}
 
     def __init__(self, env_cfg: dict[str, Any], bank=None, device="cuda:0", max_jobs: int | None = None,
-                 tape_capacity: int = 0, log_capacity: int = 0, decima_obs: bool = False):
+                 tape_capacity: int = 0, log_capacity: int = 0, decima_obs: bool = True):
         self.num_executors: int = env_cfg["num_executors"]
         self.moving_delay = env_cfg["moving_delay"]
         self.beta: float = env_cfg.get("beta", 0)
@@ -42,7 +42,9 @@ class SparkSchedSimEnv(Env):
             raise ValueError(f"'{sampler}' is not a valid data sampler.")
         self._batched = BatchedSparkSchedSimEnv(env_cfg, num_envs=1, bank=bank, device=device,
                                                 max_jobs=max_jobs, tape_capacity=tape_capacity,
-                                                log_capacity=log_capacity, decima_obs=decima_obs)
+                                                log_capacity=log_capacity, decima_obs=decima_obs,
+                                                decima_policy=decima_obs)  # one env: the buffers are tiny, so
+        # the Decima wrappers / DecimaScheduler work on any env, as `scheduler.env_wrapper_cls(env)` expects
         self.wall_time: float = 0
         self.jobs: dict[int, SimpleNamespace] = {}
         self.active_job_ids: list[int] = []

@@ -2,8 +2,9 @@
 `schedule(obs) -> (action, info)`, attributes `name` and `env_wrapper_cls`."""
 from .scheduler import Scheduler
 from .heuristics import RandomScheduler, RoundRobinScheduler, find_stage, preprocess_obs
+from .decima import DecimaScheduler
 
-__all__ = ["Scheduler", "RoundRobinScheduler", "RandomScheduler", "make_scheduler",
+__all__ = ["Scheduler", "RoundRobinScheduler", "RandomScheduler", "DecimaScheduler", "make_scheduler",
            "find_stage", "preprocess_obs"]
 
 

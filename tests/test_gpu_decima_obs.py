@@ -65,8 +65,8 @@ def test_decima_wrappers_on_facade(bank):
     cfg = {"num_executors": 10, "job_arrival_cap": 6, "job_arrival_rate": 4.0e-5,
            "moving_delay": 2000.0, "warmup_delay": 1000.0}
     with pytest.raises(ValueError):
-        DecimaEnvWrapper(SparkSchedSimEnv(cfg, bank=bank))  # needs decima_obs=True
-    env = DecimaEnvWrapper(SparkSchedSimEnv(cfg, bank=bank, decima_obs=True))
+        DecimaEnvWrapper(SparkSchedSimEnv(cfg, bank=bank, decima_obs=False))  # built without the Decima buffers
+    env = DecimaEnvWrapper(SparkSchedSimEnv(cfg, bank=bank))  # default: any env can be wrapped (examples.py:84-88)
     obs, _ = env.reset(seed=3)
     steps = 0
     done = False

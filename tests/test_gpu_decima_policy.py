@@ -149,3 +149,40 @@ def test_rollout_decima_records_the_python_loop(bank):
             n_term += int(h["terminated"][b])
     assert n_reset >= B and n_term >= B
     assert (envs[0].hdr()["wall_time"] == e.hdr()["wall_time"]).all()
+
+
+def test_decima_scheduler_plugin_runs_like_examples_py(bank):
+    """examples.py:76-102 with the drop-in classes: make_scheduler -> env_wrapper_cls(env) -> schedule/step loop.  The
+    episode must equal the batched device rollout from the same seed (same Philox policy stream)."""
+    from spark_sched_sim_b200 import metrics
+    from spark_sched_sim_b200.batched_env import BatchedSparkSchedSimEnv
+    from spark_sched_sim_b200.env import SparkSchedSimEnv
+    from spark_sched_sim_b200.schedulers import make_scheduler
+
+    cfg = {"num_executors": 10, "job_arrival_cap": 6, "job_arrival_rate": 4.0e-5,
+           "moving_delay": 2000.0, "warmup_delay": 1000.0}
+    agent_cfg = {"agent_cls": "DecimaScheduler", "embed_dim": 16, "gnn_mlp_kwargs": {"hid_dims": [32, 16]},
+                 "policy_mlp_kwargs": {"hid_dims": [64, 64]}, "num_executors": 10,
+                 "state_dict_path": osp.join(GOLDEN_DIR, "decima_model.npz")}
+    scheduler = make_scheduler(agent_cfg)
+    env = scheduler.env_wrapper_cls(SparkSchedSimEnv(cfg, bank=bank))
+    obs, _ = env.reset(seed=77, options=None)
+    terminated = truncated = False
+    steps, lg = 0, []
+    while not (terminated or truncated):
+        action, info = scheduler.schedule(obs)
+        assert set(action) == {"stage_idx", "job_idx", "num_exec"} and np.isfinite(info["lgprob"])
+        lg.append(info["lgprob"])
+        obs, _, terminated, truncated, _ = env.step(action)
+        steps += 1
+    assert terminated and steps > 20
+    jct = metrics.avg_job_duration(env) * 1e-3
+    # the same episode through the batched API
+    ref = BatchedSparkSchedSimEnv(cfg, num_envs=1, bank=bank, decima_policy=True)
+    ref.set_decima_weights(weights())
+    ref.reset_host(np.array([77], np.uint64))
+    tr = ref.rollout_decima(steps, host=torch.empty(steps * 32, dtype=torch.uint8).pin_memory())
+    assert bool(ref.hdr()[0]["terminated"]) and ref.hdr()[0]["wall_time"] == env.unwrapped.wall_time
+    assert np.allclose(tr[0]["lgprob"], np.array(lg, np.float32))
+    ta, tc, _ = ref.jobs(0)
+    assert jct == pytest.approx(np.mean(tc - ta) * 1e-3)

@@ -246,7 +246,7 @@ def main() -> None:
         flush.fill_(k & 0xFF)  # evict L2 between timed iterations (untimed)
         ev0[k].record()
         env.rollout_fair(D, True, True, seed_step)
-        launches += 2
+        launches += 3  # k_rollout_fair + the two ssb_collect_stats kernels
         allreduce_stats()
         ev1[k].record()
     barrier()

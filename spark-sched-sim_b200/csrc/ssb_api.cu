@@ -190,19 +190,21 @@ __global__ void k_traj_post(Params p, ssb_transition *traj, int K)
     t.flags |= (o.terminated ? 1 : 0) | (o.truncated ? 2 : 0);
 }
 
-// collect_stats sums, one block, fixed order: warp w handles envs w, w + 32, ...; lanes over the env's jobs
-__global__ void __launch_bounds__(1024) k_collect_stats(Params p, double *out)
+// collect_stats sums in a fixed order: block k reduces the envs k, k + STATS_BLOCKS, ... (one warp per env, lanes
+// over its jobs) into part[k][6]; a last warp adds the blocks' partial sums in block order.
+constexpr int STATS_BLOCKS = 128;
+__global__ void __launch_bounds__(256) k_collect_stats_part(Params p, double *part)
 {
-    __shared__ double part[32][6];
+    __shared__ double sh[8][6];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double acc[6] = {0, 0, 0, 0, 0, 0};
-    for (int b = w; b < p.B; b += 32) {
+    for (int b = (int)blockIdx.x + w * STATS_BLOCKS; b < p.B; b += 8 * STATS_BLOCKS) {
         const EnvHdr &h = p.hdr[b];
         const JobRec *jb = p.job + (size_t)b * p.Jc;
         const double wall = h.wall_time;
         double jt = 0.0, cd = 0.0;
         int nc = 0, na = 0;
-        for (int j = lane; j < h.next_arrival; j += 32) {  // jobs that have arrived, in id order per lane
+        for (int j = lane; j < h.next_arrival; j += 32) {  // jobs that have arrived
             const JobRec &J = jb[j];
             jt += fmin(J.t_completed, wall) - J.t_arrival;
             if (J.state == JOB_COMPLETED) { nc++; cd += J.t_completed - J.t_arrival; }
@@ -218,12 +220,20 @@ __global__ void __launch_bounds__(1024) k_collect_stats(Params p, double *out)
         acc[2] += nc; acc[3] += na; acc[4] += cd; acc[5] += wall;
     }
     if (lane == 0)
-        for (int i = 0; i < 6; i++) part[w][i] = acc[i];
+        for (int i = 0; i < 6; i++) sh[w][i] = acc[i];
     __syncthreads();
+    if (threadIdx.x < 6) {
+        double s = 0.0;
+        for (int i = 0; i < 8; i++) s += sh[i][threadIdx.x];
+        part[(size_t)blockIdx.x * 8 + threadIdx.x] = s;
+    }
+}
+__global__ void k_collect_stats_final(const double *part, double *out)
+{
     if (threadIdx.x < 8) {
         double s = 0.0;
         if (threadIdx.x < 6)
-            for (int i = 0; i < 32; i++) s += part[i][threadIdx.x];
+            for (int k = 0; k < STATS_BLOCKS; k++) s += part[(size_t)k * 8 + threadIdx.x];
         out[threadIdx.x] = s;
     }
 }
@@ -324,6 +334,7 @@ void carve(Carver &cv, const ssb_config &c, const ssb_bank &bk, const Dims &d, P
     p.tape = cv.take<double>(c.tape_capacity > 0 ? B * (size_t)c.tape_capacity : 1);
     p.log = cv.take<LogRow>(c.log_capacity > 0 ? B * (size_t)c.log_capacity : 1);
     p.stats = cv.take<ssb_stats>(B);
+    p.stats_part = cv.take<double>(128 * 8);
     p.prof = cv.take<unsigned long long>(B * 16);
     p.obs_hdr = cv.take<ssb_obs_hdr>(B);
     p.obs_nodes = cv.take<float>(B * d.Sc * 3);
@@ -970,7 +981,8 @@ int ssb_get_debug_counters(ssb_env *env, uint64_t **out)
 int ssb_collect_stats(ssb_env *env, double *out, void *stream)
 {
     if (!env || !out) return SSB_E_INVALID;
-    k_collect_stats<<<1, 1024, 0, (cudaStream_t)stream>>>(env->p, out);
+    k_collect_stats_part<<<STATS_BLOCKS, 256, 0, (cudaStream_t)stream>>>(env->p, env->p.stats_part);
+    k_collect_stats_final<<<1, 32, 0, (cudaStream_t)stream>>>(env->p.stats_part, out);
     CUDA_TRY(cudaGetLastError());
     return SSB_OK;
 }

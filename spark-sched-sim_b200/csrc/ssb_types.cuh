@@ -136,6 +136,7 @@ struct Params {
     double *tape;      // [B][tape_cap]
     LogRow *log;       // [B][log_cap]
     ssb_stats *stats;  // [B]
+    double *stats_part;  // [128][8] partial sums of ssb_collect_stats
     unsigned long long *prof;  // [B][16] cycle counters per phase (written only when built with -DSSB_PROFILE)
     // observation slabs
     ssb_obs_hdr *obs_hdr;

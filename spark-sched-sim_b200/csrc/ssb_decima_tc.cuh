@@ -91,20 +91,24 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols)
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-// 16 consecutive fp32 columns of this thread's TMEM lane
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v)
+// N (a multiple of 16) consecutive fp32 columns of this thread's TMEM lane: all loads are issued before the single wait
+template <int N>
+__device__ __forceinline__ void tmem_ld_row(uint32_t taddr, float *v)
 {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
-        "[%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
+    uint32_t r[N];
+#pragma unroll
+    for (int c = 0; c < N; c += 16)
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+            "[%16];"
+            : "=r"(r[c + 0]), "=r"(r[c + 1]), "=r"(r[c + 2]), "=r"(r[c + 3]), "=r"(r[c + 4]), "=r"(r[c + 5]),
+              "=r"(r[c + 6]), "=r"(r[c + 7]), "=r"(r[c + 8]), "=r"(r[c + 9]), "=r"(r[c + 10]), "=r"(r[c + 11]),
+              "=r"(r[c + 12]), "=r"(r[c + 13]), "=r"(r[c + 14]), "=r"(r[c + 15])
+            : "r"(taddr + c)
+            : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-    for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+    for (int i = 0; i < N; i++) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ float to_tf32(float x)
 {
@@ -425,8 +429,7 @@ __device__ __forceinline__ void run_tile(const Params &p, const TileArgs &a, con
         if (STAMPS && tile == (int)blockIdx.x) TC_STAMP(5);
         {
             float v[S::H1];
-#pragma unroll
-            for (int c = 0; c < S::H1; c += 16) tmem_ld16(trow + c, v + c);
+            tmem_ld_row<S::H1>(trow, v);
 #pragma unroll
             for (int i = 0; i < S::H1; i++) v[i] = act_tc<S::TANH>(v[i] + bias[i]);
             write_a_row<S::H1>(a_hi, a_lo, tid, v);
@@ -444,8 +447,7 @@ __device__ __forceinline__ void run_tile(const Params &p, const TileArgs &a, con
         tc_fence_after();
         if (STAMPS && tile == (int)blockIdx.x) TC_STAMP(7);
         float v2[S::H2];
-#pragma unroll
-        for (int c = 0; c < S::H2; c += 16) tmem_ld16(trow + c, v2 + c);
+        tmem_ld_row<S::H2>(trow, v2);
 #pragma unroll
         for (int i = 0; i < S::H2; i++) v2[i] = act_tc<S::TANH>(v2[i] + bias[S::H1 + i]);
         if constexpr (S::OUT > 1) {
@@ -461,8 +463,7 @@ __device__ __forceinline__ void run_tile(const Params &p, const TileArgs &a, con
             parity ^= 1;
             tc_fence_after();
             float o[S::OUT];
-#pragma unroll
-            for (int c = 0; c < S::OUT; c += 16) tmem_ld16(trow + c, o + c);
+            tmem_ld_row<S::OUT>(trow, o);
 #pragma unroll
             for (int i = 0; i < S::OUT; i++) o[i] += bias[S::H1 + S::H2 + i];
             scatter_row<ST>(p, id, o);

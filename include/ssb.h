@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SSB_ABI_VERSION 2
+#define SSB_ABI_VERSION 3
 
 /* status codes of the entry points */
 enum {
@@ -270,6 +270,8 @@ typedef struct {
     int32_t *action;     /* [B][4]: stage_idx, job_idx, num_exec (Decima format), #stage candidates */
     float *lgprob;       /* [B]: log pi(stage) + log pi(num_exec) */
     int32_t node_stride, exec_stride;
+    float *entropy;      /* [B]: (H(stage distribution) + H(num_exec distribution)) / log(E * num_nodes), the
+                            per-observation entropy evaluate_actions returns (scheduler.py:131-137, utils.py:26-42) */
 } ssb_policy_views;
 int ssb_set_decima_weights(ssb_env *env, const float *weights, int32_t n_floats);
 int ssb_decima_policy(ssb_env *env, const int32_t *forced_stage, const int32_t *forced_num_exec,

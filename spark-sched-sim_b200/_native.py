@@ -9,7 +9,7 @@ import numpy as np
 
 PKG_DIR = osp.dirname(osp.abspath(__file__))
 LIB_PATH = osp.join(PKG_DIR, "_lib", "libssb.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class SsbConfig(C.Structure):
@@ -42,6 +42,7 @@ class SsbPolicyViews(C.Structure):
         ("lgprob", C.c_void_p),
         ("node_stride", C.c_int32),
         ("exec_stride", C.c_int32),
+        ("entropy", C.c_void_p),
     ]
 
 

@@ -110,6 +110,7 @@ class BatchedSparkSchedSimEnv:
             self.pol_exec_logits = self._view(pv.exec_logits, B * Ep * 4, torch.float32).view(B, Ep)
             self.pol_action = self._view(pv.action, B * 4 * 4, torch.int32).view(B, 4)
             self.pol_lgprob = self._view(pv.lgprob, B * 4, torch.float32)
+            self.pol_entropy = self._view(pv.entropy, B * 4, torch.float32)
 
     # ---------------------------------------------------------------- plumbing
     def _view(self, ptr, nbytes, dtype):

@@ -363,6 +363,7 @@ void carve(Carver &cv, const ssb_config &c, const ssb_bank &bk, const Dims &d, P
         p.pol_exec_logits = cv.take<float>(B * p.Epad);
         p.pol_action = cv.take<int32_t>(B * 4);
         p.pol_lgprob = cv.take<float>(B);
+        p.pol_entropy = cv.take<float>(B);
         p.traj_d = cv.take<int32_t>(4);
         p.pol_act_a = cv.take<int32_t>(B);
         p.pol_act_n = cv.take<int32_t>(B);
@@ -959,6 +960,7 @@ int ssb_get_policy_views(ssb_env *env, ssb_policy_views *out)
     out->exec_logits = env->p.pol_exec_logits;
     out->action = env->p.pol_action;
     out->lgprob = env->p.pol_lgprob;
+    out->entropy = env->p.pol_entropy;
     out->node_stride = env->p.Sc;
     out->exec_stride = env->p.Epad;
     return SSB_OK;

@@ -50,8 +50,10 @@ __device__ __forceinline__ void st16(float *p, const float (&v)[16])
     for (int i = 0; i < 4; i++) reinterpret_cast<float4 *>(p)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
 }
 
-// softmax-sample (or take `forced` if >= 0) over logits[0..n) ; returns the index, adds log prob
-__device__ inline int sample_w(const float *logits, int n, int forced, float u, int lane, float &lgprob)
+// softmax-sample (or take `forced` if >= 0) over logits[0..n) ; returns the index, adds log prob; *entropy (optional)
+// receives -sum p log p with the probabilities clamped to [eps, 1 - eps] (utils.evaluate, decima/utils.py:26-42)
+__device__ inline int sample_w(const float *logits, int n, int forced, float u, int lane, float &lgprob,
+                               float *entropy = nullptr)
 {
     float mx = -INFINITY;
     for (int i = lane; i < n; i += 32) mx = fmaxf(mx, logits[i]);
@@ -72,6 +74,16 @@ __device__ inline int sample_w(const float *logits, int n, int forced, float u, 
         idx = __shfl_sync(FULL, idx, 0);
     }
     if (idx >= 0 && idx < n) lgprob += logf(expf(logits[idx] - mx) / sum);
+    if (entropy) {
+        const float eps = 1.1920929e-07f;  // torch.finfo(float32).eps (torch.distributions.utils.clamp_probs)
+        float hsum = 0.0f;
+        for (int i = lane; i < n; i += 32) {
+            const float pr = fminf(fmaxf(expf(logits[i] - mx) / sum, eps), 1.0f - eps);
+            hsum -= pr * logf(pr);
+        }
+        for (int off = 16; off; off >>= 1) hsum += __shfl_xor_sync(FULL, hsum, off);
+        *entropy = hsum;
+    }
     return idx;
 }
 

@@ -673,9 +673,9 @@ __global__ void __launch_bounds__(128) k_pol_sample_stage(Params p, const int32_
     const EnvHdr &h = p.hdr[b];
     const uint4 rw = philox4x32_10(h.policy_draws, 0u, 4u, 0u, (uint32_t)h.seed, (uint32_t)(h.seed >> 32));
     const float u1 = ((float)(rw.x >> 8) + 0.5f) * (1.0f / 16777216.0f);
-    float lgprob = 0.0f;
+    float lgprob = 0.0f, h_stage = 0.0f;
     const int stage_idx = n_cand > 0 ? sample_w(p.pol_stage_logits + (size_t)b * p.Sc, n_cand,
-                                                forced_stage ? forced_stage[b] : -1, u1, lane, lgprob) : -1;
+                                                forced_stage ? forced_stage[b] : -1, u1, lane, lgprob, &h_stage) : -1;
     int job_idx = -1, cap = 0;
     if (stage_idx >= 0 && stage_idx < n_cand) {
         const uint8_t *smask = p.dec_stage_mask + (size_t)b * p.Sc;
@@ -702,6 +702,7 @@ __global__ void __launch_bounds__(128) k_pol_sample_stage(Params p, const int32_
         int32_t *act = p.pol_action + (size_t)b * 4;
         act[0] = stage_idx; act[1] = job_idx; act[2] = 0; act[3] = n_cand;
         p.pol_lgprob[b] = lgprob;
+        p.pol_entropy[b] = h_stage;  // completed by k_pol_sample_exec
         if (cap > 0) base = atomicAdd(&p.pl_cnt[CNT_EXEC], cap);
     }
     base = __shfl_sync(FULL, base, 0);
@@ -720,15 +721,18 @@ k_pol_sample_exec(Params p, const int32_t *forced_num_exec, int32_t *stage_idx_o
     const uint32_t pd = h.policy_draws;
     const uint4 rw = philox4x32_10(pd, 0u, 4u, 0u, (uint32_t)h.seed, (uint32_t)(h.seed >> 32));
     const float u2 = ((float)(rw.y >> 8) + 0.5f) * (1.0f / 16777216.0f);
-    float lgprob = p.pol_lgprob[b];
+    float lgprob = p.pol_lgprob[b], h_exec = 0.0f;
     int num_exec = 0;
     if (cap > 0)
         num_exec = sample_w(p.pol_exec_logits + (size_t)b * p.Epad, cap, forced_num_exec ? forced_num_exec[b] : -1,
-                            u2, lane, lgprob);
+                            u2, lane, lgprob, &h_exec);
     __syncwarp();
     if (lane == 0) {
         act[2] = num_exec;
         p.pol_lgprob[b] = lgprob;
+        // evaluate_actions: (stage entropy + exec entropy) / log(num_executors * nodes in the observation)
+        const int N = p.obs_hdr[b].num_nodes;
+        p.pol_entropy[b] = N > 0 ? (p.pol_entropy[b] + h_exec) / logf((float)(p.E * N)) : 0.0f;
         h.policy_draws = pd + 1;
         if (stage_idx_out) stage_idx_out[b] = act[0];
         if (num_exec_out) num_exec_out[b] = 1 + num_exec;

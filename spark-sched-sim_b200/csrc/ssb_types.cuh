@@ -159,6 +159,7 @@ struct Params {
     float *pol_exec_logits;               // [B][Epad]
     int32_t *pol_action;                  // [B][4]
     float *pol_lgprob;                    // [B]
+    float *pol_entropy;                   // [B]
     int32_t *pol_act_a, *pol_act_n;       // [B] env-format actions of ssb_rollout_decima
     int32_t *traj_d;                      // row index of the rollout-buffer slab being written
     int Epad;

@@ -52,6 +52,14 @@ def test_policy_scores_match_reference(bank, name):
         worst = max(worst, float(np.abs(sl - tr["pol_stage_logits"][so:so + ns]).max()),
                     float(np.abs(el - tr["pol_exec_logits"][eo:eo + ne]).max()))
         assert abs(float(env.pol_lgprob[slot].item()) - float(tr["pol_lgprob"][k])) < 1e-4, k
+        # evaluate_actions' entropy (scheduler.py:131-137, utils.py:26-42) from the REFERENCE's recorded scores
+        def _h(z):
+            z = z.astype(np.float64); pr = np.exp(z - z.max()); pr /= pr.sum()
+            pr = np.clip(pr, np.finfo(np.float32).eps, 1 - np.finfo(np.float32).eps)
+            return float(-(pr * np.log(pr)).sum())
+        want_h = (_h(tr["pol_stage_logits"][so:so + ns]) + (_h(tr["pol_exec_logits"][eo:eo + ne]) if ne else 0.0)) \
+            / np.log(tr["num_executors"] * int(tr["N"][k]))
+        assert abs(float(env.pol_entropy[slot].item()) - want_h) < 2e-4, (k, want_h)
         # env-format action (DecimaActWrapper) and the step it drives
         assert (int(a[slot].item()), int(n[slot].item())) == tuple(tr["actions"][k]), k
         env.step(a, n)

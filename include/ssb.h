@@ -277,6 +277,19 @@ int ssb_set_decima_weights(ssb_env *env, const float *weights, int32_t n_floats)
 int ssb_decima_policy(ssb_env *env, const int32_t *forced_stage, const int32_t *forced_num_exec,
                       int32_t *stage_idx_out, int32_t *num_exec_out, void *stream);
 int ssb_get_policy_views(ssb_env *env, ssb_policy_views *out);
+/* Stored observations and their re-evaluation -- RolloutBuffer.obsns (rollout_worker.py:18-46) and
+ * DecimaScheduler.evaluate_actions (scheduler.py:101-139), forward pass only:
+ *   ssb_decima_snapshot: runs the adapter and copies what the policy reads of every env's observation (header,
+ *     edge list, dag_ptr, the adapter's features / masks / caps / level bits / depth) into dst (DEVICE,
+ *     ssb_decima_snapshot_bytes).
+ *   ssb_decima_evaluate: evaluates the policy on a stored snapshot with the given actions (DEVICE i32[B] each, in
+ *     Decima's format: stage_idx = index among the schedulable stages, num_exec in [0, cap)) and writes
+ *     lgprob_out / entropy_out (DEVICE f32[B], may be NULL).  The envs' state, current observation and sampling
+ *     stream are left untouched. */
+int ssb_decima_snapshot_bytes(ssb_env *env, size_t *bytes);
+int ssb_decima_snapshot(ssb_env *env, void *dst, void *stream);
+int ssb_decima_evaluate(ssb_env *env, const void *snapshot, const int32_t *stage_sel, const int32_t *exec_sel,
+                        float *lgprob_out, float *entropy_out, void *stream);
 /* Decima rollout collection (trainers/rollout_worker.py:135-157 with DecimaScheduler): num_decisions times
  * { ssb_decima_policy (sampled actions) ; ssb_step(max_events) } for every env, everything stream-ordered on the
  * device, each call's (wall time, action, lgprob, reward, flags) stored at traj[b * num_decisions + d] (DEVICE,

@@ -128,7 +128,8 @@ EXPORTS = [
     "ssb_load_trace", "ssb_clear_trace", "ssb_reset", "ssb_step", "ssb_reset_host", "ssb_step_host", "ssb_step_fair_host", "ssb_set_autoreset", "ssb_set_mean_time_limit",
     "ssb_rollout_fair", "ssb_rollout_fair_traj", "ssb_discounted_returns", "ssb_group_baselines", "ssb_fair_actions", "ssb_get_views", "ssb_get_stats", "ssb_collect_stats", "ssb_reset_stats",
     "ssb_get_jobs", "ssb_get_log", "ssb_decima_obs", "ssb_get_decima_views",
-    "ssb_set_decima_weights", "ssb_decima_policy", "ssb_rollout_decima", "ssb_get_policy_views", "ssb_get_debug_counters",
+    "ssb_set_decima_weights", "ssb_decima_policy", "ssb_rollout_decima", "ssb_decima_snapshot_bytes",
+    "ssb_decima_snapshot", "ssb_decima_evaluate", "ssb_get_policy_views", "ssb_get_debug_counters",
 ]
 
 _lib = None
@@ -165,6 +166,9 @@ def lib():
     L.ssb_set_mean_time_limit.argtypes = [vp, C.c_double]
     L.ssb_step_fair_host.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, vp]
     L.ssb_rollout_decima.argtypes = [vp, i32, i32, vp, vp]
+    L.ssb_decima_snapshot_bytes.argtypes = [vp, C.POINTER(C.c_size_t)]
+    L.ssb_decima_snapshot.argtypes = [vp, vp, vp]
+    L.ssb_decima_evaluate.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     L.ssb_rollout_fair.argtypes = [vp, i32, i32, i32, u64, vp]
     L.ssb_rollout_fair_traj.argtypes = [vp, i32, i32, i32, u64, vp, vp]
     L.ssb_discounted_returns.argtypes = [vp, vp, vp, i32, i32, C.c_double, vp, vp]

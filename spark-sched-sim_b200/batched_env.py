@@ -343,6 +343,28 @@ class BatchedSparkSchedSimEnv:
                                            a.data_ptr(), n.data_ptr(), self._stream()), "ssb_decima_policy")
         return a, n
 
+    def decima_snapshot(self, out: "torch.Tensor | None" = None) -> torch.Tensor:
+        """Stores what the policy reads of every env's current observation (RolloutBuffer.obsns) in a device
+        uint8 tensor."""
+        n = C.c_size_t()
+        nat.check(self.L.ssb_decima_snapshot_bytes(self._h, C.byref(n)), "ssb_decima_snapshot_bytes")
+        if out is None:
+            out = torch.empty(n.value, dtype=torch.uint8, device=self.device)
+        assert out.numel() >= n.value
+        nat.check(self.L.ssb_decima_snapshot(self._h, out.data_ptr(), self._stream()), "ssb_decima_snapshot")
+        return out
+
+    def decima_evaluate(self, snapshot: torch.Tensor, stage_sel, exec_sel):
+        """DecimaScheduler.evaluate_actions (forward only) on a stored snapshot: (lgprobs, entropies) f32[B] for the
+        given Decima-format actions; the envs themselves are left untouched."""
+        a = self._dev(stage_sel, torch.int32)
+        n = self._dev(exec_sel, torch.int32)
+        lg = torch.empty(self.num_envs, dtype=torch.float32, device=self.device)
+        en = torch.empty(self.num_envs, dtype=torch.float32, device=self.device)
+        nat.check(self.L.ssb_decima_evaluate(self._h, snapshot.data_ptr(), a.data_ptr(), n.data_ptr(), lg.data_ptr(),
+                                             en.data_ptr(), self._stream()), "ssb_decima_evaluate")
+        return lg, en
+
     def rollout_decima(self, num_decisions, max_events=0, out: "torch.Tensor | None" = None,
                        host: "torch.Tensor | None" = None):
         """Decima rollout collection on the device: num_decisions x { decima_policy ; step } with every call's

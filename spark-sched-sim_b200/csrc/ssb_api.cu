@@ -364,6 +364,14 @@ void carve(Carver &cv, const ssb_config &c, const ssb_bank &bk, const Dims &d, P
         p.pol_action = cv.take<int32_t>(B * 4);
         p.pol_lgprob = cv.take<float>(B);
         p.pol_entropy = cv.take<float>(B);
+        {   // scratch that parks the live observation during ssb_decima_evaluate (same layout as a snapshot)
+            size_t sb = 0;
+            const size_t parts[8] = {B * sizeof(ssb_obs_hdr), B * d.Mc * 2 * sizeof(int32_t),
+                                     B * (c.max_jobs + 1) * sizeof(int32_t), B * d.Sc * 5 * sizeof(float), B * d.Sc,
+                                     B * c.max_jobs * sizeof(int32_t), B * d.Mc * sizeof(uint64_t), B * sizeof(int32_t)};
+            for (size_t x : parts) sb += (x + 255) & ~size_t(255);
+            p.pol_snap = cv.take<char>(sb);
+        }
         p.traj_d = cv.take<int32_t>(4);
         p.pol_act_a = cv.take<int32_t>(B);
         p.pol_act_n = cv.take<int32_t>(B);
@@ -850,18 +858,19 @@ int ssb_set_decima_weights(ssb_env *env, const float *weights, int32_t n_floats)
     return SSB_OK;
 }
 
-int ssb_decima_policy(ssb_env *env, const int32_t *forced_stage, const int32_t *forced_num_exec,
-                      int32_t *stage_idx_out, int32_t *num_exec_out, void *stream)
+// run_adapter = false: the adapter's outputs are already in place (restored from a snapshot);
+// advance_draws = false: the Philox policy stream of the envs is left where it is (pure evaluation)
+static int decima_policy_impl(ssb_env *env, const int32_t *forced_stage, const int32_t *forced_num_exec,
+                              int32_t *stage_idx_out, int32_t *num_exec_out, bool run_adapter, bool advance_draws,
+                              cudaStream_t s)
 {
-    if (!env || !env->p.pol_w) return SSB_E_INVALID;  // needs SSB_FLAG_DECIMA_POLICY
-    cudaStream_t s = (cudaStream_t)stream;
     // observation adapter -> row lists -> one tensor-core tile pass per MLP (ssb_decima_tc.cuh)
     const Params &p = env->p;
     const int32_t *cnt = p.pl_cnt;
     const int warp_grid = (p.B + 3) / 4;
     int rc;
     CUDA_TRY(cudaMemsetAsync(p.pl_cnt, 0, sizeof(int32_t) * tc::CNT_TOTAL, s));
-    k_decima_obs<<<env->grid, WARPS_PER_CTA * 32, 0, s>>>(p);
+    if (run_adapter) k_decima_obs<<<env->grid, WARPS_PER_CTA * 32, 0, s>>>(p);
     tc::k_pol_plan_a<<<warp_grid, 128, 0, s>>>(p);
     tc::k_pol_plan_scan<<<1, 32, 0, s>>>(p);
     tc::k_pol_plan_b<<<warp_grid, 128, 0, s>>>(p);
@@ -881,9 +890,89 @@ int ssb_decima_policy(ssb_env *env, const int32_t *forced_stage, const int32_t *
     if ((rc = launch_tile<tc::ST_STAGE>(env, nullptr, nullptr, cnt + tc::CNT_CAND, 0, 1, s))) return rc;
     tc::k_pol_sample_stage<<<warp_grid, 128, 0, s>>>(p, forced_stage);
     if ((rc = launch_tile<tc::ST_EXEC>(env, p.pl_exec, nullptr, cnt + tc::CNT_EXEC, 0, 1, s))) return rc;
-    tc::k_pol_sample_exec<<<warp_grid, 128, 0, s>>>(p, forced_num_exec, stage_idx_out, num_exec_out);
+    tc::k_pol_sample_exec<<<warp_grid, 128, 0, s>>>(p, forced_num_exec, stage_idx_out, num_exec_out,
+                                                    advance_draws ? 1 : 0);
     CUDA_TRY(cudaGetLastError());
     return SSB_OK;
+}
+
+int ssb_decima_policy(ssb_env *env, const int32_t *forced_stage, const int32_t *forced_num_exec,
+                      int32_t *stage_idx_out, int32_t *num_exec_out, void *stream)
+{
+    if (!env || !env->p.pol_w) return SSB_E_INVALID;  // needs SSB_FLAG_DECIMA_POLICY
+    return decima_policy_impl(env, forced_stage, forced_num_exec, stage_idx_out, num_exec_out, true, true,
+                              (cudaStream_t)stream);
+}
+
+// ---- stored observations (RolloutBuffer.obsns) and their re-evaluation (DecimaScheduler.evaluate_actions)
+namespace {
+struct SnapPart { void *ptr; size_t bytes; };
+int snapshot_parts(const ssb_env *env, SnapPart *out)
+{
+    const Params &p = env->p;
+    const size_t B = p.B;
+    int n = 0;
+    out[n++] = {p.obs_hdr, B * sizeof(ssb_obs_hdr)};
+    out[n++] = {p.obs_edges, B * p.Mc * 2 * sizeof(int32_t)};
+    out[n++] = {p.obs_dag_ptr, B * (p.Jc + 1) * sizeof(int32_t)};
+    out[n++] = {p.dec_feat, B * p.Sc * 5 * sizeof(float)};
+    out[n++] = {p.dec_stage_mask, B * p.Sc};
+    out[n++] = {p.dec_caps, B * p.Jc * sizeof(int32_t)};
+    out[n++] = {p.dec_edge_bits, B * p.Mc * sizeof(uint64_t)};
+    out[n++] = {p.dec_depth, B * sizeof(int32_t)};
+    return n;
+}
+size_t snapshot_bytes(const ssb_env *env)
+{
+    SnapPart parts[8];
+    const int n = snapshot_parts(env, parts);
+    size_t total = 0;
+    for (int i = 0; i < n; i++) total += (parts[i].bytes + 255) & ~size_t(255);
+    return total;
+}
+int snapshot_copy(const ssb_env *env, char *buf, bool to_buf, cudaStream_t s)
+{
+    SnapPart parts[8];
+    const int n = snapshot_parts(env, parts);
+    size_t off = 0;
+    for (int i = 0; i < n; i++) {
+        if (to_buf) CUDA_TRY(cudaMemcpyAsync(buf + off, parts[i].ptr, parts[i].bytes, cudaMemcpyDeviceToDevice, s));
+        else CUDA_TRY(cudaMemcpyAsync(parts[i].ptr, buf + off, parts[i].bytes, cudaMemcpyDeviceToDevice, s));
+        off += (parts[i].bytes + 255) & ~size_t(255);
+    }
+    return SSB_OK;
+}
+}  // namespace
+
+int ssb_decima_snapshot_bytes(ssb_env *env, size_t *bytes)
+{
+    if (!env || !bytes || !env->p.dec_feat) return SSB_E_INVALID;
+    *bytes = snapshot_bytes(env);
+    return SSB_OK;
+}
+
+int ssb_decima_snapshot(ssb_env *env, void *dst, void *stream)
+{
+    if (!env || !dst || !env->p.dec_feat) return SSB_E_INVALID;
+    k_decima_obs<<<env->grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(env->p);  // the adapter's view of the state
+    CUDA_TRY(cudaGetLastError());
+    return snapshot_copy(env, static_cast<char *>(dst), true, (cudaStream_t)stream);
+}
+
+int ssb_decima_evaluate(ssb_env *env, const void *snapshot, const int32_t *stage_sel, const int32_t *exec_sel,
+                        float *lgprob_out, float *entropy_out, void *stream)
+{
+    if (!env || !snapshot || !stage_sel || !exec_sel || !env->p.pol_w) return SSB_E_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t B = env->p.B;
+    int rc;
+    // the live observation is parked in the handle's scratch while the stored one is evaluated
+    if ((rc = snapshot_copy(env, env->p.pol_snap, true, s))) return rc;
+    if ((rc = snapshot_copy(env, const_cast<char *>(static_cast<const char *>(snapshot)), false, s))) return rc;
+    if ((rc = decima_policy_impl(env, stage_sel, exec_sel, nullptr, nullptr, false, false, s))) return rc;
+    if (lgprob_out) CUDA_TRY(cudaMemcpyAsync(lgprob_out, env->p.pol_lgprob, B * 4, cudaMemcpyDeviceToDevice, s));
+    if (entropy_out) CUDA_TRY(cudaMemcpyAsync(entropy_out, env->p.pol_entropy, B * 4, cudaMemcpyDeviceToDevice, s));
+    return snapshot_copy(env, env->p.pol_snap, false, s);
 }
 
 __global__ void k_traj_next(Params p) { if (threadIdx.x == 0 && blockIdx.x == 0) *p.traj_d += 1; }

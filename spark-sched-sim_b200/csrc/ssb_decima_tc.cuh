@@ -710,7 +710,8 @@ __global__ void __launch_bounds__(128) k_pol_sample_stage(Params p, const int32_
 }
 
 __global__ void __launch_bounds__(128)
-k_pol_sample_exec(Params p, const int32_t *forced_num_exec, int32_t *stage_idx_out, int32_t *num_exec_out)
+k_pol_sample_exec(Params p, const int32_t *forced_num_exec, int32_t *stage_idx_out, int32_t *num_exec_out,
+                  int advance_draws)
 {
     const int b = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (b >= p.B) return;
@@ -733,7 +734,7 @@ k_pol_sample_exec(Params p, const int32_t *forced_num_exec, int32_t *stage_idx_o
         // evaluate_actions: (stage entropy + exec entropy) / log(num_executors * nodes in the observation)
         const int N = p.obs_hdr[b].num_nodes;
         p.pol_entropy[b] = N > 0 ? (p.pol_entropy[b] + h_exec) / logf((float)(p.E * N)) : 0.0f;
-        h.policy_draws = pd + 1;
+        if (advance_draws) h.policy_draws = pd + 1;
         if (stage_idx_out) stage_idx_out[b] = act[0];
         if (num_exec_out) num_exec_out[b] = 1 + num_exec;
     }

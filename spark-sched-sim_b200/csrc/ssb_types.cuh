@@ -160,6 +160,7 @@ struct Params {
     int32_t *pol_action;                  // [B][4]
     float *pol_lgprob;                    // [B]
     float *pol_entropy;                   // [B]
+    char *pol_snap;                       // scratch: the live observation during ssb_decima_evaluate
     int32_t *pol_act_a, *pol_act_n;       // [B] env-format actions of ssb_rollout_decima
     int32_t *traj_d;                      // row index of the rollout-buffer slab being written
     int Epad;

@@ -194,3 +194,39 @@ def test_decima_scheduler_plugin_runs_like_examples_py(bank):
     assert np.allclose(tr[0]["lgprob"], np.array(lg, np.float32))
     ta, tc, _ = ref.jobs(0)
     assert jct == pytest.approx(np.mean(tc - ta) * 1e-3)
+
+
+def test_evaluate_actions_on_stored_observations(bank):
+    """RolloutBuffer.obsns + evaluate_actions (forward): observations stored during a sampled rollout are re-evaluated
+    later with the stored actions -- lgprobs and entropies come back bit for bit, and neither the envs' state nor
+    their sampling stream is disturbed (a twin env that never evaluates stays identical)."""
+    from spark_sched_sim_b200.batched_env import BatchedSparkSchedSimEnv
+
+    B, K = 32, 40
+    cfg = {"num_executors": 10, "job_arrival_cap": 8, "job_arrival_rate": 4.0e-5,
+           "moving_delay": 2000.0, "warmup_delay": 1000.0}
+    envs = []
+    for _ in range(2):
+        e = BatchedSparkSchedSimEnv(cfg, num_envs=B, bank=bank, decima_policy=True)
+        e.set_decima_weights(weights())
+        e.reset_host(np.arange(B, dtype=np.uint64) + 400)
+        envs.append(e)
+    env, twin = envs
+    snaps, acts, lgs, ens = [], [], [], []
+    for k in range(K):
+        snaps.append(env.decima_snapshot())
+        a, n = env.decima_policy()
+        acts.append(env.pol_action.clone())
+        lgs.append(env.pol_lgprob.clone()); ens.append(env.pol_entropy.clone())
+        if k % 7 == 3 and k > 3:  # interleave an evaluation of an older observation
+            lg, en = env.decima_evaluate(snaps[k - 3], acts[k - 3][:, 0].contiguous(), acts[k - 3][:, 2].contiguous())
+            assert torch.equal(lg, lgs[k - 3]) and torch.equal(en, ens[k - 3]), k
+        env.step(a, n)
+        a2, n2 = twin.decima_policy()
+        twin.step(a2, n2)
+        assert torch.equal(a, a2) and torch.equal(n, n2), k
+    for k in range(K):
+        lg, en = env.decima_evaluate(snaps[k], acts[k][:, 0].contiguous(), acts[k][:, 2].contiguous())
+        assert torch.equal(lg, lgs[k]) and torch.equal(en, ens[k]), k
+    assert np.array_equal(env.hdr()["wall_time"], twin.hdr()["wall_time"])
+    assert torch.isfinite(torch.stack(ens)).all() and (torch.stack(ens) >= 0).all()

@@ -44,3 +44,33 @@ def test_make_scheduler_factory():
     assert s.name == "FIFO"
     with pytest.raises(AssertionError):
         make_scheduler({"agent_cls": "Nope"})
+
+
+def test_decima_scheduler_constructor_contract():
+    """schedulers.DecimaScheduler keeps the reference's constructor keywords (schedulers/decima/scheduler.py:22-69)
+    and refuses what the device policy does not implement -- no GPU needed for that."""
+    import os.path as osp
+
+    from helpers import GOLDEN_DIR
+    from spark_sched_sim_b200.decima import DecimaEnvWrapper
+    from spark_sched_sim_b200.schedulers import DecimaScheduler, make_scheduler
+
+    agent_cfg = {"agent_cls": "DecimaScheduler", "embed_dim": 16, "gnn_mlp_kwargs": {"hid_dims": [32, 16], "act_cls": "LeakyReLU"},
+                 "policy_mlp_kwargs": {"hid_dims": [64, 64], "act_cls": "Tanh"}, "num_executors": 10,
+                 "state_dict_path": osp.join(GOLDEN_DIR, "decima_model.npz"), "training_mode": False}
+    s = make_scheduler(agent_cfg)
+    assert isinstance(s, DecimaScheduler) and s.env_wrapper_cls is DecimaEnvWrapper and s.name.startswith("Decima:")
+    assert len(s._state_dict) == 42 and sum(v.size for v in s._state_dict.values()) == 20802
+    with pytest.raises(ValueError):
+        DecimaScheduler(10, embed_dim=32, state_dict_path=agent_cfg["state_dict_path"])
+    with pytest.raises(ValueError):
+        DecimaScheduler(10)  # no weights
+    with pytest.raises(ValueError):
+        s.schedule({"dag_ptr": [0]})  # not an observation of DecimaEnvWrapper
+
+
+def test_stats_from_sums():
+    from spark_sched_sim_b200 import parallel
+
+    d = parallel.stats_from_sums([50.0, 2.0, 30.0, 44.0, 600000.0, 9.0, 0.0, 0.0])
+    assert d == {"avg_num_jobs": 25.0, "num_completed_jobs": 15.0, "num_job_arrivals": 22.0, "avg_job_duration": 20.0}

@@ -217,6 +217,15 @@ typedef struct {
 int ssb_rollout_fair_traj(ssb_env *env, int32_t num_decisions, int32_t dynamic_partition, int32_t auto_reset,
                           uint64_t seed_step, ssb_transition *traj, void *stream);
 
+/* Fixed-duration rollouts that span resets (RolloutWorkerAsync.collect_rollout, trainers/rollout_worker.py:160-206):
+ * every env keeps deciding (fair / FIFO policy, auto-reset with seed + seed_step * reset_count) until its accumulated
+ * simulated time in this call reaches rollout_duration (ms) or max_decisions rows are written; the rows' wall_time is
+ * that accumulated time, flags 1 / 2 mark the steps after which the env was reset.  num_steps (DEVICE i32[B]) and
+ * elapsed (DEVICE f64[B], the buffer's closing wall_times entry) may be NULL.  The envs continue where they stopped
+ * at the next call. */
+int ssb_rollout_fair_async(ssb_env *env, int32_t max_decisions, double rollout_duration, int32_t dynamic_partition,
+                           uint64_t seed_step, ssb_transition *traj, int32_t *num_steps, double *elapsed, void *stream);
+
 /* ---- what the trainer derives from the rollout buffers before a policy update
  * (trainers/trainer.py:172-212 _preprocess_rollouts).  Plain functions on DEVICE buffers, no handle:
  * traj = ssb_transition[B][stride], num_steps = i32[B] rows stored per rollout (clamped to stride),

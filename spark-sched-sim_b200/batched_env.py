@@ -183,6 +183,19 @@ class BatchedSparkSchedSimEnv:
         episode's first observation with hdr["was_reset"] = 1."""
         nat.check(self.L.ssb_set_autoreset(self._h, int(bool(enable)), int(seed_step)), "ssb_set_autoreset")
 
+    def rollout_fair_async(self, max_decisions, rollout_duration, dynamic_partition=True, seed_step=1):
+        """Fixed-duration rollouts spanning resets (RolloutWorkerAsync.collect_rollout, rollout_worker.py:160-206).
+        Returns (traj uint8 device tensor [B * max_decisions * 32], num_steps i32[B], elapsed f64[B])."""
+        nbytes = self.num_envs * int(max_decisions) * nat.TRANSITION_DTYPE.itemsize
+        traj = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        num = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
+        el = torch.zeros(self.num_envs, dtype=torch.float64, device=self.device)
+        nat.check(self.L.ssb_rollout_fair_async(self._h, int(max_decisions), float(rollout_duration),
+                                                int(dynamic_partition), int(seed_step), traj.data_ptr(),
+                                                num.data_ptr(), el.data_ptr(), self._stream()),
+                  "ssb_rollout_fair_async")
+        return traj, num, el
+
     def set_mean_time_limit(self, mean_ms: float) -> None:
         """StochasticTimeLimit on the device: every reset without an explicit limit (and every auto-reset) draws
         the episode's time limit ~ Exp(mean_ms) from the episode seed's Philox LIMIT stream."""

@@ -156,6 +156,52 @@ k_rollout_fair(Params p, int num_decisions, int dynamic_partition, int auto_rese
 #endif
 }
 
+// RolloutWorkerAsync.collect_rollout (trainers/rollout_worker.py:160-206): the rollout ends when the env's accumulated
+// simulated time reaches `duration` (or after max_decisions rows), resets do not end it, and the time axis of the
+// stored rows is that accumulated time.  (A kernel of its own, so that the default rollout kernel stays as measured.)
+template <int NS>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, NS == 1 ? 7 : 4)
+k_rollout_fair_async(Params p, int max_decisions, double duration, int dynamic_partition, uint64_t seed_step,
+                     ssb_transition *traj, int32_t *num_steps, double *elapsed_out)
+{
+    const int b = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= p.B) return;
+    Sim sim(p, b, lane);
+    int d = 0, fresh = 0;
+    double elapsed = 0.0;
+    while (d < max_decisions && elapsed < duration) {
+        if (sim.h->error) break;
+        if (sim.h->done || sim.oh->truncated) {  // :196-200, applied when the loop comes back around
+            fresh = 4;
+            const uint64_t seed = sim.h->base_seed + seed_step * (uint64_t)sim.h->reset_count;
+            const double tl = sim.next_time_limit(seed);
+            const bool was_trunc = !sim.h->done;
+            __syncwarp();
+            if (lane == 0) { sim.h->reset_count += 1; if (was_trunc) sim.stats->episodes++; }
+            sim.reset_w(seed, tl);
+            continue;
+        }
+        int a = -1, n = 1;
+        sim.fair_action_w(dynamic_partition != 0, a, n);
+        const double wall0 = sim.oh->wall_time;
+        sim.template step_w<NS>(a, n);
+        if (traj && lane == 0) {  // rollout_buffer.add(obs, elapsed_time, action, lgprob, reward) (:191)
+            ssb_transition t;
+            t.wall_time = elapsed; t.reward = sim.oh->reward; t.stage_idx = a; t.num_exec = n;
+            t.flags = (sim.oh->terminated ? 1 : 0) | (sim.oh->truncated ? 2 : 0) | fresh;
+            t.lgprob = 0.0f;
+            traj[(size_t)b * max_decisions + d] = t;
+        }
+        elapsed += sim.oh->wall_time - wall0;  // the duration of this step (:194)
+        fresh = 0;
+        d++;
+    }
+    if (lane == 0) {
+        if (num_steps) num_steps[b] = d;
+        if (elapsed_out) elapsed_out[b] = elapsed;
+    }
+}
+
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_decima_obs(Params p)
 {
     __shared__ uint64_t Sk[WARPS_PER_CTA][64];
@@ -741,6 +787,20 @@ int ssb_rollout_fair_traj(ssb_env *env, int32_t num_decisions, int32_t dynamic_p
     else
         k_rollout_fair<2><<<env->grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(
             env->p, num_decisions, dynamic_partition, auto_reset, seed_step, traj);
+    CUDA_TRY(cudaGetLastError());
+    return SSB_OK;
+}
+
+int ssb_rollout_fair_async(ssb_env *env, int32_t max_decisions, double rollout_duration, int32_t dynamic_partition,
+                           uint64_t seed_step, ssb_transition *traj, int32_t *num_steps, double *elapsed, void *stream)
+{
+    if (!env || max_decisions < 0 || !(rollout_duration > 0.0)) return SSB_E_INVALID;
+    if (env->p.E <= 32)
+        k_rollout_fair_async<1><<<env->grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(
+            env->p, max_decisions, rollout_duration, dynamic_partition, seed_step, traj, num_steps, elapsed);
+    else
+        k_rollout_fair_async<2><<<env->grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(
+            env->p, max_decisions, rollout_duration, dynamic_partition, seed_step, traj, num_steps, elapsed);
     CUDA_TRY(cudaGetLastError());
     return SSB_OK;
 }

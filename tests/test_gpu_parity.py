@@ -463,6 +463,53 @@ def test_stochastic_time_limit_on_device(bank):
     assert n_trunc > B
 
 
+def test_async_rollouts_match_reference_loop(bank):
+    """ssb_rollout_fair_async == RolloutWorkerAsync.collect_rollout (rollout_worker.py:160-206) restated over the
+    oracle: fixed simulated duration per call, resets inside the rollout, time axis = accumulated time, state carried
+    over to the next call."""
+    from oracle import OracleEnv
+    from spark_sched_sim_b200 import _native as nat
+    from spark_sched_sim_b200.batched_env import BatchedSparkSchedSimEnv
+
+    B, KMAX, DUR, STEP = 4, 2000, 2.0e6, 9
+    cfg = {"num_executors": 10, "job_arrival_cap": 5, "job_arrival_rate": 4.0e-5,
+           "moving_delay": 2000.0, "warmup_delay": 1000.0}
+    env = BatchedSparkSchedSimEnv(cfg, num_envs=B, bank=bank)
+    seeds = np.arange(80, 80 + B, dtype=np.uint64)
+    env.reset_host(seeds)
+    calls = []
+    for _ in range(3):
+        traj, num, el = env.rollout_fair_async(KMAX, DUR, True, STEP)
+        calls.append((traj.cpu().numpy().view(nat.TRANSITION_DTYPE).reshape(B, KMAX), num.cpu().numpy(),
+                      el.cpu().numpy()))
+    assert (env.hdr()["error"] == 0).all()
+    n_resets = 0
+    for b in range(B):
+        orc = OracleEnv(bank, 10, 5, 2000.0, 1000.0, 4.0e-5)
+        resets = 0
+        orc.reset_seed(int(seeds[b])); resets += 1
+        next_wall = 0.0
+        for tr, num, el in calls:  # one collect_rollout() each
+            elapsed, step = 0.0, 0
+            while elapsed < DUR and step < KMAX:
+                wall = next_wall
+                a, n = orc.fair_action(True)
+                rc, rew, term = orc.step(a, n)
+                assert rc == 0
+                next_wall = orc.wall_time
+                r = tr[b, step]
+                assert (r["wall_time"], r["stage_idx"], r["num_exec"], r["reward"]) == (elapsed, a, n, rew), (b, step)
+                assert (r["flags"] & 1) == int(term), (b, step)
+                elapsed += next_wall - wall
+                if term:
+                    orc.reset_seed(int(seeds[b]) + STEP * resets); resets += 1
+                    next_wall = 0.0
+                    n_resets += 1
+                step += 1
+            assert num[b] == step and el[b] == elapsed, (b, num[b], step)
+    assert n_resets >= B
+
+
 def test_rollout_with_discounted_reward(bank):
     """beta > 0: the continuously discounted reward (:866-869) goes through exp(); transitions match the
     oracle with rewards at 1e-12 relative (device exp vs libm), everything else exactly."""

@@ -235,6 +235,15 @@ int ssb_rollout_fair_async(ssb_env *env, int32_t max_decisions, double rollout_d
 int ssb_discounted_returns(const ssb_transition *traj, const int32_t *num_steps, const double *final_wall,
                            int32_t num_rollouts_total, int32_t stride, double beta, double *returns,
                            void *stream);
+/* ReturnsCalculator._calc_differential_returns (returns_calculator.py:52-65, :78-89).  The calculator's state is a
+ * window of the latest `cap` steps with a positive duration over all rollouts (CircularArray): window = DEVICE
+ * f64[2][cap][2], a ping-pong pair, zero-filled before the first call, with *which (HOST int, 0 at first) naming the
+ * current half -- the call flips it.  scratch = DEVICE i32[2 * B + 1].  Steps: the new (dt, reward) rows of all
+ * rollouts, in rollout order, replace the oldest rows; avg_num_jobs (DEVICE f64[1], output) = -sum(reward) / sum(dt)
+ * over the window, rows added in order; R_k = -(-r_k - dt_k * avg_num_jobs) + R_{k+1} -> returns f64[B][stride]. */
+int ssb_differential_returns(const ssb_transition *traj, const int32_t *num_steps, const double *final_wall,
+                             int32_t num_rollouts_total, int32_t stride, double *window, int32_t cap, int32_t *which,
+                             int32_t *scratch, double *avg_num_jobs, double *returns, void *stream);
 /* Baseline.average (trainers/utils/baselines.py:12-37): consecutive groups of `group_size` rollouts ran the
  * same job sequence; baseline[b][k] = mean over the group of every member's returns linearly interpolated
  * (np.interp) at rollout b's step time k -> baselines f64[B][stride].  group_size <= 128. */

@@ -28,6 +28,41 @@ def discounted_returns(rewards, times, beta):
     return out
 
 
+class DifferentialReturns:
+    """ReturnsCalculator with buff_cap (returns_calculator.py:24-65, :78-89): CircularArray window of the latest
+    `cap` (dt, reward) rows with dt > 0 over all rollouts in order; avg_num_jobs = -sum(reward) / sum(dt) with the
+    rows added one after the other (ndarray.sum(0) of a C-contiguous (cap, 2) array)."""
+
+    def __init__(self, cap):
+        self.cap = cap
+        self.data = np.zeros((cap, 2))
+        self.avg_num_jobs = None
+
+    def __call__(self, rewards_list, times_list):
+        dts = [np.asarray(t[1:], dtype=np.float64) - np.asarray(t[:-1], dtype=np.float64) for t in times_list]
+        rows = [(float(dt), float(r)) for d, rs in zip(dts, rewards_list) for dt, r in zip(d, rs) if dt > 0]
+        rows = rows[-self.cap:]
+        keep = self.cap - len(rows)
+        if keep > 0:
+            self.data[:keep] = self.data[self.cap - keep:].copy()
+        if rows:
+            self.data[keep:] = np.asarray(rows)
+        total_time = rew_sum = 0.0
+        for i in range(self.cap):
+            total_time += self.data[i, 0]
+            rew_sum += self.data[i, 1]
+        self.avg_num_jobs = -rew_sum / total_time
+        out = []
+        for d, rs in zip(dts, rewards_list):
+            ret = np.zeros(len(rs))
+            R = 0.0
+            for k in range(len(rs) - 1, -1, -1):
+                R = -((-float(rs[k])) - float(d[k]) * self.avg_num_jobs) + R
+                ret[k] = R
+            out.append(ret)
+        return out
+
+
 def interp1(x, xp, fp):
     """np.interp for one point; xp non-decreasing with repeats allowed."""
     n = len(xp)

@@ -815,6 +815,28 @@ int ssb_discounted_returns(const ssb_transition *traj, const int32_t *num_steps,
     return SSB_OK;
 }
 
+int ssb_differential_returns(const ssb_transition *traj, const int32_t *num_steps, const double *final_wall, int32_t B,
+                             int32_t stride, double *window, int32_t cap, int32_t *which, int32_t *scratch,
+                             double *avg_num_jobs, double *returns, void *stream)
+{
+    if (!traj || !num_steps || !final_wall || !window || !which || !scratch || !avg_num_jobs || !returns || B < 1 ||
+        stride < 1 || cap < 1 || (*which != 0 && *which != 1))
+        return SSB_E_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    int32_t *cnt = scratch, *off = scratch + B;
+    const double *src = window + (size_t)*which * cap * 2;
+    double *dst = window + (size_t)(1 - *which) * cap * 2;
+    learn::k_diff_count<<<(B + 3) / 4, 128, 0, s>>>(traj, num_steps, final_wall, B, stride, cnt);
+    learn::k_diff_scan<<<1, 32, 0, s>>>(cnt, B, off);
+    learn::k_diff_keep<<<64, 256, 0, s>>>(src, dst, cap, off, B);
+    learn::k_diff_fill<<<(B + 3) / 4, 128, 0, s>>>(traj, num_steps, final_wall, B, stride, off, dst, cap);
+    learn::k_diff_avg<<<1, 32, 0, s>>>(dst, cap, avg_num_jobs);
+    learn::k_diff_returns<<<(B + 127) / 128, 128, 0, s>>>(traj, num_steps, final_wall, B, stride, avg_num_jobs, returns);
+    CUDA_TRY(cudaGetLastError());
+    *which = 1 - *which;
+    return SSB_OK;
+}
+
 int ssb_group_baselines(const ssb_transition *traj, const double *returns, const int32_t *num_steps, int32_t B,
                         int32_t stride, int32_t group_size, double *baselines, void *stream)
 {

@@ -104,3 +104,99 @@ k_group_baselines(const ssb_transition *traj, const double *returns, const int32
 
 }  // namespace learn
 }  // namespace ssb
+
+namespace ssb {
+namespace learn {
+
+// ---- differential returns (returns_calculator.py:52-65, :78-89) --------------------------------------------------
+// avg_num_jobs = (total job time) / (total time) over a window of the latest `cap` steps with dt > 0, taken over all
+// rollouts in order (CircularArray.extend); then R_k = -(job_time_k - dt_k * avg_num_jobs) + R_{k+1}.
+
+// per rollout: number of steps with a positive duration
+__global__ void __launch_bounds__(128)
+k_diff_count(const ssb_transition *traj, const int32_t *num_steps, const double *final_wall, int B, int stride, int32_t *cnt)
+{
+    const int b = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= B) return;
+    const int n = min(num_steps[b], stride);
+    int c = 0;
+    for (int k = lane; k < n; k += 32)
+        c += (step_time(traj, final_wall, b, stride, n, k + 1) - step_time(traj, final_wall, b, stride, n, k)) > 0.0;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (lane == 0) cnt[b] = c;
+}
+// exclusive prefix of the counts (one thread: B is a few thousand) -> off[0..B], off[B] = total
+__global__ void k_diff_scan(const int32_t *cnt, int B, int32_t *off)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    int run = 0;
+    for (int b = 0; b < B; b++) { off[b] = run; run += cnt[b]; }
+    off[B] = run;
+}
+// CircularArray.extend into `dst` (the other half of a ping-pong pair): the kept tail of `src`, then the new rows
+__global__ void __launch_bounds__(256)
+k_diff_keep(const double *src, double *dst, int cap, const int32_t *off, int B)
+{
+    const int total = off[B], num_new = total < cap ? total : cap, num_keep = cap - num_new;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < num_keep; i += gridDim.x * blockDim.x) {
+        dst[2 * i] = src[2 * (i + num_new)];
+        dst[2 * i + 1] = src[2 * (i + num_new) + 1];
+    }
+}
+__global__ void __launch_bounds__(128)
+k_diff_fill(const ssb_transition *traj, const int32_t *num_steps, const double *final_wall, int B, int stride,
+            const int32_t *off, double *dst, int cap)
+{
+    const int b = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= B) return;
+    const int total = off[B], num_new = total < cap ? total : cap, num_keep = cap - num_new, first = total - num_new;
+    const int n = min(num_steps[b], stride);
+    int run = off[b];  // global index of this rollout's next filtered row
+    for (int k0 = 0; k0 < n; k0 += 32) {
+        const int k = k0 + lane;
+        double dt = 0.0;
+        if (k < n) dt = step_time(traj, final_wall, b, stride, n, k + 1) - step_time(traj, final_wall, b, stride, n, k);
+        const bool keep = k < n && dt > 0.0;
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            const int g = run + __popc(m & ((1u << lane) - 1u));
+            if (g >= first) {
+                dst[2 * (size_t)(num_keep + g - first)] = dt;
+                dst[2 * (size_t)(num_keep + g - first) + 1] = traj[(size_t)b * stride + k].reward;
+            }
+        }
+        run += __popc(m);
+    }
+}
+// total_time, rew_sum = buff.data.sum(0): numpy adds the rows one after the other; avg = -rew_sum / total_time
+__global__ void k_diff_avg(const double *buf, int cap, double *avg_num_jobs)
+{
+    __shared__ double col[2];
+    if (threadIdx.x < 2) {
+        double s = 0.0;
+        for (int i = 0; i < cap; i++) s = __dadd_rn(s, buf[2 * (size_t)i + threadIdx.x]);
+        col[threadIdx.x] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *avg_num_jobs = __ddiv_rn(-col[1], col[0]);
+}
+__global__ void __launch_bounds__(128)
+k_diff_returns(const ssb_transition *traj, const int32_t *num_steps, const double *final_wall, int B, int stride,
+               const double *avg_num_jobs, double *returns)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int n = min(num_steps[b], stride);
+    const double avg = *avg_num_jobs;
+    double R = 0.0;
+    for (int k = n - 1; k >= 0; k--) {
+        const double dt = step_time(traj, final_wall, b, stride, n, k + 1) - step_time(traj, final_wall, b, stride, n, k);
+        const double job_time = -traj[(size_t)b * stride + k].reward;
+        const double expected = __dmul_rn(dt, avg);
+        R = __dadd_rn(-__dadd_rn(job_time, -expected), R);  // R = -(job_time - expected_job_time) + R
+        returns[(size_t)b * stride + k] = R;
+    }
+}
+
+}  // namespace learn
+}  // namespace ssb

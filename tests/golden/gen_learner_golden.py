@@ -45,6 +45,26 @@ def main():
         out[f"{name}_rewards"] = np.concatenate([np.asarray(r) for r in rewards_list])
         out[f"{name}_returns"] = np.concatenate(returns_list)
         out[f"{name}_baselines"] = np.concatenate(baselines_list)
+    # differential returns: one calculator, three consecutive calls (the window carries over); caps below and above
+    # the number of rows per call
+    for name, cap in (("diff_small", 150), ("diff_large", 5000)):
+        calc = rc.ReturnsCalculator(buff_cap=cap)
+        for call in range(3):
+            n = 6
+            times_list, rewards_list = [], []
+            for i in range(n):
+                K = int(rng.integers(20, 120))
+                steps = np.where(rng.random(K) < 0.35, 0.0, np.round(rng.exponential(4000.0, K)))
+                ts = np.concatenate([[0.0], np.cumsum(steps)])
+                times_list.append(ts.tolist())
+                rewards_list.append((-(ts[1:] - ts[:-1]) * rng.integers(1, 30, K)).tolist())
+            returns_list = calc(rewards_list, times_list, [set()] * n)
+            key = f"{name}_c{call}"
+            out[f"{key}_meta"] = np.array([cap, calc.avg_num_jobs])
+            out[f"{key}_len"] = np.array([len(r) for r in rewards_list])
+            out[f"{key}_times"] = np.concatenate([np.asarray(t) for t in times_list])
+            out[f"{key}_rewards"] = np.concatenate([np.asarray(r) for r in rewards_list])
+            out[f"{key}_returns"] = np.concatenate(returns_list)
     np.savez_compressed(osp.join(osp.dirname(osp.abspath(__file__)), "learner_vectors.npz"), **out)
     print({k: v.shape for k, v in out.items()})
 

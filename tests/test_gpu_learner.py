@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from test_learner_oracle import CASES
+from test_learner_oracle import CASES, DIFF_CASES
 
 pytestmark = pytest.mark.gpu
 
@@ -80,3 +80,19 @@ def test_on_fused_rollouts(bank):
     g_base = base.cpu().numpy()
     for i in range(B):
         assert np.array_equal(g_base[i, :n[i]], o_base[i]), i
+
+
+@pytest.mark.parametrize("name", sorted(DIFF_CASES))
+def test_differential_returns_reference_vectors(name):
+    """ssb_differential_returns over three consecutive calls of one calculator (the window carries over):
+    avg_num_jobs and the returns equal the reference's ReturnsCalculator(buff_cap) bit for bit."""
+    from spark_sched_sim_b200.returns import ReturnsCalculator
+
+    calc = ReturnsCalculator(buff_cap=DIFF_CASES[name][0]["cap"])
+    for c in DIFF_CASES[name]:
+        B, stride = len(c["lens"]), int(c["lens"].max()) + 2
+        traj, num, final = pack(c["times"], c["rewards"], stride)
+        got = calc(traj, num, final, stride).cpu().numpy()
+        assert float(calc.avg_num_jobs.item()) == c["avg_num_jobs"]
+        for i in range(B):
+            assert np.array_equal(got[i, :c["lens"][i]], c["returns"][i]), i

@@ -244,6 +244,16 @@ int ssb_discounted_returns(const ssb_transition *traj, const int32_t *num_steps,
 int ssb_differential_returns(const ssb_transition *traj, const int32_t *num_steps, const double *final_wall,
                              int32_t num_rollouts_total, int32_t stride, double *window, int32_t cap, int32_t *which,
                              int32_t *scratch, double *avg_num_jobs, double *returns, void *stream);
+/* PPO._compute_loss (trainers/ppo.py:104-140): the clip loss of one mini-batch and the adjoint seeds of its backward
+ * pass.  All arrays DEVICE.  The per-sample arrays new_lgprob / old_lgprob / entropy (f32) and returns / baselines
+ * (f64) are indexed by idx[i] (i32[n], NULL = 0..n-1): advantage = float(returns - baselines), normalised with the
+ * batch mean and unbiased std (+1e-8); ratio = exp(new - old); policy_loss = -mean(min(adv * ratio, adv *
+ * clamp(ratio, 1 - clip, 1 + clip))); entropy_loss = -mean(entropy); out f32[4] = { policy_loss + entropy_coeff *
+ * entropy_loss, policy_loss, entropy_loss, mean((ratio - 1) - log_ratio) }.  grad_lgprob / grad_entropy (f32[n], in
+ * batch order, may be NULL) = d loss / d new_lgprob, d loss / d entropy.  scratch = DEVICE f64[640]. */
+int ssb_ppo_loss(const float *new_lgprob, const float *old_lgprob, const float *entropy, const double *returns,
+                 const double *baselines, const int32_t *idx, int32_t n, float clip_range, float entropy_coeff,
+                 double *scratch, float *out, float *grad_lgprob, float *grad_entropy, void *stream);
 /* Baseline.average (trainers/utils/baselines.py:12-37): consecutive groups of `group_size` rollouts ran the
  * same job sequence; baseline[b][k] = mean over the group of every member's returns linearly interpolated
  * (np.interp) at rollout b's step time k -> baselines f64[B][stride].  group_size <= 128. */

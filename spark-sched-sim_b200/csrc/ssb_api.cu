@@ -837,6 +837,23 @@ int ssb_differential_returns(const ssb_transition *traj, const int32_t *num_step
     return SSB_OK;
 }
 
+int ssb_ppo_loss(const float *new_lgprob, const float *old_lgprob, const float *entropy, const double *returns,
+                 const double *baselines, const int32_t *idx, int32_t n, float clip_range, float entropy_coeff,
+                 double *scratch, float *out, float *grad_lgprob, float *grad_entropy, void *stream)
+{
+    if (!new_lgprob || !old_lgprob || !entropy || !returns || !baselines || !scratch || !out || n < 1)
+        return SSB_E_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    double *part = scratch, *part2 = scratch + 2 * learn::PPO_BLOCKS;
+    learn::k_ppo_moments<<<learn::PPO_BLOCKS, learn::PPO_THREADS, 0, s>>>(returns, baselines, idx, n, part);
+    learn::k_ppo_terms<<<learn::PPO_BLOCKS, learn::PPO_THREADS, 0, s>>>(new_lgprob, old_lgprob, entropy, returns,
+                                                                        baselines, idx, n, clip_range, entropy_coeff,
+                                                                        part, part2, grad_lgprob, grad_entropy);
+    learn::k_ppo_final<<<1, 32, 0, s>>>(part2, n, entropy_coeff, out);
+    CUDA_TRY(cudaGetLastError());
+    return SSB_OK;
+}
+
 int ssb_group_baselines(const ssb_transition *traj, const double *returns, const int32_t *num_steps, int32_t B,
                         int32_t stride, int32_t group_size, double *baselines, void *stream)
 {

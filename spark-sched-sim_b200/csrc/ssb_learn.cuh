@@ -200,3 +200,92 @@ k_diff_returns(const ssb_transition *traj, const int32_t *num_steps, const doubl
 
 }  // namespace learn
 }  // namespace ssb
+
+namespace ssb {
+namespace learn {
+
+// ---- PPO clip loss head (trainers/ppo.py:104-140 `_compute_loss`) ------------------------------------------------
+// Forward values and the adjoint seeds of the backward pass (d loss / d lgprob_i, d loss / d entropy_i) for one
+// mini-batch of samples.  Sums are taken in f64 in a fixed order (block partition + tree), results rounded to f32.
+constexpr int PPO_BLOCKS = 128, PPO_THREADS = 256;
+
+__device__ __forceinline__ double block_sum(double v, double *sh)
+{
+    for (int off = 16; off; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = 0.0;
+    for (int i = 0; i < PPO_THREADS / 32; i++) s += sh[i];
+    return s;
+}
+__device__ __forceinline__ float ppo_advantage(const double *returns, const double *baselines, int i)
+{
+    return (float)(returns[i] - baselines[i]);  // `returns - baselines` in f64, then torch.tensor(...).float()
+}
+// part[k] = { sum a, sum a^2 } of block k's samples
+__global__ void __launch_bounds__(PPO_THREADS)
+k_ppo_moments(const double *returns, const double *baselines, const int32_t *idx, int n, double *part)
+{
+    __shared__ double sh[PPO_THREADS / 32];
+    double s1 = 0.0, s2 = 0.0;
+    for (int i = blockIdx.x * PPO_THREADS + threadIdx.x; i < n; i += PPO_BLOCKS * PPO_THREADS) {
+        const double a = ppo_advantage(returns, baselines, idx ? idx[i] : i);
+        s1 += a; s2 += a * a;
+    }
+    s1 = block_sum(s1, sh);
+    s2 = block_sum(s2, sh);
+    if (threadIdx.x == 0) { part[2 * blockIdx.x] = s1; part[2 * blockIdx.x + 1] = s2; }
+}
+// per-sample terms; part2[k] = { sum min(pl1, pl2), sum entropy, sum (ratio - 1 - log_ratio) }
+__global__ void __launch_bounds__(PPO_THREADS)
+k_ppo_terms(const float *new_lgprob, const float *old_lgprob, const float *entropy, const double *returns,
+            const double *baselines, const int32_t *idx, int n, float clip_range, float entropy_coeff,
+            const double *part, double *part2, float *grad_lgprob, float *grad_entropy)
+{
+    __shared__ double sh[PPO_THREADS / 32];
+    double s1 = 0.0, s2 = 0.0;
+    for (int k = 0; k < PPO_BLOCKS; k++) { s1 += part[2 * k]; s2 += part[2 * k + 1]; }
+    const double mean = s1 / n;
+    // torch.std: the unbiased estimator; (advgs - mean) / (std + 1e-8) in f32 (ppo.py:116-117)
+    const double var = n > 1 ? fmax(s2 - n * mean * mean, 0.0) / (n - 1) : nan("");
+    const float meanf = (float)mean, denom = (float)sqrt(var) + 1e-8f;
+    const float lo = 1.0f - clip_range, hi = 1.0f + clip_range, inv_n = 1.0f / (float)n;
+    double t_min = 0.0, t_ent = 0.0, t_kl = 0.0;
+    for (int i = blockIdx.x * PPO_THREADS + threadIdx.x; i < n; i += PPO_BLOCKS * PPO_THREADS) {
+        const int r = idx ? idx[i] : i;
+        const float adv = (ppo_advantage(returns, baselines, r) - meanf) / denom;
+        const float log_ratio = new_lgprob[r] - old_lgprob[r];
+        const float ratio = expf(log_ratio);
+        const float pl1 = adv * ratio, pl2 = adv * fminf(fmaxf(ratio, lo), hi);
+        t_min += fminf(pl1, pl2);
+        t_ent += entropy[r];
+        t_kl += (ratio - 1.0f) - log_ratio;
+        // d(-mean(min(pl1, pl2))) / d lgprob: through pl1 always when it is the smaller one, through both (the clamp
+        // passes the gradient) while the ratio is inside the clip range
+        const bool inside = ratio >= lo && ratio <= hi;
+        if (grad_lgprob) grad_lgprob[i] = (inside || pl1 < pl2) ? -inv_n * adv * ratio : 0.0f;
+        if (grad_entropy) grad_entropy[i] = -entropy_coeff * inv_n;
+    }
+    t_min = block_sum(t_min, sh);
+    t_ent = block_sum(t_ent, sh);
+    t_kl = block_sum(t_kl, sh);
+    if (threadIdx.x == 0) {
+        part2[3 * blockIdx.x] = t_min; part2[3 * blockIdx.x + 1] = t_ent; part2[3 * blockIdx.x + 2] = t_kl;
+    }
+}
+// out = { loss, policy_loss, entropy_loss, approx_kl_div }
+__global__ void k_ppo_final(const double *part2, int n, float entropy_coeff, float *out)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    double t_min = 0.0, t_ent = 0.0, t_kl = 0.0;
+    for (int k = 0; k < PPO_BLOCKS; k++) { t_min += part2[3 * k]; t_ent += part2[3 * k + 1]; t_kl += part2[3 * k + 2]; }
+    const float policy_loss = (float)(-t_min / n), entropy_loss = (float)(-t_ent / n);
+    out[0] = policy_loss + entropy_coeff * entropy_loss;
+    out[1] = policy_loss;
+    out[2] = entropy_loss;
+    out[3] = (float)(t_kl / n);
+}
+
+}  // namespace learn
+}  // namespace ssb

@@ -96,3 +96,40 @@ def test_differential_returns_reference_vectors(name):
         assert float(calc.avg_num_jobs.item()) == c["avg_num_jobs"]
         for i in range(B):
             assert np.array_equal(got[i, :c["lens"][i]], c["returns"][i]), i
+
+
+@pytest.mark.parametrize("n,clip,coeff,use_idx", [(1, 0.2, 0.04, False), (7, 0.2, 0.04, False), (5000, 0.2, 0.04, True),
+                                                  (300000, 0.1, 0.0, False)])
+def test_ppo_loss_head_matches_torch_autograd(n, clip, coeff, use_idx):
+    """ssb_ppo_loss vs the trainer's `_compute_loss` (ppo.py:104-140) written in plain torch fp32 with autograd for
+    the adjoint seeds.  Tolerance: 2e-5 relative on the four scalars (torch sums in f32, the kernel in f64),
+    1e-5 relative on the per-sample gradients."""
+    from spark_sched_sim_b200.ppo import PPOLoss
+
+    g = torch.Generator(device="cuda").manual_seed(n)
+    total = n * 2 if use_idx else n
+    old = -3.0 * torch.rand(total, device="cuda", generator=g)
+    new = (old + 0.3 * torch.randn(total, device="cuda", generator=g)).requires_grad_()
+    ent = torch.rand(total, device="cuda", generator=g).requires_grad_()
+    ret = -1e5 * torch.rand(total, device="cuda", generator=g, dtype=torch.float64)
+    base = ret + 2e4 * torch.randn(total, device="cuda", generator=g, dtype=torch.float64)
+    idx = torch.randperm(total, device="cuda", generator=g)[:n].to(torch.int32) if use_idx else None
+    out, g_lp, g_en = PPOLoss(clip, coeff)(new.detach(), old, ent.detach(), ret, base, idx)
+    out = out.cpu().numpy()
+    if n == 1:  # std of one sample is nan in torch as well
+        assert np.isnan(out[0]) and np.isnan(out[1])
+        return
+    sel = idx.long() if use_idx else slice(None)
+    advgs = (ret - base)[sel].float()
+    advgs = (advgs - advgs.mean()) / (advgs.std() + 1e-8)
+    log_ratio = new[sel] - old[sel]
+    ratio = log_ratio.exp()
+    policy_loss = -torch.min(advgs * ratio, advgs * torch.clamp(ratio, 1 - clip, 1 + clip)).mean()
+    entropy_loss = -ent[sel].mean()
+    loss = policy_loss + coeff * entropy_loss
+    kl = ((ratio - 1) - log_ratio).mean()
+    loss.backward()
+    want = np.array([loss.item(), policy_loss.item(), entropy_loss.item(), kl.item()])
+    assert np.allclose(out, want, rtol=2e-5, atol=1e-7), (out, want)
+    assert torch.allclose(g_lp, new.grad[sel], rtol=1e-5, atol=2e-6 / n)  # atol: f32 cancellation in torch's adv - mean
+    assert torch.allclose(g_en, ent.grad[sel], rtol=1e-6, atol=0.0)

@@ -254,6 +254,14 @@ int ssb_differential_returns(const ssb_transition *traj, const int32_t *num_step
 int ssb_ppo_loss(const float *new_lgprob, const float *old_lgprob, const float *entropy, const double *returns,
                  const double *baselines, const int32_t *idx, int32_t n, float clip_range, float entropy_coeff,
                  double *scratch, float *out, float *grad_lgprob, float *grad_entropy, void *stream);
+/* TrainableScheduler.update_parameters (schedulers/scheduler.py:37-54) after the backward pass: clip_grad_norm_(grads,
+ * max_grad_norm) (skipped when max_grad_norm <= 0), then one torch.optim.Adam step (no weight decay, no amsgrad) on
+ * the flat parameter vector (the ssb_set_decima_weights layout).  All arrays DEVICE f32[n]; step = 1 for the first
+ * update; scratch = DEVICE f64[128]; grad_norm_out (DEVICE f32[1], may be NULL) receives the norm before clipping.
+ * With several GPUs the caller all-reduces `grad` (NCCL, mean) before this call. */
+int ssb_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int32_t n, int32_t step, float lr,
+                  float beta1, float beta2, float eps, float max_grad_norm, double *scratch, float *grad_norm_out,
+                  void *stream);
 /* Baseline.average (trainers/utils/baselines.py:12-37): consecutive groups of `group_size` rollouts ran the
  * same job sequence; baseline[b][k] = mean over the group of every member's returns linearly interpolated
  * (np.interp) at rollout b's step time k -> baselines f64[B][stride].  group_size <= 128. */

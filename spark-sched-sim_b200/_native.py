@@ -126,7 +126,7 @@ STATS_DTYPE = np.dtype([(f, "<u8") for f in STATS_FIELDS])
 EXPORTS = [
     "ssb_abi_version", "ssb_last_cuda_error", "ssb_workspace_bytes", "ssb_create", "ssb_destroy",
     "ssb_load_trace", "ssb_clear_trace", "ssb_reset", "ssb_step", "ssb_reset_host", "ssb_step_host", "ssb_step_fair_host", "ssb_set_autoreset", "ssb_set_mean_time_limit",
-    "ssb_rollout_fair", "ssb_rollout_fair_traj", "ssb_rollout_fair_async", "ssb_discounted_returns", "ssb_differential_returns", "ssb_group_baselines", "ssb_ppo_loss", "ssb_fair_actions", "ssb_get_views", "ssb_get_stats", "ssb_collect_stats", "ssb_reset_stats",
+    "ssb_rollout_fair", "ssb_rollout_fair_traj", "ssb_rollout_fair_async", "ssb_discounted_returns", "ssb_differential_returns", "ssb_group_baselines", "ssb_ppo_loss", "ssb_adam_step", "ssb_fair_actions", "ssb_get_views", "ssb_get_stats", "ssb_collect_stats", "ssb_reset_stats",
     "ssb_get_jobs", "ssb_get_log", "ssb_decima_obs", "ssb_get_decima_views",
     "ssb_set_decima_weights", "ssb_decima_policy", "ssb_rollout_decima", "ssb_decima_snapshot_bytes",
     "ssb_decima_snapshot", "ssb_decima_evaluate", "ssb_get_policy_views", "ssb_get_debug_counters",
@@ -175,6 +175,7 @@ def lib():
     L.ssb_discounted_returns.argtypes = [vp, vp, vp, i32, i32, C.c_double, vp, vp]
     L.ssb_group_baselines.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp]
     L.ssb_ppo_loss.argtypes = [vp, vp, vp, vp, vp, vp, i32, C.c_float, C.c_float, vp, vp, vp, vp, vp]
+    L.ssb_adam_step.argtypes = [vp, vp, vp, vp, i32, i32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, vp, vp, vp]
     L.ssb_differential_returns.argtypes = [vp, vp, vp, i32, i32, vp, i32, C.POINTER(i32), vp, vp, vp, vp]
     L.ssb_fair_actions.argtypes = [vp, i32, vp, vp, vp]
     L.ssb_get_views.argtypes = [vp, C.POINTER(SsbViews)]

@@ -854,6 +854,20 @@ int ssb_ppo_loss(const float *new_lgprob, const float *old_lgprob, const float *
     return SSB_OK;
 }
 
+int ssb_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int32_t n, int32_t step, float lr,
+                  float beta1, float beta2, float eps, float max_grad_norm, double *scratch, float *grad_norm_out,
+                  void *stream)
+{
+    if (!param || !grad || !exp_avg || !exp_avg_sq || !scratch || n < 1 || step < 1) return SSB_E_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    learn::k_grad_sqsum<<<learn::PPO_BLOCKS, learn::PPO_THREADS, 0, s>>>(grad, n, scratch);
+    const int blocks = std::min(learn::PPO_BLOCKS, (n + learn::PPO_THREADS - 1) / learn::PPO_THREADS);
+    learn::k_adam_step<<<blocks, learn::PPO_THREADS, 0, s>>>(param, grad, exp_avg, exp_avg_sq, n, step, lr, beta1, beta2,
+                                                             eps, max_grad_norm, scratch, grad_norm_out);
+    CUDA_TRY(cudaGetLastError());
+    return SSB_OK;
+}
+
 int ssb_group_baselines(const ssb_transition *traj, const double *returns, const int32_t *num_steps, int32_t B,
                         int32_t stride, int32_t group_size, double *baselines, void *stream)
 {

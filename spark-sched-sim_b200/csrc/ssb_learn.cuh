@@ -289,3 +289,43 @@ __global__ void k_ppo_final(const double *part2, int n, float entropy_coeff, flo
 
 }  // namespace learn
 }  // namespace ssb
+
+namespace ssb {
+namespace learn {
+
+// ---- parameter update (TrainableScheduler.update_parameters, schedulers/scheduler.py:37-54: loss.backward();
+// clip_grad_norm_(max_grad_norm); optim.step() with torch.optim.Adam, trainer.py opt_cls / opt_kwargs) ------------
+// part[k] = block k's sum of g^2 (f64)
+__global__ void __launch_bounds__(PPO_THREADS) k_grad_sqsum(const float *grad, int n, double *part)
+{
+    __shared__ double sh[PPO_THREADS / 32];
+    double s = 0.0;
+    for (int i = blockIdx.x * PPO_THREADS + threadIdx.x; i < n; i += PPO_BLOCKS * PPO_THREADS) s += (double)grad[i] * grad[i];
+    s = block_sum(s, sh);
+    if (threadIdx.x == 0) part[blockIdx.x] = s;
+}
+// clip_grad_norm_: g *= min(1, max_norm / (||g|| + 1e-6)); then Adam (no weight decay, no amsgrad):
+// m += (g - m) * (1 - b1); v = v * b2 + (1 - b2) * g * g; p -= (lr / (1 - b1^t)) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
+__global__ void __launch_bounds__(PPO_THREADS)
+k_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int n, int step, float lr, float beta1,
+            float beta2, float eps, float max_grad_norm, const double *part, float *grad_norm_out)
+{
+    double ss = 0.0;
+    for (int k = 0; k < PPO_BLOCKS; k++) ss += part[k];
+    const float total_norm = (float)sqrt(ss);
+    float coef = 1.0f;
+    if (max_grad_norm > 0.0f) coef = fminf(max_grad_norm / (total_norm + 1e-6f), 1.0f);
+    if (grad_norm_out && blockIdx.x == 0 && threadIdx.x == 0) *grad_norm_out = total_norm;
+    const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+    const float step_size = (float)((double)lr / bc1), bc2_sqrt = (float)sqrt(bc2);
+    for (int i = blockIdx.x * PPO_THREADS + threadIdx.x; i < n; i += gridDim.x * PPO_THREADS) {
+        const float g = grad[i] * coef;
+        const float m = exp_avg[i] + (g - exp_avg[i]) * (1.0f - beta1);
+        const float v = exp_avg_sq[i] * beta2 + (1.0f - beta2) * g * g;
+        exp_avg[i] = m; exp_avg_sq[i] = v;
+        param[i] = param[i] - step_size * (m / (sqrtf(v) / bc2_sqrt + eps));
+    }
+}
+
+}  // namespace learn
+}  // namespace ssb

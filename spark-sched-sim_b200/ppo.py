@@ -39,3 +39,30 @@ class PPOLoss:
             self._scratch.data_ptr(), out.data_ptr(), g_lp.data_ptr(), g_en.data_ptr(), _stream(new_lgprob)),
             "ssb_ppo_loss")
         return out, g_lp, g_en
+
+
+class Adam:
+    """clip_grad_norm_ + torch.optim.Adam on one flat float32 device vector (TrainableScheduler.update_parameters,
+    schedulers/scheduler.py:37-54; opt_kwargs / max_grad_norm of the trainer's config).  `params` is updated in place;
+    hand it to BatchedSparkSchedSimEnv.set_decima_weights afterwards."""
+
+    def __init__(self, params: torch.Tensor, lr=3e-4, betas=(0.9, 0.999), eps=1e-8, max_grad_norm=None):
+        assert params.is_cuda and params.dtype == torch.float32 and params.is_contiguous()
+        self.params = params
+        self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
+        self.max_grad_norm = float(max_grad_norm) if max_grad_norm else 0.0
+        self.exp_avg = torch.zeros_like(params)
+        self.exp_avg_sq = torch.zeros_like(params)
+        self.grad_norm = torch.zeros(1, dtype=torch.float32, device=params.device)
+        self._scratch = torch.empty(128, dtype=torch.float64, device=params.device)
+        self.num_steps = 0
+
+    def step(self, grads: torch.Tensor):
+        assert grads.is_cuda and grads.dtype == torch.float32 and grads.is_contiguous()
+        assert grads.numel() == self.params.numel()
+        self.num_steps += 1
+        nat.check(nat.lib().ssb_adam_step(
+            self.params.data_ptr(), grads.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
+            int(self.params.numel()), self.num_steps, self.lr, self.betas[0], self.betas[1], self.eps,
+            self.max_grad_norm, self._scratch.data_ptr(), self.grad_norm.data_ptr(), _stream(grads)), "ssb_adam_step")
+        return self.grad_norm

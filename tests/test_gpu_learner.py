@@ -133,3 +133,28 @@ def test_ppo_loss_head_matches_torch_autograd(n, clip, coeff, use_idx):
     assert np.allclose(out, want, rtol=2e-5, atol=1e-7), (out, want)
     assert torch.allclose(g_lp, new.grad[sel], rtol=1e-5, atol=2e-6 / n)  # atol: f32 cancellation in torch's adv - mean
     assert torch.allclose(g_en, ent.grad[sel], rtol=1e-6, atol=0.0)
+
+
+@pytest.mark.parametrize("n,max_norm", [(20802, 0.5), (20802, None), (5, 0.5), (1 << 20, 0.5)])
+def test_adam_step_matches_torch(n, max_norm):
+    """ssb_adam_step vs clip_grad_norm_ + torch.optim.Adam over 5 consecutive updates of one flat vector
+    (20 802 = the Decima parameter count).  Tolerance 2e-6 relative + 1e-8 absolute on the parameters (torch's
+    fused arithmetic order differs in the last bit), 1e-6 relative on the gradient norm."""
+    from spark_sched_sim_b200.ppo import Adam
+
+    g = torch.Generator(device="cuda").manual_seed(n)
+    p0 = torch.randn(n, device="cuda", generator=g) * 0.1
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref], lr=3e-4)
+    mine = p0.clone()
+    adam = Adam(mine, lr=3e-4, max_grad_norm=max_norm)
+    for it in range(5):
+        grad = torch.randn(n, device="cuda", generator=g) * (10.0 if it % 2 == 0 else 1e-3)
+        ref.grad = grad.clone()
+        want_norm = torch.linalg.vector_norm(grad)
+        if max_norm:
+            torch.nn.utils.clip_grad_norm_([ref], max_norm)
+        opt.step()
+        norm = adam.step(grad)
+        assert torch.allclose(norm[0], want_norm, rtol=1e-6)
+        assert torch.allclose(mine, ref.detach(), rtol=2e-6, atol=1e-8), (it, (mine - ref.detach()).abs().max())

@@ -23,3 +23,24 @@ env2.reset_host((np.arange(32) + 9).astype(np.uint64))
 env2.rollout_fair(400, True, True, 32)
 torch.cuda.synchronize()
 print('e50 ok', env2.stats()['decisions'], (env2.hdr()['error'] != 0).sum())
+# learner-side kernels on the fused rollouts' buffers: returns (discounted, differential), group baseline, PPO loss
+# head, Adam step
+from spark_sched_sim_b200.ppo import Adam, PPOLoss
+from spark_sched_sim_b200.returns import Baseline, ReturnsCalculator
+env3 = BatchedSparkSchedSimEnv(cfg, num_envs=16, bank=synthetic_bank(0))
+env3.reset_host((np.arange(16) // 4 + 3).astype(np.uint64))
+K = 700
+traj = env3.rollout_fair_traj(K, True, auto_reset=False)
+num = torch.from_numpy(env3.stats_per_env()["decisions"].astype(np.int32)).cuda()
+final = torch.from_numpy(env3.hdr()["wall_time"].copy()).cuda()
+ret = ReturnsCalculator(beta=5e-3)(traj, num, final, K)
+diff = ReturnsCalculator(buff_cap=300)
+diff(traj, num, final, K); diff(traj, num, final, K)
+base = Baseline(4, 4)(traj, ret, num)
+n = 16 * K
+lp = torch.rand(n, device='cuda') - 2.0
+PPOLoss(0.2, 0.04)(lp, lp + 0.1, torch.rand(n, device='cuda'), ret.reshape(-1).contiguous(), base.reshape(-1).contiguous())
+prm = torch.randn(20802, device='cuda')
+Adam(prm, max_grad_norm=0.5).step(torch.randn(20802, device='cuda'))
+torch.cuda.synchronize()
+print('learner ok', int(num.sum()), float(diff.avg_num_jobs))

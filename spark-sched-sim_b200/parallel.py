@@ -47,6 +47,24 @@ def allreduce_stats(stats: dict, device: torch.device | str = "cpu", group=None)
     return {k: float(v) for k, v in zip(STAT_KEYS, vec.tolist())}
 
 
+def allreduce_gradients(grads: torch.Tensor, num_samples: int, group=None) -> tuple[torch.Tensor, int]:
+    """Data-parallel policy update: every rank holds d(sum of its samples' loss terms)/d(theta) as one flat vector
+    (the layout of ssb_set_decima_weights / ssb_adam_step; = its mini-batch size x the gradient that follows from
+    ssb_ppo_loss's adjoint seeds, which carry the local 1/n).  Sums the vectors and the sample counts over the ranks in
+    ONE all-reduce (the count rides as a last element) and divides, so that every rank steps Adam with the gradient
+    of the mean loss over all ranks' samples -- what the reference's single learner computes over all workers'
+    rollouts (trainers/ppo.py:52-70).  In place on `grads`; returns (grads, total samples)."""
+    assert grads.dim() == 1 and grads.is_floating_point()
+    buf = torch.empty(grads.numel() + 1, dtype=grads.dtype, device=grads.device)
+    buf[:-1] = grads
+    buf[-1] = float(num_samples)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    total = int(round(float(buf[-1].item())))
+    grads.copy_(buf[:-1] / max(total, 1))
+    return grads, total
+
+
 def rollout_summary(sum_job_time: float, sum_wall_time: float, num_completed: float,
                     num_arrived: float, sum_completed_duration: float) -> dict:
     """collect_stats (rollout_worker.py:122-129) from sums that can be all-reduced:

@@ -70,6 +70,37 @@ def test_two_rank_sharding_and_stats_allreduce():
     assert total["episodes"] == world * envs_per_rank
 
 
+def _grad_worker(rank, world, port, out):
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(7)
+    per_sample = torch.randn(10, 33, generator=g)  # every rank draws the same table, owns a slice of it
+    lo, hi = parallel.shard_range(10, rank, world)
+    mine = per_sample[lo:hi].sum(0)
+    avg, total = parallel.allreduce_gradients(mine.clone(), hi - lo)
+    if rank == 0:
+        out.put((avg, total, per_sample.mean(0)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_allreduce():
+    """Each rank contributes the summed gradient of its own samples and their count; every rank ends up with the
+    gradient of the mean over ALL samples."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_grad_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    avg, total, want = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert total == 10
+    assert torch.allclose(avg, want, rtol=1e-6, atol=1e-7)
+
+
 def test_shard_range_and_reference_seeds():
     for total in (1, 7, 4096, 65536):
         for world in (1, 2, 3, 8):

@@ -323,6 +323,14 @@ int ssb_get_policy_views(ssb_env *env, ssb_policy_views *out);
  *     lgprob_out / entropy_out (DEVICE f32[B], may be NULL).  The envs' state, current observation and sampling
  *     stream are left untouched. */
 int ssb_decima_snapshot_bytes(ssb_env *env, size_t *bytes);
+/* First stage of the backward pass of evaluate_actions -- the adjoint of utils.evaluate (decima/utils.py:26-42:
+ * softmax, clamp_probs, log-prob of the stored action, entropy) and of the aggregation scheduler.py:131-137: from
+ * grad_lgprob / grad_entropy (DEVICE f32[B]: d loss / d lgprob, d loss / d entropy of every env, e.g. ssb_ppo_loss's
+ * adjoint seeds) to d loss / d scores of the stage head (grad_stage_logits, DEVICE f32[B][node_stride]) and of the
+ * executor-count head (grad_exec_logits, DEVICE f32[B][exec_stride]); strides as in ssb_policy_views, zeros outside
+ * the candidates.  Uses the scores and actions of the last ssb_decima_evaluate / ssb_decima_policy call. */
+int ssb_decima_head_adjoint(ssb_env *env, const float *grad_lgprob, const float *grad_entropy,
+                            float *grad_stage_logits, float *grad_exec_logits, void *stream);
 int ssb_decima_snapshot(ssb_env *env, void *dst, void *stream);
 int ssb_decima_evaluate(ssb_env *env, const void *snapshot, const int32_t *stage_sel, const int32_t *exec_sel,
                         float *lgprob_out, float *entropy_out, void *stream);

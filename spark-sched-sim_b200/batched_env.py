@@ -378,6 +378,19 @@ class BatchedSparkSchedSimEnv:
                                              en.data_ptr(), self._stream()), "ssb_decima_evaluate")
         return lg, en
 
+    def decima_head_adjoint(self, grad_lgprob: torch.Tensor, grad_entropy: torch.Tensor):
+        """First stage of evaluate_actions' backward pass: d loss / d scores of the stage head [B, node_stride] and of
+        the executor-count head [B, exec_stride] from d loss / d lgprob, d loss / d entropy (f32[B]), for the scores
+        and actions of the last decima_evaluate / decima_policy call."""
+        for t in (grad_lgprob, grad_entropy):
+            assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() == self.num_envs
+        gs = torch.empty_like(self.pol_stage_logits)
+        ge = torch.empty_like(self.pol_exec_logits)
+        nat.check(self.L.ssb_decima_head_adjoint(self._h, grad_lgprob.data_ptr(), grad_entropy.data_ptr(),
+                                                 gs.data_ptr(), ge.data_ptr(), self._stream()),
+                  "ssb_decima_head_adjoint")
+        return gs, ge
+
     def rollout_decima(self, num_decisions, max_events=0, out: "torch.Tensor | None" = None,
                        host: "torch.Tensor | None" = None):
         """Decima rollout collection on the device: num_decisions x { decima_policy ; step } with every call's

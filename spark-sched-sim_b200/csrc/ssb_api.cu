@@ -1057,6 +1057,17 @@ int snapshot_copy(const ssb_env *env, char *buf, bool to_buf, cudaStream_t s)
 }
 }  // namespace
 
+int ssb_decima_head_adjoint(ssb_env *env, const float *grad_lgprob, const float *grad_entropy,
+                            float *grad_stage_logits, float *grad_exec_logits, void *stream)
+{
+    if (!env || !env->p.pol_w || !grad_lgprob || !grad_entropy || !grad_stage_logits || !grad_exec_logits)
+        return SSB_E_INVALID;
+    tc::k_pol_head_adjoint<<<(env->p.B + 3) / 4, 128, 0, (cudaStream_t)stream>>>(env->p, grad_lgprob, grad_entropy,
+                                                                                 grad_stage_logits, grad_exec_logits);
+    CUDA_TRY(cudaGetLastError());
+    return SSB_OK;
+}
+
 int ssb_decima_snapshot_bytes(ssb_env *env, size_t *bytes)
 {
     if (!env || !bytes || !env->p.dec_feat) return SSB_E_INVALID;

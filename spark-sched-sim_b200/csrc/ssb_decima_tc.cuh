@@ -741,5 +741,56 @@ k_pol_sample_exec(Params p, const int32_t *forced_num_exec, int32_t *stage_idx_o
     }
 }
 
+// ------------------------------------------------------------------ backward pass, first stage
+// Adjoint of utils.evaluate (decima/utils.py:26-42) + the aggregation in evaluate_actions (scheduler.py:131-137):
+// from d loss / d lgprob and d loss / d entropy of every env's stored action to d loss / d scores of the two heads.
+//   p = softmax(z), q = clamp(p, eps, 1 - eps), lgprob = log q_a, H = -sum_j q_j log q_j
+//   G_j = d loss / d p_j = g_lp [j == a] / q_a - g_H (log q_j + 1), both terms only where p_j is not clamped
+//   d loss / d z_i = p_i (G_i - sum_j G_j p_j)
+__device__ inline void softmax_adjoint_w(const float *z, int n, int sel, float g_lp, float g_h, int lane, float *dz)
+{
+    const float eps = 1.1920929e-07f;
+    float mx = -INFINITY;
+    for (int i = lane; i < n; i += 32) mx = fmaxf(mx, z[i]);
+    for (int off = 16; off; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, off));
+    float sum = 0.0f;
+    for (int i = lane; i < n; i += 32) sum += expf(z[i] - mx);
+    for (int off = 16; off; off >>= 1) sum += __shfl_xor_sync(FULL, sum, off);
+    auto G = [&](int i, float pr) {
+        const bool inside = pr >= eps && pr <= 1.0f - eps;
+        if (!inside) return 0.0f;
+        float g = -g_h * (logf(pr) + 1.0f);
+        if (i == sel) g += g_lp / pr;
+        return g;
+    };
+    float dot = 0.0f;
+    for (int i = lane; i < n; i += 32) {
+        const float pr = expf(z[i] - mx) / sum;
+        dot += G(i, pr) * pr;
+    }
+    for (int off = 16; off; off >>= 1) dot += __shfl_xor_sync(FULL, dot, off);
+    for (int i = lane; i < n; i += 32) {
+        const float pr = expf(z[i] - mx) / sum;
+        dz[i] = pr * (G(i, pr) - dot);
+    }
+}
+__global__ void __launch_bounds__(128)
+k_pol_head_adjoint(Params p, const float *grad_lgprob, const float *grad_entropy, float *grad_stage, float *grad_exec)
+{
+    const int b = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= p.B) return;
+    float *ds = grad_stage + (size_t)b * p.Sc, *de = grad_exec + (size_t)b * p.Epad;
+    const int32_t *act = p.pol_action + (size_t)b * 4;
+    const int n_cand = act[3], job_idx = act[1];
+    const int cap = job_idx >= 0 ? p.dec_caps[(size_t)b * p.Jc + job_idx] : 0;
+    const int N = p.obs_hdr[b].num_nodes;
+    for (int i = lane; i < p.Sc; i += 32) ds[i] = 0.0f;
+    for (int i = lane; i < p.Epad; i += 32) de[i] = 0.0f;
+    if (n_cand <= 0 || N <= 0) return;
+    const float g_lp = grad_lgprob[b], g_h = grad_entropy[b] / logf((float)(p.E * N));
+    softmax_adjoint_w(p.pol_stage_logits + (size_t)b * p.Sc, n_cand, act[0], g_lp, g_h, lane, ds);
+    if (cap > 0) softmax_adjoint_w(p.pol_exec_logits + (size_t)b * p.Epad, cap, act[2], g_lp, g_h, lane, de);
+}
+
 }  // namespace tc
 }  // namespace ssb

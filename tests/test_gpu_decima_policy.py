@@ -230,3 +230,49 @@ def test_evaluate_actions_on_stored_observations(bank):
         assert torch.equal(lg, lgs[k]) and torch.equal(en, ens[k]), k
     assert np.array_equal(env.hdr()["wall_time"], twin.hdr()["wall_time"])
     assert torch.isfinite(torch.stack(ens)).all() and (torch.stack(ens) >= 0).all()
+
+
+def test_head_adjoint_matches_torch_autograd(bank):
+    """ssb_decima_head_adjoint (first stage of evaluate_actions' backward pass) vs autograd through the reference's
+    utils.evaluate written in plain torch fp32 (softmax, clamp_probs, log-prob of the stored action, entropy,
+    normalisation by log(num_executors * num_nodes)) on the scores the device produced.  Tolerance: 1e-5 relative
+    + 1e-7 absolute on every score gradient; zero outside the candidates."""
+    from torch.distributions.utils import clamp_probs
+
+    from spark_sched_sim_b200.batched_env import BatchedSparkSchedSimEnv
+
+    B, E = 48, 10
+    cfg = {"num_executors": E, "job_arrival_cap": 10, "job_arrival_rate": 4.0e-5,
+           "moving_delay": 2000.0, "warmup_delay": 1000.0}
+    env = BatchedSparkSchedSimEnv(cfg, num_envs=B, bank=bank, decima_policy=True)
+    env.set_decima_weights(weights())
+    env.reset_host(np.arange(B, dtype=np.uint64) + 77)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for k in range(30):
+        a, n = env.decima_policy()
+        if k in (0, 12, 29):
+            g_lp = torch.randn(B, device="cuda", generator=g)
+            g_en = torch.randn(B, device="cuda", generator=g)
+            gs, ge = env.decima_head_adjoint(g_lp, g_en)
+            act = env.pol_action.cpu().numpy()
+            caps = env.dec_commit_caps.cpu().numpy()
+            hdr = env.hdr()
+            for b in range(B):
+                n_cand, job, N = int(act[b, 3]), int(act[b, 1]), int(hdr["num_nodes"][b])
+                if n_cand <= 0:
+                    assert not gs[b].any() and not ge[b].any()
+                    continue
+                cap = int(caps[b, job])
+                zs = env.pol_stage_logits[b, :n_cand].clone().requires_grad_()
+                ze = env.pol_exec_logits[b, :cap].clone().requires_grad_()
+                lg = en = 0.0
+                for z, sel in ((zs, int(act[b, 0])), (ze, int(act[b, 2]))):
+                    q = clamp_probs(torch.softmax(z, 0))
+                    lg = lg + q.log()[sel]
+                    en = en - (q.log() * q).sum()
+                en = en / torch.log(torch.tensor(float(E * N), device="cuda"))
+                (g_lp[b] * lg + g_en[b] * en).backward()
+                assert torch.allclose(gs[b, :n_cand], zs.grad, rtol=1e-5, atol=1e-7), (k, b)
+                assert torch.allclose(ge[b, :cap], ze.grad, rtol=1e-5, atol=1e-7), (k, b)
+                assert not gs[b, n_cand:].any() and not ge[b, cap:].any()
+        env.step(a, n)

@@ -322,6 +322,18 @@ int ssb_get_policy_views(ssb_env *env, ssb_policy_views *out);
  *     Decima's format: stage_idx = index among the schedulable stages, num_exec in [0, cap)) and writes
  *     lgprob_out / entropy_out (DEVICE f32[B], may be NULL).  The envs' state, current observation and sampling
  *     stream are left untouched. */
+/* Second stage: backward of the two score heads' MLPs (StagePolicyNetwork / ExecPolicyNetwork,
+ * scheduler.py:279-385) for the candidates of the last ssb_decima_evaluate / ssb_decima_policy call.
+ * grad_weights (DEVICE f32[20 802], the ssb_set_decima_weights layout) is ACCUMULATED into (zero it first).
+ * grad_stage_inputs (DEVICE f32[num stage candidates][56], may be NULL) / grad_exec_inputs (DEVICE
+ * f32[num executor-count rows][40], may be NULL) receive d loss / d input row in list order (stage rows: node
+ * features 5, node embedding 16, job embedding 16, global embedding 16, padding; executor-count rows: 3 job
+ * features, job embedding 16, global embedding 16, count / E, padding); stage_inputs / exec_inputs (same shapes, may
+ * be NULL) the gathered input rows themselves.  num_rows (HOST int32[2], may be NULL) = the two row counts; the
+ * call synchronises the stream when it is given. */
+int ssb_decima_head_backward(ssb_env *env, const float *grad_stage_logits, const float *grad_exec_logits,
+                             float *grad_weights, float *grad_stage_inputs, float *grad_exec_inputs,
+                             float *stage_inputs, float *exec_inputs, int32_t *num_rows, void *stream);
 int ssb_decima_snapshot_bytes(ssb_env *env, size_t *bytes);
 /* First stage of the backward pass of evaluate_actions -- the adjoint of utils.evaluate (decima/utils.py:26-42:
  * softmax, clamp_probs, log-prob of the stored action, entropy) and of the aggregation scheduler.py:131-137: from

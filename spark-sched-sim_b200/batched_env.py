@@ -391,6 +391,27 @@ class BatchedSparkSchedSimEnv:
                   "ssb_decima_head_adjoint")
         return gs, ge
 
+    def decima_head_backward(self, grad_stage_logits: torch.Tensor, grad_exec_logits: torch.Tensor,
+                             grad_weights: torch.Tensor, want_inputs: bool = False):
+        """Second stage of the backward pass: the two score heads' MLPs.  Accumulates their weight / bias gradients
+        into grad_weights (f32[20802], ABI layout) and returns d loss / d input row of the stage head
+        [num candidates, 56] and of the executor-count head [num rows, 40] (list order); with want_inputs also the
+        gathered input rows."""
+        assert grad_weights.is_cuda and grad_weights.dtype == torch.float32 and grad_weights.numel() == 20802
+        B = self.num_envs
+        S, Ep = self.pol_stage_logits.shape[1], self.pol_exec_logits.shape[1]
+        gxs = torch.zeros(B * S, 56, dtype=torch.float32, device=self.device)
+        gxe = torch.zeros(B * Ep, 40, dtype=torch.float32, device=self.device)
+        xs = torch.zeros_like(gxs) if want_inputs else None
+        xe = torch.zeros_like(gxe) if want_inputs else None
+        n = (C.c_int32 * 2)()
+        nat.check(self.L.ssb_decima_head_backward(
+            self._h, grad_stage_logits.data_ptr(), grad_exec_logits.data_ptr(), grad_weights.data_ptr(),
+            gxs.data_ptr(), gxe.data_ptr(), xs.data_ptr() if want_inputs else None,
+            xe.data_ptr() if want_inputs else None, n, self._stream()), "ssb_decima_head_backward")
+        out = (gxs[:n[0]], gxe[:n[1]])
+        return out + (xs[:n[0]], xe[:n[1]]) if want_inputs else out
+
     def rollout_decima(self, num_decisions, max_events=0, out: "torch.Tensor | None" = None,
                        host: "torch.Tensor | None" = None):
         """Decima rollout collection on the device: num_decisions x { decima_policy ; step } with every call's

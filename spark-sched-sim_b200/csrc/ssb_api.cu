@@ -1068,6 +1068,38 @@ int ssb_decima_head_adjoint(ssb_env *env, const float *grad_lgprob, const float 
     return SSB_OK;
 }
 
+int ssb_decima_head_backward(ssb_env *env, const float *grad_stage_logits, const float *grad_exec_logits,
+                             float *grad_weights, float *grad_stage_inputs, float *grad_exec_inputs,
+                             float *stage_inputs, float *exec_inputs, int32_t *num_rows, void *stream)
+{
+    if (!env || !env->p.pol_w || !grad_stage_logits || !grad_exec_logits || !grad_weights) return SSB_E_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    const Params &p = env->p;
+    static bool prepared = false;
+    if (!prepared) {
+        CUDA_TRY(cudaFuncSetAttribute(tc::k_mlp_backward<tc::ST_STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)tc::BwdSmem<tc::ST_STAGE>::BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(tc::k_mlp_backward<tc::ST_EXEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)tc::BwdSmem<tc::ST_EXEC>::BYTES));
+        prepared = true;
+    }
+    tc::TileArgs as{nullptr, nullptr, p.pl_cnt + tc::CNT_CAND, 0};
+    tc::k_mlp_backward<tc::ST_STAGE><<<env->num_sms, 128, tc::BwdSmem<tc::ST_STAGE>::BYTES, s>>>(
+        p, as, grad_stage_logits, grad_stage_inputs, stage_inputs, grad_weights);
+    tc::TileArgs ae{p.pl_exec, nullptr, p.pl_cnt + tc::CNT_EXEC, 0};
+    tc::k_mlp_backward<tc::ST_EXEC><<<env->num_sms, 128, tc::BwdSmem<tc::ST_EXEC>::BYTES, s>>>(
+        p, ae, grad_exec_logits, grad_exec_inputs, exec_inputs, grad_weights);
+    CUDA_TRY(cudaGetLastError());
+    if (num_rows) {
+        int32_t c[tc::CNT_OVERFLOW + 1];
+        CUDA_TRY(cudaMemcpyAsync(c, p.pl_cnt, sizeof(c), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        num_rows[0] = c[tc::CNT_CAND];
+        num_rows[1] = c[tc::CNT_EXEC];
+    }
+    return SSB_OK;
+}
+
 int ssb_decima_snapshot_bytes(ssb_env *env, size_t *bytes)
 {
     if (!env || !bytes || !env->p.dec_feat) return SSB_E_INVALID;

@@ -18,6 +18,14 @@ constexpr int mlp(int in, int h1, int h2, int out) { return h1 * in + h1 + h2 * 
 constexpr int TOTAL = mlp(5, 32, 16, 16) + 2 * mlp(16, 32, 16, 16) + mlp(21, 32, 16, 16) + mlp(16, 32, 16, 16) +
                       mlp(53, 64, 64, 1) + mlp(36, 64, 64, 1);
 static_assert(TOTAL == 20802, "Decima parameter count");
+// offsets of the seven MLPs in the ABI vector (W1 [h1][in], b1, W2 [h2][h1], b2, W3 [out][h2], b3 each)
+constexpr int PREP = 0;
+constexpr int MSG = PREP + mlp(5, 32, 16, 16);
+constexpr int UPD = MSG + mlp(16, 32, 16, 16);
+constexpr int DAG = UPD + mlp(16, 32, 16, 16);
+constexpr int GLOB = DAG + mlp(21, 32, 16, 16);
+constexpr int STAGE = GLOB + mlp(16, 32, 16, 16);
+constexpr int EXEC = STAGE + mlp(53, 64, 64, 1);
 }  // namespace dw
 namespace dd {
 __host__ __device__ constexpr int pad4(int n) { return (n + 3) & ~3; }

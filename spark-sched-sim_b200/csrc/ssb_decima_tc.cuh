@@ -792,5 +792,155 @@ k_pol_head_adjoint(Params p, const float *grad_lgprob, const float *grad_entropy
     if (cap > 0) softmax_adjoint_w(p.pol_exec_logits + (size_t)b * p.Epad, cap, act[2], g_lp, g_h, lane, de);
 }
 
+// ------------------------------------------------------------------ backward pass, second stage: one MLP
+// Backward of one three-layer MLP over a row list (the same lists and gathers as the forward tile pass), first
+// correct version on the CUDA cores in fp32: per 128-row tile the forward activations are recomputed into shared
+// memory, the deltas are propagated per row (thread r <-> row r), and the weight / bias gradients of the tile --
+// sums over its rows of activation x delta -- are added to the flat gradient vector (ABI layout of
+// ssb_set_decima_weights) with atomics.  d loss / d input row goes to dX [rows][K0] in list order, the gathered
+// input rows optionally to X_out (what a later stage needs to scatter / chain).
+template <int ST> struct DwOffset;
+template <> struct DwOffset<ST_PREP>  { static constexpr int V = dw::PREP; };
+template <> struct DwOffset<ST_SINK>  { static constexpr int V = dw::UPD; };
+template <> struct DwOffset<ST_MSG>   { static constexpr int V = dw::MSG; };
+template <> struct DwOffset<ST_RCV>   { static constexpr int V = dw::UPD; };
+template <> struct DwOffset<ST_DAG>   { static constexpr int V = dw::DAG; };
+template <> struct DwOffset<ST_GLOB>  { static constexpr int V = dw::GLOB; };
+template <> struct DwOffset<ST_STAGE> { static constexpr int V = dw::STAGE; };
+template <> struct DwOffset<ST_EXEC>  { static constexpr int V = dw::EXEC; };
+
+template <int ST>
+struct BwdSmem {
+    using S = Spec<ST>;
+    static constexpr int SX = S::K0 + 1, S1 = S::H1 + 1, S2 = S::H2 + 1, S3 = S::OUT | 1;  // odd strides: no conflicts
+    static constexpr int X = 0, A1 = X + 128 * SX, A2 = A1 + 128 * S1, D1 = A2 + 128 * S2, D2 = D1 + 128 * S1;
+    static constexpr int D3 = D2 + 128 * S2, W = D3 + 128 * S3;
+    static constexpr int WN = dd::mlp(S::IN, S::H1, S::H2, S::OUT);
+    static constexpr size_t BYTES = (size_t)(W + WN) * 4;
+};
+
+template <bool TANH>
+__device__ __forceinline__ float dact_tc(float a)  // derivative from the activation's OUTPUT
+{
+    if (TANH) return 1.0f - a * a;
+    return a > 0.0f ? 1.0f : 0.2f;
+}
+// d loss / d output o of row (row, id)
+template <int ST>
+__device__ __forceinline__ float upstream(const Params &p, const float *g_out, int row, int id, int o)
+{
+    using S = Spec<ST>;
+    if (id < 0) return 0.0f;
+    if constexpr (ST == ST_STAGE) return g_out[p.pl_cand_out[id]];
+    else if constexpr (ST == ST_EXEC) return g_out[id];
+    else return g_out[(size_t)row * S::OUT + o];
+}
+
+template <int ST>
+__global__ void __launch_bounds__(128)
+k_mlp_backward(Params p, TileArgs a, const float *g_out, float *dX, float *X_out, float *dW)
+{
+    using S = Spec<ST>;
+    using L = BwdSmem<ST>;
+    extern __shared__ float bsm[];
+    const int n_rows = *a.count;
+    if (n_rows <= 0) return;
+    const int32_t *list = a.list + (a.offset ? *a.offset : 0);
+    const int n_tiles = (n_rows + 127) >> 7, tid = threadIdx.x;
+    if ((int)blockIdx.x >= n_tiles) return;
+    float *X = bsm + L::X, *A1 = bsm + L::A1, *A2 = bsm + L::A2, *D1 = bsm + L::D1, *D2 = bsm + L::D2, *D3 = bsm + L::D3;
+    float *W = bsm + L::W;
+    for (int i = tid; i < L::WN; i += 128) W[i] = p.pol_w[S::W + i];
+    // dd layout: per layer the transposed weight [in][out], then the bias, each padded to 4 floats
+    const float *w1 = W, *b1 = w1 + dd::pad4(S::IN * S::H1);
+    const float *w2 = W + dd::layer(S::IN, S::H1), *b2 = w2 + dd::pad4(S::H1 * S::H2);
+    const float *w3 = w2 + dd::layer(S::H1, S::H2), *b3 = w3 + dd::pad4(S::H2 * S::OUT);
+    (void)b3;
+    float *g = dW + DwOffset<ST>::V;  // ABI layout: W1 [H1][IN], b1, W2 [H2][H1], b2, W3 [OUT][H2], b3
+    constexpr int G_B1 = S::H1 * S::IN, G_W2 = G_B1 + S::H1, G_B2 = G_W2 + S::H2 * S::H1, G_W3 = G_B2 + S::H2,
+                  G_B3 = G_W3 + S::OUT * S::H2;
+    __syncthreads();
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int row = tile * 128 + tid;
+        int id = -1;
+        if (row < n_rows) id = (ST == ST_STAGE) ? row : list[row];
+        {
+            float in[S::K0];
+            gather_row<ST>(p, a, id, in);
+#pragma unroll
+            for (int k = 0; k < S::K0; k++) X[tid * L::SX + k] = in[k];
+            if (X_out && row < n_rows) {
+#pragma unroll
+                for (int k = 0; k < S::K0; k++) X_out[(size_t)row * S::K0 + k] = in[k];
+            }
+        }
+        // forward (recomputed)
+        for (int i = 0; i < S::H1; i++) {
+            float s = b1[i];
+            for (int k = 0; k < S::IN; k++) s = fmaf(X[tid * L::SX + k], w1[k * S::H1 + i], s);
+            A1[tid * L::S1 + i] = act_tc<S::TANH>(s);
+        }
+        for (int j = 0; j < S::H2; j++) {
+            float s = b2[j];
+            for (int i = 0; i < S::H1; i++) s = fmaf(A1[tid * L::S1 + i], w2[i * S::H2 + j], s);
+            A2[tid * L::S2 + j] = act_tc<S::TANH>(s);
+        }
+        // backward, this thread's row
+        for (int o = 0; o < S::OUT; o++) D3[tid * L::S3 + o] = upstream<ST>(p, g_out, row, id, o);
+        for (int j = 0; j < S::H2; j++) {
+            float s = 0.0f;
+            for (int o = 0; o < S::OUT; o++) s = fmaf(w3[j * S::OUT + o], D3[tid * L::S3 + o], s);
+            D2[tid * L::S2 + j] = s * dact_tc<S::TANH>(A2[tid * L::S2 + j]);
+        }
+        for (int i = 0; i < S::H1; i++) {
+            float s = 0.0f;
+            for (int j = 0; j < S::H2; j++) s = fmaf(w2[i * S::H2 + j], D2[tid * L::S2 + j], s);
+            D1[tid * L::S1 + i] = s * dact_tc<S::TANH>(A1[tid * L::S1 + i]);
+        }
+        if (dX && row < n_rows) {
+            for (int k = 0; k < S::K0; k++) {
+                float s = 0.0f;
+                if (k < S::IN)
+                    for (int i = 0; i < S::H1; i++) s = fmaf(w1[k * S::H1 + i], D1[tid * L::S1 + i], s);
+                dX[(size_t)row * S::K0 + k] = s;
+            }
+        }
+        __syncthreads();
+        // the tile's weight and bias gradients: sums over its 128 rows
+        for (int idx = tid; idx < S::IN * S::H1; idx += 128) {
+            const int k = idx / S::H1, i = idx - k * S::H1;
+            float s = 0.0f;
+            for (int r = 0; r < 128; r++) s = fmaf(X[r * L::SX + k], D1[r * L::S1 + i], s);
+            atomicAdd(g + i * S::IN + k, s);
+        }
+        for (int idx = tid; idx < S::H1 * S::H2; idx += 128) {
+            const int i = idx / S::H2, j = idx - i * S::H2;
+            float s = 0.0f;
+            for (int r = 0; r < 128; r++) s = fmaf(A1[r * L::S1 + i], D2[r * L::S2 + j], s);
+            atomicAdd(g + G_W2 + j * S::H1 + i, s);
+        }
+        for (int idx = tid; idx < S::H2 * S::OUT; idx += 128) {
+            const int j = idx / S::OUT, o = idx - j * S::OUT;
+            float s = 0.0f;
+            for (int r = 0; r < 128; r++) s = fmaf(A2[r * L::S2 + j], D3[r * L::S3 + o], s);
+            atomicAdd(g + G_W3 + o * S::H2 + j, s);
+        }
+        for (int idx = tid; idx < S::H1 + S::H2 + S::OUT; idx += 128) {
+            float s = 0.0f;
+            if (idx < S::H1) {
+                for (int r = 0; r < 128; r++) s += D1[r * L::S1 + idx];
+                atomicAdd(g + G_B1 + idx, s);
+            } else if (idx < S::H1 + S::H2) {
+                for (int r = 0; r < 128; r++) s += D2[r * L::S2 + idx - S::H1];
+                atomicAdd(g + G_B2 + idx - S::H1, s);
+            } else {
+                for (int r = 0; r < 128; r++) s += D3[r * L::S3 + idx - S::H1 - S::H2];
+                atomicAdd(g + G_B3 + idx - S::H1 - S::H2, s);
+            }
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace tc
 }  // namespace ssb

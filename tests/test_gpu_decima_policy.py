@@ -276,3 +276,52 @@ def test_head_adjoint_matches_torch_autograd(bank):
                 assert torch.allclose(ge[b, :cap], ze.grad, rtol=1e-5, atol=1e-7), (k, b)
                 assert not gs[b, n_cand:].any() and not ge[b, cap:].any()
         env.step(a, n)
+
+
+def test_head_mlp_backward_matches_torch_autograd(bank):
+    """ssb_decima_head_backward (backward of the stage / executor-count score MLPs on the candidates' rows) vs torch
+    autograd through the same MLPs in fp32 on the gathered input rows the kernel reports.  The upstream gradient of a
+    score is a function of the score itself (sin(3 s)), so no row order has to be assumed: the recomputed scores
+    equal the device's as a multiset (1e-5); d loss / d input rows, weight and bias gradients agree within 2e-4 of
+    each tensor's largest entry (the tcgen05 and torch scores differ by ~1e-6, fp32 atomics over ~1e3 rows)."""
+    from spark_sched_sim_b200.batched_env import BatchedSparkSchedSimEnv
+
+    B, E = 48, 10
+    cfg = {"num_executors": E, "job_arrival_cap": 10, "job_arrival_rate": 4.0e-5,
+           "moving_delay": 2000.0, "warmup_delay": 1000.0}
+    env = BatchedSparkSchedSimEnv(cfg, num_envs=B, bank=bank, decima_policy=True)
+    w = weights()
+    env.set_decima_weights(w)
+    env.reset_host(np.arange(B, dtype=np.uint64) + 91)
+    keys = list(w.keys())
+    flat_off = np.concatenate([[0], np.cumsum([w[k].size for k in keys])])
+    for k in range(25):
+        a, n = env.decima_policy()
+        if k in (3, 24):
+            gs = torch.sin(3.0 * env.pol_stage_logits)
+            ge = torch.sin(3.0 * env.pol_exec_logits)
+            gw = torch.zeros(20802, device="cuda")
+            dxs, dxe, xs, xe = env.decima_head_backward(gs, ge, gw, want_inputs=True)
+            act = env.pol_action.cpu().numpy()
+            caps = env.dec_commit_caps.cpu().numpy()
+            dev_scores = {
+                "stage": torch.cat([env.pol_stage_logits[b, :act[b, 3]] for b in range(B)]),
+                "exec": torch.cat([env.pol_exec_logits[b, :caps[b, act[b, 1]]] for b in range(B) if act[b, 1] >= 0])}
+            for first, X, dX, in_dim, mode in ((30, xs, dxs, 53, "stage"), (36, xe, dxe, 36, "exec")):
+                Ws = [torch.from_numpy(w[keys[first + i]]).cuda().requires_grad_() for i in range(6)]
+                Xt = X[:, :in_dim].clone().requires_grad_()
+                h = torch.tanh(Xt @ Ws[0].T + Ws[1])
+                h = torch.tanh(h @ Ws[2].T + Ws[3])
+                out = (h @ Ws[4].T + Ws[5]).squeeze(1)
+                assert out.numel() == dev_scores[mode].numel() > 0
+                assert torch.allclose(torch.sort(out.detach())[0], torch.sort(dev_scores[mode])[0], rtol=1e-5, atol=1e-5)
+                (out * torch.sin(3.0 * out.detach())).sum().backward()
+                # (the two sides' scores differ by ~1e-6, and so do their sin(3 s): compare against the largest entry)
+                tol = 2e-4 * float(Xt.grad.abs().max()) + 1e-6
+                assert float((dX[:, :in_dim] - Xt.grad).abs().max()) <= tol, (k, mode)
+                assert not dX[:, in_dim:].any()
+                for i in range(6):
+                    got = gw[flat_off[first + i]:flat_off[first + i + 1]].view(Ws[i].shape)
+                    tol = 2e-4 * float(Ws[i].grad.abs().max()) + 1e-6
+                    assert float((got - Ws[i].grad).abs().max()) <= tol, (k, mode, keys[first + i])
+        env.step(a, n)

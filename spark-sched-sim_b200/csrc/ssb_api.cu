@@ -471,6 +471,35 @@ struct ssb_env {
     uint64_t auto_seed_step;
 };
 
+struct BackwardScratch { float *gs, *ge, *d_hdag, *d_hglob; size_t floats; };
+BackwardScratch backward_scratch(const Params &p, float *base)
+{
+    BackwardScratch b{};
+    size_t off = 0;
+    auto take = [&](size_t n) { float *q = base ? base + off : nullptr; off += (n + 63) & ~size_t(63); return q; };
+    b.gs = take((size_t)p.B * p.Sc);
+    b.ge = take((size_t)p.B * p.Epad);
+    b.d_hdag = take((size_t)p.B * p.Jc * 16);
+    b.d_hglob = take((size_t)p.B * 16);
+    b.floats = off;
+    return b;
+}
+template <int ST>
+int launch_mlp_backward(ssb_env *env, const int32_t *list, const int32_t *count, const float *g_out, float *dW,
+                        tc::BwdBufs bw, cudaStream_t s)
+{
+    static bool prepared = false;
+    if (!prepared) {
+        CUDA_TRY(cudaFuncSetAttribute(tc::k_mlp_backward<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)tc::BwdSmem<ST>::BYTES));
+        prepared = true;
+    }
+    tc::TileArgs a{list, nullptr, count, 0};
+    tc::k_mlp_backward<ST><<<env->num_sms, 128, tc::BwdSmem<ST>::BYTES, s>>>(env->p, a, g_out, nullptr, nullptr, dW, bw);
+    CUDA_TRY(cudaGetLastError());
+    return SSB_OK;
+}
+
 template <int ST>
 int launch_tile(ssb_env *env, const int32_t *list, const int32_t *offset, const int32_t *count, int level,
                 int ctas_per_sm, cudaStream_t s)
@@ -1085,10 +1114,10 @@ int ssb_decima_head_backward(ssb_env *env, const float *grad_stage_logits, const
     }
     tc::TileArgs as{nullptr, nullptr, p.pl_cnt + tc::CNT_CAND, 0};
     tc::k_mlp_backward<tc::ST_STAGE><<<env->num_sms, 128, tc::BwdSmem<tc::ST_STAGE>::BYTES, s>>>(
-        p, as, grad_stage_logits, grad_stage_inputs, stage_inputs, grad_weights);
+        p, as, grad_stage_logits, grad_stage_inputs, stage_inputs, grad_weights, tc::BwdBufs{nullptr, nullptr, nullptr});
     tc::TileArgs ae{p.pl_exec, nullptr, p.pl_cnt + tc::CNT_EXEC, 0};
     tc::k_mlp_backward<tc::ST_EXEC><<<env->num_sms, 128, tc::BwdSmem<tc::ST_EXEC>::BYTES, s>>>(
-        p, ae, grad_exec_logits, grad_exec_inputs, exec_inputs, grad_weights);
+        p, ae, grad_exec_logits, grad_exec_inputs, exec_inputs, grad_weights, tc::BwdBufs{nullptr, nullptr, nullptr});
     CUDA_TRY(cudaGetLastError());
     if (num_rows) {
         int32_t c[tc::CNT_OVERFLOW + 1];
@@ -1097,6 +1126,37 @@ int ssb_decima_head_backward(ssb_env *env, const float *grad_stage_logits, const
         num_rows[0] = c[tc::CNT_CAND];
         num_rows[1] = c[tc::CNT_EXEC];
     }
+    return SSB_OK;
+}
+
+int ssb_decima_backward_bytes(ssb_env *env, size_t *bytes)
+{
+    if (!env || !bytes || !env->p.pol_w) return SSB_E_INVALID;
+    *bytes = backward_scratch(env->p, nullptr).floats * sizeof(float);
+    return SSB_OK;
+}
+
+int ssb_decima_backward(ssb_env *env, const float *grad_lgprob, const float *grad_entropy, float *grad_weights,
+                        float *grad_node_embeddings, void *scratch, void *stream)
+{
+    if (!env || !env->p.pol_w || !grad_lgprob || !grad_entropy || !grad_weights || !grad_node_embeddings || !scratch ||
+        (reinterpret_cast<uintptr_t>(scratch) & 15))
+        return SSB_E_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    const Params &p = env->p;
+    const BackwardScratch b = backward_scratch(p, static_cast<float *>(scratch));
+    CUDA_TRY(cudaMemsetAsync(grad_node_embeddings, 0, sizeof(float) * (size_t)p.B * p.Sc * 16, s));
+    CUDA_TRY(cudaMemsetAsync(b.d_hdag, 0, sizeof(float) * (size_t)p.B * p.Jc * 16, s));
+    CUDA_TRY(cudaMemsetAsync(b.d_hglob, 0, sizeof(float) * (size_t)p.B * 16, s));
+    tc::k_pol_head_adjoint<<<(p.B + 3) / 4, 128, 0, s>>>(p, grad_lgprob, grad_entropy, b.gs, b.ge);
+    CUDA_TRY(cudaGetLastError());
+    const tc::BwdBufs bw{grad_node_embeddings, b.d_hdag, b.d_hglob};
+    int rc;
+    // heads first (their input gradients feed all three summaries), then the global summary, then the job summaries
+    if ((rc = launch_mlp_backward<tc::ST_STAGE>(env, nullptr, p.pl_cnt + tc::CNT_CAND, b.gs, grad_weights, bw, s))) return rc;
+    if ((rc = launch_mlp_backward<tc::ST_EXEC>(env, p.pl_exec, p.pl_cnt + tc::CNT_EXEC, b.ge, grad_weights, bw, s))) return rc;
+    if ((rc = launch_mlp_backward<tc::ST_GLOB>(env, p.pl_jobs, p.pl_cnt + tc::CNT_JOBS, nullptr, grad_weights, bw, s))) return rc;
+    if ((rc = launch_mlp_backward<tc::ST_DAG>(env, p.pl_all, p.pl_cnt + tc::CNT_ALL, nullptr, grad_weights, bw, s))) return rc;
     return SSB_OK;
 }
 

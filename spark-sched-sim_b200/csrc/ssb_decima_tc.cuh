@@ -825,20 +825,66 @@ __device__ __forceinline__ float dact_tc(float a)  // derivative from the activa
     if (TANH) return 1.0f - a * a;
     return a > 0.0f ? 1.0f : 0.2f;
 }
+// gradients with respect to the encoder's outputs, accumulated while the backward pass walks up the network
+struct BwdBufs {
+    float *d_h;      // [B][Sc][16]  node embeddings (NodeEncoder's output)
+    float *d_hdag;   // [B][Jc][16]  job summaries
+    float *d_hglob;  // [B][16]      global summary
+};
+__device__ __forceinline__ int job_of_node(const Params &p, int b, int n)
+{
+    const int32_t *dag_ptr = p.obs_dag_ptr + (size_t)b * (p.Jc + 1);
+    int lo = 0, hi = p.obs_hdr[b].num_active_jobs;
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (dag_ptr[mid] <= n) lo = mid; else hi = mid; }
+    return lo;
+}
 // d loss / d output o of row (row, id)
 template <int ST>
-__device__ __forceinline__ float upstream(const Params &p, const float *g_out, int row, int id, int o)
+__device__ __forceinline__ float upstream(const Params &p, const float *g_out, const BwdBufs &bw, int row, int id, int o)
 {
     using S = Spec<ST>;
     if (id < 0) return 0.0f;
     if constexpr (ST == ST_STAGE) return g_out[p.pl_cand_out[id]];
     else if constexpr (ST == ST_EXEC) return g_out[id];
-    else return g_out[(size_t)row * S::OUT + o];
+    else if constexpr (ST == ST_GLOB) return g_out ? g_out[(size_t)row * S::OUT + o] : bw.d_hglob[(size_t)(id / p.Jc) * 16 + o];
+    else if constexpr (ST == ST_DAG) {
+        if (g_out) return g_out[(size_t)row * S::OUT + o];
+        const int b = id / p.Sc;
+        return bw.d_hdag[((size_t)b * p.Jc + job_of_node(p, b, id - b * p.Sc)) * 16 + o];
+    } else return g_out[(size_t)row * S::OUT + o];
+}
+// where a row's input gradient goes (the adjoint of gather_row)
+template <int ST>
+__device__ __forceinline__ void consume_dx(const Params &p, const BwdBufs &bw, int id, const float *dx)
+{
+    if (id < 0) return;
+    if constexpr (ST == ST_STAGE) {
+        if (!bw.d_h) return;
+        const int node = p.pl_cand[id], jid = p.pl_cand_job[id], b = node / p.Sc;
+        for (int i = 0; i < 16; i++) {
+            atomicAdd(bw.d_h + (size_t)node * 16 + i, dx[5 + i]);
+            atomicAdd(bw.d_hdag + (size_t)jid * 16 + i, dx[21 + i]);
+            atomicAdd(bw.d_hglob + (size_t)b * 16 + i, dx[37 + i]);
+        }
+    } else if constexpr (ST == ST_EXEC) {
+        if (!bw.d_hdag) return;
+        const int b = id / p.Epad, job_idx = p.pol_action[(size_t)b * 4 + 1];
+        for (int i = 0; i < 16; i++) {
+            atomicAdd(bw.d_hdag + ((size_t)b * p.Jc + job_idx) * 16 + i, dx[3 + i]);
+            atomicAdd(bw.d_hglob + (size_t)b * 16 + i, dx[19 + i]);
+        }
+    } else if constexpr (ST == ST_GLOB) {
+        if (!bw.d_hdag) return;
+        for (int i = 0; i < 16; i++) atomicAdd(bw.d_hdag + (size_t)id * 16 + i, dx[i]);
+    } else if constexpr (ST == ST_DAG) {
+        if (!bw.d_h) return;
+        for (int i = 0; i < 16; i++) atomicAdd(bw.d_h + (size_t)id * 16 + i, dx[5 + i]);
+    }
 }
 
 template <int ST>
 __global__ void __launch_bounds__(128)
-k_mlp_backward(Params p, TileArgs a, const float *g_out, float *dX, float *X_out, float *dW)
+k_mlp_backward(Params p, TileArgs a, const float *g_out, float *dX, float *X_out, float *dW, BwdBufs bw)
 {
     using S = Spec<ST>;
     using L = BwdSmem<ST>;
@@ -886,7 +932,7 @@ k_mlp_backward(Params p, TileArgs a, const float *g_out, float *dX, float *X_out
             A2[tid * L::S2 + j] = act_tc<S::TANH>(s);
         }
         // backward, this thread's row
-        for (int o = 0; o < S::OUT; o++) D3[tid * L::S3 + o] = upstream<ST>(p, g_out, row, id, o);
+        for (int o = 0; o < S::OUT; o++) D3[tid * L::S3 + o] = upstream<ST>(p, g_out, bw, row, id, o);
         for (int j = 0; j < S::H2; j++) {
             float s = 0.0f;
             for (int o = 0; o < S::OUT; o++) s = fmaf(w3[j * S::OUT + o], D3[tid * L::S3 + o], s);
@@ -897,13 +943,20 @@ k_mlp_backward(Params p, TileArgs a, const float *g_out, float *dX, float *X_out
             for (int j = 0; j < S::H2; j++) s = fmaf(w2[i * S::H2 + j], D2[tid * L::S2 + j], s);
             D1[tid * L::S1 + i] = s * dact_tc<S::TANH>(A1[tid * L::S1 + i]);
         }
-        if (dX && row < n_rows) {
+        if (row < n_rows) {
+            float dx[S::K0];
+#pragma unroll
             for (int k = 0; k < S::K0; k++) {
                 float s = 0.0f;
                 if (k < S::IN)
                     for (int i = 0; i < S::H1; i++) s = fmaf(w1[k * S::H1 + i], D1[tid * L::S1 + i], s);
-                dX[(size_t)row * S::K0 + k] = s;
+                dx[k] = s;
             }
+            if (dX) {
+#pragma unroll
+                for (int k = 0; k < S::K0; k++) dX[(size_t)row * S::K0 + k] = dx[k];
+            }
+            consume_dx<ST>(p, bw, id, dx);
         }
         __syncthreads();
         // the tile's weight and bias gradients: sums over its 128 rows

@@ -325,3 +325,92 @@ def test_head_mlp_backward_matches_torch_autograd(bank):
                     tol = 2e-4 * float(Ws[i].grad.abs().max()) + 1e-6
                     assert float((got - Ws[i].grad).abs().max()) <= tol, (k, mode, keys[first + i])
         env.step(a, n)
+
+
+def test_backward_down_to_node_embeddings_matches_torch_autograd(bank):
+    """ssb_decima_backward vs torch autograd through everything above NodeEncoder, per env: node embeddings h (the
+    numpy oracle's, a leaf) -> DagEncoder -> GlobalEncoder -> stage / executor-count heads -> utils.evaluate ->
+    loss = sum_b c1_b lgprob_b + c2_b entropy_b.  Compared: d loss / d h per env and the summed gradients of the four
+    MLPs' 24 tensors, each within 3e-4 of its largest entry (device h vs oracle h differ by ~1e-6; fp32 atomics)."""
+    import decima_policy as oracle_pol
+    from torch.distributions.utils import clamp_probs
+
+    from spark_sched_sim_b200.batched_env import BatchedSparkSchedSimEnv
+
+    B, E = 24, 10
+    cfg = {"num_executors": E, "job_arrival_cap": 8, "job_arrival_rate": 4.0e-5,
+           "moving_delay": 2000.0, "warmup_delay": 1000.0}
+    env = BatchedSparkSchedSimEnv(cfg, num_envs=B, bank=bank, decima_policy=True)
+    w = weights()
+    env.set_decima_weights(w)
+    env.reset_host(np.arange(B, dtype=np.uint64) + 301)
+    keys = list(w.keys())
+    flat_off = np.concatenate([[0], np.cumsum([w[k].size for k in keys])])
+    wf = {k: v.astype(np.float32) for k, v in w.items()}
+
+    def mlp(x, Ws, act):
+        x = act(x @ Ws[0].T + Ws[1])
+        x = act(x @ Ws[2].T + Ws[3])
+        return x @ Ws[4].T + Ws[5]
+
+    leaky = lambda t: torch.nn.functional.leaky_relu(t, 0.2)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for k in range(22):
+        a, n = env.decima_policy()
+        if k in (2, 21):
+            c1 = torch.randn(B, device="cuda", generator=g)
+            c2 = torch.randn(B, device="cuda", generator=g)
+            gw = torch.zeros(20802, device="cuda")
+            d_h = env.decima_backward(c1, c2, gw).cpu()
+            assert not gw[:flat_off[18]].any()  # NodeEncoder's tensors: not part of this stage
+            Wt = {i: torch.from_numpy(wf[keys[i]]).requires_grad_() for i in range(18, 42)}
+            hdr = env.hdr().copy()
+            act = env.pol_action.cpu().numpy()
+            env.decima_obs()
+            loss = 0.0
+            leaves = []
+            for b in range(B):
+                if hdr["terminated"][b]:
+                    leaves.append(None)
+                    continue
+                obs, d = env.obs(b, hdr), env.decima_obs_host(b, hdr)
+                x = d["features"].astype(np.float32)
+                dag_ptr = np.asarray(obs["dag_ptr"])
+                h_np, _, _ = oracle_pol.encode(wf, x, np.asarray(obs["edge_links"]).reshape(-1, 2),
+                                               d["edge_bits"].astype(np.uint64), int(d["depth"]), dag_ptr)
+                h = torch.from_numpy(h_np).requires_grad_()
+                leaves.append(h)
+                xt = torch.from_numpy(x)
+                N, Ja = x.shape[0], len(dag_ptr) - 1
+                z = mlp(torch.cat([xt, h], 1), [Wt[i] for i in range(18, 24)], leaky)
+                seg = torch.from_numpy(np.repeat(np.arange(Ja), np.diff(dag_ptr))).long()
+                h_dag = torch.zeros(Ja, 16).index_add(0, seg, z)
+                h_glob = mlp(h_dag, [Wt[i] for i in range(24, 30)], leaky).sum(0)
+                idx = torch.from_numpy(np.flatnonzero(d["stage_mask"])).long()
+                inp = torch.cat([xt[idx], h[idx], h_dag[seg[idx]], h_glob.expand(len(idx), 16)], 1)
+                zs = mlp(inp, [Wt[i] for i in range(30, 36)], torch.tanh)[:, 0]
+                job, cap = int(act[b, 1]), int(d["commit_caps"][act[b, 1]])
+                cnt = (torch.arange(cap, dtype=torch.float64) / E).float()[:, None]
+                inp = torch.cat([xt[dag_ptr[job], :3].expand(cap, 3), h_dag[job].expand(cap, 16),
+                                 h_glob.expand(cap, 16), cnt], 1)
+                ze = mlp(inp, [Wt[i] for i in range(36, 42)], torch.tanh)[:, 0]
+                lg = en = 0.0
+                for zz, sel in ((zs, int(act[b, 0])), (ze, int(act[b, 2]))):
+                    q = clamp_probs(torch.softmax(zz, 0))
+                    lg = lg + q.log()[sel]
+                    en = en - (q.log() * q).sum()
+                en = en / np.log(np.float32(E * N))
+                loss = loss + float(c1[b]) * lg + float(c2[b]) * en
+            loss.backward()
+            for b in range(B):
+                if leaves[b] is None:
+                    continue
+                N = leaves[b].shape[0]
+                tol = 3e-4 * float(leaves[b].grad.abs().max()) + 1e-6
+                assert float((d_h[b, :N] - leaves[b].grad).abs().max()) <= tol, (k, b)
+                assert not d_h[b, N:].any()
+            for i in range(18, 42):
+                got = gw[flat_off[i]:flat_off[i + 1]].view(Wt[i].shape).cpu()
+                tol = 3e-4 * float(Wt[i].grad.abs().max()) + 1e-6
+                assert float((got - Wt[i].grad).abs().max()) <= tol, (k, keys[i])
+        env.step(a, n)

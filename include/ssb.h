@@ -334,16 +334,19 @@ int ssb_get_policy_views(ssb_env *env, ssb_policy_views *out);
 int ssb_decima_head_backward(ssb_env *env, const float *grad_stage_logits, const float *grad_exec_logits,
                              float *grad_weights, float *grad_stage_inputs, float *grad_exec_inputs,
                              float *stage_inputs, float *exec_inputs, int32_t *num_rows, void *stream);
-/* The backward pass of evaluate_actions as far as it is on the device: loss seeds -> score heads
- * (ssb_decima_head_adjoint, ssb_decima_head_backward) -> global summary (GlobalEncoder, scheduler.py:260-276) -> job
- * summaries (DagEncoder, :244-257), for the observation / actions of the last ssb_decima_evaluate / ssb_decima_policy
- * call.  grad_weights (DEVICE f32[20 802]) is accumulated into: the stage, executor-count, global and job-summary
- * MLPs' tensors are complete, NodeEncoder's (mlp_prep / mlp_msg / mlp_update) are left untouched.
- * grad_node_embeddings (DEVICE f32[B][node_stride][16], overwritten) = d loss / d NodeEncoder's output, what the
- * message-passing levels' backward pass starts from.  scratch: DEVICE, ssb_decima_backward_bytes. */
+/* The backward pass of evaluate_actions (loss.backward(), schedulers/scheduler.py:42) for the observation / actions
+ * of the last ssb_decima_evaluate / ssb_decima_policy call: loss seeds -> score heads (ssb_decima_head_adjoint,
+ * ssb_decima_head_backward) -> global summary (GlobalEncoder, scheduler.py:260-276) -> job summaries (DagEncoder,
+ * :244-257) -> with through_node_encoder != 0 also NodeEncoder (:173-241: the message-passing levels in reverse,
+ * sinks, mlp_prep).  grad_weights (DEVICE f32[20 802], the ssb_set_decima_weights layout) is accumulated into;
+ * with through_node_encoder == 0 NodeEncoder's tensors (mlp_prep / mlp_msg / mlp_update) are left untouched and
+ * grad_node_embeddings (DEVICE f32[B][node_stride][16], overwritten) = d loss / d NodeEncoder's output; with
+ * through_node_encoder != 0 that buffer is working storage.  The policy's intermediate buffers (embeddings,
+ * messages) are overwritten: run ssb_decima_evaluate again before anything that reads them.
+ * scratch: DEVICE, ssb_decima_backward_bytes, 16-byte aligned. */
 int ssb_decima_backward_bytes(ssb_env *env, size_t *bytes);
 int ssb_decima_backward(ssb_env *env, const float *grad_lgprob, const float *grad_entropy, float *grad_weights,
-                        float *grad_node_embeddings, void *scratch, void *stream);
+                        float *grad_node_embeddings, int32_t through_node_encoder, void *scratch, void *stream);
 int ssb_decima_snapshot_bytes(ssb_env *env, size_t *bytes);
 /* First stage of the backward pass of evaluate_actions -- the adjoint of utils.evaluate (decima/utils.py:26-42:
  * softmax, clamp_probs, log-prob of the stored action, entropy) and of the aggregation scheduler.py:131-137: from

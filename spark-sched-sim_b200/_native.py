@@ -178,7 +178,7 @@ def lib():
     L.ssb_decima_head_adjoint.argtypes = [vp, vp, vp, vp, vp, vp]
     L.ssb_decima_head_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(i32), vp]
     L.ssb_decima_backward_bytes.argtypes = [vp, C.POINTER(C.c_size_t)]
-    L.ssb_decima_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    L.ssb_decima_backward.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp]
     L.ssb_adam_step.argtypes = [vp, vp, vp, vp, i32, i32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, vp, vp, vp]
     L.ssb_differential_returns.argtypes = [vp, vp, vp, i32, i32, vp, i32, C.POINTER(i32), vp, vp, vp, vp]
     L.ssb_fair_actions.argtypes = [vp, i32, vp, vp, vp]

@@ -412,10 +412,12 @@ class BatchedSparkSchedSimEnv:
         out = (gxs[:n[0]], gxe[:n[1]])
         return out + (xs[:n[0]], xe[:n[1]]) if want_inputs else out
 
-    def decima_backward(self, grad_lgprob: torch.Tensor, grad_entropy: torch.Tensor, grad_weights: torch.Tensor):
-        """evaluate_actions' backward pass down to NodeEncoder's output (score heads, global and job summaries):
-        accumulates those MLPs' gradients into grad_weights (f32[20802]) and returns d loss / d node embeddings
-        [B, node_stride, 16]."""
+    def decima_backward(self, grad_lgprob: torch.Tensor, grad_entropy: torch.Tensor, grad_weights: torch.Tensor,
+                        through_node_encoder: bool = True):
+        """evaluate_actions' backward pass for the last decima_evaluate / decima_policy call: accumulates the
+        gradients of all 42 tensors into grad_weights (f32[20802], ABI layout).  through_node_encoder=False stops
+        above NodeEncoder (score heads, global and job summaries only) and returns d loss / d node embeddings
+        [B, node_stride, 16]; otherwise the returned buffer is working storage."""
         assert grad_weights.is_cuda and grad_weights.dtype == torch.float32 and grad_weights.numel() == 20802
         n = C.c_size_t()
         nat.check(self.L.ssb_decima_backward_bytes(self._h, C.byref(n)), "ssb_decima_backward_bytes")
@@ -423,8 +425,8 @@ class BatchedSparkSchedSimEnv:
             self._bwd_scratch = torch.empty(n.value, dtype=torch.uint8, device=self.device)
         d_h = torch.empty(self.num_envs, self.pol_stage_logits.shape[1], 16, dtype=torch.float32, device=self.device)
         nat.check(self.L.ssb_decima_backward(self._h, grad_lgprob.data_ptr(), grad_entropy.data_ptr(),
-                                             grad_weights.data_ptr(), d_h.data_ptr(), self._bwd_scratch.data_ptr(),
-                                             self._stream()), "ssb_decima_backward")
+                                             grad_weights.data_ptr(), d_h.data_ptr(), int(through_node_encoder),
+                                             self._bwd_scratch.data_ptr(), self._stream()), "ssb_decima_backward")
         return d_h
 
     def rollout_decima(self, num_decisions, max_events=0, out: "torch.Tensor | None" = None,

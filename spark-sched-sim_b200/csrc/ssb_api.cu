@@ -471,7 +471,7 @@ struct ssb_env {
     uint64_t auto_seed_step;
 };
 
-struct BackwardScratch { float *gs, *ge, *d_hdag, *d_hglob; size_t floats; };
+struct BackwardScratch { float *gs, *ge, *d_hdag, *d_hglob, *d_hinit, *d_msg; size_t floats; };
 BackwardScratch backward_scratch(const Params &p, float *base)
 {
     BackwardScratch b{};
@@ -481,12 +481,14 @@ BackwardScratch backward_scratch(const Params &p, float *base)
     b.ge = take((size_t)p.B * p.Epad);
     b.d_hdag = take((size_t)p.B * p.Jc * 16);
     b.d_hglob = take((size_t)p.B * 16);
+    b.d_hinit = take((size_t)p.B * p.Sc * 16);
+    b.d_msg = take((size_t)p.B * p.Sc * 16);
     b.floats = off;
     return b;
 }
 template <int ST>
-int launch_mlp_backward(ssb_env *env, const int32_t *list, const int32_t *count, const float *g_out, float *dW,
-                        tc::BwdBufs bw, cudaStream_t s)
+int launch_mlp_backward(ssb_env *env, const int32_t *list, const int32_t *offset, const int32_t *count, int level,
+                        const float *g_out, float *dW, tc::BwdBufs bw, cudaStream_t s)
 {
     static bool prepared = false;
     if (!prepared) {
@@ -494,7 +496,7 @@ int launch_mlp_backward(ssb_env *env, const int32_t *list, const int32_t *count,
                                       (int)tc::BwdSmem<ST>::BYTES));
         prepared = true;
     }
-    tc::TileArgs a{list, nullptr, count, 0};
+    tc::TileArgs a{list, offset, count, level};
     tc::k_mlp_backward<ST><<<env->num_sms, 128, tc::BwdSmem<ST>::BYTES, s>>>(env->p, a, g_out, nullptr, nullptr, dW, bw);
     CUDA_TRY(cudaGetLastError());
     return SSB_OK;
@@ -1137,7 +1139,7 @@ int ssb_decima_backward_bytes(ssb_env *env, size_t *bytes)
 }
 
 int ssb_decima_backward(ssb_env *env, const float *grad_lgprob, const float *grad_entropy, float *grad_weights,
-                        float *grad_node_embeddings, void *scratch, void *stream)
+                        float *grad_node_embeddings, int32_t through_node_encoder, void *scratch, void *stream)
 {
     if (!env || !env->p.pol_w || !grad_lgprob || !grad_entropy || !grad_weights || !grad_node_embeddings || !scratch ||
         (reinterpret_cast<uintptr_t>(scratch) & 15))
@@ -1150,13 +1152,43 @@ int ssb_decima_backward(ssb_env *env, const float *grad_lgprob, const float *gra
     CUDA_TRY(cudaMemsetAsync(b.d_hglob, 0, sizeof(float) * (size_t)p.B * 16, s));
     tc::k_pol_head_adjoint<<<(p.B + 3) / 4, 128, 0, s>>>(p, grad_lgprob, grad_entropy, b.gs, b.ge);
     CUDA_TRY(cudaGetLastError());
-    const tc::BwdBufs bw{grad_node_embeddings, b.d_hdag, b.d_hglob};
+    const tc::BwdBufs bw{grad_node_embeddings, b.d_hdag, b.d_hglob, b.d_hinit, b.d_msg};
+    const int32_t *cnt = p.pl_cnt;
+    float *gw = grad_weights;
     int rc;
     // heads first (their input gradients feed all three summaries), then the global summary, then the job summaries
-    if ((rc = launch_mlp_backward<tc::ST_STAGE>(env, nullptr, p.pl_cnt + tc::CNT_CAND, b.gs, grad_weights, bw, s))) return rc;
-    if ((rc = launch_mlp_backward<tc::ST_EXEC>(env, p.pl_exec, p.pl_cnt + tc::CNT_EXEC, b.ge, grad_weights, bw, s))) return rc;
-    if ((rc = launch_mlp_backward<tc::ST_GLOB>(env, p.pl_jobs, p.pl_cnt + tc::CNT_JOBS, nullptr, grad_weights, bw, s))) return rc;
-    if ((rc = launch_mlp_backward<tc::ST_DAG>(env, p.pl_all, p.pl_cnt + tc::CNT_ALL, nullptr, grad_weights, bw, s))) return rc;
+    if ((rc = launch_mlp_backward<tc::ST_STAGE>(env, nullptr, nullptr, cnt + tc::CNT_CAND, 0, b.gs, gw, bw, s))) return rc;
+    if ((rc = launch_mlp_backward<tc::ST_EXEC>(env, p.pl_exec, nullptr, cnt + tc::CNT_EXEC, 0, b.ge, gw, bw, s))) return rc;
+    if ((rc = launch_mlp_backward<tc::ST_GLOB>(env, p.pl_jobs, nullptr, cnt + tc::CNT_JOBS, 0, nullptr, gw, bw, s))) return rc;
+    if ((rc = launch_mlp_backward<tc::ST_DAG>(env, p.pl_all, nullptr, cnt + tc::CNT_ALL, 0, nullptr, gw, bw, s))) return rc;
+    if (!through_node_encoder) return SSB_OK;
+    // NodeEncoder (scheduler.py:191-234), the levels in the reverse of the forward order.  Level k's backward needs
+    // the embeddings as they were BEFORE level k and the level's messages; the forward pass overwrites both in
+    // place, so they are recomputed: reset (PREP), sinks, levels dmax-1 .. k+1, then level k's messages.  First
+    // correct version: O(depth^2) tile passes instead of saving every level's rows.
+    CUDA_TRY(cudaMemsetAsync(b.d_hinit, 0, sizeof(float) * (size_t)p.B * p.Sc * 16, s));
+    CUDA_TRY(cudaMemsetAsync(b.d_msg, 0, sizeof(float) * (size_t)p.B * p.Sc * 16, s));
+    for (int k = 0; k < env->dmax; k++) {
+        if ((rc = launch_tile<tc::ST_PREP>(env, p.pl_all, nullptr, cnt + tc::CNT_ALL, 0, 4, s))) return rc;
+        if ((rc = launch_tile<tc::ST_SINK>(env, p.pl_sink, nullptr, cnt + tc::CNT_SINK, 0, 4, s))) return rc;
+        for (int j = env->dmax - 1; j > k; j--) {
+            if ((rc = launch_tile<tc::ST_MSG>(env, p.pl_lvl, cnt + tc::OFF_LVL + 2 * j, cnt + tc::CNT_LVL + 2 * j, j, 4, s)))
+                return rc;
+            if ((rc = launch_tile<tc::ST_RCV>(env, p.pl_lvl, cnt + tc::OFF_LVL + 2 * j + 1, cnt + tc::CNT_LVL + 2 * j + 1,
+                                              j, 4, s)))
+                return rc;
+        }
+        if ((rc = launch_tile<tc::ST_MSG>(env, p.pl_lvl, cnt + tc::OFF_LVL + 2 * k, cnt + tc::CNT_LVL + 2 * k, k, 4, s)))
+            return rc;
+        if ((rc = launch_mlp_backward<tc::ST_RCV>(env, p.pl_lvl, cnt + tc::OFF_LVL + 2 * k + 1,
+                                                  cnt + tc::CNT_LVL + 2 * k + 1, k, nullptr, gw, bw, s)))
+            return rc;
+        if ((rc = launch_mlp_backward<tc::ST_MSG>(env, p.pl_lvl, cnt + tc::OFF_LVL + 2 * k, cnt + tc::CNT_LVL + 2 * k, k,
+                                                  nullptr, gw, bw, s)))
+            return rc;
+    }
+    if ((rc = launch_mlp_backward<tc::ST_SINK>(env, p.pl_sink, nullptr, cnt + tc::CNT_SINK, 0, nullptr, gw, bw, s))) return rc;
+    if ((rc = launch_mlp_backward<tc::ST_PREP>(env, p.pl_all, nullptr, cnt + tc::CNT_ALL, 0, nullptr, gw, bw, s))) return rc;
     return SSB_OK;
 }
 

@@ -830,6 +830,8 @@ struct BwdBufs {
     float *d_h;      // [B][Sc][16]  node embeddings (NodeEncoder's output)
     float *d_hdag;   // [B][Jc][16]  job summaries
     float *d_hglob;  // [B][16]      global summary
+    float *d_hinit;  // [B][Sc][16]  mlp_prep's output (NodeEncoder's h_init)
+    float *d_msg;    // [B][Sc][16]  the current level's messages (zero between levels)
 };
 __device__ __forceinline__ int job_of_node(const Params &p, int b, int n)
 {
@@ -851,11 +853,34 @@ __device__ __forceinline__ float upstream(const Params &p, const float *g_out, c
         if (g_out) return g_out[(size_t)row * S::OUT + o];
         const int b = id / p.Sc;
         return bw.d_hdag[((size_t)b * p.Jc + job_of_node(p, b, id - b * p.Sc)) * 16 + o];
+    } else if constexpr (ST == ST_RCV || ST == ST_SINK) {
+        return g_out ? g_out[(size_t)row * S::OUT + o] : bw.d_h[(size_t)id * 16 + o];
+    } else if constexpr (ST == ST_MSG) {
+        return g_out ? g_out[(size_t)row * S::OUT + o] : bw.d_msg[(size_t)id * 16 + o];
+    } else if constexpr (ST == ST_PREP) {
+        if (g_out) return g_out[(size_t)row * S::OUT + o];
+        // h = h_init for observations without message passing (_forward_no_mp, scheduler.py:236-241)
+        return bw.d_hinit[(size_t)id * 16 + o] + (p.dec_depth[id / p.Sc] == 0 ? bw.d_h[(size_t)id * 16 + o] : 0.0f);
     } else return g_out[(size_t)row * S::OUT + o];
+}
+// what else the row's output gradient does besides entering the MLP (delta = this row's upstream gradient)
+template <int ST>
+__device__ __forceinline__ void after_upstream(const Params &p, const BwdBufs &bw, int id, const float *delta, int stride)
+{
+    if (id < 0 || !bw.d_h) return;
+    if constexpr (ST == ST_RCV) {
+        // h[r] = h_init[r] + update(agg[r]) OVERWRITES h[r]: the gradient passes to h_init, nothing to the old value
+        for (int o = 0; o < 16; o++) {
+            bw.d_hinit[(size_t)id * 16 + o] += delta[o * stride];
+            bw.d_h[(size_t)id * 16 + o] = 0.0f;
+        }
+    } else if constexpr (ST == ST_MSG) {
+        for (int o = 0; o < 16; o++) bw.d_msg[(size_t)id * 16 + o] = 0.0f;  // consumed: clean for the next level
+    }
 }
 // where a row's input gradient goes (the adjoint of gather_row)
 template <int ST>
-__device__ __forceinline__ void consume_dx(const Params &p, const BwdBufs &bw, int id, const float *dx)
+__device__ __forceinline__ void consume_dx(const Params &p, const BwdBufs &bw, int id, const float *dx, int level)
 {
     if (id < 0) return;
     if constexpr (ST == ST_STAGE) {
@@ -879,6 +904,24 @@ __device__ __forceinline__ void consume_dx(const Params &p, const BwdBufs &bw, i
     } else if constexpr (ST == ST_DAG) {
         if (!bw.d_h) return;
         for (int i = 0; i < 16; i++) atomicAdd(bw.d_h + (size_t)id * 16 + i, dx[5 + i]);
+    } else if constexpr (ST == ST_RCV) {
+        // agg[u] = sum of msg[v] over u's edges masked at this level: d msg[v] += d agg[u]
+        if (!bw.d_msg) return;
+        const int b = id / p.Sc, u = id - b * p.Sc;
+        const int32_t *edges = p.obs_edges + (size_t)b * p.Mc * 2;
+        const uint64_t *ebits = p.dec_edge_bits + (size_t)b * p.Mc;
+        const int M = p.obs_hdr[b].num_edges;
+        for (int e = p.pol_row_start[id]; e < M && edges[2 * e] == u; e++) {
+            if (!((ebits[e] >> level) & 1)) continue;
+            float *dst = bw.d_msg + ((size_t)b * p.Sc + edges[2 * e + 1]) * 16;
+            for (int i = 0; i < 16; i++) atomicAdd(dst + i, dx[i]);
+        }
+    } else if constexpr (ST == ST_MSG) {
+        if (!bw.d_h) return;
+        for (int i = 0; i < 16; i++) bw.d_h[(size_t)id * 16 + i] += dx[i];  // the sender's embedding before this level
+    } else if constexpr (ST == ST_SINK) {
+        if (!bw.d_hinit) return;
+        for (int i = 0; i < 16; i++) bw.d_hinit[(size_t)id * 16 + i] += dx[i];
     }
 }
 
@@ -933,6 +976,7 @@ k_mlp_backward(Params p, TileArgs a, const float *g_out, float *dX, float *X_out
         }
         // backward, this thread's row
         for (int o = 0; o < S::OUT; o++) D3[tid * L::S3 + o] = upstream<ST>(p, g_out, bw, row, id, o);
+        if (!g_out) after_upstream<ST>(p, bw, id, D3 + tid * L::S3, 1);
         for (int j = 0; j < S::H2; j++) {
             float s = 0.0f;
             for (int o = 0; o < S::OUT; o++) s = fmaf(w3[j * S::OUT + o], D3[tid * L::S3 + o], s);
@@ -956,7 +1000,7 @@ k_mlp_backward(Params p, TileArgs a, const float *g_out, float *dX, float *X_out
 #pragma unroll
                 for (int k = 0; k < S::K0; k++) dX[(size_t)row * S::K0 + k] = dx[k];
             }
-            consume_dx<ST>(p, bw, id, dx);
+            consume_dx<ST>(p, bw, id, dx, a.level);
         }
         __syncthreads();
         // the tile's weight and bias gradients: sums over its 128 rows

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SSB_ABI_VERSION 3
+#define SSB_ABI_VERSION 4
 
 /* status codes of the entry points */
 enum {
@@ -322,18 +322,16 @@ int ssb_get_policy_views(ssb_env *env, ssb_policy_views *out);
  *     Decima's format: stage_idx = index among the schedulable stages, num_exec in [0, cap)) and writes
  *     lgprob_out / entropy_out (DEVICE f32[B], may be NULL).  The envs' state, current observation and sampling
  *     stream are left untouched. */
-/* Second stage: backward of the two score heads' MLPs (StagePolicyNetwork / ExecPolicyNetwork,
- * scheduler.py:279-385) for the candidates of the last ssb_decima_evaluate / ssb_decima_policy call.
- * grad_weights (DEVICE f32[20 802], the ssb_set_decima_weights layout) is ACCUMULATED into (zero it first).
- * grad_stage_inputs (DEVICE f32[num stage candidates][56], may be NULL) / grad_exec_inputs (DEVICE
- * f32[num executor-count rows][40], may be NULL) receive d loss / d input row in list order (stage rows: node
- * features 5, node embedding 16, job embedding 16, global embedding 16, padding; executor-count rows: 3 job
- * features, job embedding 16, global embedding 16, count / E, padding); stage_inputs / exec_inputs (same shapes, may
- * be NULL) the gathered input rows themselves.  num_rows (HOST int32[2], may be NULL) = the two row counts; the
- * call synchronises the stream when it is given. */
-int ssb_decima_head_backward(ssb_env *env, const float *grad_stage_logits, const float *grad_exec_logits,
-                             float *grad_weights, float *grad_stage_inputs, float *grad_exec_inputs,
-                             float *stage_inputs, float *exec_inputs, int32_t *num_rows, void *stream);
+int ssb_decima_snapshot_bytes(ssb_env *env, size_t *bytes);
+int ssb_decima_snapshot(ssb_env *env, void *dst, void *stream);
+int ssb_decima_evaluate(ssb_env *env, const void *snapshot, const int32_t *stage_sel, const int32_t *exec_sel,
+                        float *lgprob_out, float *entropy_out, void *stream);
+/* For the policy update, where forward and backward pass of one mini-batch work on the same stored observation:
+ * ssb_decima_snapshot_load parks the live observation and puts the stored one in place, ssb_decima_evaluate with
+ * snapshot == NULL evaluates it, ssb_decima_backward differentiates that evaluation, ssb_decima_snapshot_unload
+ * restores the live observation.  No step / reset / policy call on the handle between load and unload. */
+int ssb_decima_snapshot_load(ssb_env *env, const void *snapshot, void *stream);
+int ssb_decima_snapshot_unload(ssb_env *env, void *stream);
 /* The backward pass of evaluate_actions (loss.backward(), schedulers/scheduler.py:42) for the observation / actions
  * of the last ssb_decima_evaluate / ssb_decima_policy call: loss seeds -> score heads (ssb_decima_head_adjoint,
  * ssb_decima_head_backward) -> global summary (GlobalEncoder, scheduler.py:260-276) -> job summaries (DagEncoder,
@@ -347,7 +345,6 @@ int ssb_decima_head_backward(ssb_env *env, const float *grad_stage_logits, const
 int ssb_decima_backward_bytes(ssb_env *env, size_t *bytes);
 int ssb_decima_backward(ssb_env *env, const float *grad_lgprob, const float *grad_entropy, float *grad_weights,
                         float *grad_node_embeddings, int32_t through_node_encoder, void *scratch, void *stream);
-int ssb_decima_snapshot_bytes(ssb_env *env, size_t *bytes);
 /* First stage of the backward pass of evaluate_actions -- the adjoint of utils.evaluate (decima/utils.py:26-42:
  * softmax, clamp_probs, log-prob of the stored action, entropy) and of the aggregation scheduler.py:131-137: from
  * grad_lgprob / grad_entropy (DEVICE f32[B]: d loss / d lgprob, d loss / d entropy of every env, e.g. ssb_ppo_loss's
@@ -356,9 +353,18 @@ int ssb_decima_snapshot_bytes(ssb_env *env, size_t *bytes);
  * the candidates.  Uses the scores and actions of the last ssb_decima_evaluate / ssb_decima_policy call. */
 int ssb_decima_head_adjoint(ssb_env *env, const float *grad_lgprob, const float *grad_entropy,
                             float *grad_stage_logits, float *grad_exec_logits, void *stream);
-int ssb_decima_snapshot(ssb_env *env, void *dst, void *stream);
-int ssb_decima_evaluate(ssb_env *env, const void *snapshot, const int32_t *stage_sel, const int32_t *exec_sel,
-                        float *lgprob_out, float *entropy_out, void *stream);
+/* Second stage: backward of the two score heads' MLPs (StagePolicyNetwork / ExecPolicyNetwork,
+ * scheduler.py:279-385) for the candidates of the last ssb_decima_evaluate / ssb_decima_policy call.
+ * grad_weights (DEVICE f32[20 802], the ssb_set_decima_weights layout) is ACCUMULATED into (zero it first).
+ * grad_stage_inputs (DEVICE f32[num stage candidates][56], may be NULL) / grad_exec_inputs (DEVICE
+ * f32[num executor-count rows][40], may be NULL) receive d loss / d input row in list order (stage rows: node
+ * features 5, node embedding 16, job embedding 16, global embedding 16, padding; executor-count rows: 3 job
+ * features, job embedding 16, global embedding 16, count / E, padding); stage_inputs / exec_inputs (same shapes, may
+ * be NULL) the gathered input rows themselves.  num_rows (HOST int32[2], may be NULL) = the two row counts; the
+ * call synchronises the stream when it is given. */
+int ssb_decima_head_backward(ssb_env *env, const float *grad_stage_logits, const float *grad_exec_logits,
+                             float *grad_weights, float *grad_stage_inputs, float *grad_exec_inputs,
+                             float *stage_inputs, float *exec_inputs, int32_t *num_rows, void *stream);
 /* Decima rollout collection (trainers/rollout_worker.py:135-157 with DecimaScheduler): num_decisions times
  * { ssb_decima_policy (sampled actions) ; ssb_step(max_events) } for every env, everything stream-ordered on the
  * device, each call's (wall time, action, lgprob, reward, flags) stored at traj[b * num_decisions + d] (DEVICE,

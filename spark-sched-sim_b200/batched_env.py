@@ -333,10 +333,14 @@ class BatchedSparkSchedSimEnv:
     def set_decima_weights(self, state_dict) -> None:
         """Uploads a DecimaScheduler state dict (torch tensors or numpy arrays keyed as in
         models/decima/model.pt): 42 tensors / 20 802 float32 parameters."""
-        flat = np.concatenate([np.asarray(state_dict[k].detach().cpu().numpy()
-                                          if hasattr(state_dict[k], "detach") else state_dict[k],
-                                          dtype=np.float32).reshape(-1)
-                               for k in self.DECIMA_PARAM_ORDER])
+        if isinstance(state_dict, (torch.Tensor, np.ndarray)):  # the flat vector itself (state_dict order)
+            flat = np.asarray(state_dict.detach().cpu().numpy() if hasattr(state_dict, "detach") else state_dict,
+                              dtype=np.float32).reshape(-1)
+        else:
+            flat = np.concatenate([np.asarray(state_dict[k].detach().cpu().numpy()
+                                              if hasattr(state_dict[k], "detach") else state_dict[k],
+                                              dtype=np.float32).reshape(-1)
+                                   for k in self.DECIMA_PARAM_ORDER])
         assert flat.size == nat.DECIMA_NUM_PARAMS, flat.size
         flat = np.ascontiguousarray(flat)
         nat.check(self.L.ssb_set_decima_weights(self._h, flat.ctypes.data, flat.size),
@@ -367,14 +371,25 @@ class BatchedSparkSchedSimEnv:
         nat.check(self.L.ssb_decima_snapshot(self._h, out.data_ptr(), self._stream()), "ssb_decima_snapshot")
         return out
 
-    def decima_evaluate(self, snapshot: torch.Tensor, stage_sel, exec_sel):
-        """DecimaScheduler.evaluate_actions (forward only) on a stored snapshot: (lgprobs, entropies) f32[B] for the
-        given Decima-format actions; the envs themselves are left untouched."""
+    def decima_snapshot_load(self, snapshot: torch.Tensor):
+        """Puts a stored observation in place (the live one is parked) for decima_evaluate(None, ...) +
+        decima_backward; undo with decima_snapshot_unload()."""
+        nat.check(self.L.ssb_decima_snapshot_load(self._h, snapshot.data_ptr(), self._stream()),
+                  "ssb_decima_snapshot_load")
+
+    def decima_snapshot_unload(self):
+        nat.check(self.L.ssb_decima_snapshot_unload(self._h, self._stream()), "ssb_decima_snapshot_unload")
+
+    def decima_evaluate(self, snapshot: "torch.Tensor | None", stage_sel, exec_sel):
+        """DecimaScheduler.evaluate_actions (forward only) on a stored snapshot (None: the one decima_snapshot_load
+        put in place): (lgprobs, entropies) f32[B] for the given Decima-format actions; the envs themselves are
+        left untouched."""
         a = self._dev(stage_sel, torch.int32)
         n = self._dev(exec_sel, torch.int32)
         lg = torch.empty(self.num_envs, dtype=torch.float32, device=self.device)
         en = torch.empty(self.num_envs, dtype=torch.float32, device=self.device)
-        nat.check(self.L.ssb_decima_evaluate(self._h, snapshot.data_ptr(), a.data_ptr(), n.data_ptr(), lg.data_ptr(),
+        nat.check(self.L.ssb_decima_evaluate(self._h, snapshot.data_ptr() if snapshot is not None else None,
+                                             a.data_ptr(), n.data_ptr(), lg.data_ptr(),
                                              en.data_ptr(), self._stream()), "ssb_decima_evaluate")
         return lg, en
 

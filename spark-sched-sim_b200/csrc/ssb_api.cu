@@ -467,6 +467,7 @@ struct ssb_env {
     ssb_transition *dg_traj;
     int dg_k, dg_events, dg_autoreset, no_graph;
     uint64_t dg_seed_step;
+    int snap_loaded;    // ssb_decima_snapshot_load: a stored observation is in place, the live one parked
     int auto_reset;     // ssb_set_autoreset
     uint64_t auto_seed_step;
 };
@@ -1207,20 +1208,38 @@ int ssb_decima_snapshot(ssb_env *env, void *dst, void *stream)
     return snapshot_copy(env, static_cast<char *>(dst), true, (cudaStream_t)stream);
 }
 
+int ssb_decima_snapshot_load(ssb_env *env, const void *snapshot, void *stream)
+{
+    if (!env || !snapshot || !env->p.pol_w || env->snap_loaded) return SSB_E_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc;
+    // the live observation is parked in the handle's scratch while the stored one is worked on
+    if ((rc = snapshot_copy(env, env->p.pol_snap, true, s))) return rc;
+    if ((rc = snapshot_copy(env, const_cast<char *>(static_cast<const char *>(snapshot)), false, s))) return rc;
+    env->snap_loaded = 1;
+    return SSB_OK;
+}
+
+int ssb_decima_snapshot_unload(ssb_env *env, void *stream)
+{
+    if (!env || !env->p.pol_w || !env->snap_loaded) return SSB_E_INVALID;
+    env->snap_loaded = 0;
+    return snapshot_copy(env, env->p.pol_snap, false, (cudaStream_t)stream);
+}
+
 int ssb_decima_evaluate(ssb_env *env, const void *snapshot, const int32_t *stage_sel, const int32_t *exec_sel,
                         float *lgprob_out, float *entropy_out, void *stream)
 {
-    if (!env || !snapshot || !stage_sel || !exec_sel || !env->p.pol_w) return SSB_E_INVALID;
+    if (!env || !stage_sel || !exec_sel || !env->p.pol_w) return SSB_E_INVALID;
+    if (!snapshot && !env->snap_loaded) return SSB_E_INVALID;  // NULL: the snapshot ssb_decima_snapshot_load put in place
     cudaStream_t s = (cudaStream_t)stream;
     const size_t B = env->p.B;
     int rc;
-    // the live observation is parked in the handle's scratch while the stored one is evaluated
-    if ((rc = snapshot_copy(env, env->p.pol_snap, true, s))) return rc;
-    if ((rc = snapshot_copy(env, const_cast<char *>(static_cast<const char *>(snapshot)), false, s))) return rc;
+    if (snapshot && (rc = ssb_decima_snapshot_load(env, snapshot, stream))) return rc;
     if ((rc = decima_policy_impl(env, stage_sel, exec_sel, nullptr, nullptr, false, false, s))) return rc;
     if (lgprob_out) CUDA_TRY(cudaMemcpyAsync(lgprob_out, env->p.pol_lgprob, B * 4, cudaMemcpyDeviceToDevice, s));
     if (entropy_out) CUDA_TRY(cudaMemcpyAsync(entropy_out, env->p.pol_entropy, B * 4, cudaMemcpyDeviceToDevice, s));
-    return snapshot_copy(env, env->p.pol_snap, false, s);
+    return snapshot ? ssb_decima_snapshot_unload(env, stream) : SSB_OK;
 }
 
 __global__ void k_traj_next(Params p) { if (threadIdx.x == 0 && blockIdx.x == 0) *p.traj_d += 1; }

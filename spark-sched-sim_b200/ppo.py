@@ -66,3 +66,31 @@ class Adam:
             int(self.params.numel()), self.num_steps, self.lr, self.betas[0], self.betas[1], self.eps,
             self.max_grad_norm, self._scratch.data_ptr(), self.grad_norm.data_ptr(), _stream(grads)), "ssb_adam_step")
         return self.grad_norm
+
+
+def ppo_minibatch_update(env, snapshot, stage_sel, exec_sel, old_lgprob, returns, baselines, loss_fn: PPOLoss,
+                         adam: Adam, target_kl=None, allreduce=None):
+    """One mini-batch of PPO._train (trainers/ppo.py:72-102) on the device, the mini-batch being the B observations of
+    one stored snapshot: evaluate_actions -> clip loss -> backward -> (gradient all-reduce) -> clip_grad_norm_ + Adam
+    -> new weights into the policy.  `adam.params` is the flat weight vector (ssb_set_decima_weights layout).
+    Returns (info, stepped): info = the loss head's four scalars on the host; stepped is False when the KL early
+    stop (approx_kl_div > 1.5 * target_kl) skipped the update, as the trainer does.
+    allreduce: optional callable(grads, num_samples) -> (grads, total) for several GPUs
+    (parallel.allreduce_gradients)."""
+    B = env.num_envs
+    env.decima_snapshot_load(snapshot)
+    try:
+        lg, en = env.decima_evaluate(None, stage_sel, exec_sel)
+        out, g_lp, g_en = loss_fn(lg, old_lgprob, en, returns, baselines)
+        info = dict(zip(PPOLoss.KEYS, out.tolist()))
+        if target_kl is not None and info["approx_kl_div"] > 1.5 * target_kl:
+            return info, False
+        grads = torch.zeros_like(adam.params)
+        env.decima_backward(g_lp, g_en, grads)
+    finally:
+        env.decima_snapshot_unload()
+    if allreduce is not None:
+        grads, _ = allreduce(grads * B, B)
+    adam.step(grads)
+    env.set_decima_weights(adam.params)
+    return info, True

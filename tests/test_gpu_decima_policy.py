@@ -524,3 +524,66 @@ def test_full_backward_matches_torch_autograd(bank):
                 assert float((got - Wt[i].grad).abs().max()) <= tol, (k, keys[i], float((got - Wt[i].grad).abs().max()), tol)
             # the backward pass overwrote the intermediate buffers: the next policy call recomputes everything
         env.step(a, n)
+
+
+def test_ppo_minibatch_update_on_stored_snapshots(bank):
+    """The pieces of PPO._train (trainers/ppo.py:72-102) strung together on the device over stored observations:
+    snapshot load -> evaluate -> clip loss -> backward -> clip_grad_norm_ + Adam -> new weights.  Checked: the
+    evaluation inside the update reproduces the rollout's lgprobs (ratio 1: approx KL 0, policy loss = -mean of the
+    normalised advantages = 0), the gradient of a stored observation equals the gradient of the same observation
+    when it was live, the live observation survives the update, repeated updates raise the surrogate objective,
+    and the KL early stop skips the step."""
+    from spark_sched_sim_b200.batched_env import BatchedSparkSchedSimEnv
+    from spark_sched_sim_b200.ppo import Adam, PPOLoss, ppo_minibatch_update
+
+    B = 32
+    cfg = {"num_executors": 10, "job_arrival_cap": 8, "job_arrival_rate": 4.0e-5,
+           "moving_delay": 2000.0, "warmup_delay": 1000.0}
+    env = BatchedSparkSchedSimEnv(cfg, num_envs=B, bank=bank, decima_policy=True)
+    w = weights()
+    env.set_decima_weights(w)
+    env.reset_host(np.arange(B, dtype=np.uint64) + 700)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    snaps, acts, lgs = [], [], []
+    live_grad = None
+    for k in range(12):
+        snaps.append(env.decima_snapshot())
+        a, n = env.decima_policy()
+        acts.append(env.pol_action.clone()); lgs.append(env.pol_lgprob.clone())
+        if k == 6:  # gradient of this observation while it is the live one
+            c1 = torch.randn(B, device="cuda", generator=g); c2 = torch.randn(B, device="cuda", generator=g)
+            live_grad = torch.zeros(20802, device="cuda")
+            env.decima_backward(c1, c2, live_grad)
+        env.step(a, n)
+    wall = env.hdr()["wall_time"].copy()
+    # the same gradient from the stored observation, many decisions later
+    env.decima_snapshot_load(snaps[6])
+    lg, _ = env.decima_evaluate(None, acts[6][:, 0].contiguous(), acts[6][:, 2].contiguous())
+    assert torch.equal(lg, lgs[6])
+    stored_grad = torch.zeros(20802, device="cuda")
+    env.decima_backward(c1, c2, stored_grad)
+    env.decima_snapshot_unload()
+    assert float((stored_grad - live_grad).abs().max()) <= 1e-4 * float(live_grad.abs().max())  # atomics' order only
+    # PPO updates on one mini-batch
+    flat = torch.from_numpy(np.concatenate([w[k].astype(np.float32).reshape(-1) for k in w])).cuda()
+    adam = Adam(flat.clone(), lr=3e-4, max_grad_norm=0.5)
+    loss_fn = PPOLoss(0.2, 0.04)
+    ret = -1e4 * torch.rand(B, device="cuda", generator=g, dtype=torch.float64)
+    base = ret + 2e3 * torch.randn(B, device="cuda", generator=g, dtype=torch.float64)
+    k = 4
+    args = (snaps[k], acts[k][:, 0].contiguous(), acts[k][:, 2].contiguous(), lgs[k], ret, base, loss_fn, adam)
+    info0, stepped = ppo_minibatch_update(env, *args)
+    assert stepped and abs(info0["approx_kl_div"]) < 1e-6 and abs(info0["policy_loss"]) < 1e-5
+    assert float(adam.grad_norm.item()) > 0 and not torch.equal(adam.params, flat)
+    losses = [info0["loss"]]
+    for _ in range(5):
+        info, stepped = ppo_minibatch_update(env, *args)
+        assert stepped
+        losses.append(info["loss"])
+    assert losses[-1] < losses[0] - 1e-4, losses  # the surrogate loss goes down on the batch it is trained on
+    _, stepped = ppo_minibatch_update(env, *args, target_kl=0.0)
+    assert not stepped  # approx KL > 0 after six updates: early stop
+    assert np.array_equal(env.hdr()["wall_time"], wall)  # the live observation came back
+    a, n = env.decima_policy()
+    env.step(a, n)
+    assert (env.hdr()["error"] == 0).all()

@@ -1,7 +1,9 @@
 """Small workload for compute-sanitizer (memcheck / initcheck): Decima rollout on the tensor-core path with auto-reset,
 and a two-slot (E = 50) fused fair rollout.  Usage on the GPU box:
     compute-sanitizer --tool memcheck python profiles/sanitizer_run.py
-Round 1: memcheck 0 errors, initcheck 0 errors (after zeroing the weight blobs' padding)."""
+Round 1: memcheck 0 errors; initcheck 0 errors in kernels (after zeroing the weight blobs' padding) -- what it still
+reports with the snapshot calls below are "cudaMemcpy source" records only: ssb_decima_snapshot copies the whole
+observation slabs device-to-device, including the never-written tails beyond num_nodes / num_edges of each env."""
 import sys, os.path as osp
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
 import numpy as np, torch
@@ -15,6 +17,17 @@ env.set_decima_weights({k: z[k] for k in z.files})
 env.reset_host((np.arange(B) + 5).astype(np.uint64))
 env.set_autoreset(True, 64)
 tr = env.rollout_decima(60)
+# the policy's backward pass on the live observation and on a stored one
+snap = env.decima_snapshot()
+env.decima_policy()
+gw = torch.zeros(20802, device='cuda')
+env.decima_backward(torch.randn(B, device='cuda'), torch.randn(B, device='cuda'), gw)
+acts = env.pol_action.clone()
+env.decima_snapshot_load(snap)
+env.decima_evaluate(None, acts[:, 0].contiguous(), acts[:, 2].contiguous())
+env.decima_backward(torch.randn(B, device='cuda'), torch.randn(B, device='cuda'), gw)
+env.decima_snapshot_unload()
+assert torch.isfinite(gw).all() and gw.abs().sum() > 0
 torch.cuda.synchronize()
 h = env.hdr()
 print('decima ok', env.stats()['decisions'], (h['error'] != 0).sum())

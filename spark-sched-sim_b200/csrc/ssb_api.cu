@@ -498,7 +498,10 @@ int launch_mlp_backward(ssb_env *env, const int32_t *list, const int32_t *offset
         prepared = true;
     }
     tc::TileArgs a{list, offset, count, level};
-    tc::k_mlp_backward<ST><<<env->num_sms, 128, tc::BwdSmem<ST>::BYTES, s>>>(env->p, a, g_out, nullptr, nullptr, dW, bw);
+    // as many CTAs per SM as the tile's shared memory allows (1 for the 64-wide score heads, 2-3 for the GNN MLPs)
+    constexpr int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (size_t)220 * 1024 / (tc::BwdSmem<ST>::BYTES + 1024)));
+    tc::k_mlp_backward<ST><<<env->num_sms * per_sm, 128, tc::BwdSmem<ST>::BYTES, s>>>(env->p, a, g_out, nullptr, nullptr,
+                                                                                       dW, bw);
     CUDA_TRY(cudaGetLastError());
     return SSB_OK;
 }

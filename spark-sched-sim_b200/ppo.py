@@ -94,3 +94,33 @@ def ppo_minibatch_update(env, snapshot, stage_sel, exec_sel, old_lgprob, returns
     adam.step(grads)
     env.set_decima_weights(adam.params)
     return info, True
+
+
+def ppo_train(env, batches, loss_fn: PPOLoss, adam: Adam, num_epochs=3, target_kl=0.01, allreduce=None,
+              generator=None):
+    """PPO._train (trainers/ppo.py:72-102) over stored rollouts on the device.  `batches`: a list of mini-batches
+    (snapshot, stage_sel, exec_sel, old_lgprob, returns, baselines), each the B observations of one stored snapshot
+    (the reference draws its mini-batches by shuffling all samples; here the order of the snapshots is shuffled every
+    epoch).  Stops for good as soon as a mini-batch's approximate KL exceeds 1.5 * target_kl, before stepping on it,
+    as the trainer does.  Returns the trainer's summary: |mean| of the policy losses, entropy losses and approximate
+    KL divergences of the mini-batches visited, plus the number of parameter updates."""
+    import numpy as np
+
+    policy_losses, entropy_losses, kls = [], [], []
+    updates = 0
+    go = True
+    for _ in range(num_epochs):
+        if not go:
+            break
+        order = torch.randperm(len(batches), generator=generator).tolist()
+        for i in order:
+            info, stepped = ppo_minibatch_update(env, *batches[i], loss_fn, adam, target_kl=target_kl,
+                                                 allreduce=allreduce)
+            policy_losses.append(info["policy_loss"]); entropy_losses.append(info["entropy_loss"])
+            kls.append(info["approx_kl_div"])
+            if not stepped:
+                go = False
+                break
+            updates += 1
+    return {"policy loss": float(np.abs(np.mean(policy_losses))), "entropy": float(np.abs(np.mean(entropy_losses))),
+            "approx kl div": float(np.abs(np.mean(kls))), "num_updates": updates}

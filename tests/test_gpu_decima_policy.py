@@ -583,6 +583,18 @@ def test_ppo_minibatch_update_on_stored_snapshots(bank):
     assert losses[-1] < losses[0] - 1e-4, losses  # the surrogate loss goes down on the batch it is trained on
     _, stepped = ppo_minibatch_update(env, *args, target_kl=0.0)
     assert not stepped  # approx KL > 0 after six updates: early stop
+    # PPO._train over several stored mini-batches: epochs, shuffled order, summary dict, early stop
+    from spark_sched_sim_b200.ppo import ppo_train
+
+    batches = [(snaps[j], acts[j][:, 0].contiguous(), acts[j][:, 2].contiguous(), lgs[j], ret, base) for j in (1, 3, 5, 8)]
+    env.set_decima_weights(w)  # back to the rollout's policy, so that the first pass has ratio 1
+    adam2 = Adam(flat.clone(), lr=3e-4, max_grad_norm=0.5)
+    summary = ppo_train(env, batches, loss_fn, adam2, num_epochs=2, target_kl=None,
+                        generator=torch.Generator().manual_seed(0))
+    assert summary["num_updates"] == 8 and summary["entropy"] > 0 and np.isfinite(summary["policy loss"])
+    summary = ppo_train(env, batches, loss_fn, adam2, num_epochs=2, target_kl=1e-9,
+                        generator=torch.Generator().manual_seed(0))
+    assert summary["num_updates"] == 0 and summary["approx kl div"] > 1.5e-9  # stopped on the first mini-batch
     assert np.array_equal(env.hdr()["wall_time"], wall)  # the live observation came back
     a, n = env.decima_policy()
     env.step(a, n)

@@ -17,6 +17,7 @@
 
 #include "ssb_decima.cuh"
 #include "ssb_decima_tc.cuh"
+#include "ssb_backward.cuh"
 #include "ssb_learn.cuh"
 #include "ssb_sim.cuh"
 
@@ -487,25 +488,8 @@ BackwardScratch backward_scratch(const Params &p, float *base)
     b.floats = off;
     return b;
 }
-template <int ST>
-int launch_mlp_backward(ssb_env *env, const int32_t *list, const int32_t *offset, const int32_t *count, int level,
-                        const float *g_out, float *dW, tc::BwdBufs bw, cudaStream_t s)
-{
-    static bool prepared = false;
-    if (!prepared) {
-        CUDA_TRY(cudaFuncSetAttribute(tc::k_mlp_backward<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)tc::BwdSmem<ST>::BYTES));
-        prepared = true;
-    }
-    tc::TileArgs a{list, offset, count, level};
-    // as many CTAs per SM as the tile's shared memory allows (1 for the 64-wide score heads, 2-3 for the GNN MLPs)
-    constexpr int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (size_t)220 * 1024 / (tc::BwdSmem<ST>::BYTES + 1024)));
-    tc::k_mlp_backward<ST><<<env->num_sms * per_sm, 128, tc::BwdSmem<ST>::BYTES, s>>>(env->p, a, g_out, nullptr, nullptr,
-                                                                                       dW, bw);
-    CUDA_TRY(cudaGetLastError());
-    return SSB_OK;
-}
-
+int launch_mlp_backward(int stage, ssb_env *env, const int32_t *list, const int32_t *offset, const int32_t *count,
+                        int level, const float *g_out, float *dW, const bwd::Bufs &bw, cudaStream_t s);
 template <int ST>
 int launch_tile(ssb_env *env, const int32_t *list, const int32_t *offset, const int32_t *count, int level,
                 int ctas_per_sm, cudaStream_t s)
@@ -520,6 +504,14 @@ int prepare_tile_kernel()
 {
     CUDA_TRY(cudaFuncSetAttribute(tc::k_tile_mlp<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)tc::Smem<ST>::BYTES));
+    return SSB_OK;
+}
+
+int launch_mlp_backward(int stage, ssb_env *env, const int32_t *list, const int32_t *offset, const int32_t *count,
+                        int level, const float *g_out, float *dW, const bwd::Bufs &bw, cudaStream_t s)
+{
+    CUDA_TRY(bwd::mlp_backward(stage, env->p, env->num_sms, list, offset, count, level, g_out, nullptr, nullptr, dW, bw,
+                               true, s));
     return SSB_OK;
 }
 
@@ -1097,9 +1089,8 @@ int ssb_decima_head_adjoint(ssb_env *env, const float *grad_lgprob, const float 
 {
     if (!env || !env->p.pol_w || !grad_lgprob || !grad_entropy || !grad_stage_logits || !grad_exec_logits)
         return SSB_E_INVALID;
-    tc::k_pol_head_adjoint<<<(env->p.B + 3) / 4, 128, 0, (cudaStream_t)stream>>>(env->p, grad_lgprob, grad_entropy,
-                                                                                 grad_stage_logits, grad_exec_logits);
-    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(bwd::head_adjoint(env->p, grad_lgprob, grad_entropy, grad_stage_logits, grad_exec_logits,
+                               (cudaStream_t)stream));
     return SSB_OK;
 }
 
@@ -1110,21 +1101,11 @@ int ssb_decima_head_backward(ssb_env *env, const float *grad_stage_logits, const
     if (!env || !env->p.pol_w || !grad_stage_logits || !grad_exec_logits || !grad_weights) return SSB_E_INVALID;
     cudaStream_t s = (cudaStream_t)stream;
     const Params &p = env->p;
-    static bool prepared = false;
-    if (!prepared) {
-        CUDA_TRY(cudaFuncSetAttribute(tc::k_mlp_backward<tc::ST_STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)tc::BwdSmem<tc::ST_STAGE>::BYTES));
-        CUDA_TRY(cudaFuncSetAttribute(tc::k_mlp_backward<tc::ST_EXEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)tc::BwdSmem<tc::ST_EXEC>::BYTES));
-        prepared = true;
-    }
-    tc::TileArgs as{nullptr, nullptr, p.pl_cnt + tc::CNT_CAND, 0};
-    tc::k_mlp_backward<tc::ST_STAGE><<<env->num_sms, 128, tc::BwdSmem<tc::ST_STAGE>::BYTES, s>>>(
-        p, as, grad_stage_logits, grad_stage_inputs, stage_inputs, grad_weights, tc::BwdBufs{nullptr, nullptr, nullptr});
-    tc::TileArgs ae{p.pl_exec, nullptr, p.pl_cnt + tc::CNT_EXEC, 0};
-    tc::k_mlp_backward<tc::ST_EXEC><<<env->num_sms, 128, tc::BwdSmem<tc::ST_EXEC>::BYTES, s>>>(
-        p, ae, grad_exec_logits, grad_exec_inputs, exec_inputs, grad_weights, tc::BwdBufs{nullptr, nullptr, nullptr});
-    CUDA_TRY(cudaGetLastError());
+    const bwd::Bufs none{nullptr, nullptr, nullptr, nullptr, nullptr};
+    CUDA_TRY(bwd::mlp_backward(tc::ST_STAGE, p, env->num_sms, nullptr, nullptr, p.pl_cnt + tc::CNT_CAND, 0,
+                               grad_stage_logits, grad_stage_inputs, stage_inputs, grad_weights, none, false, s));
+    CUDA_TRY(bwd::mlp_backward(tc::ST_EXEC, p, env->num_sms, p.pl_exec, nullptr, p.pl_cnt + tc::CNT_EXEC, 0,
+                               grad_exec_logits, grad_exec_inputs, exec_inputs, grad_weights, none, false, s));
     if (num_rows) {
         int32_t c[tc::CNT_OVERFLOW + 1];
         CUDA_TRY(cudaMemcpyAsync(c, p.pl_cnt, sizeof(c), cudaMemcpyDeviceToHost, s));
@@ -1154,17 +1135,16 @@ int ssb_decima_backward(ssb_env *env, const float *grad_lgprob, const float *gra
     CUDA_TRY(cudaMemsetAsync(grad_node_embeddings, 0, sizeof(float) * (size_t)p.B * p.Sc * 16, s));
     CUDA_TRY(cudaMemsetAsync(b.d_hdag, 0, sizeof(float) * (size_t)p.B * p.Jc * 16, s));
     CUDA_TRY(cudaMemsetAsync(b.d_hglob, 0, sizeof(float) * (size_t)p.B * 16, s));
-    tc::k_pol_head_adjoint<<<(p.B + 3) / 4, 128, 0, s>>>(p, grad_lgprob, grad_entropy, b.gs, b.ge);
-    CUDA_TRY(cudaGetLastError());
-    const tc::BwdBufs bw{grad_node_embeddings, b.d_hdag, b.d_hglob, b.d_hinit, b.d_msg};
+    CUDA_TRY(bwd::head_adjoint(p, grad_lgprob, grad_entropy, b.gs, b.ge, s));
+    const bwd::Bufs bw{grad_node_embeddings, b.d_hdag, b.d_hglob, b.d_hinit, b.d_msg};
     const int32_t *cnt = p.pl_cnt;
     float *gw = grad_weights;
     int rc;
     // heads first (their input gradients feed all three summaries), then the global summary, then the job summaries
-    if ((rc = launch_mlp_backward<tc::ST_STAGE>(env, nullptr, nullptr, cnt + tc::CNT_CAND, 0, b.gs, gw, bw, s))) return rc;
-    if ((rc = launch_mlp_backward<tc::ST_EXEC>(env, p.pl_exec, nullptr, cnt + tc::CNT_EXEC, 0, b.ge, gw, bw, s))) return rc;
-    if ((rc = launch_mlp_backward<tc::ST_GLOB>(env, p.pl_jobs, nullptr, cnt + tc::CNT_JOBS, 0, nullptr, gw, bw, s))) return rc;
-    if ((rc = launch_mlp_backward<tc::ST_DAG>(env, p.pl_all, nullptr, cnt + tc::CNT_ALL, 0, nullptr, gw, bw, s))) return rc;
+    if ((rc = launch_mlp_backward(tc::ST_STAGE, env, nullptr, nullptr, cnt + tc::CNT_CAND, 0, b.gs, gw, bw, s))) return rc;
+    if ((rc = launch_mlp_backward(tc::ST_EXEC, env, p.pl_exec, nullptr, cnt + tc::CNT_EXEC, 0, b.ge, gw, bw, s))) return rc;
+    if ((rc = launch_mlp_backward(tc::ST_GLOB, env, p.pl_jobs, nullptr, cnt + tc::CNT_JOBS, 0, nullptr, gw, bw, s))) return rc;
+    if ((rc = launch_mlp_backward(tc::ST_DAG, env, p.pl_all, nullptr, cnt + tc::CNT_ALL, 0, nullptr, gw, bw, s))) return rc;
     if (!through_node_encoder) return SSB_OK;
     // NodeEncoder (scheduler.py:191-234), the levels in the reverse of the forward order.  Level k's backward needs
     // the embeddings as they were BEFORE level k and the level's messages; the forward pass overwrites both in
@@ -1184,15 +1164,15 @@ int ssb_decima_backward(ssb_env *env, const float *grad_lgprob, const float *gra
         }
         if ((rc = launch_tile<tc::ST_MSG>(env, p.pl_lvl, cnt + tc::OFF_LVL + 2 * k, cnt + tc::CNT_LVL + 2 * k, k, 4, s)))
             return rc;
-        if ((rc = launch_mlp_backward<tc::ST_RCV>(env, p.pl_lvl, cnt + tc::OFF_LVL + 2 * k + 1,
+        if ((rc = launch_mlp_backward(tc::ST_RCV, env, p.pl_lvl, cnt + tc::OFF_LVL + 2 * k + 1,
                                                   cnt + tc::CNT_LVL + 2 * k + 1, k, nullptr, gw, bw, s)))
             return rc;
-        if ((rc = launch_mlp_backward<tc::ST_MSG>(env, p.pl_lvl, cnt + tc::OFF_LVL + 2 * k, cnt + tc::CNT_LVL + 2 * k, k,
+        if ((rc = launch_mlp_backward(tc::ST_MSG, env, p.pl_lvl, cnt + tc::OFF_LVL + 2 * k, cnt + tc::CNT_LVL + 2 * k, k,
                                                   nullptr, gw, bw, s)))
             return rc;
     }
-    if ((rc = launch_mlp_backward<tc::ST_SINK>(env, p.pl_sink, nullptr, cnt + tc::CNT_SINK, 0, nullptr, gw, bw, s))) return rc;
-    if ((rc = launch_mlp_backward<tc::ST_PREP>(env, p.pl_all, nullptr, cnt + tc::CNT_ALL, 0, nullptr, gw, bw, s))) return rc;
+    if ((rc = launch_mlp_backward(tc::ST_SINK, env, p.pl_sink, nullptr, cnt + tc::CNT_SINK, 0, nullptr, gw, bw, s))) return rc;
+    if ((rc = launch_mlp_backward(tc::ST_PREP, env, p.pl_all, nullptr, cnt + tc::CNT_ALL, 0, nullptr, gw, bw, s))) return rc;
     return SSB_OK;
 }
 

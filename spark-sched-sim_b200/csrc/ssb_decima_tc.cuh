@@ -548,7 +548,7 @@ __device__ inline void plan_bits_w(const Params &p, int b, int lane, int N, int 
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(128) k_pol_plan_a(Params p)
+static __global__ void __launch_bounds__(128) k_pol_plan_a(Params p)
 {
     __shared__ int hist_s[4][2 * MAX_LEVELS];
     const int b = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
@@ -603,7 +603,7 @@ __global__ void __launch_bounds__(128) k_pol_plan_a(Params p)
 }
 
 // exclusive scan of the 2 * MAX_LEVELS level-list lengths; cursors start at the offsets
-__global__ void k_pol_plan_scan(Params p)
+static __global__ void k_pol_plan_scan(Params p)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     int run = 0;
@@ -617,7 +617,7 @@ __global__ void k_pol_plan_scan(Params p)
 }
 
 // Pass B: fill the per-level sender / receiver lists
-__global__ void __launch_bounds__(128) k_pol_plan_b(Params p)
+static __global__ void __launch_bounds__(128) k_pol_plan_b(Params p)
 {
     __shared__ int hist_s[4][2 * MAX_LEVELS];
     const int b = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
@@ -651,7 +651,7 @@ __global__ void __launch_bounds__(128) k_pol_plan_b(Params p)
 }
 
 // h_glob = sum over the active jobs of the global MLP's outputs (:265-276), in job order
-__global__ void __launch_bounds__(128) k_pol_glob_sum(Params p)
+static __global__ void __launch_bounds__(128) k_pol_glob_sum(Params p)
 {
     const int b = blockIdx.x * 8 + (threadIdx.x >> 4), c = threadIdx.x & 15;
     if (b >= p.B) return;
@@ -663,7 +663,7 @@ __global__ void __launch_bounds__(128) k_pol_glob_sum(Params p)
 }
 
 // stage sampling (utils.sample, decima/utils.py:19-23) + the rows of the executor-count head
-__global__ void __launch_bounds__(128) k_pol_sample_stage(Params p, const int32_t *forced_stage)
+static __global__ void __launch_bounds__(128) k_pol_sample_stage(Params p, const int32_t *forced_stage)
 {
     const int b = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (b >= p.B) return;
@@ -710,7 +710,7 @@ __global__ void __launch_bounds__(128) k_pol_sample_stage(Params p, const int32_
     for (int c = lane; c < cap; c += 32) p.pl_exec[base + c] = b * p.Epad + c;
 }
 
-__global__ void __launch_bounds__(128)
+static __global__ void __launch_bounds__(128)
 k_pol_sample_exec(Params p, const int32_t *forced_num_exec, int32_t *stage_idx_out, int32_t *num_exec_out,
                   int advance_draws)
 {
@@ -774,7 +774,7 @@ __device__ inline void softmax_adjoint_w(const float *z, int n, int sel, float g
         dz[i] = pr * (G(i, pr) - dot);
     }
 }
-__global__ void __launch_bounds__(128)
+static __global__ void __launch_bounds__(128)
 k_pol_head_adjoint(Params p, const float *grad_lgprob, const float *grad_entropy, float *grad_stage, float *grad_exec)
 {
     const int b = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;

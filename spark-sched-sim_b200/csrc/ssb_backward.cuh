@@ -1,7 +1,7 @@
 // ssb_backward.cuh -- host-side launchers of the policy's backward kernels.  The kernels (ssb_decima_tc.cuh:
 // k_pol_head_adjoint, k_mlp_backward<ST>) are instantiated in their own translation unit (ssb_backward.cu): the
 // rollout kernels of ssb_api.cu are bound by instruction supply and their speed moves by several percent with the
-// code that is laid out around them, so nothing that is not on the simulation path is compiled into that unit.
+// code that is laid out around them (-5.5 % with these kernels instantiated there), so they are kept out of it.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SSB_ABI_VERSION 4
+#define SSB_ABI_VERSION 5
 
 /* status codes of the entry points */
 enum {
@@ -68,7 +68,7 @@ typedef struct {
     double job_arrival_rate; /* 1/ms */
     double beta;             /* continuous discount (trainer.beta_discount), 0 = undiscounted */
     int32_t flags;           /* SSB_FLAG_* */
-    int32_t pad;
+    int32_t history_capacity; /* executor-history rows per env and episode (ssb_get_history); 0 = not recorded */
 } ssb_config;
 
 #define SSB_FLAG_DECIMA_OBS 1    /* allocate the Decima observation buffers (ssb_decima_obs) */
@@ -258,6 +258,8 @@ int ssb_ppo_loss(const float *new_lgprob, const float *old_lgprob, const float *
  * max_grad_norm) (skipped when max_grad_norm <= 0), then one torch.optim.Adam step (no weight decay, no amsgrad) on
  * the flat parameter vector (the ssb_set_decima_weights layout).  All arrays DEVICE f32[n]; step = 1 for the first
  * update; scratch = DEVICE f64[128]; grad_norm_out (DEVICE f32[1], may be NULL) receives the norm before clipping.
+ * A non-finite norm (the reference's clip_grad_norm_(error_if_nonfinite=True) raises) leaves param / exp_avg /
+ * exp_avg_sq untouched: check grad_norm_out.
  * With several GPUs the caller all-reduces `grad` (NCCL, mean) before this call. */
 int ssb_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int32_t n, int32_t step, float lr,
                   float beta1, float beta2, float eps, float max_grad_norm, double *scratch, float *grad_norm_out,
@@ -393,6 +395,17 @@ int ssb_get_jobs(ssb_env *env, int32_t env_index, int32_t *n_jobs, double *t_arr
 int ssb_get_log(ssb_env *env, int32_t env_index, int64_t lo, int64_t hi, int64_t *n_rows, double *t,
                 uint8_t *type, int16_t *job, int16_t *stage, int32_t *task, int16_t *exec,
                 double *t_accepted);
+
+/* Executor history (components/executor.py:25-44 `history`, Executor.add_history; the renderer's input,
+ * spark_sched_sim.py:408-424): every add_history call of env_index's current episode in call order -- t[i] = the
+ * wall time of the call (= the release time that closes the executor's previous entry), exec[i] = executor id,
+ * job[i] = the job the executor belongs to from then on (-1 = common pool).  Called when an executor arrives at a
+ * job (:445) and when an idle executor of a saturated job drains to the common pool (:782).  Executor e's list in
+ * the reference's format is [[t_1, -1], [t_2, job_1], ..., [None, job_n]] over its rows (t_k, job_k).  Needs
+ * ssb_config.history_capacity > 0; *n_rows = calls so far (may exceed the stored capacity).  HOST outputs,
+ * synchronous; any output may be NULL. */
+int ssb_get_history(ssb_env *env, int32_t env_index, int64_t *n_rows, double *t, int16_t *exec, int16_t *job,
+                    int64_t capacity);
 
 #ifdef __cplusplus
 }

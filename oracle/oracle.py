@@ -85,6 +85,9 @@ def lib():
         L.orc_log_size.restype = C.c_int64
         L.orc_log_size.argtypes = [C.c_void_p]
         L.orc_log_copy.argtypes = [C.c_void_p, C.c_int64, C.c_int64] + [C.c_void_p] * 7
+        L.orc_history_size.restype = C.c_int64
+        L.orc_history_size.argtypes = [C.c_void_p]
+        L.orc_history_copy.argtypes = [C.c_void_p] + [C.c_void_p] * 3
         L.orc_run_fair_episode.restype = C.c_int64
         L.orc_run_fair_episode.argtypes = [C.c_void_p, C.c_uint64, C.c_int32, C.POINTER(C.c_int64)]
         L.orc_philox4x32_10.argtypes = [C.c_void_p] * 3
@@ -203,6 +206,14 @@ class OracleEnv:
         self.L.orc_log_copy(self.h, lo, hi, *[_p(out[x]) for x in (
             "ev_t", "ev_type", "ev_job", "ev_stage", "ev_task", "ev_exec", "ev_tacc")])
         return out
+
+    def history(self):
+        """Every Executor.add_history call of the episode in call order: (t, executor id, job id or -1)."""
+        n = self.L.orc_history_size(self.h)
+        t, ex, jb = np.zeros(n), np.zeros(n, np.int32), np.zeros(n, np.int32)
+        if n:
+            self.L.orc_history_copy(self.h, _p(t), _p(ex), _p(jb))
+        return {"hist_t": t, "hist_exec": ex, "hist_job": jb}
 
     def log_size(self):
         return self.L.orc_log_size(self.h)

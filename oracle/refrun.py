@@ -10,7 +10,8 @@ instrumentation (no source edits) that records
 * the duration tape: every value `TPCHDataSampler.task_duration` returned, in call order,
 * every popped event `(t, type, job, stage, task, executor, t_accepted)` (spark_sched_sim.py:326-329),
 * every action and everything `step()` returned, including the whole observation dict,
-* final per-job completion times.
+* final per-job completion times,
+* every executor's `history` list (executor.py:25-44) as the episode left it.
 
 `tests/golden/gen_golden.py` serialises these as fixtures; the C oracle (oracle/sim_oracle.c) is
 pinned against them, and the CUDA path is compared with the oracle.
@@ -47,11 +48,12 @@ def _import_product_bank():
 _SETUP_DONE = {}
 
 
-def setup(bank_seed: int = 0) -> str:
+def setup(bank_seed: int = 0, bank_kind: str = "appd") -> str:
     """Puts the shim + reference on sys.path, writes the synthetic dataset, chdirs next to it."""
-    if bank_seed in _SETUP_DONE:
-        os.chdir(_SETUP_DONE[bank_seed])
-        return _SETUP_DONE[bank_seed]
+    key = (bank_seed, bank_kind)
+    if key in _SETUP_DONE:
+        os.chdir(_SETUP_DONE[key])
+        return _SETUP_DONE[key]
     if not reference_available():
         raise RuntimeError(f"reference not found at {REFERENCE}")
     for p in (REFERENCE, osp.join(HERE, "refshim")):
@@ -83,11 +85,11 @@ def setup(bank_seed: int = 0) -> str:
             except ImportError:
                 sys.modules[name] = _Stub(name)
     bank = _import_product_bank()
-    root = f"/tmp/ssb_refdata_seed{bank_seed}"
+    root = f"/tmp/ssb_refdata_{bank_kind}_seed{bank_seed}"
     if not osp.isdir(osp.join(root, "data", "tpch", "100g")):
-        bank.write_tpch_dir(root, bank.make_synthetic_tpch(bank_seed))
+        bank.write_tpch_dir(root, bank.make_synthetic_tpch(bank_seed, bank_kind))
     os.chdir(root)
-    _SETUP_DONE[bank_seed] = root
+    _SETUP_DONE[key] = root
     return root
 
 
@@ -148,9 +150,10 @@ def run_episode(
     max_steps: int | None = None,
     bank_seed: int = 0,
     decima: bool = False,
+    bank_kind: str = "appd",
 ) -> dict:
     """One reference episode -> trace dict of numpy arrays (see module docstring)."""
-    setup(bank_seed)
+    setup(bank_seed, bank_kind)
     import gymnasium
     from philox_ref import PhiloxNpRandom
 
@@ -306,6 +309,16 @@ def run_episode(
         dutils.sample = orig_sample
 
     evarr = np.array(events, dtype=np.float64).reshape(-1, 7)
+    # executor.history (executor.py:25-44) as the reference left it: per executor the list [[t, job_id], ...] whose
+    # last entry has t = None; stored as its add_history calls (t_k = history[k-1][0], job_k = history[k][1])
+    hist_ptr, hist_t, hist_job = [0], [], []
+    for ex in env.executors:
+        h = ex.history
+        assert h[0][1] == -1 and h[-1][0] is None
+        for k in range(1, len(h)):
+            hist_t.append(float(h[k - 1][0]))
+            hist_job.append(int(h[k][1]))
+        hist_ptr.append(len(hist_t))
     trace = {
         "num_executors": env_cfg["num_executors"],
         "moving_delay": float(env_cfg["moving_delay"]),
@@ -318,6 +331,8 @@ def run_episode(
         "rng": rng,
         "policy": policy,
         "policy_seed": policy_seed,
+        "bank_seed": bank_seed,
+        "bank_kind": bank_kind,
         "job_t_arrival": np.array([float(j.t_arrival) for j in jobs], np.float64),
         "job_template": np.array(job_template, np.int32),
         "job_t_completed": np.array([float(j.t_completed) for j in jobs], np.float64),
@@ -360,6 +375,9 @@ def run_episode(
         "ev_task": evarr[:, 4].astype(np.int32),
         "ev_exec": evarr[:, 5].astype(np.int16),
         "ev_tacc": evarr[:, 6].copy(),
+        "hist_ptr": np.array(hist_ptr, np.int32),
+        "hist_t": np.array(hist_t, np.float64),
+        "hist_job": np.array(hist_job, np.int32),
         "final_wall": float(env.wall_time),
         "avg_job_duration_s": float(
             np.mean([min(j.t_completed, env.wall_time) - j.t_arrival for j in jobs]) * 1e-3),
@@ -367,15 +385,45 @@ def run_episode(
     return trace
 
 
-def slim(trace: dict) -> dict:
-    """Replaces the bulky per-step observations and per-event rows by digests (big episodes)."""
+def decima_digest(feat, caps, depth, edge_bits, stage_mask) -> int:
+    """sha256 over what DecimaObsWrapper adds to one observation (features, exec_mask as caps, edge masks as per-edge
+    level bits, stage mask)."""
+    h = hashlib.sha256()
+    h.update(np.ascontiguousarray(feat, dtype=np.float32).tobytes())
+    h.update(np.asarray(caps, dtype=np.int32).tobytes())
+    h.update(np.asarray([depth], dtype=np.int32).tobytes())
+    h.update(np.ascontiguousarray(edge_bits, dtype=np.uint64).tobytes())
+    h.update(np.ascontiguousarray(stage_mask, dtype=np.uint8).tobytes())
+    return int.from_bytes(h.digest()[:8], "little")
+
+
+def slim(trace: dict, logit_stride: int = 1) -> dict:
+    """Replaces the bulky per-step observations and per-event rows by digests (big episodes).  Decima-driven
+    episodes keep the policy's recorded scores of every `logit_stride`-th decision (`pol_kept` = their indices) and
+    the log-probability of every decision."""
     t = dict(trace)
+    if len(t["dec_depth"]):  # per-observation digest of the Decima adapter's outputs
+        n = e = s = 0
+        dig = []
+        for k in range(len(t["N"])):
+            N, M, Ja = int(t["N"][k]), int(t["M"][k]), int(t["Ja"][k])
+            dig.append(decima_digest(t["dec_feat"][n:n + N], t["dec_caps"][s:s + Ja], int(t["dec_depth"][k]),
+                                     t["dec_edge_bits"][e:e + M], t["dec_stage_mask"][n:n + N]))
+            n += N; e += M; s += Ja
+        t["dec_digest"] = np.array(dig, np.uint64)
+    if len(t["pol_stage_count"]) and logit_stride > 1:
+        keep = np.arange(0, len(t["pol_stage_count"]), logit_stride)
+        so = np.concatenate([[0], np.cumsum(t["pol_stage_count"])])
+        eo = np.concatenate([[0], np.cumsum(t["pol_exec_count"])])
+        t["pol_stage_logits"] = np.concatenate([t["pol_stage_logits"][so[k]:so[k + 1]] for k in keep])
+        t["pol_exec_logits"] = np.concatenate([t["pol_exec_logits"][eo[k]:eo[k + 1]] for k in keep])
+        t["pol_kept"] = keep.astype(np.int32)
     ec = t["ev_count"]
     lo = np.concatenate([[0], ec[:-1]])
     t["ev_digest"] = np.array(
         [events_digest(trace, int(a), int(b)) for a, b in zip(lo, ec)], np.uint64)
     for k in ("nodes", "edges", "dag_ptr", "supplies", "ev_t", "ev_type", "ev_job", "ev_stage",
-              "ev_task", "ev_exec", "ev_tacc", "tape_meta", "dec_feat", "dec_caps", "dec_depth",
+              "ev_task", "ev_exec", "ev_tacc", "tape_meta", "dec_feat", "dec_caps",
               "dec_edge_bits", "dec_stage_mask"):
         t.pop(k)
     t["slim"] = True

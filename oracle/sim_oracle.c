@@ -335,6 +335,8 @@ struct orc_env {
     uint8_t *active_stage_mask; int32_t *node_idx;
     /* log */
     int log_on; int64_t log_n, log_cap; Event *log;
+    /* executor.history (executor.py:25-44): one row per add_history call, in call order */
+    int64_t hist_n, hist_cap; double *hist_t; int32_t *hist_exec, *hist_job;
     int64_t n_events;
     int done;
     int error;
@@ -599,6 +601,23 @@ static int find_schedulable_stages(Env *e, const int *job_ids, int n_ids, int so
 static int job_saturated(const Job *j) { return j->saturated_stage_count == j->n_stages; } /* job.py:54-55 */
 static int stage_completed(const Stage *s) { return s->completed == s->num_tasks; }        /* stage.py:38-39 */
 
+/* Executor.add_history (executor.py:34-44): closes the executor's latest history entry with the wall time and opens
+ * a new one for job_id (-1 = common pool).  Kept as the flat sequence of calls; executor k's list is
+ * [[t_1, -1], [t_2, job_1], ..., [None, job_n]] for its calls (t_i, job_i). */
+static void add_history(Env *e, int executor_id, int job_id)
+{
+    if (e->hist_n == e->hist_cap) {
+        e->hist_cap = e->hist_cap ? e->hist_cap * 2 : 256;
+        e->hist_t = (double *)realloc(e->hist_t, sizeof(double) * e->hist_cap);
+        e->hist_exec = (int32_t *)realloc(e->hist_exec, sizeof(int32_t) * e->hist_cap);
+        e->hist_job = (int32_t *)realloc(e->hist_job, sizeof(int32_t) * e->hist_cap);
+    }
+    e->hist_t[e->hist_n] = e->wall_time;
+    e->hist_exec[e->hist_n] = executor_id;
+    e->hist_job[e->hist_n] = job_id;
+    e->hist_n++;
+}
+
 static void detach_executor(Env *e, Job *job, Executor *ex) /* job.py:86-89 */
 {
     CHECK(job->local[ex->id]);
@@ -654,7 +673,10 @@ static void move_idle_executors(Env *e, int src, const int *ids, int n_ids)
     int dst = sat ? POOL_COMMON : pool_of_job(e, job_id);
     for (int i = 0; i < n_ids; i++) {
         move_executor_to_pool(e, ids[i], dst, 0);
-        if (dst == POOL_COMMON) detach_executor(e, &e->jobs[job_id], &e->executors[ids[i]]);
+        if (dst == POOL_COMMON) {
+            detach_executor(e, &e->jobs[job_id], &e->executors[ids[i]]);
+            add_history(e, ids[i], -1); /* :782 */
+        }
     }
 }
 
@@ -800,6 +822,7 @@ static void handle_executor_arrival(Env *e, Executor *ex, Stage *stage) /* :440-
 {
     Job *job = &e->jobs[stage->job_id];
     attach_executor(e, job, ex);
+    add_history(e, ex->id, job->id); /* :445 */
     int sp = pool_of_stage(e, stage);
     e->n_moving_to[sp] -= 1; /* record_executor_arrival, executor_tracker.py:182-184 */
     CHECK(e->n_moving_to[sp] >= 0);
@@ -1057,6 +1080,7 @@ static void build_episode(Env *e, int n_jobs, const double *t_arrival, const int
     e->counter = 0;
     e->launch_idx = 0;
     e->log_n = 0;
+    e->hist_n = 0;
     e->n_events = 0;
     e->done = 0;
     e->n_jobs = n_jobs;
@@ -1213,6 +1237,7 @@ void orc_destroy(orc_env *e)
     }
     free(e->t_pred_ptr); free(e->t_pred); free(e->t_succ_ptr); free(e->t_succ);
     free(e->executors); free(e->exec_loc); free(e->pq); free(e->log); free(e->tape_own);
+    free(e->hist_t); free(e->hist_exec); free(e->hist_job);
     free(e);
 }
 
@@ -1388,6 +1413,12 @@ void orc_log_copy(const orc_env *e, int64_t lo, int64_t hi, double *t, uint8_t *
         t[k] = ev->t; type[k] = (uint8_t)ev->type; job[k] = (int16_t)ev->job; stage[k] = (int16_t)ev->stage;
         task[k] = ev->task; exec[k] = (int16_t)ev->exec; tacc[k] = ev->t_accepted;
     }
+}
+
+int64_t orc_history_size(const orc_env *e) { return e->hist_n; }
+void orc_history_copy(const orc_env *e, double *t, int32_t *exec, int32_t *job)
+{
+    for (int64_t i = 0; i < e->hist_n; i++) { t[i] = e->hist_t[i]; exec[i] = e->hist_exec[i]; job[i] = e->hist_job[i]; }
 }
 
 int64_t orc_run_fair_episode(orc_env *e, uint64_t seed, int32_t dynamic_partition, int64_t *events)

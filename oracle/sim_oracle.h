@@ -90,6 +90,11 @@ int64_t orc_log_size(const orc_env *env);
 void orc_log_copy(const orc_env *env, int64_t lo, int64_t hi, double *t, uint8_t *type, int16_t *job,
                   int16_t *stage, int32_t *task, int16_t *exec, double *t_accepted);
 
+/* executor.history (components/executor.py:25-44; only the renderer reads it): every add_history call of the episode
+ * in call order -- (wall time, executor id, job id or -1 for the common pool) */
+int64_t orc_history_size(const orc_env *env);
+void orc_history_copy(const orc_env *env, double *t, int32_t *exec, int32_t *job);
+
 /* whole fair/FIFO episodes back to back (CPU baseline): returns decisions made, <0 on error */
 int64_t orc_run_fair_episode(orc_env *env, uint64_t seed, int32_t dynamic_partition, int64_t *events);
 

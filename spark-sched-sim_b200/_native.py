@@ -9,7 +9,7 @@ import numpy as np
 
 PKG_DIR = osp.dirname(osp.abspath(__file__))
 LIB_PATH = osp.join(PKG_DIR, "_lib", "libssb.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class SsbConfig(C.Structure):
@@ -25,7 +25,7 @@ class SsbConfig(C.Structure):
         ("job_arrival_rate", C.c_double),
         ("beta", C.c_double),
         ("flags", C.c_int32),
-        ("pad", C.c_int32),
+        ("history_capacity", C.c_int32),
     ]
 
 
@@ -127,7 +127,7 @@ EXPORTS = [
     "ssb_abi_version", "ssb_last_cuda_error", "ssb_workspace_bytes", "ssb_create", "ssb_destroy",
     "ssb_load_trace", "ssb_clear_trace", "ssb_reset", "ssb_step", "ssb_reset_host", "ssb_step_host", "ssb_step_fair_host", "ssb_set_autoreset", "ssb_set_mean_time_limit",
     "ssb_rollout_fair", "ssb_rollout_fair_traj", "ssb_rollout_fair_async", "ssb_discounted_returns", "ssb_differential_returns", "ssb_group_baselines", "ssb_ppo_loss", "ssb_adam_step", "ssb_fair_actions", "ssb_get_views", "ssb_get_stats", "ssb_collect_stats", "ssb_reset_stats",
-    "ssb_get_jobs", "ssb_get_log", "ssb_decima_obs", "ssb_get_decima_views",
+    "ssb_get_jobs", "ssb_get_log", "ssb_get_history", "ssb_decima_obs", "ssb_get_decima_views",
     "ssb_set_decima_weights", "ssb_decima_policy", "ssb_rollout_decima", "ssb_decima_snapshot_bytes",
     "ssb_decima_snapshot", "ssb_decima_snapshot_load", "ssb_decima_snapshot_unload", "ssb_decima_evaluate", "ssb_decima_head_adjoint", "ssb_decima_head_backward", "ssb_decima_backward_bytes", "ssb_decima_backward", "ssb_get_policy_views", "ssb_get_debug_counters",
 ]
@@ -196,6 +196,7 @@ def lib():
     L.ssb_get_debug_counters.argtypes = [vp, C.POINTER(vp)]
     L.ssb_get_jobs.argtypes = [vp, i32, C.POINTER(i32), vp, vp, vp, vp, i32]
     L.ssb_get_log.argtypes = [vp, i32, i64, i64, C.POINTER(i64)] + [vp] * 7
+    L.ssb_get_history.argtypes = [vp, i32, C.POINTER(i64), vp, vp, vp, i64]
     if L.ssb_abi_version() != ABI_VERSION:
         raise ImportError("libssb ABI version mismatch; rebuild")
     _lib = L

@@ -39,13 +39,17 @@ WAVE_FRESH, WAVE_FIRST, WAVE_REST = 0, 1, 2
 MAX_STAGES_PER_JOB = 64  # parent/child/active/frontier sets are u64 bitmasks on the device
 
 
-def make_synthetic_tpch(seed: int = 0) -> dict:
-    """SURVEY.md App. D generator, verbatim: {(size, q): (adj int[n,n], td dict)}."""
-    rng = np.random.default_rng(seed)
+def make_synthetic_tpch(seed: int = 0, kind: str = "appd") -> dict:
+    """SURVEY.md App. D generator, verbatim: {(size, q): (adj int[n,n], td dict)}.
+    kind "wide": the same generator with 30..64 stages per template and few tasks per stage -- a test workload
+    for the code paths that only jobs of more than 32 stages reach (the u64 halves of the stage bitmasks)."""
+    assert kind in ("appd", "wide")
+    rng = np.random.default_rng(seed if kind == "appd" else (seed, 64))
+    wide = kind == "wide"
     data = {}
     for si, size in enumerate(QUERY_SIZES):
         for q in range(1, NUM_QUERIES + 1):
-            n = int(rng.integers(2, 19))
+            n = int(rng.integers(30, 65)) if wide else int(rng.integers(2, 19))
             adj = np.zeros((n, n), dtype=int)
             for v in range(1, n):
                 k = int(rng.integers(1, min(3, v) + 1))
@@ -53,7 +57,7 @@ def make_synthetic_tpch(seed: int = 0) -> dict:
                     adj[u, v] = 1
             td = {}
             for s in range(n):
-                ntasks = int(rng.integers(1, 60 * (1 + si)))
+                ntasks = int(rng.integers(1, (6 if wide else 60) * (1 + si)))
                 base = float(rng.uniform(200, 4000)) * (1 + 0.3 * si)
                 d = {"fresh_durations": {}, "first_wave": {}, "rest_wave": {}}
                 for e in EXEC_LEVELS:
@@ -248,13 +252,14 @@ def build_bank(data: dict) -> TemplateBank:
 _SYNTH_CACHE: dict = {}
 
 
-def synthetic_bank(seed: int = 0) -> TemplateBank:
-    """The App. D workload as a TemplateBank (cached per process)."""
-    if seed not in _SYNTH_CACHE:
-        bank = build_bank(make_synthetic_tpch(seed))
-        bank.meta = {"source": f"synthetic(App.D, default_rng({seed}))"}
-        _SYNTH_CACHE[seed] = bank
-    return _SYNTH_CACHE[seed]
+def synthetic_bank(seed: int = 0, kind: str = "appd") -> TemplateBank:
+    """The App. D workload (or its "wide" test variant, see make_synthetic_tpch) as a TemplateBank (cached)."""
+    key = (seed, kind)
+    if key not in _SYNTH_CACHE:
+        bank = build_bank(make_synthetic_tpch(seed, kind))
+        bank.meta = {"source": f"synthetic({kind}, default_rng({seed}))"}
+        _SYNTH_CACHE[key] = bank
+    return _SYNTH_CACHE[key]
 
 
 def executor_intervals(exec_cap: int) -> np.ndarray:

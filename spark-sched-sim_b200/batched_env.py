@@ -42,7 +42,7 @@ class BatchedSparkSchedSimEnv:
     def __init__(self, env_cfg: dict, num_envs: int, bank: TemplateBank | None = None,
                  device: str | torch.device = "cuda:0", max_jobs: int | None = None,
                  tape_capacity: int = 0, log_capacity: int = 0, decima_obs: bool = False,
-                 decima_policy: bool = False):
+                 decima_policy: bool = False, history_capacity: int = 0):
         self.L = nat.lib()
         if not torch.cuda.is_available():
             raise RuntimeError("BatchedSparkSchedSimEnv needs a CUDA device (no CPU fallback)")
@@ -63,7 +63,8 @@ class BatchedSparkSchedSimEnv:
             float(env_cfg.get("warmup_delay", 0.0)), float(env_cfg["job_arrival_rate"]),
             float(env_cfg.get("beta", 0.0)),
             (nat.FLAG_DECIMA_OBS if (decima_obs or decima_policy) else 0)
-            | (nat.FLAG_DECIMA_POLICY if decima_policy else 0), 0)
+            | (nat.FLAG_DECIMA_POLICY if decima_policy else 0), int(history_capacity))
+        self.history_capacity = int(history_capacity)
         decima_obs = decima_obs or decima_policy
         self._bank_struct, self._bank_keep = nat.make_bank_struct(self.bank)
         nbytes = C.c_size_t()
@@ -484,6 +485,29 @@ class BatchedSparkSchedSimEnv:
         if with_state:
             return ta[:k], tc[:k], tm[:k], st[:k]
         return ta[:k], tc[:k], tm[:k]
+
+    def history(self, b: int = 0) -> dict:
+        """Every Executor.add_history call of env b's current episode in call order (executor.py:34-44):
+        hist_t (wall time), hist_exec, hist_job (-1 = common pool).  Needs history_capacity > 0."""
+        n = C.c_int64()
+        cap = max(self.history_capacity, 1)
+        t, ex, jb = np.zeros(cap), np.zeros(cap, np.int16), np.zeros(cap, np.int16)
+        nat.check(self.L.ssb_get_history(self._h, int(b), C.byref(n), t.ctypes.data, ex.ctypes.data,
+                                         jb.ctypes.data, cap), "ssb_get_history")
+        if n.value > self.history_capacity:
+            raise RuntimeError(f"executor history overflow: {n.value} rows > history_capacity {self.history_capacity}")
+        k = int(n.value)
+        return {"hist_t": t[:k], "hist_exec": ex[:k].astype(np.int32), "hist_job": jb[:k].astype(np.int32)}
+
+    def executor_histories(self, b: int = 0) -> list:
+        """`[executor.history for executor in env.executors]` in the reference's format (spark_sched_sim.py:411):
+        per executor [[t_release, job_id], ..., [None, job_id]], job_id -1 = common pool."""
+        h = self.history(b)
+        out = [[[None, -1]] for _ in range(self.num_executors)]
+        for t, e, j in zip(h["hist_t"], h["hist_exec"], h["hist_job"]):
+            out[e][-1][0] = float(t)
+            out[e].append([None, int(j)])
+        return out
 
     def log_size(self, b: int = 0) -> int:
         n = C.c_int64()

@@ -43,6 +43,14 @@ constexpr int WARPS_PER_CTA = SSB_WARPS_PER_CTA;
         }                                                                                \
     } while (0)
 
+// The stream-taking entry points launch on the handle's device whatever the caller's current device is
+// (a stream of another device fails the launch with a plain CUDA error instead of an opaque one later).
+#define SSB_ON_DEVICE(env)                                                   \
+    do {                                                                     \
+        int cur_ = -1;                                                       \
+        if (cudaGetDevice(&cur_) != cudaSuccess || cur_ != (env)->device) CUDA_TRY(cudaSetDevice((env)->device)); \
+    } while (0)
+
 // ------------------------------------------------------------------------------------ kernels
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 k_reset(Params p, const uint64_t *seeds, const double *time_limits, const uint8_t *mask)
@@ -383,6 +391,7 @@ void carve(Carver &cv, const ssb_config &c, const ssb_bank &bk, const Dims &d, P
     p.trace_tmpl = cv.take<int32_t>(c.tape_capacity > 0 ? B * c.max_jobs : 1);
     p.tape = cv.take<double>(c.tape_capacity > 0 ? B * (size_t)c.tape_capacity : 1);
     p.log = cv.take<LogRow>(c.log_capacity > 0 ? B * (size_t)c.log_capacity : 1);
+    p.hist = cv.take<HistRow>(c.history_capacity > 0 ? B * (size_t)c.history_capacity : 1);
     p.stats = cv.take<ssb_stats>(B);
     p.stats_part = cv.take<double>(128 * 8);
     p.prof = cv.take<unsigned long long>(B * 16);
@@ -564,6 +573,7 @@ int ssb_create(const ssb_config *cfg, const ssb_bank *bk, int device, void *work
     p.B = cfg->num_envs; p.E = cfg->num_executors; p.Jc = cfg->max_jobs; p.Sc = d.Sc; p.Mc = d.Mc;
     p.TAB = d.TAB; p.RT = d.RT; p.P = d.P; p.Cc = d.Cc; p.max_stages = d.max_stages;
     p.tape_cap = cfg->tape_capacity; p.log_cap = cfg->log_capacity;
+    p.hist_cap = cfg->history_capacity > 0 ? cfg->history_capacity : 0;
     p.job_arrival_cap = cfg->job_arrival_cap;
     p.moving_delay = cfg->moving_delay; p.warmup_delay = cfg->warmup_delay;
     p.mean_interarrival = 1 / cfg->job_arrival_rate;  // tpch.py:42
@@ -709,6 +719,7 @@ int ssb_clear_trace(ssb_env *env, int32_t b)
 int ssb_reset(ssb_env *env, const uint64_t *seeds, const double *time_limits, const uint8_t *mask, void *stream)
 {
     if (!env) return SSB_E_INVALID;
+    SSB_ON_DEVICE(env);
     k_reset<<<env->grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(env->p, seeds, time_limits, mask);
     CUDA_TRY(cudaGetLastError());
     return SSB_OK;
@@ -731,7 +742,15 @@ int ssb_step(ssb_env *env, const int32_t *stage_idx, const int32_t *num_exec, co
              int32_t max_events, void *stream)
 {
     if (!env || !stage_idx || !num_exec) return SSB_E_INVALID;
+    SSB_ON_DEVICE(env);
     return step_launch(env, stage_idx, num_exec, mask, max_events, nullptr, nullptr, 0, (cudaStream_t)stream);
+}
+
+// The captured graph of ssb_rollout_decima holds Params and the auto-reset arguments BY VALUE: every setter that
+// changes one of them drops the graph, the next rollout call captures it again.
+static void drop_decision_graph(ssb_env *env)
+{
+    if (env->dg_exec) { cudaGraphExecDestroy(env->dg_exec); env->dg_exec = nullptr; }
 }
 
 int ssb_set_autoreset(ssb_env *env, int32_t enable, uint64_t seed_step)
@@ -739,6 +758,7 @@ int ssb_set_autoreset(ssb_env *env, int32_t enable, uint64_t seed_step)
     if (!env) return SSB_E_INVALID;
     env->auto_reset = enable ? 1 : 0;
     env->auto_seed_step = seed_step;
+    drop_decision_graph(env);
     return SSB_OK;
 }
 
@@ -746,6 +766,7 @@ int ssb_set_mean_time_limit(ssb_env *env, double mean_ms)
 {
     if (!env || !(mean_ms >= 0.0)) return SSB_E_INVALID;
     env->p.mean_time_limit = mean_ms;
+    drop_decision_graph(env);
     return SSB_OK;
 }
 
@@ -811,6 +832,7 @@ int ssb_rollout_fair_traj(ssb_env *env, int32_t num_decisions, int32_t dynamic_p
                           uint64_t seed_step, ssb_transition *traj, void *stream)
 {
     if (!env || num_decisions < 0) return SSB_E_INVALID;
+    SSB_ON_DEVICE(env);
     if (env->p.E <= 32)
         k_rollout_fair<1><<<env->grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(
             env->p, num_decisions, dynamic_partition, auto_reset, seed_step, traj);
@@ -825,6 +847,7 @@ int ssb_rollout_fair_async(ssb_env *env, int32_t max_decisions, double rollout_d
                            uint64_t seed_step, ssb_transition *traj, int32_t *num_steps, double *elapsed, void *stream)
 {
     if (!env || max_decisions < 0 || !(rollout_duration > 0.0)) return SSB_E_INVALID;
+    SSB_ON_DEVICE(env);
     if (env->p.E <= 32)
         k_rollout_fair_async<1><<<env->grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(
             env->p, max_decisions, rollout_duration, dynamic_partition, seed_step, traj, num_steps, elapsed);
@@ -844,6 +867,7 @@ int ssb_rollout_fair(ssb_env *env, int32_t num_decisions, int32_t dynamic_partit
 int ssb_fair_actions(ssb_env *env, int32_t dynamic_partition, int32_t *stage_idx, int32_t *num_exec, void *stream)
 {
     if (!env || !stage_idx || !num_exec) return SSB_E_INVALID;
+    SSB_ON_DEVICE(env);
     k_fair_actions<<<env->grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(env->p, dynamic_partition,
                                                                                stage_idx, num_exec);
     CUDA_TRY(cudaGetLastError());
@@ -868,6 +892,7 @@ int ssb_get_views(ssb_env *env, ssb_views *out)
 int ssb_decima_obs(ssb_env *env, void *stream)
 {
     if (!env || !env->p.dec_feat) return SSB_E_INVALID;  // needs SSB_FLAG_DECIMA_OBS
+    SSB_ON_DEVICE(env);
     k_decima_obs<<<env->grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(env->p);
     CUDA_TRY(cudaGetLastError());
     return SSB_OK;
@@ -969,6 +994,7 @@ int ssb_decima_policy(ssb_env *env, const int32_t *forced_stage, const int32_t *
                       int32_t *stage_idx_out, int32_t *num_exec_out, void *stream)
 {
     if (!env || !env->p.pol_w) return SSB_E_INVALID;  // needs SSB_FLAG_DECIMA_POLICY
+    SSB_ON_DEVICE(env);
     return decima_policy_impl(env, forced_stage, forced_num_exec, stage_idx_out, num_exec_out, true, true,
                               (cudaStream_t)stream);
 }
@@ -1018,6 +1044,7 @@ int ssb_decima_head_adjoint(ssb_env *env, const float *grad_lgprob, const float 
 {
     if (!env || !env->p.pol_w || !grad_lgprob || !grad_entropy || !grad_stage_logits || !grad_exec_logits)
         return SSB_E_INVALID;
+    SSB_ON_DEVICE(env);
     CUDA_TRY(bwd::head_adjoint(env->p, grad_lgprob, grad_entropy, grad_stage_logits, grad_exec_logits,
                                (cudaStream_t)stream));
     return SSB_OK;
@@ -1028,6 +1055,7 @@ int ssb_decima_head_backward(ssb_env *env, const float *grad_stage_logits, const
                              float *stage_inputs, float *exec_inputs, int32_t *num_rows, void *stream)
 {
     if (!env || !env->p.pol_w || !grad_stage_logits || !grad_exec_logits || !grad_weights) return SSB_E_INVALID;
+    SSB_ON_DEVICE(env);
     cudaStream_t s = (cudaStream_t)stream;
     const Params &p = env->p;
     const bwd::Bufs none{nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -1058,6 +1086,7 @@ int ssb_decima_backward(ssb_env *env, const float *grad_lgprob, const float *gra
     if (!env || !env->p.pol_w || !grad_lgprob || !grad_entropy || !grad_weights || !grad_node_embeddings || !scratch ||
         (reinterpret_cast<uintptr_t>(scratch) & 15))
         return SSB_E_INVALID;
+    SSB_ON_DEVICE(env);
     cudaStream_t s = (cudaStream_t)stream;
     const Params &p = env->p;
     const BackwardScratch b = backward_scratch(p, static_cast<float *>(scratch));
@@ -1115,6 +1144,7 @@ int ssb_decima_snapshot_bytes(ssb_env *env, size_t *bytes)
 int ssb_decima_snapshot(ssb_env *env, void *dst, void *stream)
 {
     if (!env || !dst || !env->p.dec_feat) return SSB_E_INVALID;
+    SSB_ON_DEVICE(env);
     k_decima_obs<<<env->grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(env->p);  // the adapter's view of the state
     CUDA_TRY(cudaGetLastError());
     return snapshot_copy(env, static_cast<char *>(dst), true, (cudaStream_t)stream);
@@ -1123,6 +1153,7 @@ int ssb_decima_snapshot(ssb_env *env, void *dst, void *stream)
 int ssb_decima_snapshot_load(ssb_env *env, const void *snapshot, void *stream)
 {
     if (!env || !snapshot || !env->p.pol_w || env->snap_loaded) return SSB_E_INVALID;
+    SSB_ON_DEVICE(env);
     cudaStream_t s = (cudaStream_t)stream;
     int rc;
     // the live observation is parked in the handle's scratch while the stored one is worked on
@@ -1135,6 +1166,7 @@ int ssb_decima_snapshot_load(ssb_env *env, const void *snapshot, void *stream)
 int ssb_decima_snapshot_unload(ssb_env *env, void *stream)
 {
     if (!env || !env->p.pol_w || !env->snap_loaded) return SSB_E_INVALID;
+    SSB_ON_DEVICE(env);
     env->snap_loaded = 0;
     return snapshot_copy(env, env->p.pol_snap, false, (cudaStream_t)stream);
 }
@@ -1143,15 +1175,25 @@ int ssb_decima_evaluate(ssb_env *env, const void *snapshot, const int32_t *stage
                         float *lgprob_out, float *entropy_out, void *stream)
 {
     if (!env || !stage_sel || !exec_sel || !env->p.pol_w) return SSB_E_INVALID;
+    SSB_ON_DEVICE(env);
     if (!snapshot && !env->snap_loaded) return SSB_E_INVALID;  // NULL: the snapshot ssb_decima_snapshot_load put in place
     cudaStream_t s = (cudaStream_t)stream;
     const size_t B = env->p.B;
     int rc;
     if (snapshot && (rc = ssb_decima_snapshot_load(env, snapshot, stream))) return rc;
-    if ((rc = decima_policy_impl(env, stage_sel, exec_sel, nullptr, nullptr, false, false, s))) return rc;
-    if (lgprob_out) CUDA_TRY(cudaMemcpyAsync(lgprob_out, env->p.pol_lgprob, B * 4, cudaMemcpyDeviceToDevice, s));
-    if (entropy_out) CUDA_TRY(cudaMemcpyAsync(entropy_out, env->p.pol_entropy, B * 4, cudaMemcpyDeviceToDevice, s));
-    return snapshot ? ssb_decima_snapshot_unload(env, stream) : SSB_OK;
+    // whatever happens below, a snapshot this call loaded is unloaded again (the live observation comes back)
+    rc = decima_policy_impl(env, stage_sel, exec_sel, nullptr, nullptr, false, false, s);
+    if (!rc && lgprob_out &&
+        cudaMemcpyAsync(lgprob_out, env->p.pol_lgprob, B * 4, cudaMemcpyDeviceToDevice, s) != cudaSuccess) rc = SSB_E_CUDA;
+    if (!rc && entropy_out &&
+        cudaMemcpyAsync(entropy_out, env->p.pol_entropy, B * 4, cudaMemcpyDeviceToDevice, s) != cudaSuccess) rc = SSB_E_CUDA;
+    if (rc == SSB_E_CUDA && !g_cuda_err[0]) snprintf(g_cuda_err, sizeof(g_cuda_err), "ssb_decima_evaluate: %s",
+                                                      cudaGetErrorString(cudaGetLastError()));
+    if (snapshot) {
+        const int rc2 = ssb_decima_snapshot_unload(env, stream);
+        if (!rc) rc = rc2;
+    }
+    return rc;
 }
 
 __global__ void k_traj_next(Params p) { if (threadIdx.x == 0 && blockIdx.x == 0) *p.traj_d += 1; }
@@ -1174,6 +1216,7 @@ static int decima_decision(ssb_env *env, int32_t num_decisions, int32_t max_even
 int ssb_rollout_decima(ssb_env *env, int32_t num_decisions, int32_t max_events, ssb_transition *traj, void *stream)
 {
     if (!env || !env->p.pol_w || num_decisions < 0) return SSB_E_INVALID;
+    SSB_ON_DEVICE(env);
     cudaStream_t caller = (cudaStream_t)stream, s = caller;
     // the legacy default stream cannot be captured: run on the handle's own stream, ordered after / before the
     // caller's stream with events
@@ -1251,6 +1294,7 @@ int ssb_get_debug_counters(ssb_env *env, uint64_t **out)
 int ssb_collect_stats(ssb_env *env, double *out, void *stream)
 {
     if (!env || !out) return SSB_E_INVALID;
+    SSB_ON_DEVICE(env);
     k_collect_stats_part<<<STATS_BLOCKS, 256, 0, (cudaStream_t)stream>>>(env->p, env->p.stats_part);
     k_collect_stats_final<<<1, 32, 0, (cudaStream_t)stream>>>(env->p.stats_part, out);
     CUDA_TRY(cudaGetLastError());
@@ -1260,6 +1304,7 @@ int ssb_collect_stats(ssb_env *env, double *out, void *stream)
 int ssb_reset_stats(ssb_env *env, void *stream)
 {
     if (!env) return SSB_E_INVALID;
+    SSB_ON_DEVICE(env);
     k_zero_stats<<<(env->p.B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(env->p.stats, env->p.B);
     CUDA_TRY(cudaGetLastError());
     return SSB_OK;
@@ -1283,6 +1328,27 @@ int ssb_get_jobs(ssb_env *env, int32_t b, int32_t *n_jobs, double *t_arrival, do
         if (t_completed) t_completed[j] = jr[j].t_completed;
         if (tmpl) tmpl[j] = jr[j].tmpl;
         if (state) state[j] = jr[j].state;
+    }
+    return SSB_OK;
+}
+
+int ssb_get_history(ssb_env *env, int32_t b, int64_t *n_rows, double *t, int16_t *exec, int16_t *job, int64_t capacity)
+{
+    if (!env || b < 0 || b >= env->p.B || !n_rows) return SSB_E_INVALID;
+    CUDA_TRY(cudaSetDevice(env->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    EnvHdr h;
+    CUDA_TRY(cudaMemcpy(&h, env->p.hdr + b, sizeof(EnvHdr), cudaMemcpyDeviceToHost));
+    *n_rows = h.hist_n;
+    int64_t n = std::min<int64_t>(std::min<int64_t>(h.hist_n, env->p.hist_cap), capacity);
+    if (n <= 0) return SSB_OK;
+    std::vector<HistRow> rows(n);
+    CUDA_TRY(cudaMemcpy(rows.data(), env->p.hist + (size_t)b * env->p.hist_cap, sizeof(HistRow) * n,
+                        cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < n; i++) {
+        if (t) t[i] = rows[i].t;
+        if (exec) exec[i] = rows[i].exec;
+        if (job) job[i] = rows[i].job;
     }
     return SSB_OK;
 }

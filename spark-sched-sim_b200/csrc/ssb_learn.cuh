@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(PPO_THREADS) k_grad_sqsum(const float *grad, i
     s = block_sum(s, sh);
     if (threadIdx.x == 0) part[blockIdx.x] = s;
 }
-// clip_grad_norm_: g *= min(1, max_norm / (||g|| + 1e-6)); then Adam (no weight decay, no amsgrad):
+// clip_grad_norm_: g *= min(1, max_norm / (||g|| + 1e-6)) (a non-finite norm leaves everything untouched); then Adam (no weight decay, no amsgrad):
 // m += (g - m) * (1 - b1); v = v * b2 + (1 - b2) * g * g; p -= (lr / (1 - b1^t)) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
 __global__ void __launch_bounds__(PPO_THREADS)
 k_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int n, int step, float lr, float beta1,
@@ -316,6 +316,9 @@ k_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, 
     float coef = 1.0f;
     if (max_grad_norm > 0.0f) coef = fminf(max_grad_norm / (total_norm + 1e-6f), 1.0f);
     if (grad_norm_out && blockIdx.x == 0 && threadIdx.x == 0) *grad_norm_out = total_norm;
+    // clip_grad_norm_(..., error_if_nonfinite=True) (schedulers/scheduler.py:46-48) raises on a NaN / Inf norm before
+    // optim.step(): nothing is written here either; the caller sees the non-finite norm in grad_norm_out and raises
+    if (!isfinite(total_norm)) return;
     const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
     const float step_size = (float)((double)lr / bc1), bc2_sqrt = (float)sqrt(bc2);
     for (int i = blockIdx.x * PPO_THREADS + threadIdx.x; i < n; i += gridDim.x * PPO_THREADS) {

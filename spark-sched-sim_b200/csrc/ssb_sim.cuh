@@ -554,6 +554,18 @@ struct Sim {
     }
 
     // ------------------------------------------------------------ executor motion
+    // Executor.add_history (components/executor.py:34-44; read by the renderer only, spark_sched_sim.py:408-424):
+    // "executor e now belongs to job (-1: the common pool) since wall_time".  Optional export, off by default.
+    __device__ SSB_RARE void add_history(int e, int job)
+    {
+        const int n = h->hist_n;
+        if (n < p.hist_cap) {
+            HistRow r;
+            r.t = h->wall_time; r.exec = (int16_t)e; r.job = (int16_t)job; r.pad = 0;
+            p.hist[(size_t)b * p.hist_cap + n] = r;
+        }
+        h->hist_n = n + 1;
+    }
     __device__ void detach_executor(int j, int e)  // job.py:86-89
     {
         SSB_CHK(jb[j].n_local > 0);
@@ -626,7 +638,10 @@ struct Sim {
         int dst = sat ? POOL_COMMON : pool_of_job(j);
         for (int i = 0; i < n; i++) {
             move_executor_to_pool(ids[i], dst, false);
-            if (dst == POOL_COMMON) detach_executor(j, ids[i]);
+            if (dst == POOL_COMMON) {
+                detach_executor(j, ids[i]);
+                if (p.hist_cap > 0) add_history(ids[i], -1);  // :782
+            }
         }
     }
     // _move_executor_to_stage (:799-819) with _try_backup_schedule (:784-797) unrolled into a loop
@@ -706,6 +721,7 @@ struct Sim {
         SSB_CHK(!ex[e].has_task);  // job.py:82
         jb[j].n_local += 1;
         ex[e].job_id = (int16_t)j;
+        if (p.hist_cap > 0) add_history(e, j);  // :445
         StageRec &r = st[jb[j].node_base + s];
         SSB_CHK(r.moving_to > 0);
         r.moving_to -= 1;  // record_executor_arrival
@@ -1696,6 +1712,7 @@ struct Sim {
             H.use_tape = (trace && H.tape_len >= 0) ? 1 : 0;
             H.pending = 0;
             H.policy_draws = 0;
+            H.hist_n = 0;
         }
         __syncwarp();
         if (h->error) {

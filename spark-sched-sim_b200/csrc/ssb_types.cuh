@@ -89,6 +89,14 @@ struct __align__(16) LogRow {
 };
 static_assert(sizeof(LogRow) == 32, "LogRow layout");
 
+struct __align__(16) HistRow {  // one Executor.add_history call (executor.py:34-44)
+    double t;     // wall time of the call = release time of the executor's previous history entry
+    int16_t exec;
+    int16_t job;  // job the executor now belongs to, -1 = common pool
+    int32_t pad;
+};
+static_assert(sizeof(HistRow) == 16, "HistRow layout");
+
 struct __align__(16) EnvHdr {
     double wall_time, time_limit, wall_old;
     uint64_t seed, base_seed;
@@ -100,13 +108,14 @@ struct __align__(16) EnvHdr {
     int32_t done, trace_jobs, tape_len, n_nodes_total;
     int32_t n_edges_total, reset_count, use_tape, pending;
     uint32_t policy_draws;  // Philox policy-stream counter (on-device action sampling)
-    int32_t pad2[3];
+    int32_t hist_n;         // add_history calls of this episode (rows beyond hist_cap are counted, not stored)
+    int32_t pad2[2];
 };
 
 // Everything a kernel needs, passed by value.
 struct Params {
     int B, E, Jc, Sc, Mc, TAB, RT, P, Cc, max_stages;
-    int tape_cap, log_cap, job_arrival_cap;
+    int tape_cap, log_cap, job_arrival_cap, hist_cap;
     double moving_delay, warmup_delay, mean_interarrival, beta;
     double mean_time_limit;  // > 0: every reset without an explicit limit draws one (StochasticTimeLimit)
     // template bank (read-only)
@@ -135,6 +144,7 @@ struct Params {
     int32_t *trace_tmpl;  // [B][Jc]
     double *tape;      // [B][tape_cap]
     LogRow *log;       // [B][log_cap]
+    HistRow *hist;     // [B][hist_cap] executor history (only with ssb_config.history_capacity > 0)
     ssb_stats *stats;  // [B]
     double *stats_part;  // [128][8] partial sums of ssb_collect_stats
     unsigned long long *prof;  // [B][16] cycle counters per phase (written only when built with -DSSB_PROFILE)

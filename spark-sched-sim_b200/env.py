@@ -29,7 +29,8 @@ class SparkSchedSimEnv(Env):
     metadata = {"render_modes": [], "render_fps": 30}
 
     def __init__(self, env_cfg: dict[str, Any], bank=None, device="cuda:0", max_jobs: int | None = None,
-                 tape_capacity: int = 0, log_capacity: int = 0, decima_obs: bool = True):
+                 tape_capacity: int = 0, log_capacity: int = 0, decima_obs: bool = True,
+                 history_capacity: int = 0):
         self.num_executors: int = env_cfg["num_executors"]
         self.moving_delay = env_cfg["moving_delay"]
         self.beta: float = env_cfg.get("beta", 0)
@@ -43,7 +44,8 @@ class SparkSchedSimEnv(Env):
         self._batched = BatchedSparkSchedSimEnv(env_cfg, num_envs=1, bank=bank, device=device,
                                                 max_jobs=max_jobs, tape_capacity=tape_capacity,
                                                 log_capacity=log_capacity, decima_obs=decima_obs,
-                                                decima_policy=decima_obs)  # one env: the buffers are tiny, so
+                                                decima_policy=decima_obs,
+                                                history_capacity=history_capacity)  # one env: the buffers are tiny, so
         # the Decima wrappers / DecimaScheduler work on any env, as `scheduler.env_wrapper_cls(env)` expects
         self.wall_time: float = 0
         self.jobs: dict[int, SimpleNamespace] = {}
@@ -68,6 +70,10 @@ class SparkSchedSimEnv(Env):
             seed = (1 << 40) + self._auto_seed
         hdr = self._batched.reset_host(np.array([seed], np.uint64), np.array([time_limit], np.float64))
         self._raise_on_error(int(hdr[0]["error"]))
+        # per-episode host state starts empty (:145, :173); job_duration_buff survives resets (:83)
+        self.jobs = {}
+        self.active_job_ids = []
+        self.completed_job_ids = set()
         return self._finish(hdr)[0], self.info
 
     def step(self, action: dict):
@@ -109,6 +115,12 @@ class SparkSchedSimEnv(Env):
         return {"wall_time": self.wall_time}
 
     @property
+    def executors(self) -> list:
+        """`env.executors[i].history` as the renderer reads it (spark_sched_sim.py:411, executor.py:25-44); needs
+        `history_capacity > 0` at construction."""
+        return [SimpleNamespace(id_=i, history=h) for i, h in enumerate(self._batched.executor_histories(0))]
+
+    @property
     def avg_job_duration(self) -> float:
         return np.mean(self.job_duration_buff).item() * 1e-3
 
@@ -128,10 +140,6 @@ class SparkSchedSimEnv(Env):
         o = self._batched.obs(0, hdr)
         ta, tc, tm, st = self._batched.jobs(0, with_state=True)
         newly_done = [j for j in range(len(ta)) if st[j] == 2 and j not in self.completed_job_ids]
-        if not self.jobs or len(self.jobs) != len(ta) or any(
-                self.jobs[j].t_arrival != ta[j] for j in range(len(ta))):
-            self.completed_job_ids = set()
-            newly_done = [j for j in range(len(ta)) if st[j] == 2]
         self.jobs = {j: SimpleNamespace(id_=j, t_arrival=float(ta[j]), t_completed=float(tc[j]),
                                         template=int(tm[j]), query_num=int(tm[j]) % 22 + 1,
                                         query_size_idx=int(tm[j]) // 22)

@@ -65,6 +65,19 @@ def allreduce_gradients(grads: torch.Tensor, num_samples: int, group=None) -> tu
     return grads, total
 
 
+def allreduce_weighted_mean(value: torch.Tensor, weight: float, group=None) -> float:
+    """Mean of a per-rank scalar weighted by the ranks' sample counts (one all-reduce of two numbers): the collective
+    form of a statistic that decides control flow, e.g. PPO's approximate-KL early stop -- every rank gets the same
+    number, so every rank takes the same branch."""
+    buf = torch.empty(2, dtype=torch.float64, device=value.device)
+    buf[0] = value.reshape(-1)[0].double() * float(weight)
+    buf[1] = float(weight)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    s, w = buf.tolist()
+    return s / w if w else 0.0
+
+
 def rollout_summary(sum_job_time: float, sum_wall_time: float, num_completed: float,
                     num_arrived: float, sum_completed_duration: float) -> dict:
     """collect_stats (rollout_worker.py:122-129) from sums that can be all-reduced:

@@ -46,7 +46,8 @@ class Adam:
     schedulers/scheduler.py:37-54; opt_kwargs / max_grad_norm of the trainer's config).  `params` is updated in place;
     hand it to BatchedSparkSchedSimEnv.set_decima_weights afterwards."""
 
-    def __init__(self, params: torch.Tensor, lr=3e-4, betas=(0.9, 0.999), eps=1e-8, max_grad_norm=None):
+    def __init__(self, params: torch.Tensor, lr=3e-4, betas=(0.9, 0.999), eps=1e-8, max_grad_norm=None,
+                 check_finite: bool = True):
         assert params.is_cuda and params.dtype == torch.float32 and params.is_contiguous()
         self.params = params
         self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
@@ -56,6 +57,8 @@ class Adam:
         self.grad_norm = torch.zeros(1, dtype=torch.float32, device=params.device)
         self._scratch = torch.empty(128, dtype=torch.float64, device=params.device)
         self.num_steps = 0
+        # read the norm back after every step and raise on NaN / Inf as the reference does (one 4-byte D2H per update)
+        self.check_finite = bool(check_finite)
 
     def step(self, grads: torch.Tensor):
         assert grads.is_cuda and grads.dtype == torch.float32 and grads.is_contiguous()
@@ -65,6 +68,10 @@ class Adam:
             self.params.data_ptr(), grads.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
             int(self.params.numel()), self.num_steps, self.lr, self.betas[0], self.betas[1], self.eps,
             self.max_grad_norm, self._scratch.data_ptr(), self.grad_norm.data_ptr(), _stream(grads)), "ssb_adam_step")
+        if self.check_finite and not bool(torch.isfinite(self.grad_norm).item()):
+            # clip_grad_norm_(..., error_if_nonfinite=True), schedulers/scheduler.py:46-48; the kernel skipped the update
+            self.num_steps -= 1
+            raise RuntimeError("The total norm for gradients is non-finite, so it cannot be clipped.")
         return self.grad_norm
 
 
@@ -76,13 +83,22 @@ def ppo_minibatch_update(env, snapshot, stage_sel, exec_sel, old_lgprob, returns
     Returns (info, stepped): info = the loss head's four scalars on the host; stepped is False when the KL early
     stop (approx_kl_div > 1.5 * target_kl) skipped the update, as the trainer does.
     allreduce: optional callable(grads, num_samples) -> (grads, total) for several GPUs
-    (parallel.allreduce_gradients)."""
+    (parallel.allreduce_gradients).  With it the early stop is decided on the approximate KL averaged over ALL
+    ranks' samples (one small all-reduce before the branch), so every rank steps or stops together -- a rank that
+    stopped on its local value would leave the others waiting in the gradient all-reduce for ever.  The advantage
+    normalisation stays per rank (each rank's mini-batch uses its own mean / std), which is the one place where N
+    ranks differ from a single learner over the union of the samples."""
     B = env.num_envs
     env.decima_snapshot_load(snapshot)
     try:
         lg, en = env.decima_evaluate(None, stage_sel, exec_sel)
         out, g_lp, g_en = loss_fn(lg, old_lgprob, en, returns, baselines)
         info = dict(zip(PPOLoss.KEYS, out.tolist()))
+        if allreduce is not None:
+            from . import parallel
+
+            info["approx_kl_div_local"] = info["approx_kl_div"]
+            info["approx_kl_div"] = parallel.allreduce_weighted_mean(out[3:4], B)
         if target_kl is not None and info["approx_kl_div"] > 1.5 * target_kl:
             return info, False
         grads = torch.zeros_like(adam.params)

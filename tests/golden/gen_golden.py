@@ -58,6 +58,14 @@ CASES = {
     "decima_e10_j8_s5_philox": (cfg(10, 8), "decima", 5, "philox", None, False),
     "decima_e50_j6_s3_philox": (cfg(50, 6), "decima", 3, "philox", None, False),
     "decima_e50_j14_s4_philox": (cfg(50, 14), "decima", 4, "philox", None, False),
+    # Decima at the configured scales (slim: per-observation digests of the adapter's outputs, the recorded scores of
+    # every (8th) decision): the headline shape, and config/decima_tpch.yaml:80-87 (50 executors, 200 jobs)
+    "decima_c2_s1234_philox": (C2, "decima", 1234, "philox", None, True),
+    "decima_c3_s42_philox": (cfg(50, 200), "decima", 42, "philox", None, True, {"logit_stride": 8}),
+    # templates of 30..64 stages ("wide" bank): the 64-bit halves of every stage bitmask, adapter path for ns > 32
+    "wide_e10_j6_fair_s31_philox": (cfg(10, 6), "fair", 31, "philox", None, False, {"bank_kind": "wide"}),
+    "wide_e50_j5_random_s32_philox": (cfg(50, 5), "random", 32, "philox", None, False, {"bank_kind": "wide"}),
+    "decima_wide_e10_j5_s33_philox": (cfg(10, 5), "decima", 33, "philox", None, False, {"bank_kind": "wide"}),
 }
 
 
@@ -74,16 +82,19 @@ def main(argv):
     import spark_sched_sim_b200.bank as bankmod
 
     names = argv or list(CASES)
-    checksum = bankmod.synthetic_bank(0).checksum()
     if any(n.startswith("decima_") for n in names):
         export_decima_weights()
     for name in names:
-        env_cfg, policy, seed, rng, tl, slim = CASES[name]
-        # small cases also record what the reference's DecimaObsWrapper makes of every observation
-        tr = refrun.run_episode(env_cfg, policy, seed, rng=rng, time_limit=tl, decima=not slim)
+        env_cfg, policy, seed, rng, tl, slim = CASES[name][:6]
+        extra = CASES[name][6] if len(CASES[name]) > 6 else {}
+        kind = extra.get("bank_kind", "appd")
+        # small cases (and every Decima-driven one) also record what the reference's DecimaObsWrapper makes of
+        # every observation
+        tr = refrun.run_episode(env_cfg, policy, seed, rng=rng, time_limit=tl,
+                                decima=(not slim) or policy == "decima", bank_kind=kind)
         if slim:
-            tr = refrun.slim(tr)
-        tr["bank_checksum"] = checksum
+            tr = refrun.slim(tr, extra.get("logit_stride", 1))
+        tr["bank_checksum"] = bankmod.synthetic_bank(0, kind).checksum()
         path = osp.join(HERE, name + ".npz")
         np.savez_compressed(path, **tr)
         print(f"{name}: steps={len(tr['actions'])} launches={len(tr['tape'])} "

@@ -15,7 +15,7 @@ def golden_names(slim=None):
     names = [n for n in names if n not in ("decima_model", "learner_vectors")]  # fixtures that are not traces
     if slim is None:
         return names
-    return [n for n in names if n.startswith(("c2_", "c4_")) == slim]
+    return [n for n in names if n.startswith(("c2_", "c4_", "decima_c2_", "decima_c3_")) == slim]
 
 
 def load_golden(name):
@@ -28,7 +28,30 @@ def load_golden(name):
     for k in ("rng", "policy", "bank_checksum"):
         tr[k] = str(tr[k])
     tr["slim"] = "slim" in tr
+    tr["bank_kind"] = str(tr["bank_kind"]) if "bank_kind" in tr else "appd"
+    tr["bank_seed"] = int(tr["bank_seed"]) if "bank_seed" in tr else 0
     return tr
+
+
+def bank_for(tr):
+    """The template bank the trace was recorded on (App. D workload unless the trace says otherwise)."""
+    import spark_sched_sim_b200.bank as bankmod
+
+    b = bankmod.synthetic_bank(tr["bank_seed"], tr["bank_kind"])
+    assert b.checksum() == tr["bank_checksum"], "bank differs from the one the fixture was recorded on"
+    return b
+
+
+def decima_digest(feat, caps, depth, edge_bits, stage_mask):
+    import hashlib
+
+    h = hashlib.sha256()
+    h.update(np.ascontiguousarray(feat, dtype=np.float32).tobytes())
+    h.update(np.asarray(caps, dtype=np.int32).tobytes())
+    h.update(np.asarray([depth], dtype=np.int32).tobytes())
+    h.update(np.ascontiguousarray(edge_bits, dtype=np.uint64).tobytes())
+    h.update(np.ascontiguousarray(stage_mask, dtype=np.uint8).tobytes())
+    return int.from_bytes(h.digest()[:8], "little")
 
 
 def obs_digest(o):
@@ -110,3 +133,12 @@ def replay_and_compare(env, tr, mode, check_policy=None, reward_rtol=0.0):
             assert np.array_equal(lg[key], tr[key]), key
     _, tc, _ = env.job_times()
     assert np.array_equal(tc, tr["job_t_completed"]), "job completion times"
+    if "hist_ptr" in tr and hasattr(env, "history"):
+        # executor.history (executor.py:25-44): per executor, the add_history calls in order
+        hs = env.history()
+        for e in range(tr["num_executors"]):
+            lo, hi = int(tr["hist_ptr"][e]), int(tr["hist_ptr"][e + 1])
+            sel = hs["hist_exec"] == e
+            assert np.array_equal(hs["hist_t"][sel], tr["hist_t"][lo:hi]), (e, "history times")
+            assert np.array_equal(hs["hist_job"][sel], tr["hist_job"][lo:hi]), (e, "history jobs")
+        assert len(hs["hist_t"]) == int(tr["hist_ptr"][-1]), "history length"

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import decima_obs as oracle_dec
-from helpers import golden_names, load_golden
+from helpers import bank_for, golden_names, load_golden
 
 pytestmark = pytest.mark.gpu
 
@@ -19,10 +19,11 @@ def env_cfg_of(tr):
 
 
 @pytest.mark.parametrize("name", golden_names(slim=False))
-def test_decima_obs_matches_reference_wrapper(bank, name):
+def test_decima_obs_matches_reference_wrapper(name):
     from spark_sched_sim_b200.batched_env import BatchedSparkSchedSimEnv
 
     tr = load_golden(name)
+    bank = bank_for(tr)
     E = tr["num_executors"]
     B, slot = 2, 1
     env = BatchedSparkSchedSimEnv(env_cfg_of(tr), num_envs=B, bank=bank,

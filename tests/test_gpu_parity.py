@@ -5,7 +5,7 @@ beta > 0 (exp())."""
 import numpy as np
 import pytest
 
-from helpers import golden_names, load_golden, replay_and_compare
+from helpers import bank_for, golden_names, load_golden, replay_and_compare
 
 pytestmark = pytest.mark.gpu
 
@@ -27,7 +27,8 @@ class CudaAdapter:
         self.B, self.slot, self.tr, self.max_events = B, slot, tr, max_events
         self.env = BatchedSparkSchedSimEnv(
             env_cfg_of(tr), num_envs=B, bank=bank, max_jobs=len(tr["job_template"]) + 4,
-            tape_capacity=len(tr["tape"]) + 8, log_capacity=int(tr["ev_count"][-1]) + 64)
+            tape_capacity=len(tr["tape"]) + 8, log_capacity=int(tr["ev_count"][-1]) + 64,
+            history_capacity=(int(tr["hist_ptr"][-1]) + 8) if "hist_ptr" in tr else 0)
         self.hdr = None
 
     def reset_trace(self, ta, tm, tape):
@@ -71,24 +72,27 @@ class CudaAdapter:
     def job_times(self):
         return self.env.jobs(self.slot)
 
+    def history(self):
+        return self.env.history(self.slot)
+
     def fair_action(self, dynamic_partition):
         a, n = self.env.fair_actions(dynamic_partition)
         return int(a[self.slot].item()), int(n[self.slot].item())
 
 
 @pytest.mark.parametrize("name", golden_names())
-def test_cuda_replays_reference_tape(bank, name):
+def test_cuda_replays_reference_tape(name):
     tr = load_golden(name)
-    env = CudaAdapter(bank, tr)
+    env = CudaAdapter(bank_for(tr), tr)
     replay_and_compare(env, tr, "tape", check_policy=env.fair_action,
                        reward_rtol=1e-12 if tr["beta"] > 0 else 0.0)
 
 
 @pytest.mark.parametrize("name", [n for n in golden_names() if "philox" in n])
-def test_cuda_replays_reference_from_seed(bank, name):
+def test_cuda_replays_reference_from_seed(name):
     """On-device Philox sampling of jobs and durations against the Philox-plugged reference run."""
     tr = load_golden(name)
-    env = CudaAdapter(bank, tr)
+    env = CudaAdapter(bank_for(tr), tr)
     replay_and_compare(env, tr, "seed", check_policy=env.fair_action,
                        reward_rtol=1e-12 if tr["beta"] > 0 else 0.0)
 
@@ -556,7 +560,7 @@ def test_facade_runs_like_examples_py(bank, name):
     tr = load_golden(name)
     cfg = env_cfg_of(tr)
     cfg["data_sampler_cls"] = "TPCHDataSampler"
-    env = SparkSchedSimEnv(cfg, bank=bank)
+    env = SparkSchedSimEnv(cfg, bank=bank, history_capacity=int(tr["hist_ptr"][-1]) + 8)
     scheduler = RoundRobinScheduler(cfg["num_executors"], dynamic_partition=(tr["policy"] == "fair"))
     obs, _ = env.reset(seed=tr["seed"], options=None)
     terminated = truncated = False
@@ -570,6 +574,12 @@ def test_facade_runs_like_examples_py(bank, name):
         assert len(obs["exec_supplies"]) == tr["Ja"][k + 1]
         k += 1
     assert k == len(tr["actions"])
+    # executor.history as the renderer reads it (spark_sched_sim.py:411): [[t_release, job_id], ..., [None, job_id]]
+    for e, ex in enumerate(env.executors):
+        lo, hi = int(tr["hist_ptr"][e]), int(tr["hist_ptr"][e + 1])
+        assert ex.history[0][1] == -1 and ex.history[-1][0] is None and len(ex.history) == hi - lo + 1
+        assert [h[0] for h in ex.history[:-1]] == tr["hist_t"][lo:hi].tolist()
+        assert [h[1] for h in ex.history[1:]] == tr["hist_job"][lo:hi].tolist()
     assert metrics.avg_job_duration(env) * 1e-3 == pytest.approx(
         np.mean(tr["job_t_completed"] - tr["job_t_arrival"]) * 1e-3, rel=1e-12)
     assert env.num_completed_jobs == len(tr["job_template"]) and env.all_jobs_complete

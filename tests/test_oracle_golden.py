@@ -4,7 +4,7 @@ Rewards with beta > 0 go through exp() and are compared at 1e-12 relative (SURVE
 import numpy as np
 import pytest
 
-from helpers import golden_names, load_golden, replay_and_compare
+from helpers import bank_for, golden_names, load_golden, replay_and_compare
 from oracle import OracleEnv
 
 
@@ -14,27 +14,27 @@ def make_oracle(bank, tr):
 
 
 @pytest.mark.parametrize("name", golden_names())
-def test_oracle_replays_reference_tape(bank, name):
+def test_oracle_replays_reference_tape(name):
     tr = load_golden(name)
-    assert tr["bank_checksum"] == bank.checksum(), "synthetic bank differs from the fixtures' bank"
-    env = make_oracle(bank, tr)
+    env = make_oracle(bank_for(tr), tr)  # (checks the bank's checksum against the fixture's)
     replay_and_compare(env, tr, "tape", check_policy=env.fair_action,
                        reward_rtol=1e-12 if tr["beta"] > 0 else 0.0)
 
 
 @pytest.mark.parametrize("name", [n for n in golden_names() if "philox" in n])
-def test_oracle_replays_reference_from_seed(bank, name):
+def test_oracle_replays_reference_from_seed(name):
     """Philox-plugged reference runs: the oracle samples jobs and durations itself (tpch.py logic)."""
     tr = load_golden(name)
-    env = make_oracle(bank, tr)
+    env = make_oracle(bank_for(tr), tr)
     replay_and_compare(env, tr, "seed", check_policy=env.fair_action,
                        reward_rtol=1e-12 if tr["beta"] > 0 else 0.0)
 
 
-def test_bank_matches_reference_sampler(bank):
+def test_bank_matches_reference_sampler():
     """num_tasks / rough_task_duration per stage as the reference computed them (tpch.py:162-196)."""
     for name in golden_names():
         tr = load_golden(name)
+        bank = bank_for(tr)
         ts = np.concatenate([np.arange(bank.stage_base[t], bank.stage_base[t + 1])
                              for t in tr["job_template"]])
         assert np.array_equal(bank.num_tasks[ts], tr["st_num_tasks"])

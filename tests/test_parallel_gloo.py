@@ -114,3 +114,82 @@ def test_shard_range_and_reference_seeds():
     s = parallel.rollout_summary(10.0, 5.0, 2, 3, 4000.0)
     assert s["avg_num_jobs"] == 2.0 and s["avg_job_duration"] == 2.0
     assert parallel.allreduce_stats({k: 1 for k in parallel.STAT_KEYS})["events"] == 1.0
+
+
+class _StubEnv:
+    """Duck-typed stand-in for the batched env: what ppo_minibatch_update calls, on CPU tensors."""
+
+    num_envs = 4
+
+    def __init__(self):
+        self.loaded = 0
+        self.weights_set = 0
+
+    def decima_snapshot_load(self, snapshot):
+        self.loaded += 1
+
+    def decima_snapshot_unload(self):
+        self.loaded -= 1
+
+    def decima_evaluate(self, snapshot, stage_sel, exec_sel):
+        return torch.zeros(4), torch.zeros(4)
+
+    def decima_backward(self, g_lp, g_en, grads):
+        grads += 1.0
+
+    def set_decima_weights(self, params):
+        self.weights_set += 1
+
+
+class _StubAdam:
+    def __init__(self):
+        self.params = torch.zeros(5)
+        self.steps = 0
+
+    def step(self, grads):
+        self.steps += 1
+        self.last = grads.clone()
+
+
+def _kl_worker(rank, world, port, kls, out):
+    from spark_sched_sim_b200 import ppo
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    results = []
+    for kl_pair in kls:
+        env, adam = _StubEnv(), _StubAdam()
+        loss_fn = lambda lg, old, en, ret, base, kl=kl_pair[rank]: (  # noqa: E731
+            torch.tensor([0.5, 0.4, 0.1, kl]), torch.zeros(4), torch.zeros(4))
+        info, stepped = ppo.ppo_minibatch_update(env, None, None, None, None, None, None, loss_fn, adam,
+                                                 target_kl=0.01, allreduce=parallel.allreduce_gradients)
+        results.append((stepped, info["approx_kl_div"], info["approx_kl_div_local"], adam.steps, env.loaded))
+    gathered = [None] * world
+    dist.all_gather_object(gathered, results)
+    if rank == 0:
+        out.put(gathered)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_kl_early_stop_is_collective():
+    """The ranks' local approximate KLs straddle 1.5 * target_kl: the decision is taken on their sample-weighted
+    mean, both ranks take the same branch (no rank is left waiting in the gradient all-reduce), and the stored
+    observation is unloaded on both branches."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    # (rank 0, rank 1): mean 0.0125 < 0.015 -> both step; mean 0.0175 > 0.015 -> both stop; both low; both high
+    kls = [(0.020, 0.005), (0.030, 0.005), (0.001, 0.002), (0.05, 0.06)]
+    procs = [ctx.Process(target=_kl_worker, args=(r, world, port, kls, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    gathered = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = [True, False, True, False]
+    for r in range(world):
+        for i, (stepped, kl, kl_local, steps, loaded) in enumerate(gathered[r]):
+            assert stepped == want[i] and steps == int(want[i]) and loaded == 0
+            assert abs(kl - sum(kls[i]) / 2) < 1e-7 and abs(kl_local - kls[i][r]) < 1e-7

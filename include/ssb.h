@@ -194,6 +194,24 @@ int ssb_step_fair_host(ssb_env *env, const int32_t *stage_idx, const int32_t *nu
                        int32_t max_events, int32_t dynamic_partition, ssb_obs_hdr *hdr_out, int32_t *next_stage_idx,
                        int32_t *next_num_exec);
 
+/* The observation graphs of all envs for a HOST caller (what reset() / step() return as obs, spark_sched_sim.py:393-399),
+ * packed: env b's rows follow env b-1's, no padding.  Call after ssb_reset_host / ssb_step_host on the same handle.
+ *   offsets  HOST i32[(B + 1) * 3]: (first node, first edge, first job) of env b; row B = the totals.
+ *   nodes f32[total nodes][3], edge_links i32[total edges][2] (ids local to the env's graph), exec_supplies
+ *   i32[total jobs], dag_ptr i32[total jobs + B] (env b's num_active_jobs + 1 entries start at offsets[3b+2] + b);
+ *   any of the four may be NULL.  *_capacity: rows the caller's arrays can hold (SSB_E_WORKSPACE if too small --
+ *   offsets[] is valid then and tells the sizes needed).
+ * scratch: DEVICE, ssb_packed_obs_bytes, 256-byte aligned (the library owns no device memory).  Two launches, the
+ * D2H of the offsets, and one D2H per array of exactly the packed size; synchronous. */
+typedef struct {
+    int32_t *offsets;
+    float *nodes;
+    int32_t *edge_links, *dag_ptr, *exec_supplies;
+    int64_t node_capacity, edge_capacity, job_capacity;
+} ssb_packed_obs;
+int ssb_packed_obs_bytes(ssb_env *env, size_t *bytes);
+int ssb_get_obs_host(ssb_env *env, ssb_packed_obs *out, void *scratch, size_t scratch_bytes);
+
 /* fused rollout: every env takes `num_decisions` decisions with the built-in fair (dynamic_partition
  * = 1) or FIFO (= 0) policy (round_robin.py:14-49) evaluated on the observation it just wrote.
  * auto_reset != 0: a finished env re-seeds itself with seed + seed_step * reset_count
@@ -315,6 +333,12 @@ int ssb_set_decima_weights(ssb_env *env, const float *weights, int32_t n_floats)
 int ssb_decima_policy(ssb_env *env, const int32_t *forced_stage, const int32_t *forced_num_exec,
                       int32_t *stage_idx_out, int32_t *num_exec_out, void *stream);
 int ssb_get_policy_views(ssb_env *env, ssb_policy_views *out);
+/* Rows the last ssb_decima_policy / ssb_decima_evaluate call pushed through each of the policy's MLPs, for
+ * measurement (HOST int64[8], synchronous): [0] nodes (mlp_prep and the DagEncoder each see every node), [1] sink
+ * nodes (mlp_update, scheduler.py:207-211), [2] schedulable stages (stage score head), [3] active jobs
+ * (GlobalEncoder), [4] executor-count rows, [5] message senders and [6] receivers summed over the levels
+ * (mlp_msg / mlp_update, :214-232), [7] the multiply-adds of those MLPs at the model's real widths (App. E). */
+int ssb_decima_work(ssb_env *env, int64_t *out);
 /* Stored observations and their re-evaluation -- RolloutBuffer.obsns (rollout_worker.py:18-46) and
  * DecimaScheduler.evaluate_actions (scheduler.py:101-139), forward pass only:
  *   ssb_decima_snapshot: runs the adapter and copies what the policy reads of every env's observation (header,

@@ -61,6 +61,19 @@ class SsbDecimaViews(C.Structure):
     ]
 
 
+class SsbPackedObs(C.Structure):
+    _fields_ = [
+        ("offsets", C.c_void_p),
+        ("nodes", C.c_void_p),
+        ("edge_links", C.c_void_p),
+        ("dag_ptr", C.c_void_p),
+        ("exec_supplies", C.c_void_p),
+        ("node_capacity", C.c_int64),
+        ("edge_capacity", C.c_int64),
+        ("job_capacity", C.c_int64),
+    ]
+
+
 class SsbBank(C.Structure):
     _fields_ = [
         ("num_templates", C.c_int32),
@@ -129,7 +142,7 @@ EXPORTS = [
     "ssb_rollout_fair", "ssb_rollout_fair_traj", "ssb_rollout_fair_async", "ssb_discounted_returns", "ssb_differential_returns", "ssb_group_baselines", "ssb_ppo_loss", "ssb_adam_step", "ssb_fair_actions", "ssb_get_views", "ssb_get_stats", "ssb_collect_stats", "ssb_reset_stats",
     "ssb_get_jobs", "ssb_get_log", "ssb_get_history", "ssb_decima_obs", "ssb_get_decima_views",
     "ssb_set_decima_weights", "ssb_decima_policy", "ssb_rollout_decima", "ssb_decima_snapshot_bytes",
-    "ssb_decima_snapshot", "ssb_decima_snapshot_load", "ssb_decima_snapshot_unload", "ssb_decima_evaluate", "ssb_decima_head_adjoint", "ssb_decima_head_backward", "ssb_decima_backward_bytes", "ssb_decima_backward", "ssb_get_policy_views", "ssb_get_debug_counters",
+    "ssb_decima_snapshot", "ssb_decima_snapshot_load", "ssb_decima_snapshot_unload", "ssb_decima_evaluate", "ssb_decima_head_adjoint", "ssb_decima_head_backward", "ssb_decima_backward_bytes", "ssb_decima_backward", "ssb_get_policy_views", "ssb_decima_work", "ssb_packed_obs_bytes", "ssb_get_obs_host", "ssb_get_debug_counters",
 ]
 
 _lib = None
@@ -190,6 +203,9 @@ def lib():
     L.ssb_set_decima_weights.argtypes = [vp, vp, i32]
     L.ssb_decima_policy.argtypes = [vp, vp, vp, vp, vp, vp]
     L.ssb_get_policy_views.argtypes = [vp, C.POINTER(SsbPolicyViews)]
+    L.ssb_decima_work.argtypes = [vp, vp]
+    L.ssb_packed_obs_bytes.argtypes = [vp, C.POINTER(C.c_size_t)]
+    L.ssb_get_obs_host.argtypes = [vp, C.POINTER(SsbPackedObs), vp, C.c_size_t]
     L.ssb_get_stats.argtypes = [vp, C.POINTER(vp)]
     L.ssb_reset_stats.argtypes = [vp, vp]
     L.ssb_collect_stats.argtypes = [vp, vp, vp]

@@ -259,6 +259,36 @@ class BatchedSparkSchedSimEnv:
                   "ssb_step_fair_host")
         return self._hdr_host
 
+    def obs_host(self, node_capacity: int | None = None, edge_capacity: int | None = None) -> dict:
+        """The observation graphs of ALL envs on the host, packed (ssb_get_obs_host): pinned numpy arrays
+        offsets i32[B + 1, 3] (first node / edge / job of env b; row B = totals), nodes f32[total, 3],
+        edge_links i32[total, 2], dag_ptr i32[total jobs + B], exec_supplies i32[total jobs].  Env b's slices:
+        nodes[o[b,0]:o[b+1,0]], edge_links[o[b,1]:o[b+1,1]], exec_supplies[o[b,2]:o[b+1,2]],
+        dag_ptr[o[b,2]+b : o[b+1,2]+b+1].  The arrays are reused by the next call."""
+        B = self.num_envs
+        if getattr(self, "_pack", None) is None:
+            n = C.c_size_t()
+            nat.check(self.L.ssb_packed_obs_bytes(self._h, C.byref(n)), "ssb_packed_obs_bytes")
+            ncap = node_capacity or B * self.node_stride
+            ecap = edge_capacity or B * self.edge_stride
+            pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()  # noqa: E731
+            self._pack = {
+                "scratch": torch.empty(n.value, dtype=torch.uint8, device=self.device),
+                "offsets": pin((B + 1, 3), torch.int32), "nodes": pin((ncap, 3), torch.float32),
+                "edge_links": pin((ecap, 2), torch.int32), "dag_ptr": pin((B * (self.job_stride + 1),), torch.int32),
+                "exec_supplies": pin((B * self.job_stride,), torch.int32)}
+            k = self._pack
+            self._pack_struct = nat.SsbPackedObs(
+                k["offsets"].data_ptr(), k["nodes"].data_ptr(), k["edge_links"].data_ptr(), k["dag_ptr"].data_ptr(),
+                k["exec_supplies"].data_ptr(), ncap, ecap, B * self.job_stride)
+        k = self._pack
+        nat.check(self.L.ssb_get_obs_host(self._h, C.byref(self._pack_struct), k["scratch"].data_ptr(),
+                                          k["scratch"].numel()), "ssb_get_obs_host")
+        o = k["offsets"].numpy()
+        tn, te, tj = (int(x) for x in o[B])
+        return {"offsets": o, "nodes": k["nodes"].numpy()[:tn], "edge_links": k["edge_links"].numpy()[:te],
+                "dag_ptr": k["dag_ptr"].numpy()[:tj + B], "exec_supplies": k["exec_supplies"].numpy()[:tj]}
+
     # ---------------------------------------------------------------- results
     def hdr(self) -> np.ndarray:
         """Structured numpy copy of the B observation headers (synchronises)."""
@@ -360,6 +390,13 @@ class BatchedSparkSchedSimEnv:
                                            fn.data_ptr() if fn is not None else None,
                                            a.data_ptr(), n.data_ptr(), self._stream()), "ssb_decima_policy")
         return a, n
+
+    def decima_work(self) -> dict:
+        """Rows per MLP and multiply-adds of the last decima_policy / decima_evaluate call (measurement)."""
+        out = np.zeros(8, np.int64)
+        nat.check(self.L.ssb_decima_work(self._h, out.ctypes.data), "ssb_decima_work")
+        keys = ("nodes", "sinks", "candidates", "jobs", "exec_rows", "senders", "receivers", "macs")
+        return dict(zip(keys, (int(x) for x in out)))
 
     def decima_snapshot(self, out: "torch.Tensor | None" = None) -> torch.Tensor:
         """Stores what the policy reads of every env's current observation (RolloutBuffer.obsns) in a device

@@ -296,6 +296,50 @@ __global__ void k_collect_stats_final(const double *part, double *out)
     }
 }
 
+// ---- packed observations: the rows of every env's observation back to back (what a host caller copies out)
+// offsets[b] = (first node, first edge, first job) of env b in the packed arrays, offsets[B] = the totals.
+// One block; every thread scans a contiguous chunk of envs, the chunk sums are scanned through shared memory.
+__global__ void __launch_bounds__(1024) k_pack_scan(Params p, int32_t *offsets)
+{
+    __shared__ int sh[3][1024];
+    const int t = threadIdx.x, per = (p.B + 1023) / 1024, lo = min(t * per, p.B), hi = min(lo + per, p.B);
+    int sn = 0, se = 0, sj = 0;
+    for (int b = lo; b < hi; b++) {
+        const ssb_obs_hdr &o = p.obs_hdr[b];
+        sn += o.num_nodes; se += o.num_edges; sj += o.num_active_jobs;
+    }
+    sh[0][t] = sn; sh[1][t] = se; sh[2][t] = sj;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+        int a = 0, b2 = 0, c = 0;
+        if (t >= off) { a = sh[0][t - off]; b2 = sh[1][t - off]; c = sh[2][t - off]; }
+        __syncthreads();
+        sh[0][t] += a; sh[1][t] += b2; sh[2][t] += c;
+        __syncthreads();
+    }
+    int on = sh[0][t] - sn, oe = sh[1][t] - se, oj = sh[2][t] - sj;
+    for (int b = lo; b < hi; b++) {
+        offsets[3 * b] = on; offsets[3 * b + 1] = oe; offsets[3 * b + 2] = oj;
+        const ssb_obs_hdr &o = p.obs_hdr[b];
+        on += o.num_nodes; oe += o.num_edges; oj += o.num_active_jobs;
+    }
+    if (t == 1023) { offsets[3 * p.B] = sh[0][t]; offsets[3 * p.B + 1] = sh[1][t]; offsets[3 * p.B + 2] = sh[2][t]; }
+}
+__global__ void __launch_bounds__(128)
+k_pack_copy(Params p, const int32_t *offsets, float *nodes, int32_t *edges, int32_t *dag_ptr, int32_t *supplies)
+{
+    const int b = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= p.B) return;
+    const ssb_obs_hdr &o = p.obs_hdr[b];
+    const int on = offsets[3 * b], oe = offsets[3 * b + 1], oj = offsets[3 * b + 2];
+    const float *sn = p.obs_nodes + (size_t)b * p.Sc * 3;
+    const int32_t *se = p.obs_edges + (size_t)b * p.Mc * 2;
+    for (int i = lane; i < 3 * o.num_nodes; i += 32) nodes[(size_t)on * 3 + i] = sn[i];
+    for (int i = lane; i < 2 * o.num_edges; i += 32) edges[(size_t)oe * 2 + i] = se[i];
+    for (int i = lane; i <= o.num_active_jobs; i += 32) dag_ptr[oj + b + i] = p.obs_dag_ptr[(size_t)b * (p.Jc + 1) + i];
+    for (int i = lane; i < o.num_active_jobs; i += 32) supplies[oj + i] = p.obs_supplies[(size_t)b * p.Jc + i];
+}
+
 __global__ void k_zero_stats(ssb_stats *s, int n)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -828,6 +872,59 @@ int ssb_step_fair_host(ssb_env *env, const int32_t *stage_idx, const int32_t *nu
     return SSB_OK;
 }
 
+// layout of the caller's scratch for the packed observation
+namespace {
+struct PackLayout { size_t off_offsets, off_nodes, off_edges, off_dag, off_sup, bytes; };
+PackLayout pack_layout(const Params &p)
+{
+    PackLayout l{};
+    size_t o = 0;
+    auto take = [&](size_t n) { size_t at = o; o += (n + 255) & ~size_t(255); return at; };
+    l.off_offsets = take(sizeof(int32_t) * 3 * ((size_t)p.B + 1));
+    l.off_nodes = take(sizeof(float) * 3 * (size_t)p.B * p.Sc);
+    l.off_edges = take(sizeof(int32_t) * 2 * (size_t)p.B * p.Mc);
+    l.off_dag = take(sizeof(int32_t) * (size_t)p.B * (p.Jc + 1));
+    l.off_sup = take(sizeof(int32_t) * (size_t)p.B * p.Jc);
+    l.bytes = o;
+    return l;
+}
+}  // namespace
+
+int ssb_packed_obs_bytes(ssb_env *env, size_t *bytes)
+{
+    if (!env || !bytes) return SSB_E_INVALID;
+    *bytes = pack_layout(env->p).bytes;
+    return SSB_OK;
+}
+
+int ssb_get_obs_host(ssb_env *env, ssb_packed_obs *out, void *scratch, size_t scratch_bytes)
+{
+    if (!env || !out || !out->offsets || !scratch || (reinterpret_cast<uintptr_t>(scratch) & 255)) return SSB_E_INVALID;
+    const Params &p = env->p;
+    const PackLayout l = pack_layout(p);
+    if (scratch_bytes < l.bytes) return SSB_E_WORKSPACE;
+    CUDA_TRY(cudaSetDevice(env->device));
+    cudaStream_t s = env->own_stream;
+    char *sc = static_cast<char *>(scratch);
+    int32_t *d_off = reinterpret_cast<int32_t *>(sc + l.off_offsets);
+    float *d_nodes = reinterpret_cast<float *>(sc + l.off_nodes);
+    int32_t *d_edges = reinterpret_cast<int32_t *>(sc + l.off_edges), *d_dag = reinterpret_cast<int32_t *>(sc + l.off_dag),
+            *d_sup = reinterpret_cast<int32_t *>(sc + l.off_sup);
+    k_pack_scan<<<1, 1024, 0, s>>>(p, d_off);
+    k_pack_copy<<<(p.B + 3) / 4, 128, 0, s>>>(p, d_off, d_nodes, d_edges, d_dag, d_sup);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out->offsets, d_off, sizeof(int32_t) * 3 * ((size_t)p.B + 1), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));  // the totals size the copies below
+    const int64_t tn = out->offsets[3 * p.B], te = out->offsets[3 * p.B + 1], tj = out->offsets[3 * p.B + 2];
+    if (tn > out->node_capacity || te > out->edge_capacity || tj > out->job_capacity) return SSB_E_WORKSPACE;
+    if (out->nodes) CUDA_TRY(cudaMemcpyAsync(out->nodes, d_nodes, sizeof(float) * 3 * tn, cudaMemcpyDeviceToHost, s));
+    if (out->edge_links) CUDA_TRY(cudaMemcpyAsync(out->edge_links, d_edges, sizeof(int32_t) * 2 * te, cudaMemcpyDeviceToHost, s));
+    if (out->dag_ptr) CUDA_TRY(cudaMemcpyAsync(out->dag_ptr, d_dag, sizeof(int32_t) * (tj + p.B), cudaMemcpyDeviceToHost, s));
+    if (out->exec_supplies) CUDA_TRY(cudaMemcpyAsync(out->exec_supplies, d_sup, sizeof(int32_t) * tj, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return SSB_OK;
+}
+
 int ssb_rollout_fair_traj(ssb_env *env, int32_t num_decisions, int32_t dynamic_partition, int32_t auto_reset,
                           uint64_t seed_step, ssb_transition *traj, void *stream)
 {
@@ -1261,6 +1358,23 @@ int ssb_rollout_decima(ssb_env *env, int32_t num_decisions, int32_t max_events, 
         CUDA_TRY(cudaEventRecord(env->ev, s));
         CUDA_TRY(cudaStreamWaitEvent(caller, env->ev, 0));
     }
+    return SSB_OK;
+}
+
+int ssb_decima_work(ssb_env *env, int64_t *out)
+{
+    if (!env || !out || !env->p.pol_w) return SSB_E_INVALID;
+    CUDA_TRY(cudaSetDevice(env->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    std::vector<int32_t> c(tc::CNT_TOTAL);
+    CUDA_TRY(cudaMemcpy(c.data(), env->p.pl_cnt, sizeof(int32_t) * tc::CNT_TOTAL, cudaMemcpyDeviceToHost));
+    int64_t send = 0, recv = 0;
+    for (int k = 0; k < tc::MAX_LEVELS; k++) { send += c[tc::CNT_LVL + 2 * k]; recv += c[tc::CNT_LVL + 2 * k + 1]; }
+    const int64_t gnn = 16 * 32 + 32 * 16 + 16 * 16;  // one 16 -> 32 -> 16 -> 16 MLP
+    out[0] = c[tc::CNT_ALL]; out[1] = c[tc::CNT_SINK]; out[2] = c[tc::CNT_CAND]; out[3] = c[tc::CNT_JOBS];
+    out[4] = c[tc::CNT_EXEC]; out[5] = send; out[6] = recv;
+    out[7] = out[0] * ((5 * 32 + 32 * 16 + 16 * 16) + (21 * 32 + 32 * 16 + 16 * 16)) + (out[1] + send + recv + out[3]) * gnn +
+             out[2] * (53 * 64 + 64 * 64 + 64) + out[4] * (36 * 64 + 64 * 64 + 64);
     return SSB_OK;
 }
 

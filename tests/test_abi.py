@@ -30,6 +30,7 @@ def test_struct_sizes_match_header():
     assert ctypes.sizeof(_native.SsbConfig) == 64
     assert ctypes.sizeof(_native.SsbViews) == 56
     assert ctypes.sizeof(_native.SsbDecimaViews) == 64
+    assert ctypes.sizeof(_native.SsbPackedObs) == 64
 
 
 def test_workspace_bytes_no_gpu(bank):

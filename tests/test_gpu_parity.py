@@ -594,3 +594,74 @@ def test_facade_runs_like_examples_py(bank, name):
     with pytest.raises(ValueError):
         SparkSchedSimEnv(dict(cfg, job_arrival_cap=None), bank=bank).reset(seed=1)
     env.close()
+
+
+def test_packed_observations_on_the_host(bank):
+    """ssb_get_obs_host: the graphs of all envs packed back to back equal the per-env slabs (and the oracle's
+    observation of the same episode)."""
+    from oracle import OracleEnv
+    from spark_sched_sim_b200.batched_env import BatchedSparkSchedSimEnv
+
+    cfg = {"num_executors": 10, "job_arrival_cap": 7, "job_arrival_rate": 4.0e-5,
+           "moving_delay": 2000.0, "warmup_delay": 1000.0}
+    B = 37
+    env = BatchedSparkSchedSimEnv(cfg, num_envs=B, bank=bank)
+    seeds = np.arange(B, dtype=np.uint64) + 900
+    env.reset_host(seeds)
+    for it in range(40):
+        a, n = env.fair_actions(True)
+        hdr = env.step_host(a.cpu().numpy(), n.cpu().numpy()).copy()
+        if it % 13 != 12:
+            continue
+        po = env.obs_host()
+        o = po["offsets"]
+        assert o.shape == (B + 1, 3) and (o[0] == 0).all()
+        assert o[B].tolist() == [int(hdr["num_nodes"].sum()), int(hdr["num_edges"].sum()), int(hdr["num_active_jobs"].sum())]
+        for b in range(B):
+            ref = env.obs(b, hdr)
+            assert np.array_equal(po["nodes"][o[b, 0]:o[b + 1, 0]], ref["nodes"])
+            assert np.array_equal(po["edge_links"][o[b, 1]:o[b + 1, 1]], ref["edge_links"])
+            assert np.array_equal(po["exec_supplies"][o[b, 2]:o[b + 1, 2]], ref["exec_supplies"])
+            assert np.array_equal(po["dag_ptr"][o[b, 2] + b:o[b + 1, 2] + b + 1], ref["dag_ptr"])
+    # env 5 against the oracle driven the same way
+    orc = OracleEnv(bank, 10, 7, 2000.0, 1000.0, 4.0e-5)
+    orc.reset_seed(int(seeds[5]))
+    for it in range(40):
+        orc.step(*orc.fair_action(True))
+    oo, b = orc.obs(), 5
+    assert np.array_equal(po["nodes"][o[b, 0]:o[b + 1, 0]], oo["nodes"])
+    assert np.array_equal(po["edge_links"][o[b, 1]:o[b + 1, 1]], oo["edge_links"])
+
+
+def test_executor_history_of_fused_rollouts_matches_oracle(bank):
+    """ssb_get_history after whole episodes run by the fused rollout kernel == the oracle's add_history calls
+    (Executor.add_history, executor.py:34-44), at 10 and at 50 executors; off by default (no rows, no cost)."""
+    from oracle import OracleEnv
+    from spark_sched_sim_b200.batched_env import BatchedSparkSchedSimEnv
+
+    for E, J in ((10, 9), (50, 12)):
+        cfg = {"num_executors": E, "job_arrival_cap": J, "job_arrival_rate": 4.0e-5,
+               "moving_delay": 2000.0, "warmup_delay": 1000.0}
+        B = 6
+        env = BatchedSparkSchedSimEnv(cfg, num_envs=B, bank=bank, history_capacity=4096)
+        seeds = np.arange(B, dtype=np.uint64) + 300 + E
+        env.reset_host(seeds)
+        env.rollout_fair(100000, True, False)
+        assert (env.hdr()["terminated"] == 1).all()
+        for b in range(B):
+            orc = OracleEnv(bank, E, J, 2000.0, 1000.0, 4.0e-5)
+            orc.reset_seed(int(seeds[b]))
+            term = False
+            while not term:
+                _, _, term = orc.step(*orc.fair_action(True))
+            want, got = orc.history(), env.history(b)
+            assert len(want["hist_t"]) > 0
+            for k in ("hist_t", "hist_exec", "hist_job"):
+                assert np.array_equal(want[k], got[k]), (E, b, k)
+            hs = env.executor_histories(b)
+            assert len(hs) == E and all(h[0][1] == -1 or len(h) == 1 for h in hs) and all(h[-1][0] is None for h in hs)
+    plain = BatchedSparkSchedSimEnv(cfg, num_envs=2, bank=bank)
+    plain.reset_host(np.array([1, 2], np.uint64))
+    plain.rollout_fair(50, True, False)
+    with pytest.raises(RuntimeError):
+        plain.history(0)  # history_capacity == 0: rows were counted but none stored

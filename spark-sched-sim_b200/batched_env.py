@@ -526,6 +526,8 @@ class BatchedSparkSchedSimEnv:
     def history(self, b: int = 0) -> dict:
         """Every Executor.add_history call of env b's current episode in call order (executor.py:34-44):
         hist_t (wall time), hist_exec, hist_job (-1 = common pool).  Needs history_capacity > 0."""
+        if self.history_capacity <= 0:
+            raise RuntimeError("executor history is not recorded: construct the env with history_capacity > 0")
         n = C.c_int64()
         cap = max(self.history_capacity, 1)
         t, ex, jb = np.zeros(cap), np.zeros(cap, np.int16), np.zeros(cap, np.int16)

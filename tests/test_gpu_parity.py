@@ -626,7 +626,7 @@ def test_packed_observations_on_the_host(bank):
     # env 5 against the oracle driven the same way
     orc = OracleEnv(bank, 10, 7, 2000.0, 1000.0, 4.0e-5)
     orc.reset_seed(int(seeds[5]))
-    for it in range(40):
+    for it in range(39):  # the last packed copy was taken after call 39 (it == 38)
         orc.step(*orc.fair_action(True))
     oo, b = orc.obs(), 5
     assert np.array_equal(po["nodes"][o[b, 0]:o[b + 1, 0]], oo["nodes"])
@@ -664,4 +664,4 @@ def test_executor_history_of_fused_rollouts_matches_oracle(bank):
     plain.reset_host(np.array([1, 2], np.uint64))
     plain.rollout_fair(50, True, False)
     with pytest.raises(RuntimeError):
-        plain.history(0)  # history_capacity == 0: rows were counted but none stored
+        plain.history(0)  # built without history_capacity: nothing was recorded

@@ -10,7 +10,9 @@
  *
  * Conventions
  *   - All device work is enqueued on the caller's stream (`stream` = cudaStream_t as void*,
- *     NULL = default stream).  `*_host` variants take HOST buffers, copy, run and synchronise.
+ *     NULL = default stream).  `*_host` variants take HOST buffers, copy, run and synchronise; they run on a stream
+ *     of the handle's own and first wait for everything the stream-taking entry points enqueued before them, so a
+ *     host-buffer call never overtakes work still queued on a caller's stream.
  *   - The library owns no device memory: the caller passes one workspace allocation
  *     (`ssb_workspace_bytes` tells how big) -- in Python that is a torch uint8 tensor -- and the
  *     observation views returned by `ssb_get_views` are pointers into it.
@@ -333,6 +335,12 @@ int ssb_set_decima_weights(ssb_env *env, const float *weights, int32_t n_floats)
 int ssb_decima_policy(ssb_env *env, const int32_t *forced_stage, const int32_t *forced_num_exec,
                       int32_t *stage_idx_out, int32_t *num_exec_out, void *stream);
 int ssb_get_policy_views(ssb_env *env, ssb_policy_views *out);
+/* One of the policy's seven MLPs (make_mlp, schedulers/decima/utils.py:45-64) applied to caller-provided rows on the
+ * tensor-core path the policy uses: mlp = 0 mlp_prep (5 -> 16), 1 mlp_msg, 2 mlp_update (16 -> 16), 3 DagEncoder
+ * (21 -> 16), 4 GlobalEncoder (16 -> 16), 5 stage score head (53 -> 1), 6 executor-count score head (36 -> 1), in
+ * state_dict order.  x = DEVICE f32[n_rows][in], out = DEVICE f32[n_rows][out].  A building block for callers that
+ * assemble their own inputs, and the accuracy probe of the tests (against an fp64 evaluation). */
+int ssb_decima_mlp_rows(ssb_env *env, int32_t mlp, const float *x, int32_t n_rows, float *out, void *stream);
 /* Rows the last ssb_decima_policy / ssb_decima_evaluate call pushed through each of the policy's MLPs, for
  * measurement (HOST int64[8], synchronous): [0] nodes (mlp_prep and the DagEncoder each see every node), [1] sink
  * nodes (mlp_update, scheduler.py:207-211), [2] schedulable stages (stage score head), [3] active jobs

@@ -142,7 +142,7 @@ EXPORTS = [
     "ssb_rollout_fair", "ssb_rollout_fair_traj", "ssb_rollout_fair_async", "ssb_discounted_returns", "ssb_differential_returns", "ssb_group_baselines", "ssb_ppo_loss", "ssb_adam_step", "ssb_fair_actions", "ssb_get_views", "ssb_get_stats", "ssb_collect_stats", "ssb_reset_stats",
     "ssb_get_jobs", "ssb_get_log", "ssb_get_history", "ssb_decima_obs", "ssb_get_decima_views",
     "ssb_set_decima_weights", "ssb_decima_policy", "ssb_rollout_decima", "ssb_decima_snapshot_bytes",
-    "ssb_decima_snapshot", "ssb_decima_snapshot_load", "ssb_decima_snapshot_unload", "ssb_decima_evaluate", "ssb_decima_head_adjoint", "ssb_decima_head_backward", "ssb_decima_backward_bytes", "ssb_decima_backward", "ssb_get_policy_views", "ssb_decima_work", "ssb_packed_obs_bytes", "ssb_get_obs_host", "ssb_get_debug_counters",
+    "ssb_decima_snapshot", "ssb_decima_snapshot_load", "ssb_decima_snapshot_unload", "ssb_decima_evaluate", "ssb_decima_head_adjoint", "ssb_decima_head_backward", "ssb_decima_backward_bytes", "ssb_decima_backward", "ssb_get_policy_views", "ssb_decima_work", "ssb_decima_mlp_rows", "ssb_packed_obs_bytes", "ssb_get_obs_host", "ssb_get_debug_counters",
 ]
 
 _lib = None
@@ -204,6 +204,7 @@ def lib():
     L.ssb_decima_policy.argtypes = [vp, vp, vp, vp, vp, vp]
     L.ssb_get_policy_views.argtypes = [vp, C.POINTER(SsbPolicyViews)]
     L.ssb_decima_work.argtypes = [vp, vp]
+    L.ssb_decima_mlp_rows.argtypes = [vp, i32, vp, i32, vp, vp]
     L.ssb_packed_obs_bytes.argtypes = [vp, C.POINTER(C.c_size_t)]
     L.ssb_get_obs_host.argtypes = [vp, C.POINTER(SsbPackedObs), vp, C.c_size_t]
     L.ssb_get_stats.argtypes = [vp, C.POINTER(vp)]

@@ -391,6 +391,21 @@ class BatchedSparkSchedSimEnv:
                                            a.data_ptr(), n.data_ptr(), self._stream()), "ssb_decima_policy")
         return a, n
 
+    MLP_NAMES = ("encoder.node_encoder.mlp_prep", "encoder.node_encoder.mlp_msg", "encoder.node_encoder.mlp_update",
+                 "encoder.dag_encoder.mlp", "encoder.global_encoder.mlp", "stage_policy_network.mlp_score",
+                 "exec_policy_network.mlp_score")
+    MLP_DIMS = ((5, 16), (16, 16), (16, 16), (21, 16), (16, 16), (53, 1), (36, 1))
+
+    def decima_mlp_rows(self, mlp: int, x: torch.Tensor) -> torch.Tensor:
+        """One of the policy's seven MLPs (index in state_dict order, MLP_NAMES) applied to the rows of x
+        (float32 device tensor [n, in]) on the tensor-core path the policy uses -> [n, out]."""
+        din, dout = self.MLP_DIMS[mlp]
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.shape[1] == din
+        out = torch.empty(x.shape[0], dout, dtype=torch.float32, device=self.device)
+        nat.check(self.L.ssb_decima_mlp_rows(self._h, int(mlp), x.data_ptr(), int(x.shape[0]), out.data_ptr(),
+                                             self._stream()), "ssb_decima_mlp_rows")
+        return out
+
     def decima_work(self) -> dict:
         """Rows per MLP and multiply-adds of the last decima_policy / decima_evaluate call (measurement)."""
         out = np.zeros(8, np.int64)

@@ -17,6 +17,7 @@
 
 #include "ssb_decima.cuh"
 #include "ssb_decima_tc.cuh"
+#include "ssb_decima_fused.cuh"
 #include "ssb_backward.cuh"
 #include "ssb_sim.cuh"
 
@@ -49,6 +50,17 @@ constexpr int WARPS_PER_CTA = SSB_WARPS_PER_CTA;
     do {                                                                     \
         int cur_ = -1;                                                       \
         if (cudaGetDevice(&cur_) != cudaSuccess || cur_ != (env)->device) CUDA_TRY(cudaSetDevice((env)->device)); \
+    } while (0)
+
+// Ordering between the caller's streams and the handle's own stream (the *_host entry points): every stream-taking
+// entry point marks the end of what it enqueued (SSB_MARK), and a *_host call first makes its own stream wait for
+// that mark (host_begin) -- work still queued on the caller's stream is never overtaken by a host-buffer call.
+#define SSB_MARK(env, stream)                                                             \
+    do {                                                                                  \
+        if ((cudaStream_t)(stream) != (env)->own_stream) {                                \
+            CUDA_TRY(cudaEventRecord((env)->ev_last, (cudaStream_t)(stream)));            \
+            (env)->dirty = 1;                                                             \
+        }                                                                                 \
     } while (0)
 
 // ------------------------------------------------------------------------------------ kernels
@@ -492,6 +504,9 @@ void carve(Carver &cv, const ssb_config &c, const ssb_bank &bk, const Dims &d, P
         p.pl_ncand = cv.take<int32_t>(B);
         p.pl_bits = cv.take<unsigned long long>(B * d.Sc * 2);
         p.pol_wblob = cv.take<float>(tc::BLOB_TOTAL);
+        p.pol_wblob3 = cv.take<uint32_t>(fz::BLOB_TOTAL);
+        p.pol_cand_rank = cv.take<int32_t>(B * d.Sc);
+        p.fz_cursor = cv.take<int32_t>(4);
     }
     *st_a = cv.take<int32_t>(B);
     *st_n = cv.take<int32_t>(B);
@@ -520,14 +535,40 @@ struct ssb_env {
     int dmax;           // upper bound of the message-passing depth: longest template chain - 1
     // CUDA graph of one ssb_rollout_decima decision and the arguments it was captured with
     cudaEvent_t ev;
+    cudaEvent_t ev_last;  // recorded after the latest work enqueued on a caller's stream (see SSB_MARK / host_begin)
+    int dirty;            // such work exists since the last *_host call
     cudaGraphExec_t dg_exec;
     ssb_transition *dg_traj;
     int dg_k, dg_events, dg_autoreset, no_graph;
     uint64_t dg_seed_step;
+    int use_tiles;      // SSB_DECIMA_TILES=1: round 1's list-driven tile launches instead of the fused policy kernel
+    int fused_group;    // environments per group of the fused policy kernel
     int snap_loaded;    // ssb_decima_snapshot_load: a stored observation is in place, the live one parked
     int auto_reset;     // ssb_set_autoreset
     uint64_t auto_seed_step;
 };
+
+static int host_begin(ssb_env *env)
+{
+    CUDA_TRY(cudaSetDevice(env->device));
+    if (env->dirty) {
+        CUDA_TRY(cudaStreamWaitEvent(env->own_stream, env->ev_last, 0));
+        env->dirty = 0;
+    }
+    return SSB_OK;
+}
+
+template <int ST>
+static int launch_mlp_rows(ssb_env *env, const float *x, int n, float *out, cudaStream_t s)
+{
+    const size_t smem = sizeof(uint32_t) * fz::Blob<ST>::WORDS;
+    CUDA_TRY(cudaFuncSetAttribute(fz::k_mlp_rows<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int tiles = (n + 127) / 128;
+    fz::k_mlp_rows<ST><<<std::min(tiles, env->num_sms * 4), 128, smem, s>>>(env->p.pol_wblob3, x, n, out);
+    CUDA_TRY(cudaGetLastError());
+    SSB_MARK(env, s);
+    return SSB_OK;
+}
 
 struct BackwardScratch { float *gs, *ge, *d_hdag, *d_hglob, *d_hinit, *d_msg; size_t floats; };
 BackwardScratch backward_scratch(const Params &p, float *base)
@@ -649,6 +690,24 @@ int ssb_create(const ssb_config *cfg, const ssb_bank *bk, int device, void *work
         env->dmax = dmax;
     }
     if (p.pol_w) {
+        const char *ut = getenv("SSB_DECIMA_TILES");
+        env->use_tiles = ut && ut[0] == '1';
+        CUDA_TRY(cudaFuncSetAttribute(fz::fused::k_decima_fused, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)fz::fused::Smem::BYTES));
+        {   // group size: one round of groups over the resident CTAs (two per SM) when that needs at most GMAX
+            // environments per group; otherwise ~3000 observation nodes per group (full 128-row tiles within a
+            // level), the group count rounded to whole rounds
+            const int ctas = 2 * env->num_sms, B = cfg->num_envs;
+            int G = (B + ctas - 1) / ctas;
+            if (G > fz::fused::GMAX) {
+                const int by_nodes = std::max(1, std::min(fz::fused::GMAX, 3072 / std::max(64, d.Sc / 4)));
+                const int rounds = (B + by_nodes * ctas - 1) / (by_nodes * ctas);
+                G = (B + rounds * ctas - 1) / (rounds * ctas);
+            }
+            G = std::max(1, std::min(G, fz::fused::GMAX));
+            if (const char *fg = getenv("SSB_FUSED_GROUP")) G = std::max(1, std::min(atoi(fg), fz::fused::GMAX));
+            env->fused_group = G;
+        }
         int rc;
         if ((rc = prepare_tile_kernel<tc::ST_PREP>()) || (rc = prepare_tile_kernel<tc::ST_SINK>()) ||
             (rc = prepare_tile_kernel<tc::ST_MSG>()) || (rc = prepare_tile_kernel<tc::ST_RCV>()) ||
@@ -712,6 +771,7 @@ int ssb_create(const ssb_config *cfg, const ssb_bank *bk, int device, void *work
     CUDA_TRY(cudaMemset(p.obs_hdr, 0, sizeof(ssb_obs_hdr) * (size_t)p.B));
     CUDA_TRY(cudaStreamCreateWithFlags(&env->own_stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreateWithFlags(&env->ev, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&env->ev_last, cudaEventDisableTiming));
     CUDA_TRY(cudaDeviceSynchronize());
     *out = env;
     return SSB_OK;
@@ -725,6 +785,7 @@ int ssb_destroy(ssb_env *env)
     cudaStreamDestroy(env->own_stream);
     if (env->dg_exec) cudaGraphExecDestroy(env->dg_exec);
     if (env->ev) cudaEventDestroy(env->ev);
+    if (env->ev_last) cudaEventDestroy(env->ev_last);
     delete env;
     return SSB_OK;
 }
@@ -766,6 +827,7 @@ int ssb_reset(ssb_env *env, const uint64_t *seeds, const double *time_limits, co
     SSB_ON_DEVICE(env);
     k_reset<<<env->grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(env->p, seeds, time_limits, mask);
     CUDA_TRY(cudaGetLastError());
+    SSB_MARK(env, stream);
     return SSB_OK;
 }
 
@@ -779,6 +841,7 @@ static int step_launch(ssb_env *env, const int32_t *stage_idx, const int32_t *nu
         k_step<2><<<env->grid, WARPS_PER_CTA * 32, 0, s>>>(env->p, stage_idx, num_exec, mask, max_events, env->auto_reset,
                                                            env->auto_seed_step, next_a, next_n, dyn);
     CUDA_TRY(cudaGetLastError());
+    SSB_MARK(env, s);
     return SSB_OK;
 }
 
@@ -818,7 +881,10 @@ int ssb_reset_host(ssb_env *env, const uint64_t *seeds, const double *time_limit
                    ssb_obs_hdr *hdr_out)
 {
     if (!env) return SSB_E_INVALID;
-    CUDA_TRY(cudaSetDevice(env->device));
+    {
+        const int rcb = host_begin(env);  // also waits for work still queued on the caller's streams
+        if (rcb) return rcb;
+    }
     cudaStream_t s = env->own_stream;
     const size_t B = env->p.B;
     if (seeds) CUDA_TRY(cudaMemcpyAsync(env->st_seed, seeds, B * 8, cudaMemcpyHostToDevice, s));
@@ -836,7 +902,10 @@ int ssb_step_host(ssb_env *env, const int32_t *stage_idx, const int32_t *num_exe
                   int32_t max_events, ssb_obs_hdr *hdr_out)
 {
     if (!env || !stage_idx || !num_exec) return SSB_E_INVALID;
-    CUDA_TRY(cudaSetDevice(env->device));
+    {
+        const int rcb = host_begin(env);  // also waits for work still queued on the caller's streams
+        if (rcb) return rcb;
+    }
     cudaStream_t s = env->own_stream;
     const size_t B = env->p.B;
     CUDA_TRY(cudaMemcpyAsync(env->st_a, stage_idx, B * 4, cudaMemcpyHostToDevice, s));
@@ -854,7 +923,10 @@ int ssb_step_fair_host(ssb_env *env, const int32_t *stage_idx, const int32_t *nu
                        int32_t *next_num_exec)
 {
     if (!env || !stage_idx || !num_exec || !next_stage_idx || !next_num_exec) return SSB_E_INVALID;
-    CUDA_TRY(cudaSetDevice(env->device));
+    {
+        const int rcb = host_begin(env);  // also waits for work still queued on the caller's streams
+        if (rcb) return rcb;
+    }
     cudaStream_t s = env->own_stream;
     const size_t B = env->p.B;
     CUDA_TRY(cudaMemcpyAsync(env->st_a, stage_idx, B * 4, cudaMemcpyHostToDevice, s));
@@ -903,7 +975,10 @@ int ssb_get_obs_host(ssb_env *env, ssb_packed_obs *out, void *scratch, size_t sc
     const Params &p = env->p;
     const PackLayout l = pack_layout(p);
     if (scratch_bytes < l.bytes) return SSB_E_WORKSPACE;
-    CUDA_TRY(cudaSetDevice(env->device));
+    {
+        const int rcb = host_begin(env);  // also waits for work still queued on the caller's streams
+        if (rcb) return rcb;
+    }
     cudaStream_t s = env->own_stream;
     char *sc = static_cast<char *>(scratch);
     int32_t *d_off = reinterpret_cast<int32_t *>(sc + l.off_offsets);
@@ -937,6 +1012,7 @@ int ssb_rollout_fair_traj(ssb_env *env, int32_t num_decisions, int32_t dynamic_p
         k_rollout_fair<2><<<env->grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(
             env->p, num_decisions, dynamic_partition, auto_reset, seed_step, traj);
     CUDA_TRY(cudaGetLastError());
+    SSB_MARK(env, stream);
     return SSB_OK;
 }
 
@@ -952,6 +1028,7 @@ int ssb_rollout_fair_async(ssb_env *env, int32_t max_decisions, double rollout_d
         k_rollout_fair_async<2><<<env->grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(
             env->p, max_decisions, rollout_duration, dynamic_partition, seed_step, traj, num_steps, elapsed);
     CUDA_TRY(cudaGetLastError());
+    SSB_MARK(env, stream);
     return SSB_OK;
 }
 
@@ -968,6 +1045,7 @@ int ssb_fair_actions(ssb_env *env, int32_t dynamic_partition, int32_t *stage_idx
     k_fair_actions<<<env->grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(env->p, dynamic_partition,
                                                                                stage_idx, num_exec);
     CUDA_TRY(cudaGetLastError());
+    SSB_MARK(env, stream);
     return SSB_OK;
 }
 
@@ -992,6 +1070,7 @@ int ssb_decima_obs(ssb_env *env, void *stream)
     SSB_ON_DEVICE(env);
     k_decima_obs<<<env->grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(env->p);
     CUDA_TRY(cudaGetLastError());
+    SSB_MARK(env, stream);
     return SSB_OK;
 }
 
@@ -1044,8 +1123,44 @@ int ssb_set_decima_weights(ssb_env *env, const float *weights, int32_t n_floats)
     tc::k_build_blob<tc::ST_GLOB><<<1, 128>>>(env->p);
     tc::k_build_blob<tc::ST_STAGE><<<1, 128>>>(env->p);
     tc::k_build_blob<tc::ST_EXEC><<<1, 128>>>(env->p);
+    CUDA_TRY(cudaMemset(env->p.pol_wblob3, 0, sizeof(uint32_t) * fz::BLOB_TOTAL));
+    fz::k_build_blob<tc::ST_PREP><<<1, 128>>>(env->p.pol_w, env->p.pol_wblob3);
+    fz::k_build_blob<tc::ST_SINK><<<1, 128>>>(env->p.pol_w, env->p.pol_wblob3);
+    fz::k_build_blob<tc::ST_MSG><<<1, 128>>>(env->p.pol_w, env->p.pol_wblob3);
+    fz::k_build_blob<tc::ST_RCV><<<1, 128>>>(env->p.pol_w, env->p.pol_wblob3);
+    fz::k_build_blob<tc::ST_DAG><<<1, 128>>>(env->p.pol_w, env->p.pol_wblob3);
+    fz::k_build_blob<tc::ST_GLOB><<<1, 128>>>(env->p.pol_w, env->p.pol_wblob3);
+    fz::k_build_blob<tc::ST_STAGE><<<1, 128>>>(env->p.pol_w, env->p.pol_wblob3);
+    fz::k_build_blob<tc::ST_EXEC><<<1, 128>>>(env->p.pol_w, env->p.pol_wblob3);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaDeviceSynchronize());
+    return SSB_OK;
+}
+
+// The backward pass and ssb_decima_work walk the row lists of the list-driven path; the fused forward kernel does not
+// build them, so they are (re)built here from the observation, the adapter's outputs and the stored action.
+__global__ void __launch_bounds__(128) k_plan_exec(Params p)
+{
+    const int b = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= p.B) return;
+    const int job_idx = p.pol_action[(size_t)b * 4 + 1];
+    const int cap = job_idx >= 0 ? p.dec_caps[(size_t)b * p.Jc + job_idx] : 0;
+    int base = 0;
+    if (lane == 0 && cap > 0) base = atomicAdd(&p.pl_cnt[tc::CNT_EXEC], cap);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    for (int c = lane; c < cap; c += 32) p.pl_exec[base + c] = b * p.Epad + c;
+}
+static int replan(ssb_env *env, cudaStream_t s)
+{
+    if (env->use_tiles) return SSB_OK;  // the list-driven forward pass left its lists in place
+    const Params &p = env->p;
+    const int warp_grid = (p.B + 3) / 4;
+    CUDA_TRY(cudaMemsetAsync(p.pl_cnt, 0, sizeof(int32_t) * tc::CNT_TOTAL, s));
+    tc::k_pol_plan_a<<<warp_grid, 128, 0, s>>>(p);
+    tc::k_pol_plan_scan<<<1, 32, 0, s>>>(p);
+    tc::k_pol_plan_b<<<warp_grid, 128, 0, s>>>(p);
+    k_plan_exec<<<warp_grid, 128, 0, s>>>(p);
+    CUDA_TRY(cudaGetLastError());
     return SSB_OK;
 }
 
@@ -1055,8 +1170,19 @@ static int decima_policy_impl(ssb_env *env, const int32_t *forced_stage, const i
                               int32_t *stage_idx_out, int32_t *num_exec_out, bool run_adapter, bool advance_draws,
                               cudaStream_t s)
 {
-    // observation adapter -> row lists -> one tensor-core tile pass per MLP (ssb_decima_tc.cuh)
     const Params &p = env->p;
+    if (!env->use_tiles) {
+        // the whole decision of every env in one persistent kernel (ssb_decima_fused.cuh)
+        CUDA_TRY(cudaMemsetAsync(p.fz_cursor, 0, sizeof(int32_t) * 4, s));
+        fz::fused::Args a{forced_stage, forced_num_exec, stage_idx_out, num_exec_out, p.fz_cursor,
+                          run_adapter ? 1 : 0, advance_draws ? 1 : 0, env->fused_group};
+        const int groups = (p.B + env->fused_group - 1) / env->fused_group;
+        fz::fused::k_decima_fused<<<std::min(groups, 2 * env->num_sms), fz::fused::THREADS, fz::fused::Smem::BYTES, s>>>(p, a);
+        CUDA_TRY(cudaGetLastError());
+        SSB_MARK(env, s);
+        return SSB_OK;
+    }
+    // round 1's path: observation adapter -> row lists -> one tensor-core tile pass per MLP (ssb_decima_tc.cuh)
     const int32_t *cnt = p.pl_cnt;
     const int warp_grid = (p.B + 3) / 4;
     int rc;
@@ -1084,6 +1210,7 @@ static int decima_policy_impl(ssb_env *env, const int32_t *forced_stage, const i
     tc::k_pol_sample_exec<<<warp_grid, 128, 0, s>>>(p, forced_num_exec, stage_idx_out, num_exec_out,
                                                     advance_draws ? 1 : 0);
     CUDA_TRY(cudaGetLastError());
+    SSB_MARK(env, s);
     return SSB_OK;
 }
 
@@ -1144,6 +1271,7 @@ int ssb_decima_head_adjoint(ssb_env *env, const float *grad_lgprob, const float 
     SSB_ON_DEVICE(env);
     CUDA_TRY(bwd::head_adjoint(env->p, grad_lgprob, grad_entropy, grad_stage_logits, grad_exec_logits,
                                (cudaStream_t)stream));
+    SSB_MARK(env, stream);
     return SSB_OK;
 }
 
@@ -1155,6 +1283,10 @@ int ssb_decima_head_backward(ssb_env *env, const float *grad_stage_logits, const
     SSB_ON_DEVICE(env);
     cudaStream_t s = (cudaStream_t)stream;
     const Params &p = env->p;
+    {
+        const int rcp = replan(env, s);
+        if (rcp) return rcp;
+    }
     const bwd::Bufs none{nullptr, nullptr, nullptr, nullptr, nullptr};
     CUDA_TRY(bwd::mlp_backward(tc::ST_STAGE, p, env->num_sms, nullptr, nullptr, p.pl_cnt + tc::CNT_CAND, 0,
                                grad_stage_logits, grad_stage_inputs, stage_inputs, grad_weights, none, false, s));
@@ -1167,6 +1299,7 @@ int ssb_decima_head_backward(ssb_env *env, const float *grad_stage_logits, const
         num_rows[0] = c[tc::CNT_CAND];
         num_rows[1] = c[tc::CNT_EXEC];
     }
+    SSB_MARK(env, s);
     return SSB_OK;
 }
 
@@ -1187,6 +1320,10 @@ int ssb_decima_backward(ssb_env *env, const float *grad_lgprob, const float *gra
     cudaStream_t s = (cudaStream_t)stream;
     const Params &p = env->p;
     const BackwardScratch b = backward_scratch(p, static_cast<float *>(scratch));
+    {
+        const int rcp = replan(env, s);
+        if (rcp) return rcp;
+    }
     CUDA_TRY(cudaMemsetAsync(grad_node_embeddings, 0, sizeof(float) * (size_t)p.B * p.Sc * 16, s));
     CUDA_TRY(cudaMemsetAsync(b.d_hdag, 0, sizeof(float) * (size_t)p.B * p.Jc * 16, s));
     CUDA_TRY(cudaMemsetAsync(b.d_hglob, 0, sizeof(float) * (size_t)p.B * 16, s));
@@ -1200,7 +1337,7 @@ int ssb_decima_backward(ssb_env *env, const float *grad_lgprob, const float *gra
     if ((rc = launch_mlp_backward(tc::ST_EXEC, env, p.pl_exec, nullptr, cnt + tc::CNT_EXEC, 0, b.ge, gw, bw, s))) return rc;
     if ((rc = launch_mlp_backward(tc::ST_GLOB, env, p.pl_jobs, nullptr, cnt + tc::CNT_JOBS, 0, nullptr, gw, bw, s))) return rc;
     if ((rc = launch_mlp_backward(tc::ST_DAG, env, p.pl_all, nullptr, cnt + tc::CNT_ALL, 0, nullptr, gw, bw, s))) return rc;
-    if (!through_node_encoder) return SSB_OK;
+    if (!through_node_encoder) { SSB_MARK(env, s); return SSB_OK; }
     // NodeEncoder (scheduler.py:191-234), the levels in the reverse of the forward order.  Level k's backward needs
     // the embeddings as they were BEFORE level k and the level's messages; the forward pass overwrites both in
     // place, so they are recomputed: reset (PREP), sinks, levels dmax-1 .. k+1, then level k's messages.  First
@@ -1228,6 +1365,7 @@ int ssb_decima_backward(ssb_env *env, const float *grad_lgprob, const float *gra
     }
     if ((rc = launch_mlp_backward(tc::ST_SINK, env, p.pl_sink, nullptr, cnt + tc::CNT_SINK, 0, nullptr, gw, bw, s))) return rc;
     if ((rc = launch_mlp_backward(tc::ST_PREP, env, p.pl_all, nullptr, cnt + tc::CNT_ALL, 0, nullptr, gw, bw, s))) return rc;
+    SSB_MARK(env, s);
     return SSB_OK;
 }
 
@@ -1244,7 +1382,10 @@ int ssb_decima_snapshot(ssb_env *env, void *dst, void *stream)
     SSB_ON_DEVICE(env);
     k_decima_obs<<<env->grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(env->p);  // the adapter's view of the state
     CUDA_TRY(cudaGetLastError());
-    return snapshot_copy(env, static_cast<char *>(dst), true, (cudaStream_t)stream);
+    const int rcs = snapshot_copy(env, static_cast<char *>(dst), true, (cudaStream_t)stream);
+    if (rcs) return rcs;
+    SSB_MARK(env, stream);
+    return SSB_OK;
 }
 
 int ssb_decima_snapshot_load(ssb_env *env, const void *snapshot, void *stream)
@@ -1257,6 +1398,7 @@ int ssb_decima_snapshot_load(ssb_env *env, const void *snapshot, void *stream)
     if ((rc = snapshot_copy(env, env->p.pol_snap, true, s))) return rc;
     if ((rc = snapshot_copy(env, const_cast<char *>(static_cast<const char *>(snapshot)), false, s))) return rc;
     env->snap_loaded = 1;
+    SSB_MARK(env, stream);
     return SSB_OK;
 }
 
@@ -1265,7 +1407,10 @@ int ssb_decima_snapshot_unload(ssb_env *env, void *stream)
     if (!env || !env->p.pol_w || !env->snap_loaded) return SSB_E_INVALID;
     SSB_ON_DEVICE(env);
     env->snap_loaded = 0;
-    return snapshot_copy(env, env->p.pol_snap, false, (cudaStream_t)stream);
+    const int rcs = snapshot_copy(env, env->p.pol_snap, false, (cudaStream_t)stream);
+    if (rcs) return rcs;
+    SSB_MARK(env, stream);
+    return SSB_OK;
 }
 
 int ssb_decima_evaluate(ssb_env *env, const void *snapshot, const int32_t *stage_sel, const int32_t *exec_sel,
@@ -1290,6 +1435,7 @@ int ssb_decima_evaluate(ssb_env *env, const void *snapshot, const int32_t *stage
         const int rc2 = ssb_decima_snapshot_unload(env, stream);
         if (!rc) rc = rc2;
     }
+    if (!rc) SSB_MARK(env, stream);
     return rc;
 }
 
@@ -1358,13 +1504,36 @@ int ssb_rollout_decima(ssb_env *env, int32_t num_decisions, int32_t max_events, 
         CUDA_TRY(cudaEventRecord(env->ev, s));
         CUDA_TRY(cudaStreamWaitEvent(caller, env->ev, 0));
     }
+    SSB_MARK(env, caller);
     return SSB_OK;
+}
+
+int ssb_decima_mlp_rows(ssb_env *env, int32_t mlp, const float *x, int32_t n_rows, float *out, void *stream)
+{
+    if (!env || !env->p.pol_w || !x || !out || n_rows < 1) return SSB_E_INVALID;
+    SSB_ON_DEVICE(env);
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (mlp) {
+    case 0: return launch_mlp_rows<tc::ST_PREP>(env, x, n_rows, out, s);
+    case 1: return launch_mlp_rows<tc::ST_MSG>(env, x, n_rows, out, s);
+    case 2: return launch_mlp_rows<tc::ST_RCV>(env, x, n_rows, out, s);
+    case 3: return launch_mlp_rows<tc::ST_DAG>(env, x, n_rows, out, s);
+    case 4: return launch_mlp_rows<tc::ST_GLOB>(env, x, n_rows, out, s);
+    case 5: return launch_mlp_rows<tc::ST_STAGE>(env, x, n_rows, out, s);
+    case 6: return launch_mlp_rows<tc::ST_EXEC>(env, x, n_rows, out, s);
+    default: return SSB_E_INVALID;
+    }
 }
 
 int ssb_decima_work(ssb_env *env, int64_t *out)
 {
     if (!env || !out || !env->p.pol_w) return SSB_E_INVALID;
     CUDA_TRY(cudaSetDevice(env->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    {
+        const int rcp = replan(env, env->own_stream);
+        if (rcp) return rcp;
+    }
     CUDA_TRY(cudaDeviceSynchronize());
     std::vector<int32_t> c(tc::CNT_TOTAL);
     CUDA_TRY(cudaMemcpy(c.data(), env->p.pl_cnt, sizeof(int32_t) * tc::CNT_TOTAL, cudaMemcpyDeviceToHost));
@@ -1412,6 +1581,7 @@ int ssb_collect_stats(ssb_env *env, double *out, void *stream)
     k_collect_stats_part<<<STATS_BLOCKS, 256, 0, (cudaStream_t)stream>>>(env->p, env->p.stats_part);
     k_collect_stats_final<<<1, 32, 0, (cudaStream_t)stream>>>(env->p.stats_part, out);
     CUDA_TRY(cudaGetLastError());
+    SSB_MARK(env, stream);
     return SSB_OK;
 }
 
@@ -1421,6 +1591,7 @@ int ssb_reset_stats(ssb_env *env, void *stream)
     SSB_ON_DEVICE(env);
     k_zero_stats<<<(env->p.B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(env->p.stats, env->p.B);
     CUDA_TRY(cudaGetLastError());
+    SSB_MARK(env, stream);
     return SSB_OK;
 }
 

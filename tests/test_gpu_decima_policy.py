@@ -617,3 +617,47 @@ def test_ppo_minibatch_update_on_stored_snapshots(bank):
     a, n = env.decima_policy()
     env.step(a, n)
     assert (env.hdr()["error"] == 0).all()
+
+
+def _mlp_fp(x, w, name, tanh, dtype):
+    """make_mlp (schedulers/decima/utils.py:45-64) in numpy at the given precision."""
+    x = x.astype(dtype)
+    for i, k in enumerate((0, 2, 4)):
+        x = x @ w[f"{name}.{k}.weight"].astype(dtype).T + w[f"{name}.{k}.bias"].astype(dtype)
+        if i < 2:
+            x = np.tanh(x) if tanh else np.where(x > 0, x, dtype(0.2) * x)
+        x = x.astype(dtype)
+    return x
+
+
+@pytest.mark.parametrize("mlp", range(7))
+def test_mlp_rows_accuracy_against_fp64(bank, mlp):
+    """Each of the policy's seven MLPs on the tensor-core path (bf16 three-term split, activations in TMEM) against an
+    fp64 evaluation of the same weights: the error must be of the size of float32 arithmetic itself -- no larger than
+    3x what torch's own float32 forward makes against fp64 on the same rows (plus 2e-7 of the output scale)."""
+    from spark_sched_sim_b200.batched_env import BatchedSparkSchedSimEnv
+
+    cfg = {"num_executors": 10, "job_arrival_cap": 4, "job_arrival_rate": 4.0e-5,
+           "moving_delay": 2000.0, "warmup_delay": 1000.0}
+    env = BatchedSparkSchedSimEnv(cfg, num_envs=2, bank=bank, decima_policy=True)
+    w = weights()
+    env.set_decima_weights(w)
+    name, (din, dout) = env.MLP_NAMES[mlp], env.MLP_DIMS[mlp]
+    rng = np.random.default_rng(100 + mlp)
+    n = 1000  # not a multiple of 128: the last tile is ragged
+    x = (rng.standard_normal((n, din)) * rng.choice([0.05, 1.0, 4.0], size=(n, 1))).astype(np.float32)
+    x[0] = 0.0
+    got = env.decima_mlp_rows(mlp, torch.from_numpy(x).cuda()).cpu().numpy().astype(np.float64)
+    truth = _mlp_fp(x, w, name, mlp >= 5, np.float64)
+    with torch.no_grad():
+        t = torch.from_numpy(x)
+        for i, k in enumerate((0, 2, 4)):
+            t = torch.nn.functional.linear(t, torch.from_numpy(w[f"{name}.{k}.weight"]), torch.from_numpy(w[f"{name}.{k}.bias"]))
+            if i < 2:
+                t = torch.tanh(t) if mlp >= 5 else torch.nn.functional.leaky_relu(t, 0.2)
+        ref32 = t.numpy().astype(np.float64)
+    scale = np.abs(truth).max()
+    err_ours, err_torch = np.abs(got - truth).max(), np.abs(ref32 - truth).max()
+    print(f"mlp {mlp} {name}: scale {scale:.3g}  ours-vs-fp64 {err_ours:.3g}  torch32-vs-fp64 {err_torch:.3g}")
+    assert got.shape == (n, dout)
+    assert err_ours <= 3.0 * err_torch + 2e-7 * scale, (err_ours, err_torch, scale)

@@ -21,7 +21,7 @@ cfg = {"num_executors": 10, "job_arrival_cap": 8, "job_arrival_rate": 4.0e-5, "m
 z = np.load(osp.join(REPO, "tests", "golden", "decima_model.npz"))
 envs = []
 for tiles in (0, 1):
-    os.environ["SSB_DECIMA_TILES"] = str(tiles)
+    os.environ["SSB_DECIMA_MODE"] = str(2 if tiles else int(os.environ.get("MODE_A", "1")))
     e = BatchedSparkSchedSimEnv(cfg, num_envs=B, bank=synthetic_bank(0), max_jobs=10, tape_capacity=len(tr["tape"]) + 8,
                                 decima_policy=True)
     e.set_decima_weights({k: z[k] for k in z.files})

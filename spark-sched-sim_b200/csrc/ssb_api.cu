@@ -517,6 +517,11 @@ void carve(Carver &cv, const ssb_config &c, const ssb_bank &bk, const Dims &d, P
 
 }  // namespace
 
+// How ssb_decima_policy runs: row lists + one launch per MLP pass with the TMEM-resident bf16 three-term tiles (the
+// default for large batches), the whole decision of a group of envs in one persistent kernel (one launch: small
+// batches, e.g. the single-env facade), or round 1's shared-memory tf32 tiles (kept for A/B measurements).
+enum { POLICY_TILES = 0, POLICY_FUSED = 1, POLICY_TILES_TF32 = 2 };
+
 struct ssb_env {
     ssb_config cfg;
     Dims dims;
@@ -541,7 +546,7 @@ struct ssb_env {
     ssb_transition *dg_traj;
     int dg_k, dg_events, dg_autoreset, no_graph;
     uint64_t dg_seed_step;
-    int use_tiles;      // SSB_DECIMA_TILES=1: round 1's list-driven tile launches instead of the fused policy kernel
+    int policy_mode;    // POLICY_* below (SSB_DECIMA_MODE overrides the default)
     int fused_group;    // environments per group of the fused policy kernel
     int snap_loaded;    // ssb_decima_snapshot_load: a stored observation is in place, the live one parked
     int auto_reset;     // ssb_set_autoreset
@@ -592,7 +597,11 @@ int launch_tile(ssb_env *env, const int32_t *list, const int32_t *offset, const 
                 int ctas_per_sm, cudaStream_t s)
 {
     tc::TileArgs a{list, offset, count, level};
-    tc::k_tile_mlp<ST><<<env->num_sms * ctas_per_sm, 128, tc::Smem<ST>::BYTES, s>>>(env->p, a);
+    if (env->policy_mode == POLICY_TILES_TF32)
+        tc::k_tile_mlp<ST><<<env->num_sms * ctas_per_sm, 128, tc::Smem<ST>::BYTES, s>>>(env->p, a);
+    else
+        fz::k_tile3<ST><<<env->num_sms * (fz::Spec<ST>::OUT > 1 ? 2 * ctas_per_sm : ctas_per_sm), 128,
+                          sizeof(uint32_t) * fz::Blob<ST>::WORDS, s>>>(env->p, a);
     CUDA_TRY(cudaGetLastError());
     return SSB_OK;
 }
@@ -601,6 +610,8 @@ int prepare_tile_kernel()
 {
     CUDA_TRY(cudaFuncSetAttribute(tc::k_tile_mlp<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)tc::Smem<ST>::BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(fz::k_tile3<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(sizeof(uint32_t) * fz::Blob<ST>::WORDS)));
     return SSB_OK;
 }
 
@@ -690,8 +701,8 @@ int ssb_create(const ssb_config *cfg, const ssb_bank *bk, int device, void *work
         env->dmax = dmax;
     }
     if (p.pol_w) {
-        const char *ut = getenv("SSB_DECIMA_TILES");
-        env->use_tiles = ut && ut[0] == '1';
+        env->policy_mode = cfg->num_envs <= 2 * env->num_sms ? POLICY_FUSED : POLICY_TILES;
+        if (const char *pm = getenv("SSB_DECIMA_MODE")) env->policy_mode = std::max(0, std::min(atoi(pm), 2));
         CUDA_TRY(cudaFuncSetAttribute(fz::fused::k_decima_fused, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)fz::fused::Smem::BYTES));
         {   // group size: one round of groups over the resident CTAs (two per SM) when that needs at most GMAX
@@ -1152,7 +1163,7 @@ __global__ void __launch_bounds__(128) k_plan_exec(Params p)
 }
 static int replan(ssb_env *env, cudaStream_t s)
 {
-    if (env->use_tiles) return SSB_OK;  // the list-driven forward pass left its lists in place
+    if (env->policy_mode != POLICY_FUSED) return SSB_OK;  // the list-driven forward pass left its lists in place
     const Params &p = env->p;
     const int warp_grid = (p.B + 3) / 4;
     CUDA_TRY(cudaMemsetAsync(p.pl_cnt, 0, sizeof(int32_t) * tc::CNT_TOTAL, s));
@@ -1171,7 +1182,7 @@ static int decima_policy_impl(ssb_env *env, const int32_t *forced_stage, const i
                               cudaStream_t s)
 {
     const Params &p = env->p;
-    if (!env->use_tiles) {
+    if (env->policy_mode == POLICY_FUSED) {
         // the whole decision of every env in one persistent kernel (ssb_decima_fused.cuh)
         CUDA_TRY(cudaMemsetAsync(p.fz_cursor, 0, sizeof(int32_t) * 4, s));
         fz::fused::Args a{forced_stage, forced_num_exec, stage_idx_out, num_exec_out, p.fz_cursor,
@@ -1182,7 +1193,7 @@ static int decima_policy_impl(ssb_env *env, const int32_t *forced_stage, const i
         SSB_MARK(env, s);
         return SSB_OK;
     }
-    // round 1's path: observation adapter -> row lists -> one tensor-core tile pass per MLP (ssb_decima_tc.cuh)
+    // observation adapter -> row lists -> one tensor-core tile pass per MLP (lists: ssb_decima_tc.cuh)
     const int32_t *cnt = p.pl_cnt;
     const int warp_grid = (p.B + 3) / 4;
     int rc;

@@ -14,9 +14,11 @@
 // D at [0, 32), the three split terms of A at [32 + 32 j, 32 + 32 j + K / 2), j = 0..2 (two bf16 per 32-bit column).
 //
 // fp32 accuracy: x = b0 + b1 + b2 EXACTLY, each term a bf16 (8 significant bits: 8 + 8 + 8 = the 24 of an fp32),
-// same for the weights; a product is accumulated as the six partial products with i + j <= 2 (smallest first,
-// fp32 accumulation in TMEM); the three dropped ones are below 2^-24 relative.  Measured against an fp64 evaluation
-// of the reference's model: tests/test_gpu_decima_policy.py.
+// same for the weights; a product is accumulated as eight of the nine partial products (smallest first, fp32
+// accumulation in TMEM); the dropped b2 * w2 is below 2^-30 relative.  The activations are split by TRUNCATION (the
+// three bytes of the significand: one AND + one subtraction per term, packing by byte permute straight from the
+// remainders -- 5.5 ALU instructions per element), the weights once per upload by rounding.  Measured against an fp64
+// evaluation of the reference's model: tests/test_gpu_decima_policy.py::test_mlp_rows_accuracy_against_fp64.
 #pragma once
 #include "ssb_decima_tc.cuh"
 
@@ -165,61 +167,76 @@ struct Wg {
     int tid;          // 0..127 within the warpgroup
     int bar;          // named barrier id of the warpgroup
 };
-constexpr int COL_D = 0, COL_A = 32, COLS_PER_WG = 128;
+// TMEM column maps of one tile context.  128 columns: D at [0, 32), A term j at [32 + 32 j, ...).  64 columns (the
+// 16-wide GNN MLPs): D at [0, N), the three A terms packed at the top, [64 - 3 K / 2, 64) -- layer 1 (N 32, K 16): D
+// [0, 32) A [40, 64); layer 2 (N 16, K 32): D [0, 16) A [16, 64); layer 3: D [0, 16) A [40, 64).  A thread only ever
+// reads and writes its OWN lane, and a layer's A is written after the previous layer's D was read into registers
+// and its MMAs have completed, so the regions of consecutive layers may overlap.
+constexpr int COL_D = 0, COLS_PER_WG = 128;
+template <int COLS, int K> __device__ __forceinline__ constexpr int a_base() { return COLS == 64 ? 64 - 3 * K / 2 : 32; }
+template <int COLS, int K> __device__ __forceinline__ constexpr int a_stride() { return COLS == 64 ? K / 2 : 32; }
 
 __device__ __forceinline__ void wg_sync(const Wg &g) { asm volatile("bar.sync %0, 128;" ::"r"(g.bar) : "memory"); }
 
 // this thread's row of the next layer's A operand: v[0..K) -> three bf16 terms, two per column
-template <int K>
+template <int K, int COLS = 128>
 __device__ __forceinline__ void store_a_row(const Wg &g, const float *v)
 {
+    // truncation split: term j = the j-th byte of the significand (x & 0xffff0000 is a bf16; x minus it is exact);
+    // pack2 takes the upper halves straight from x, the first and the second remainder
 #pragma unroll
     for (int c0 = 0; c0 < K / 2; c0 += 8) {
         uint32_t t0[8], t1[8], t2[8];
 #pragma unroll
         for (int c = 0; c < 8; c++) {
-            uint32_t a0, a1, a2, b0, b1, b2;
-            split3(v[2 * (c0 + c)], a0, a1, a2);
-            split3(v[2 * (c0 + c) + 1], b0, b1, b2);
-            t0[c] = pack2(a0, b0); t1[c] = pack2(a1, b1); t2[c] = pack2(a2, b2);
+            const float x0 = v[2 * (c0 + c)], x1 = v[2 * (c0 + c) + 1];
+            const float r0 = x0 - __uint_as_float(__float_as_uint(x0) & 0xffff0000u);
+            const float r1 = x1 - __uint_as_float(__float_as_uint(x1) & 0xffff0000u);
+            const float s0 = r0 - __uint_as_float(__float_as_uint(r0) & 0xffff0000u);
+            const float s1 = r1 - __uint_as_float(__float_as_uint(r1) & 0xffff0000u);
+            t0[c] = pack2(__float_as_uint(x0), __float_as_uint(x1));
+            t1[c] = pack2(__float_as_uint(r0), __float_as_uint(r1));
+            t2[c] = pack2(__float_as_uint(s0), __float_as_uint(s1));
         }
-        tmem_st8(g.trow + COL_A + c0, t0);
-        tmem_st8(g.trow + COL_A + 32 + c0, t1);
-        tmem_st8(g.trow + COL_A + 64 + c0, t2);
+        tmem_st8(g.trow + a_base<COLS, K>() + c0, t0);
+        tmem_st8(g.trow + a_base<COLS, K>() + a_stride<COLS, K>() + c0, t1);
+        tmem_st8(g.trow + a_base<COLS, K>() + 2 * a_stride<COLS, K>() + c0, t2);
     }
     tmem_wait_st();
 }
-// D[128 x N] = A[128 x K] . W[n0 .. n0 + N)[K]^T : the six partial products with i + j <= 2, smallest first.
+// D[128 x N] = A[128 x K] . W[n0 .. n0 + N)[K]^T : eight partial products a_i * w_j (all but a_2 * w_2), smallest first.
 // w = the layer's three tiles in shared memory (term j at w + j * NTOT * K bf16).  One elected thread.
-template <int K, int N, int NTOT>
+template <int K, int N, int NTOT, int COLS = 128>
 __device__ __forceinline__ void issue_layer(const Wg &g, const uint32_t *w_words, int n0)
 {
     constexpr uint32_t idesc = umma_idesc_bf16(128, N);
     constexpr uint32_t sbo = K * 16;
-    const uint32_t wb = smem_u32(w_words) + (uint32_t)(n0 >> 3) * sbo;
     constexpr uint32_t term_bytes = NTOT * K * 2;
-    const int ai[6] = {2, 0, 1, 1, 0, 0}, wi[6] = {0, 2, 1, 0, 1, 0};
+    // one descriptor for the layer's first tile; the other terms / k-steps differ in the start-address field only
+    const uint64_t d0 = umma_desc(smem_u32(w_words) + (uint32_t)(n0 >> 3) * sbo, 128, sbo);
+    const uint32_t a0 = g.tmem + a_base<COLS, K>();
+    const int ai[8] = {2, 1, 2, 0, 1, 1, 0, 0}, wi[8] = {1, 2, 0, 2, 1, 0, 1, 0};
     bool first = true;
 #pragma unroll
-    for (int q = 0; q < 6; q++) {
+    for (int q = 0; q < 8; q++) {
 #pragma unroll
         for (int ks = 0; ks < K / 16; ks++) {
-            const uint64_t dw = umma_desc(wb + wi[q] * term_bytes + ks * 256, 128, sbo);
-            umma_bf16_ts(g.tmem + COL_D, g.tmem + COL_A + 32 * ai[q] + ks * 8, dw, idesc, first ? 0u : 1u);
+            umma_bf16_ts(g.tmem + COL_D, a0 + a_stride<COLS, K>() * ai[q] + ks * 8,
+                         d0 + (uint64_t)((wi[q] * term_bytes + ks * 256) >> 4), idesc, first ? 0u : 1u);
             first = false;
         }
     }
     umma_commit(g.mbar);
 }
 // A written by every thread -> MMAs issued -> D complete and visible to every thread of the warpgroup
-template <int K, int N, int NTOT>
+template <int K, int N, int NTOT, int COLS = 128>
 __device__ __forceinline__ void run_layer(Wg &g, const uint32_t *w_words, int n0)
 {
     tc_fence_before();
     wg_sync(g);
     if (g.tid == 0) {
         tc_fence_after();
-        issue_layer<K, N, NTOT>(g, w_words, n0);
+        issue_layer<K, N, NTOT, COLS>(g, w_words, n0);
     }
     mbar_wait(g.mbar, g.parity);
     g.parity ^= 1;
@@ -230,36 +247,45 @@ template <bool TANH>
 __device__ __forceinline__ float act(float x)
 {
     if (TANH) return tanhf(x);
-    return x > 0.0f ? x : 0.2f * x;
+    return fmaxf(x, 0.2f * x);  // LeakyReLU(0.2): the larger of x and 0.2 x (same values, two instructions)
 }
 
 // One 128-row tile through stage ST's three layers.  in[K0]: this thread's gathered input row (zeros beyond IN and
 // for rows past the end of the list); out[OUT]: its output row.  wb: the stage's blob in shared memory.
-template <int ST>
+template <int ST, int COLS = 128>
 __device__ __forceinline__ void mlp_tile(Wg &g, const uint32_t *wb, const float *in, float *out)
 {
     using S = Spec<ST>;
     using L = Blob<ST>;
+    static_assert(COLS == 128 || S::OUT > 1, "the score heads need the 128-column map");
     const float *bias = reinterpret_cast<const float *>(wb + L::BIAS);
-    store_a_row<S::K0>(g, in);
+    store_a_row<S::K0, COLS>(g, in);
     if constexpr (S::OUT > 1) {
-        run_layer<S::K0, S::H1, S::H1>(g, wb + L::W1, 0);
         {
             float v[S::H1];
-            tc::tmem_ld_row<S::H1>(g.trow + COL_D, v);
+            if constexpr (COLS == 64 && 3 * S::K0 / 2 + S::H1 > 64) {
+                // (DagEncoder, K0 32: A takes 48 of the 64 columns, so layer 1 runs 16 output columns at a time)
+                run_layer<S::K0, 16, S::H1, COLS>(g, wb + L::W1, 0);
+                tc::tmem_ld_row<16>(g.trow + COL_D, v);
+                run_layer<S::K0, 16, S::H1, COLS>(g, wb + L::W1, 16);
+                tc::tmem_ld_row<16>(g.trow + COL_D, v + 16);
+            } else {
+                run_layer<S::K0, S::H1, S::H1, COLS>(g, wb + L::W1, 0);
+                tc::tmem_ld_row<S::H1>(g.trow + COL_D, v);
+            }
 #pragma unroll
             for (int i = 0; i < S::H1; i++) v[i] = act<S::TANH>(v[i] + bias[i]);
-            store_a_row<S::H1>(g, v);
+            store_a_row<S::H1, COLS>(g, v);
         }
-        run_layer<S::H1, S::H2, S::H2>(g, wb + L::W2, 0);
+        run_layer<S::H1, S::H2, S::H2, COLS>(g, wb + L::W2, 0);
         {
             float v[S::H2];
             tc::tmem_ld_row<S::H2>(g.trow + COL_D, v);
 #pragma unroll
             for (int i = 0; i < S::H2; i++) v[i] = act<S::TANH>(v[i] + bias[S::H1 + i]);
-            store_a_row<S::H2>(g, v);
+            store_a_row<S::H2, COLS>(g, v);
         }
-        run_layer<S::H2, S::OUT, S::OUT>(g, wb + L::W3, 0);
+        run_layer<S::H2, S::OUT, S::OUT, COLS>(g, wb + L::W3, 0);
         tc::tmem_ld_row<S::OUT>(g.trow + COL_D, out);
 #pragma unroll
         for (int i = 0; i < S::OUT; i++) out[i] += bias[S::H1 + S::H2 + i];
@@ -325,6 +351,68 @@ __global__ void __launch_bounds__(128) k_mlp_rows(const uint32_t *blob_all, cons
     }
     __syncthreads();
     if (warp == 0) tmem_dealloc(g.tmem, COLS_PER_WG);
+}
+
+// ------------------------------------------------------------------ list-driven tile kernel
+// One MLP over a row list built by the planning kernels (ssb_decima_tc.cuh: all nodes, sinks, the senders / receivers
+// of one level, jobs, schedulable stages, executor-count rows): the launch sequence of round 1 with the tile routine
+// above.  128 threads = one warpgroup per CTA, 128 TMEM columns, four CTAs per SM.
+namespace fused {
+template <int ST> __device__ __forceinline__ void gather(const Params &p, int id, int level, float *in);
+}
+template <int ST>
+__global__ void __launch_bounds__(128, Spec<ST>::OUT > 1 ? 8 : 4) k_tile3(Params p, tc::TileArgs a)
+{
+    using S = Spec<ST>;
+    using L = Blob<ST>;
+    constexpr int COLS = S::OUT > 1 ? 64 : 128;  // the GNN MLPs fit the 64-column map: eight CTAs per SM
+    const int n_rows = *a.count;
+    if (n_rows <= 0) return;
+    const int32_t *list = a.list + (a.offset ? *a.offset : 0);
+    const int n_tiles = (n_rows + 127) >> 7;
+    if ((int)blockIdx.x >= n_tiles) return;
+    extern __shared__ __align__(128) uint32_t tsm[];
+    __shared__ __align__(8) unsigned long long mbar_s;
+    __shared__ uint32_t slot_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < L::WORDS / 4; i += 128)
+        reinterpret_cast<uint4 *>(tsm)[i] = reinterpret_cast<const uint4 *>(p.pol_wblob3 + blob3_offset(ST))[i];
+    if (warp == 0) tmem_alloc(smem_u32(&slot_s), COLS);
+    if (tid == 0) mbar_init(smem_u32(&mbar_s), 1);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    Wg g;
+    g.tmem = slot_s;
+    g.trow = g.tmem + ((uint32_t)(warp * 32) << 16);
+    g.mbar = smem_u32(&mbar_s);
+    g.parity = 0; g.tid = tid; g.bar = 1;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int row = tile * 128 + tid;
+        int id = -1;
+        if (row < n_rows) id = (ST == tc::ST_STAGE) ? row : list[row];
+        float in[S::K0], o[S::OUT > 1 ? S::OUT : 1];
+        if constexpr (ST == tc::ST_STAGE) {
+            // id = position in the candidate list (pl_cand: node, pl_cand_job: job row, pl_cand_out: score slot)
+#pragma unroll
+            for (int i = 0; i < S::K0; i++) in[i] = 0.0f;
+            if (id >= 0) {
+                const int node = p.pl_cand[id], jid = p.pl_cand_job[id], b = node / p.Sc;
+#pragma unroll
+                for (int i = 0; i < 5; i++) in[i] = p.dec_feat[(size_t)node * 5 + i];
+                ld16(p.pol_h + (size_t)node * 16, *reinterpret_cast<float(*)[16]>(in + 5));
+                ld16(p.pol_h_dag + (size_t)jid * 16, *reinterpret_cast<float(*)[16]>(in + 21));
+                ld16(p.pol_h_glob + (size_t)b * 16, *reinterpret_cast<float(*)[16]>(in + 37));
+            }
+        } else {
+            fused::gather<ST>(p, id, a.level, in);
+        }
+        mlp_tile<ST, COLS>(g, tsm, in, o);
+        tc::scatter_row<ST>(p, id, o);
+    }
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(g.tmem, COLS);
 }
 
 // ====================================================================== the whole policy in ONE kernel

@@ -340,7 +340,7 @@ def test_head_mlp_backward_matches_torch_autograd(bank):
                 assert not dX[:, in_dim:].any()
                 for i in range(6):
                     got = gw[flat_off[first + i]:flat_off[first + i + 1]].view(Ws[i].shape)
-                    tol = 2e-4 * float(Ws[i].grad.abs().max()) + 1e-6
+                    tol = 2e-4 * float(Ws[i].grad.abs().max()) + 3e-6
                     assert float((got - Ws[i].grad).abs().max()) <= tol, (k, mode, keys[first + i])
         env.step(a, n)
 
@@ -424,12 +424,12 @@ def test_backward_down_to_node_embeddings_matches_torch_autograd(bank):
                 if leaves[b] is None:
                     continue
                 N = leaves[b].shape[0]
-                tol = 3e-4 * float(leaves[b].grad.abs().max()) + 1e-6
+                tol = 3e-4 * float(leaves[b].grad.abs().max()) + 3e-6
                 assert float((d_h[b, :N] - leaves[b].grad).abs().max()) <= tol, (k, b)
                 assert not d_h[b, N:].any()
             for i in range(18, 42):
                 got = gw[flat_off[i]:flat_off[i + 1]].view(Wt[i].shape).cpu()
-                tol = 3e-4 * float(Wt[i].grad.abs().max()) + 1e-6
+                tol = 3e-4 * float(Wt[i].grad.abs().max()) + 3e-6  # (a last-layer bias gradient is a sum that cancels to ~0: pure rounding)
                 assert float((got - Wt[i].grad).abs().max()) <= tol, (k, keys[i])
         env.step(a, n)
 
@@ -538,7 +538,7 @@ def test_full_backward_matches_torch_autograd(bank):
                 assert max(depths) >= 2  # the level loop was exercised
             for i in range(42):
                 got = gw[flat_off[i]:flat_off[i + 1]].view(Wt[i].shape).cpu()
-                tol = 5e-4 * float(Wt[i].grad.abs().max()) + 1e-6
+                tol = 5e-4 * float(Wt[i].grad.abs().max()) + 3e-6
                 assert float((got - Wt[i].grad).abs().max()) <= tol, (k, keys[i], float((got - Wt[i].grad).abs().max()), tol)
             # the backward pass overwrote the intermediate buffers: the next policy call recomputes everything
         env.step(a, n)

@@ -15,25 +15,28 @@ F32 = np.float32
 
 
 def _mlp(x, w, prefix, act):
-    """make_mlp(in, [h1, h2], out): Linear/act/Linear/act/Linear (utils.py:45-64)."""
+    """make_mlp(in, [h1, h2], out): Linear/act/Linear/act/Linear (utils.py:45-64), in x's dtype."""
+    dt = x.dtype.type
     for i, k in enumerate((0, 2, 4)):
-        W, b = w[f"{prefix}.{k}.weight"], w[f"{prefix}.{k}.bias"]
-        x = (x @ W.T + b).astype(F32)
+        W, b = w[f"{prefix}.{k}.weight"].astype(dt), w[f"{prefix}.{k}.bias"].astype(dt)
+        x = (x @ W.T + b).astype(dt)
         if i < 2:
             x = act(x)
     return x
 
 
 def _leaky(x):
-    return np.where(x > 0, x, F32(0.2) * x).astype(F32)
+    return np.where(x > 0, x, x.dtype.type(0.2) * x).astype(x.dtype)
 
 
 def _tanh(x):
-    return np.tanh(x).astype(F32)
+    return np.tanh(x).astype(x.dtype)
 
 
 def encode(w, x, edge_links, edge_bits, depth, dag_ptr):
-    """-> (h_node [N,16], h_dag [Ja,16], h_glob [16])."""
+    """-> (h_node [N,16], h_dag [Ja,16], h_glob [16]).  Computes in x's dtype: float32 = the reference's arithmetic;
+    pass the features as float64 for the "exact" evaluation the accuracy tests measure both sides against."""
+    F32 = x.dtype.type  # noqa: N806 (shadows the module constant on purpose: everything below follows x)
     N = x.shape[0]
     pre = "encoder.node_encoder"
     h_init = _mlp(x, w, f"{pre}.mlp_prep", _leaky)
@@ -71,6 +74,7 @@ def encode(w, x, edge_links, edge_bits, depth, dag_ptr):
 
 def stage_scores(w, x, h, h_dag, h_glob, dag_ptr, stage_mask):
     """scores over the schedulable nodes, in node order (:293-320)."""
+    F32 = x.dtype.type  # noqa: N806
     idx = np.flatnonzero(stage_mask)
     job = np.searchsorted(np.asarray(dag_ptr), idx, side="right") - 1
     inp = np.concatenate([x[idx], h[idx], h_dag[job], np.broadcast_to(h_glob, (len(idx), 16))], 1).astype(F32)
@@ -79,8 +83,10 @@ def stage_scores(w, x, h, h_dag, h_glob, dag_ptr, stage_mask):
 
 def exec_scores(w, x, h_dag, h_glob, dag_ptr, job, cap, num_executors):
     """scores over num_exec = 0 .. cap-1 for the chosen job (:338-385)."""
+    F32 = x.dtype.type  # noqa: N806
     x_dag = x[dag_ptr[job], :3]
-    c = (np.arange(cap, dtype=np.int64) / num_executors).astype(F32)[:, None]
+    # (torch.arange(E) / E is a float32 tensor in the reference: the input itself is rounded to float32)
+    c = (np.arange(cap, dtype=np.int64) / num_executors).astype(np.float32).astype(F32)[:, None]
     inp = np.concatenate([np.broadcast_to(x_dag, (cap, 3)), np.broadcast_to(h_dag[job], (cap, 16)),
                           np.broadcast_to(h_glob, (cap, 16)), c], 1).astype(F32)
     return _mlp(inp, w, "exec_policy_network.mlp_score", _tanh)[:, 0]

@@ -1215,9 +1215,11 @@ static int decima_policy_impl(ssb_env *env, const int32_t *forced_stage, const i
     if ((rc = launch_tile<tc::ST_DAG>(env, p.pl_all, nullptr, cnt + tc::CNT_ALL, 0, 4, s))) return rc;
     if ((rc = launch_tile<tc::ST_GLOB>(env, p.pl_jobs, nullptr, cnt + tc::CNT_JOBS, 0, 4, s))) return rc;
     tc::k_pol_glob_sum<<<(p.B + 7) / 8, 128, 0, s>>>(p);
-    if ((rc = launch_tile<tc::ST_STAGE>(env, nullptr, nullptr, cnt + tc::CNT_CAND, 0, 1, s))) return rc;
+    // (score heads: four CTAs per SM in the TMEM path; round 1's shared-memory tiles fit one)
+    const int head_ctas = env->policy_mode == POLICY_TILES_TF32 ? 1 : 4;
+    if ((rc = launch_tile<tc::ST_STAGE>(env, nullptr, nullptr, cnt + tc::CNT_CAND, 0, head_ctas, s))) return rc;
     tc::k_pol_sample_stage<<<warp_grid, 128, 0, s>>>(p, forced_stage);
-    if ((rc = launch_tile<tc::ST_EXEC>(env, p.pl_exec, nullptr, cnt + tc::CNT_EXEC, 0, 1, s))) return rc;
+    if ((rc = launch_tile<tc::ST_EXEC>(env, p.pl_exec, nullptr, cnt + tc::CNT_EXEC, 0, head_ctas, s))) return rc;
     tc::k_pol_sample_exec<<<warp_grid, 128, 0, s>>>(p, forced_num_exec, stage_idx_out, num_exec_out,
                                                     advance_draws ? 1 : 0);
     CUDA_TRY(cudaGetLastError());

@@ -405,6 +405,17 @@ int ssb_decima_head_backward(ssb_env *env, const float *grad_stage_logits, const
  * may be NULL).  Finished envs follow ssb_set_autoreset: with it, the call after the end of an episode
  * re-seeds the env (row flagged 8); without it they idle (rows flagged with error SSB_ENV_DONE semantics). */
 int ssb_rollout_decima(ssb_env *env, int32_t num_decisions, int32_t max_events, ssb_transition *traj, void *stream);
+/* Fixed-duration Decima rollouts that span resets (RolloutWorkerAsync.collect_rollout, trainers/rollout_worker.py:160-206
+ * with DecimaScheduler; the reference trains Decima with these when `rollout_duration` is configured): every env keeps
+ * deciding with the sampled Decima policy until its accumulated simulated time in this call reaches rollout_duration
+ * (ms) or max_decisions rows are written.  Row d of env b at traj[b * max_decisions + d] (DEVICE): wall_time = the
+ * accumulated time before the step, action in the env's format, lgprob, reward, flags 1 / 2 = the step ended the
+ * episode (the env is then re-seeded with seed + seed_step * reset_count before its next decision, which carries
+ * flag 4).  num_steps (DEVICE i32[B]) / elapsed (DEVICE f64[B], the buffer's closing wall_times entry) may be NULL.
+ * Envs that have reached their duration take no part in the remaining rounds (no policy rows, no step, sampling stream
+ * untouched) and continue where they stopped at the next call.  Synchronises the stream every few rounds. */
+int ssb_rollout_decima_async(ssb_env *env, int32_t max_decisions, double rollout_duration, uint64_t seed_step,
+                             ssb_transition *traj, int32_t *num_steps, double *elapsed, void *stream);
 /* collect_stats (trainers/rollout_worker.py:122-129) over all envs as SUMS that can be all-reduced across GPUs:
  * out = DEVICE f64[8]: [0] sum over envs of avg_num_jobs = (total job time so far) / wall_time
  * (metrics.py:15-16; envs at wall_time 0 skipped), [1] number of envs counted in [0], [2] completed jobs,

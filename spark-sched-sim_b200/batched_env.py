@@ -514,6 +514,18 @@ class BatchedSparkSchedSimEnv:
         torch.cuda.current_stream(self.device).synchronize()
         return host[:nbytes].numpy().view(nat.TRANSITION_DTYPE).reshape(self.num_envs, int(num_decisions))
 
+    def rollout_decima_async(self, max_decisions, rollout_duration, seed_step=1):
+        """Fixed-duration Decima rollouts spanning resets (RolloutWorkerAsync.collect_rollout, rollout_worker.py:160-206).
+        Returns (traj uint8 device tensor [B * max_decisions * 32], num_steps i32[B], elapsed f64[B])."""
+        nbytes = self.num_envs * int(max_decisions) * nat.TRANSITION_DTYPE.itemsize
+        traj = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+        num = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
+        el = torch.zeros(self.num_envs, dtype=torch.float64, device=self.device)
+        nat.check(self.L.ssb_rollout_decima_async(self._h, int(max_decisions), float(rollout_duration), int(seed_step),
+                                                  traj.data_ptr(), num.data_ptr(), el.data_ptr(), self._stream()),
+                  "ssb_rollout_decima_async")
+        return traj, num, el
+
     def load_trace(self, b, t_arrival, template, tape=None):
         ta = np.ascontiguousarray(t_arrival, np.float64)
         tm = np.ascontiguousarray(template, np.int32)

@@ -507,6 +507,12 @@ void carve(Carver &cv, const ssb_config &c, const ssb_bank &bk, const Dims &d, P
         p.pol_wblob3 = cv.take<uint32_t>(fz::BLOB_TOTAL);
         p.pol_cand_rank = cv.take<int32_t>(B * d.Sc);
         p.fz_cursor = cv.take<int32_t>(4);
+        p.as_elapsed = cv.take<double>(B);
+        p.as_wall0 = cv.take<double>(B);
+        p.as_rows = cv.take<int32_t>(B);
+        p.as_kind = cv.take<uint8_t>(B);
+        p.as_fresh = cv.take<uint8_t>(B);
+        p.as_any = cv.take<int32_t>(4);
     }
     *st_a = cv.take<int32_t>(B);
     *st_n = cv.take<int32_t>(B);
@@ -843,14 +849,17 @@ int ssb_reset(ssb_env *env, const uint64_t *seeds, const double *time_limits, co
 }
 
 static int step_launch(ssb_env *env, const int32_t *stage_idx, const int32_t *num_exec, const uint8_t *mask,
-                       int32_t max_events, int32_t *next_a, int32_t *next_n, int dyn, cudaStream_t s)
+                       int32_t max_events, int32_t *next_a, int32_t *next_n, int dyn, cudaStream_t s,
+                       int force_autoreset = 0, uint64_t force_seed_step = 0)
 {
+    const int ar = force_autoreset ? 1 : env->auto_reset;
+    const uint64_t ss = force_autoreset ? force_seed_step : env->auto_seed_step;
     if (env->p.E <= 32)
-        k_step<1><<<env->grid, WARPS_PER_CTA * 32, 0, s>>>(env->p, stage_idx, num_exec, mask, max_events, env->auto_reset,
-                                                           env->auto_seed_step, next_a, next_n, dyn);
+        k_step<1><<<env->grid, WARPS_PER_CTA * 32, 0, s>>>(env->p, stage_idx, num_exec, mask, max_events, ar, ss, next_a,
+                                                           next_n, dyn);
     else
-        k_step<2><<<env->grid, WARPS_PER_CTA * 32, 0, s>>>(env->p, stage_idx, num_exec, mask, max_events, env->auto_reset,
-                                                           env->auto_seed_step, next_a, next_n, dyn);
+        k_step<2><<<env->grid, WARPS_PER_CTA * 32, 0, s>>>(env->p, stage_idx, num_exec, mask, max_events, ar, ss, next_a,
+                                                           next_n, dyn);
     CUDA_TRY(cudaGetLastError());
     SSB_MARK(env, s);
     return SSB_OK;
@@ -1179,9 +1188,10 @@ static int replan(ssb_env *env, cudaStream_t s)
 // advance_draws = false: the Philox policy stream of the envs is left where it is (pure evaluation)
 static int decima_policy_impl(ssb_env *env, const int32_t *forced_stage, const int32_t *forced_num_exec,
                               int32_t *stage_idx_out, int32_t *num_exec_out, bool run_adapter, bool advance_draws,
-                              cudaStream_t s)
+                              cudaStream_t s, const uint8_t *active = nullptr)
 {
-    const Params &p = env->p;
+    Params p = env->p;
+    p.pol_active = active;
     if (env->policy_mode == POLICY_FUSED) {
         // the whole decision of every env in one persistent kernel (ssb_decima_fused.cuh)
         CUDA_TRY(cudaMemsetAsync(p.fz_cursor, 0, sizeof(int32_t) * 4, s));
@@ -1452,6 +1462,47 @@ int ssb_decima_evaluate(ssb_env *env, const void *snapshot, const int32_t *stage
     return rc;
 }
 
+// ---- fixed-duration Decima rollouts spanning resets (RolloutWorkerAsync.collect_rollout, rollout_worker.py:160-206)
+// round = { who takes part ; policy ; row + step (or reset) ; bookkeeping }
+__global__ void k_dasync_begin(Params p, double duration, int max_rows)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b == 0) *p.as_any = 0;
+    if (b >= p.B) return;
+    const ssb_obs_hdr &o = p.obs_hdr[b];
+    int kind = 0;
+    if (p.as_elapsed[b] < duration && p.as_rows[b] < max_rows && !(o.error && o.error != SSB_ENV_DONE) && !p.hdr[b].error)
+        kind = (p.hdr[b].done || o.truncated) ? 2 : 1;  // the reset of :196-200, applied when the loop comes back around
+    p.as_kind[b] = (uint8_t)kind;
+}
+__global__ void k_dasync_pre(Params p, const int32_t *a, const int32_t *n, ssb_transition *traj, int max_rows)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.B || p.as_kind[b] != 1) return;
+    ssb_transition t;  // rollout_buffer.add(obs, elapsed_time, action, lgprob, reward) (:191): reward filled in below
+    t.wall_time = p.as_elapsed[b]; t.reward = 0.0; t.stage_idx = a[b]; t.num_exec = n[b];
+    t.flags = p.as_fresh[b] ? 4 : 0;
+    t.lgprob = p.pol_lgprob[b];
+    traj[(size_t)b * max_rows + p.as_rows[b]] = t;
+    p.as_wall0[b] = p.obs_hdr[b].wall_time;
+}
+__global__ void k_dasync_post(Params p, ssb_transition *traj, int max_rows, double duration)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.B) return;
+    const int kind = p.as_kind[b];
+    if (kind == 2) { p.as_fresh[b] = 1; atomicAdd(p.as_any, 1); return; }
+    if (kind != 1) return;
+    const ssb_obs_hdr &o = p.obs_hdr[b];
+    ssb_transition &t = traj[(size_t)b * max_rows + p.as_rows[b]];
+    t.reward = o.reward;
+    t.flags |= (o.terminated ? 1 : 0) | (o.truncated ? 2 : 0);
+    p.as_elapsed[b] += o.wall_time - p.as_wall0[b];  // the duration of this step (:194)
+    p.as_rows[b] += 1;
+    p.as_fresh[b] = 0;
+    if (p.as_elapsed[b] < duration && p.as_rows[b] < max_rows && !o.error) atomicAdd(p.as_any, 1);
+}
+
 __global__ void k_traj_next(Params p) { if (threadIdx.x == 0 && blockIdx.x == 0) *p.traj_d += 1; }
 
 // one decision of ssb_rollout_decima, enqueued on s (captured into a CUDA graph by the caller)
@@ -1557,6 +1608,41 @@ int ssb_decima_work(ssb_env *env, int64_t *out)
     out[4] = c[tc::CNT_EXEC]; out[5] = send; out[6] = recv;
     out[7] = out[0] * ((5 * 32 + 32 * 16 + 16 * 16) + (21 * 32 + 32 * 16 + 16 * 16)) + (out[1] + send + recv + out[3]) * gnn +
              out[2] * (53 * 64 + 64 * 64 + 64) + out[4] * (36 * 64 + 64 * 64 + 64);
+    return SSB_OK;
+}
+
+int ssb_rollout_decima_async(ssb_env *env, int32_t max_decisions, double rollout_duration, uint64_t seed_step,
+                             ssb_transition *traj, int32_t *num_steps, double *elapsed, void *stream)
+{
+    if (!env || !env->p.pol_w || max_decisions < 1 || !(rollout_duration > 0.0) || !traj) return SSB_E_INVALID;
+    SSB_ON_DEVICE(env);
+    cudaStream_t s = (cudaStream_t)stream;
+    const Params &p = env->p;
+    const int tb = (p.B + 127) / 128;
+    CUDA_TRY(cudaMemsetAsync(p.as_elapsed, 0, sizeof(double) * (size_t)p.B, s));
+    CUDA_TRY(cudaMemsetAsync(p.as_rows, 0, sizeof(int32_t) * (size_t)p.B, s));
+    CUDA_TRY(cudaMemsetAsync(p.as_fresh, 0, (size_t)p.B, s));  // (a reset round is always followed by its env's decision)
+    int any = 1, rounds = 0;
+    while (any) {
+        // a few rounds per host check of "is any env still inside its rollout"; finished envs cost nothing in the
+        // policy (treated as absent) and are masked out of the step
+        for (int r = 0; r < 8; r++, rounds++) {
+            k_dasync_begin<<<tb, 128, 0, s>>>(p, rollout_duration, max_decisions);
+            int rc = decima_policy_impl(env, nullptr, nullptr, p.pol_act_a, p.pol_act_n, true, true, s, p.as_kind);
+            if (rc) return rc;
+            k_dasync_pre<<<tb, 128, 0, s>>>(p, p.pol_act_a, p.pol_act_n, traj, max_decisions);
+            // mask = as_kind (0: untouched); finished episodes are re-seeded with seed + seed_step * reset_count
+            if ((rc = step_launch(env, p.pol_act_a, p.pol_act_n, p.as_kind, 0, nullptr, nullptr, 0, s, 1, seed_step))) return rc;
+            k_dasync_post<<<tb, 128, 0, s>>>(p, traj, max_decisions, rollout_duration);
+            CUDA_TRY(cudaGetLastError());
+        }
+        CUDA_TRY(cudaMemcpyAsync(&any, p.as_any, sizeof(int), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        if (rounds > 4 * max_decisions + 64) break;  // (every round either writes a row or resets an env)
+    }
+    if (num_steps) CUDA_TRY(cudaMemcpyAsync(num_steps, p.as_rows, sizeof(int32_t) * (size_t)p.B, cudaMemcpyDeviceToDevice, s));
+    if (elapsed) CUDA_TRY(cudaMemcpyAsync(elapsed, p.as_elapsed, sizeof(double) * (size_t)p.B, cudaMemcpyDeviceToDevice, s));
+    SSB_MARK(env, s);
     return SSB_OK;
 }
 

@@ -661,7 +661,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_decima_fused(Params p, Args a)
                 __syncwarp();
             }
             const ssb_obs_hdr &oh = p.obs_hdr[b];
-            const bool live = !(oh.terminated || oh.error);
+            const bool live = !(oh.terminated || oh.error) && (!p.pol_active || p.pol_active[b]);
             const int N = live ? oh.num_nodes : 0, M = live ? oh.num_edges : 0, Ja = live ? oh.num_active_jobs : 0;
             const int depth = live ? p.dec_depth[b] : 0;
             unsigned long long *bits = p.pl_bits + (size_t)b * p.Sc * 2;
@@ -821,7 +821,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_decima_fused(Params p, Args a)
                 // evaluate_actions: (stage entropy + exec entropy) / log(num_executors * nodes in the observation)
                 const int N = p.obs_hdr[b].num_nodes;
                 p.pol_entropy[b] = N > 0 ? (p.pol_entropy[b] + h_exec) / logf((float)(p.E * N)) : 0.0f;
-                if (a.advance_draws) h.policy_draws = pd + 1;
+                if (a.advance_draws && (!p.pol_active || p.pol_active[b])) h.policy_draws = pd + 1;
                 if (a.stage_idx_out) a.stage_idx_out[b] = act[0];
                 if (a.num_exec_out) a.num_exec_out[b] = 1 + num_exec;
             }

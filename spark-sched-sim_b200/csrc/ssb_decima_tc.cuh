@@ -555,7 +555,7 @@ static __global__ void __launch_bounds__(128) k_pol_plan_a(Params p)
     if (b >= p.B) return;
     int *hist = hist_s[threadIdx.x >> 5];
     const ssb_obs_hdr &oh = p.obs_hdr[b];
-    const bool live = !(oh.terminated || oh.error);
+    const bool live = !(oh.terminated || oh.error) && (!p.pol_active || p.pol_active[b]);
     const int N = live ? oh.num_nodes : 0, M = live ? oh.num_edges : 0, Ja = live ? oh.num_active_jobs : 0;
     const int depth = live ? p.dec_depth[b] : 0;
     plan_bits_w(p, b, lane, N, M, depth, hist);
@@ -625,7 +625,7 @@ static __global__ void __launch_bounds__(128) k_pol_plan_b(Params p)
     if (p.pl_cnt[CNT_OVERFLOW]) return;
     int *hist = hist_s[threadIdx.x >> 5];
     const ssb_obs_hdr &oh = p.obs_hdr[b];
-    const bool live = !(oh.terminated || oh.error);
+    const bool live = !(oh.terminated || oh.error) && (!p.pol_active || p.pol_active[b]);
     const int N = live ? oh.num_nodes : 0, depth = live ? p.dec_depth[b] : 0;
     if (depth == 0) return;
     const unsigned long long *bits = p.pl_bits + (size_t)b * p.Sc * 2;
@@ -656,7 +656,7 @@ static __global__ void __launch_bounds__(128) k_pol_glob_sum(Params p)
     const int b = blockIdx.x * 8 + (threadIdx.x >> 4), c = threadIdx.x & 15;
     if (b >= p.B) return;
     const ssb_obs_hdr &oh = p.obs_hdr[b];
-    const int Ja = (oh.terminated || oh.error) ? 0 : oh.num_active_jobs;
+    const int Ja = (oh.terminated || oh.error || (p.pol_active && !p.pol_active[b])) ? 0 : oh.num_active_jobs;
     float s = 0.0f;
     for (int j = 0; j < Ja; j++) s += p.pol_g[((size_t)b * p.Jc + j) * 16 + c];
     p.pol_h_glob[(size_t)b * 16 + c] = s;
@@ -668,7 +668,7 @@ static __global__ void __launch_bounds__(128) k_pol_sample_stage(Params p, const
     const int b = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (b >= p.B) return;
     const ssb_obs_hdr &oh = p.obs_hdr[b];
-    const bool live = !(oh.terminated || oh.error);
+    const bool live = !(oh.terminated || oh.error) && (!p.pol_active || p.pol_active[b]);
     const int N = live ? oh.num_nodes : 0, Ja = live ? oh.num_active_jobs : 0;
     const int n_cand = live ? p.pl_ncand[b] : 0;
     const EnvHdr &h = p.hdr[b];
@@ -735,7 +735,7 @@ k_pol_sample_exec(Params p, const int32_t *forced_num_exec, int32_t *stage_idx_o
         // evaluate_actions: (stage entropy + exec entropy) / log(num_executors * nodes in the observation)
         const int N = p.obs_hdr[b].num_nodes;
         p.pol_entropy[b] = N > 0 ? (p.pol_entropy[b] + h_exec) / logf((float)(p.E * N)) : 0.0f;
-        if (advance_draws) h.policy_draws = pd + 1;
+        if (advance_draws && (!p.pol_active || p.pol_active[b])) h.policy_draws = pd + 1;
         if (stage_idx_out) stage_idx_out[b] = act[0];
         if (num_exec_out) num_exec_out[b] = 1 + num_exec;
     }

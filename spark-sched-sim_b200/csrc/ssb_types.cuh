@@ -187,6 +187,15 @@ struct Params {
     uint32_t *pol_wblob3;  // per-stage bf16 three-term weight blobs (fz::blob3_offset)
     int32_t *pol_cand_rank;  // [B][Sc] rank of a schedulable node among its env's schedulable nodes (its score's slot)
     int32_t *fz_cursor;      // [4] group cursor of the fused policy kernel
+    // optional per-env participation mask of one policy call (nullptr = all): an env with pol_active[b] == 0 is treated
+    // like a finished one (no rows, action (-1, 1)) and its sampling stream is not advanced
+    const uint8_t *pol_active;
+    // fixed-duration Decima rollouts (ssb_rollout_decima_async): per-env accumulators of the current call
+    double *as_elapsed, *as_wall0;  // [B]
+    int32_t *as_rows;               // [B] rows written so far
+    uint8_t *as_kind;               // [B] this round: 0 = not taking part, 1 = decision, 2 = reset
+    uint8_t *as_fresh;              // [B] the next row is the first after a reset
+    int32_t *as_any;                // [1] envs still taking part
     int lvl_cap;
 };
 

@@ -691,3 +691,54 @@ def test_mlp_rows_accuracy_against_fp64(bank, mlp):
     print(f"mlp {mlp} {name}: scale {scale:.3g}  ours-vs-fp64 {err_ours:.3g}  torch32-vs-fp64 {err_torch:.3g}")
     assert got.shape == (n, dout)
     assert err_ours <= 3.0 * err_torch + 2e-7 * scale, (err_ours, err_torch, scale)
+
+
+def test_decima_async_rollouts_match_the_workers_loop(bank):
+    """ssb_rollout_decima_async == RolloutWorkerAsync.collect_rollout (rollout_worker.py:160-206) with the Decima policy:
+    the worker's loop is restated in Python over single-environment handles ({ decima_policy ; step }, reset with
+    seed + seed_step * reset_count when an episode ends, time axis = accumulated time, state carried over between
+    calls); the Philox policy stream makes the sampled actions reproducible, so every row must agree exactly."""
+    from spark_sched_sim_b200 import _native as nat
+    from spark_sched_sim_b200.batched_env import BatchedSparkSchedSimEnv
+
+    B, KMAX, DUR, STEP = 5, 700, 1.5e6, 11
+    cfg = {"num_executors": 10, "job_arrival_cap": 4, "job_arrival_rate": 4.0e-5,
+           "moving_delay": 2000.0, "warmup_delay": 1000.0}
+    seeds = np.arange(B, dtype=np.uint64) + 60
+    env = BatchedSparkSchedSimEnv(cfg, num_envs=B, bank=bank, decima_policy=True)
+    env.set_decima_weights(weights())
+    env.reset_host(seeds)
+    calls = []
+    for _ in range(3):
+        traj, num, el = env.rollout_decima_async(KMAX, DUR, STEP)
+        calls.append((traj.cpu().numpy().view(nat.TRANSITION_DTYPE).reshape(B, KMAX), num.cpu().numpy(), el.cpu().numpy()))
+    assert (env.hdr()["error"] == 0).all()
+    n_resets = 0
+    for b in range(B):
+        one = BatchedSparkSchedSimEnv(cfg, num_envs=1, bank=bank, decima_policy=True)
+        one.set_decima_weights(weights())
+        hdr = one.reset_host(seeds[b:b + 1]).copy()
+        resets, next_wall = 1, 0.0
+        for tr, num, el in calls:  # one collect_rollout() each
+            elapsed, step = 0.0, 0
+            while elapsed < DUR and step < KMAX:
+                wall = next_wall
+                a, n = one.decima_policy()
+                lg = float(one.pol_lgprob[0].item())
+                one.step(a, n)
+                h = one.hdr()[0]
+                assert h["error"] == 0
+                next_wall = float(h["wall_time"])
+                r = tr[b, step]
+                assert (r["wall_time"], r["stage_idx"], r["num_exec"], r["reward"]) == (elapsed, int(a[0]), int(n[0]), h["reward"]), (b, step)
+                assert r["lgprob"] == np.float32(lg) and (r["flags"] & 1) == int(h["terminated"]), (b, step)
+                elapsed += next_wall - wall
+                if h["terminated"]:
+                    one.reset_host(np.array([int(seeds[b]) + STEP * resets], np.uint64)); resets += 1
+                    next_wall = 0.0
+                    n_resets += 1
+                    if step + 1 < num[b]:
+                        assert tr[b, step + 1]["flags"] & 4  # the next row is the first of the new episode
+                step += 1
+            assert num[b] == step and el[b] == elapsed, (b, num[b], step, el[b], elapsed)
+    assert n_resets >= B

@@ -742,3 +742,52 @@ def test_decima_async_rollouts_match_the_workers_loop(bank):
                 step += 1
             assert num[b] == step and el[b] == elapsed, (b, num[b], step, el[b], elapsed)
     assert n_resets >= B
+
+
+@pytest.mark.parametrize("fixture", ["decima_grads_e10_j8_s5", "decima_grads_e50_j14_s4"])
+def test_backward_matches_the_reference_models_gradients(fixture):
+    """ssb_decima_evaluate + ssb_decima_backward against gradients recorded from the UNMODIFIED reference
+    DecimaScheduler (tests/golden/gen_decima_grad_golden.py: its own evaluate_actions, scheduler.py:101-139, and
+    loss.backward() on a batch of observations of a recorded episode).  Env i replays the episode up to observation
+    picks[i] and stops there; one evaluate / backward over the B live observations must reproduce the reference's
+    lgprobs, entropies and all 42 parameter gradients (each tensor within 5e-4 of its largest entry: fp32 atomics)."""
+    from spark_sched_sim_b200.batched_env import BatchedSparkSchedSimEnv
+
+    g = np.load(osp.join(GOLDEN_DIR, fixture + ".npz"))
+    tr = load_golden(str(g["trace"]))
+    picks = [int(k) for k in g["picks"]]
+    B = len(picks)
+    env = BatchedSparkSchedSimEnv(env_cfg_of(tr), num_envs=B, bank=bank_for(tr), max_jobs=len(tr["job_template"]) + 2,
+                                  tape_capacity=len(tr["tape"]) + 8, decima_policy=True)
+    assert [str(x) for x in g["param_order"]] == list(env.DECIMA_PARAM_ORDER)  # the ABI's flat order == state_dict order
+    env.set_decima_weights(weights())
+    for b in range(B):
+        env.load_trace(b, tr["job_t_arrival"], tr["job_template"], tr["tape"])
+    env.reset_host(np.full(B, tr["seed"], np.uint64))
+    for k in range(max(picks)):
+        a, n = tr["actions"][k]
+        mask = np.array([k < picks[i] for i in range(B)], np.uint8)  # env i stops AT observation picks[i]
+        hdr = env.step_host(np.full(B, a, np.int32), np.full(B, n, np.int32), mask=mask)
+        assert (hdr["error"] == 0).all(), k
+    hdr = env.hdr()
+    assert [int(x) for x in hdr["num_nodes"]] == [int(tr["N"][k]) for k in picks]
+    stage_sel = torch.tensor([int(tr["pol_actions"][k][0]) for k in picks], dtype=torch.int32, device="cuda")
+    exec_sel = torch.tensor([int(tr["pol_actions"][k][2]) for k in picks], dtype=torch.int32, device="cuda")
+    snap = env.decima_snapshot()
+    env.decima_snapshot_load(snap)
+    lg, en = env.decima_evaluate(None, stage_sel, exec_sel)
+    assert np.abs(lg.cpu().numpy() - g["lgprobs"]).max() < 2e-5
+    assert np.abs(en.cpu().numpy() - g["entropies"]).max() < 2e-5
+    grads = torch.zeros(20802, dtype=torch.float32, device="cuda")
+    env.decima_backward(torch.from_numpy(g["coef_lgprob"]).cuda(), torch.from_numpy(g["coef_entropy"]).cuda(), grads)
+    env.decima_snapshot_unload()
+    got, want = grads.cpu().numpy(), g["grad"]
+    w = weights()
+    off = 0
+    for name in env.DECIMA_PARAM_ORDER:
+        n = w[name].size
+        a, b = got[off:off + n], want[off:off + n]
+        tol = 5e-4 * float(np.abs(b).max()) + 3e-6
+        assert np.abs(a - b).max() <= tol, (name, float(np.abs(a - b).max()), tol)
+        off += n
+    assert off == 20802 and np.abs(want).max() > 1.0

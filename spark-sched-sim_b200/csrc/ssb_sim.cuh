@@ -873,6 +873,7 @@ struct Sim {
         bool fast_ok;        // this executor's next launch can be sampled without the fallback chain
         bool touched;        // handled at least one event in this fast phase (its t_acc is then that event's time)
         unsigned same;       // lanes whose pending event belongs to the same stage (constant during a fast phase)
+        unsigned less;       // lanes whose 32-bit order key is smaller than this lane's (maintained by fast_batch_w)
         uint32_t rx, ry;     // task-stream draws (Philox words x, y) of launch number H.rng_base + lane
     };
     struct HotEnv {  // uniform per-environment scalars
@@ -891,7 +892,7 @@ struct Sim {
         L.kt = 0x7ff8000000000000ull; L.ks = 0xffffffffu; L.kind = 0; L.j = 0; L.s = 0;
         L.node = -1 - e; L.task = -1; L.t_acc = 0.0; L.rem = L.comp = L.mc = 0;
         L.oc_a = L.oc_b = make_uint2(0u, 0u); L.thr = L.range = 0; L.fast_ok = false;
-        L.touched = false; L.same = 0;
+        L.touched = false; L.same = 0; L.less = 0;
         if (e < p.E) {
             const ExecRec &x = ex[e];
             L.kind = x.ev_kind;
@@ -940,11 +941,28 @@ struct Sim {
         const uint4 w = philox4x32_10(H.rng_base + (uint32_t)lane, 0u, 2u, 0u, (uint32_t)h->seed, (uint32_t)(h->seed >> 32));
         L.rx = w.x; L.ry = w.y;
     }
+    // order of the pending events by (t, push counter) (event.py:34-35): a 32-bit fixed-point key, floor(16 t)
+    // saturated, almost always decides (event times are mostly whole milliseconds, which tie in the upper f64 word
+    // above 2^20 ms); equal keys take the exact path.  Empty slots sort last.
+    __device__ __forceinline__ uint32_t order_key(const HotLane &L) const
+    {
+        return L.kind ? __double2uint_rd(__dmul_rn(__longlong_as_double((long long)L.kt), 16.0)) : 0xffffffffu;
+    }
     __device__ __forceinline__ void hot_load(HotLane &L, HotEnv &H)
     {
         hot_load_slot(L, lane);
         hot_load_env(H);
         L.same = __match_any_sync(FULL, L.node);
+        if (H.quiet) {
+            // all-pairs order masks on the 32-bit keys, ONCE per fast phase; fast_batch_w maintains them
+            // (kept rolled on purpose: instruction fetch, not shuffle latency, bounds this code -- the
+            // unrolled form measured 6475 vs 4266 cycles per iteration, profiles/r01_ab_unroll.txt)
+            const uint32_t hi = order_key(L);
+            unsigned less = 0;
+#pragma unroll 1
+            for (int i = 0; i < p.E; i++) less |= (__shfl_sync(FULL, hi, i) < hi) ? (1u << i) : 0u;
+            L.less = less;
+        }
         L.rx = L.ry = 0u; H.rng_base = H.launch_idx;
         if (H.quiet && !h->use_tape) hot_refill_rng(L, H);
     }
@@ -994,16 +1012,12 @@ struct Sim {
         const bool pending = L.kind != 0;
         const unsigned pend_mask = __ballot_sync(FULL, pending);
         if (!pend_mask) return 0;
-        // order of the pending events by (t, push counter) (event.py:34-35).  A 32-bit fixed-point key,
-        // floor(16 t) saturated, almost always decides (event times are mostly whole milliseconds, which tie
-        // in the upper f64 word above 2^20 ms); equal keys take the exact path.
-        const double tq = __dmul_rn(__longlong_as_double((long long)L.kt), 16.0);
-        const uint32_t hi = pending ? __double2uint_rd(tq) : 0xffffffffu;
-        unsigned less = 0;
-        // (kept rolled on purpose: instruction fetch, not shuffle latency, bounds this loop -- the
-        // unrolled form measured 6475 vs 4266 cycles per iteration, profiles/r01_ab_unroll.txt)
-#pragma unroll 1
-        for (int i = 0; i < p.E; i++) less |= (__shfl_sync(FULL, hi, i) < hi) ? (1u << i) : 0u;
+        // order masks: maintained across iterations on the 32-bit keys (hot_load computes them once per phase, the
+        // end of this function updates them for the members); the full all-pairs loop per iteration was 21 % of all
+        // instructions the rollout kernel executed (profiles/r02_ncu_rollout_v5_by_line.txt).  Equal keys among the
+        // pending events: exact (t, seq) order for this iteration.
+        const uint32_t hi = order_key(L);
+        unsigned less = L.less;
         {
             const unsigned eq = __match_any_sync(FULL, hi) & pend_mask;
             if (__any_sync(FULL, pending && (eq & (eq - 1)))) less = exact_less_w(L.kt, L.ks);
@@ -1069,6 +1083,24 @@ struct Sim {
         L.rem -= cnt; L.comp += cnt;  // every lane on that stage tracks its counters
         // (the wall time -- the time of the last member -- is taken once per phase, in hot_flush1)
         H.launch_idx += (uint32_t)m; H.seq += (uint32_t)m; H.log_n += m; H.events += m;
+        {
+            // key masks for the next iteration: only the members' keys changed.  For member u: bit u of every
+            // lane's mask = "u's new key is smaller than mine"; u's own mask = the lanes whose key it does not exceed
+            // ... complemented: the lanes with a smaller key (equal keys: neither side, as in the full loop).
+            L.kt = member ? nt : L.kt;  // (already assigned above for members; keeps the compiler's view simple)
+            const uint32_t hi2 = order_key(L);
+            unsigned nl = L.less, mm = mem_mask;
+#pragma unroll 1
+            while (mm) {
+                const int u = __ffs((int)mm) - 1;
+                mm &= mm - 1;
+                const uint32_t ku = __shfl_sync(FULL, hi2, u);
+                const unsigned smaller = __ballot_sync(FULL, hi2 < ku);  // lanes whose key is smaller than u's
+                nl = ku < hi2 ? (nl | (1u << u)) : (nl & ~(1u << u));
+                if (lane == u) nl = smaller;
+            }
+            L.less = nl;
+        }
         return m;
     }
 

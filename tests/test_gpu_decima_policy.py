@@ -791,3 +791,42 @@ def test_backward_matches_the_reference_models_gradients(fixture):
         assert np.abs(a - b).max() <= tol, (name, float(np.abs(a - b).max()), tol)
         off += n
     assert off == 20802 and np.abs(want).max() > 1.0
+
+
+def test_decima_rollouts_at_config3_shape_are_deterministic(bank):
+    """config/decima_tpch.yaml's env (200 jobs x 50 executors, mean time limit 2e7 ms) with the sampled Decima policy
+    on 512 envs: two handles with the same seeds produce identical transitions (Philox policy stream), seed twins
+    inside a handle differ only through their sampling streams' keys (= they are identical: same seed), no env
+    errors, and the list-driven and the fused policy paths agree bit for bit."""
+    import os
+
+    from spark_sched_sim_b200 import _native as nat
+    from spark_sched_sim_b200.batched_env import BatchedSparkSchedSimEnv
+
+    B, K = 512, 40
+    cfg = {"num_executors": 50, "job_arrival_cap": 200, "job_arrival_rate": 4.0e-5,
+           "moving_delay": 2000.0, "warmup_delay": 1000.0}
+    seeds = (77 + np.arange(B) // 2).astype(np.uint64)
+    outs = []
+    try:
+        for mode in ("0", "1", "0"):
+            os.environ["SSB_DECIMA_MODE"] = mode
+            env = BatchedSparkSchedSimEnv(cfg, num_envs=B, bank=bank, decima_policy=True)
+            env.set_decima_weights(weights())
+            env.set_mean_time_limit(2.0e7)
+            env.set_autoreset(True, B)
+            env.reset_host(seeds)
+            env.rollout_fair(300, True, True, B)  # into the episodes
+            host = torch.empty(B * K * nat.TRANSITION_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+            tr = env.rollout_decima(K, host=host).copy()
+            hdr = env.hdr()
+            assert ((hdr["error"] == 0) | (hdr["error"] == 9)).all()
+            outs.append(tr)
+            env.close()
+    finally:
+        os.environ.pop("SSB_DECIMA_MODE", None)
+    for f in ("wall_time", "reward", "stage_idx", "num_exec", "flags", "lgprob"):
+        assert np.array_equal(outs[0][f], outs[1][f]), f   # list-driven == fused
+        assert np.array_equal(outs[0][f], outs[2][f]), f   # deterministic
+        assert np.array_equal(outs[0][f][0::2], outs[0][f][1::2]), f  # seed twins
+    assert (outs[0]["stage_idx"] >= 0).mean() > 0.5

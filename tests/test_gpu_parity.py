@@ -665,3 +665,30 @@ def test_executor_history_of_fused_rollouts_matches_oracle(bank):
     plain.rollout_fair(50, True, False)
     with pytest.raises(RuntimeError):
         plain.history(0)  # built without history_capacity: nothing was recorded
+
+
+def test_config4_shape_batch_properties(bank):
+    """BASELINE config 4's episode shape (200 jobs x 50 executors: two executor slots per lane) on a 1024-env batch:
+    no env errors, every episode terminates, seed twins identical, deterministic, samples equal to the oracle."""
+    from oracle import OracleEnv
+    from spark_sched_sim_b200.batched_env import BatchedSparkSchedSimEnv
+
+    B = 1024
+    cfg = {"num_executors": 50, "job_arrival_cap": 200, "job_arrival_rate": 4.0e-5,
+           "moving_delay": 2000.0, "warmup_delay": 1000.0}
+    env = BatchedSparkSchedSimEnv(cfg, num_envs=B, bank=bank)
+    seeds = (4321 + np.arange(B) // 2).astype(np.uint64)
+    walls = []
+    for rep in range(2):
+        env.reset_stats()
+        env.reset_host(seeds)
+        env.rollout_fair(1_000_000, True, auto_reset=False)
+        hdr = env.hdr()
+        assert (hdr["error"] == 0).all() and (hdr["terminated"] == 1).all()
+        walls.append(hdr["wall_time"].copy())
+    assert np.array_equal(walls[0], walls[1]) and np.array_equal(walls[0][0::2], walls[0][1::2])
+    assert env.stats()["episodes"] == B
+    for b in (0, 513, 1023):
+        orc = OracleEnv(bank, 50, 200, 2000.0, 1000.0, 4.0e-5)
+        orc.run_fair_episode(int(seeds[b]), True)
+        assert np.array_equal(orc.job_times()[1], env.jobs(b)[1])

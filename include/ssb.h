@@ -383,6 +383,9 @@ int ssb_decima_snapshot_unload(ssb_env *env, void *stream);
  * grad_node_embeddings (DEVICE f32[B][node_stride][16], overwritten) = d loss / d NodeEncoder's output; with
  * through_node_encoder != 0 that buffer is working storage.  The policy's intermediate buffers (embeddings,
  * messages) are overwritten: run ssb_decima_evaluate again before anything that reads them.
+ * The message-passing levels are replayed once, their input rows saved in the scratch (room for three rows per node
+ * slot; longer level lists fall back to recomputing the levels per level); the call synchronises the stream once
+ * (it reads the lists' lengths).
  * scratch: DEVICE, ssb_decima_backward_bytes, 16-byte aligned. */
 int ssb_decima_backward_bytes(ssb_env *env, size_t *bytes);
 int ssb_decima_backward(ssb_env *env, const float *grad_lgprob, const float *grad_entropy, float *grad_weights,

@@ -793,12 +793,17 @@ k_pol_head_adjoint(Params p, const float *grad_lgprob, const float *grad_entropy
 }
 
 // ------------------------------------------------------------------ backward pass, second stage: one MLP
-// Backward of one three-layer MLP over a row list (the same lists and gathers as the forward tile pass), first
-// correct version on the CUDA cores in fp32: per 128-row tile the forward activations are recomputed into shared
-// memory, the deltas are propagated per row (thread r <-> row r), and the weight / bias gradients of the tile --
-// sums over its rows of activation x delta -- are added to the flat gradient vector (ABI layout of
-// ssb_set_decima_weights) with atomics.  d loss / d input row goes to dX [rows][K0] in list order, the gathered
-// input rows optionally to X_out (what a later stage needs to scatter / chain).
+// Backward of one three-layer MLP over a row list (the same lists and gathers as the forward tile pass) on the CUDA
+// cores in fp32.  Per 128-row tile (thread r <-> row r) the forward activations are recomputed and the deltas
+// propagated with the weights read as broadcast 128-bit shared-memory loads (16 FMAs per 4 loads); everything a row
+// produces -- X | A1 | A2 | D1 | D2 | D3 -- lives in ONE row-major shared-memory matrix T[128][LD], so that the
+// tile's weight / bias gradients are 4 x 4 register blocks  acc += T[r][colL..+3] (x) T[r][colR..+3]  summed over the
+// rows (two loads per 16 FMAs; the bias gradients use a constant (1,0,0,0) column block as their left factor).  The
+// blocks are accumulated in registers over ALL tiles of the (persistent) CTA and added to the flat gradient vector
+// (ABI layout of ssb_set_decima_weights) once at the end.  d loss / d input row goes to dX [rows][K0] in list
+// order, the gathered input rows optionally to X_out (what a later stage needs to scatter / chain).  x_in: the
+// rows' inputs as saved by k_save_rows when the forward pass ran (message-passing levels: the embeddings they
+// read have been overwritten since), indexed by the row's position in p.pl_lvl.
 template <int ST> struct DwOffset;
 template <> struct DwOffset<ST_PREP>  { static constexpr int V = dw::PREP; };
 template <> struct DwOffset<ST_SINK>  { static constexpr int V = dw::UPD; };
@@ -812,11 +817,17 @@ template <> struct DwOffset<ST_EXEC>  { static constexpr int V = dw::EXEC; };
 template <int ST>
 struct BwdSmem {
     using S = Spec<ST>;
-    static constexpr int SX = S::K0 + 1, S1 = S::H1 + 1, S2 = S::H2 + 1, S3 = S::OUT | 1;  // odd strides: no conflicts
-    static constexpr int X = 0, A1 = X + 128 * SX, A2 = A1 + 128 * S1, D1 = A2 + 128 * S2, D2 = D1 + 128 * S1;
-    static constexpr int D3 = D2 + 128 * S2, W = D3 + 128 * S3;
+    static constexpr int O4 = (S::OUT + 3) & ~3;
+    // column offsets in T (floats); LD / 4 is odd, so a warp's 128-bit accesses to its own rows are conflict-free
+    static constexpr int CX = 0, CA1 = CX + S::K0, CA2 = CA1 + S::H1, CD1 = CA2 + S::H2, CD2 = CD1 + S::H1;
+    static constexpr int CD3 = CD2 + S::H2, CONE = CD3 + O4, COLS = CONE + 4;
+    static constexpr int LD = ((COLS / 4) & 1) ? COLS : COLS + 4;
+    static constexpr int W = 128 * LD;
     static constexpr int WN = dd::mlp(S::IN, S::H1, S::H2, S::OUT);
     static constexpr size_t BYTES = (size_t)(W + WN) * 4;
+    // 4 x 4 gradient blocks: dW1 [K0/4][H1/4], dW2 [H1/4][H2/4], dW3 [H2/4][O4/4], then the three bias vectors
+    static constexpr int N1 = (S::K0 / 4) * (S::H1 / 4), N2 = (S::H1 / 4) * (S::H2 / 4), N3 = (S::H2 / 4) * (O4 / 4);
+    static constexpr int NB = (S::H1 + S::H2 + O4) / 4, NBLK = N1 + N2 + N3 + NB, PER_THREAD = (NBLK + 127) / 128;
 };
 
 template <bool TANH>
@@ -863,6 +874,28 @@ __device__ __forceinline__ float upstream(const Params &p, const float *g_out, c
         return bw.d_hinit[(size_t)id * 16 + o] + (p.dec_depth[id / p.Sc] == 0 ? bw.d_h[(size_t)id * 16 + o] : 0.0f);
     } else return g_out[(size_t)row * S::OUT + o];
 }
+// the whole upstream row (O4 floats, zero-padded) into shared memory; 128-bit loads where the source is a 16-wide row
+template <int ST>
+__device__ __forceinline__ void upstream_row(const Params &p, const float *g_out, const BwdBufs &bw, int row, int id, float *dst)
+{
+    using S = Spec<ST>;
+    constexpr int O4 = (S::OUT + 3) & ~3;
+    if constexpr (S::OUT == 16 && (ST == ST_RCV || ST == ST_SINK || ST == ST_MSG || ST == ST_GLOB)) {
+        float v[16];
+#pragma unroll
+        for (int o = 0; o < 16; o++) v[o] = 0.0f;
+        if (id >= 0) {
+            const float *src = g_out ? g_out + (size_t)row * 16
+                             : ST == ST_MSG ? bw.d_msg + (size_t)id * 16
+                             : ST == ST_GLOB ? bw.d_hglob + (size_t)(id / p.Jc) * 16 : bw.d_h + (size_t)id * 16;
+            ld16(src, v);
+        }
+        st16(dst, v);
+    } else {
+#pragma unroll
+        for (int o = 0; o < O4; o++) dst[o] = o < S::OUT ? upstream<ST>(p, g_out, bw, row, id, o) : 0.0f;
+    }
+}
 // what else the row's output gradient does besides entering the MLP (delta = this row's upstream gradient)
 template <int ST>
 __device__ __forceinline__ void after_upstream(const Params &p, const BwdBufs &bw, int id, const float *delta, int stride)
@@ -870,12 +903,19 @@ __device__ __forceinline__ void after_upstream(const Params &p, const BwdBufs &b
     if (id < 0 || !bw.d_h) return;
     if constexpr (ST == ST_RCV) {
         // h[r] = h_init[r] + update(agg[r]) OVERWRITES h[r]: the gradient passes to h_init, nothing to the old value
-        for (int o = 0; o < 16; o++) {
-            bw.d_hinit[(size_t)id * 16 + o] += delta[o * stride];
-            bw.d_h[(size_t)id * 16 + o] = 0.0f;
-        }
+        float hi[16];
+        ld16(bw.d_hinit + (size_t)id * 16, hi);
+#pragma unroll
+        for (int o = 0; o < 16; o++) hi[o] += delta[o * stride];
+        st16(bw.d_hinit + (size_t)id * 16, hi);
+#pragma unroll
+        for (int o = 0; o < 16; o++) hi[o] = 0.0f;
+        st16(bw.d_h + (size_t)id * 16, hi);
     } else if constexpr (ST == ST_MSG) {
-        for (int o = 0; o < 16; o++) bw.d_msg[(size_t)id * 16 + o] = 0.0f;  // consumed: clean for the next level
+        float z[16];
+#pragma unroll
+        for (int o = 0; o < 16; o++) z[o] = 0.0f;
+        st16(bw.d_msg + (size_t)id * 16, z);  // consumed: clean for the next level
     }
 }
 // where a row's input gradient goes (the adjoint of gather_row)
@@ -886,10 +926,11 @@ __device__ __forceinline__ void consume_dx(const Params &p, const BwdBufs &bw, i
     if constexpr (ST == ST_STAGE) {
         if (!bw.d_h) return;
         const int node = p.pl_cand[id], jid = p.pl_cand_job[id], b = node / p.Sc;
-        for (int i = 0; i < 16; i++) {
-            atomicAdd(bw.d_h + (size_t)node * 16 + i, dx[5 + i]);
-            atomicAdd(bw.d_hdag + (size_t)jid * 16 + i, dx[21 + i]);
-            atomicAdd(bw.d_hglob + (size_t)b * 16 + i, dx[37 + i]);
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+            atomicAdd(reinterpret_cast<float4 *>(bw.d_h + (size_t)node * 16 + i), make_float4(dx[5 + i], dx[6 + i], dx[7 + i], dx[8 + i]));
+            atomicAdd(reinterpret_cast<float4 *>(bw.d_hdag + (size_t)jid * 16 + i), make_float4(dx[21 + i], dx[22 + i], dx[23 + i], dx[24 + i]));
+            atomicAdd(reinterpret_cast<float4 *>(bw.d_hglob + (size_t)b * 16 + i), make_float4(dx[37 + i], dx[38 + i], dx[39 + i], dx[40 + i]));
         }
     } else if constexpr (ST == ST_EXEC) {
         if (!bw.d_hdag) return;
@@ -903,7 +944,9 @@ __device__ __forceinline__ void consume_dx(const Params &p, const BwdBufs &bw, i
         for (int i = 0; i < 16; i++) atomicAdd(bw.d_hdag + (size_t)id * 16 + i, dx[i]);
     } else if constexpr (ST == ST_DAG) {
         if (!bw.d_h) return;
-        for (int i = 0; i < 16; i++) atomicAdd(bw.d_h + (size_t)id * 16 + i, dx[5 + i]);
+#pragma unroll
+        for (int i = 0; i < 16; i += 4)
+            atomicAdd(reinterpret_cast<float4 *>(bw.d_h + (size_t)id * 16 + i), make_float4(dx[5 + i], dx[6 + i], dx[7 + i], dx[8 + i]));
     } else if constexpr (ST == ST_RCV) {
         // agg[u] = sum of msg[v] over u's edges masked at this level: d msg[v] += d agg[u]
         if (!bw.d_msg) return;
@@ -913,41 +956,151 @@ __device__ __forceinline__ void consume_dx(const Params &p, const BwdBufs &bw, i
         const int M = p.obs_hdr[b].num_edges;
         for (int e = p.pol_row_start[id]; e < M && edges[2 * e] == u; e++) {
             if (!((ebits[e] >> level) & 1)) continue;
-            float *dst = bw.d_msg + ((size_t)b * p.Sc + edges[2 * e + 1]) * 16;
-            for (int i = 0; i < 16; i++) atomicAdd(dst + i, dx[i]);
+            float4 *dst = reinterpret_cast<float4 *>(bw.d_msg + ((size_t)b * p.Sc + edges[2 * e + 1]) * 16);
+#pragma unroll
+            for (int i = 0; i < 4; i++) atomicAdd(dst + i, make_float4(dx[4 * i], dx[4 * i + 1], dx[4 * i + 2], dx[4 * i + 3]));
         }
     } else if constexpr (ST == ST_MSG) {
         if (!bw.d_h) return;
-        for (int i = 0; i < 16; i++) bw.d_h[(size_t)id * 16 + i] += dx[i];  // the sender's embedding before this level
+        float h[16];  // the sender's embedding before this level
+        ld16(bw.d_h + (size_t)id * 16, h);
+#pragma unroll
+        for (int i = 0; i < 16; i++) h[i] += dx[i];
+        st16(bw.d_h + (size_t)id * 16, h);
     } else if constexpr (ST == ST_SINK) {
         if (!bw.d_hinit) return;
-        for (int i = 0; i < 16; i++) bw.d_hinit[(size_t)id * 16 + i] += dx[i];
+        float h[16];
+        ld16(bw.d_hinit + (size_t)id * 16, h);
+#pragma unroll
+        for (int i = 0; i < 16; i++) h[i] += dx[i];
+        st16(bw.d_hinit + (size_t)id * 16, h);
+    }
+}
+
+// one Linear + activation of the recomputed forward pass: out[o] = act(bias[o] + sum_k in[k] w[k][o]), `in` / `out` =
+// this thread's row in T, w = the layer's transposed weight [K][N] in shared memory
+template <int K, int CH, int N>
+__device__ __forceinline__ void bwd_fwd_step(const float *in, const float *w, int k4, int o0, float (&acc)[CH])
+{
+    const float4 xv = *reinterpret_cast<const float4 *>(in + k4);
+    const float x[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+    for (int kk = 0; kk < 4; kk++) {
+        if (k4 + kk < K) {
+#pragma unroll
+            for (int c = 0; c < CH; c += 4) {
+                const float4 wv = *reinterpret_cast<const float4 *>(w + (k4 + kk) * N + o0 + c);
+                acc[c] = fmaf(x[kk], wv.x, acc[c]);
+                acc[c + 1] = fmaf(x[kk], wv.y, acc[c + 1]);
+                acc[c + 2] = fmaf(x[kk], wv.z, acc[c + 2]);
+                acc[c + 3] = fmaf(x[kk], wv.w, acc[c + 3]);
+            }
+        }
+    }
+}
+template <int K, int N, bool TANH>
+__device__ __forceinline__ void bwd_layer_fwd(const float *in, const float *w, const float *bias, float *out)
+{
+    constexpr int CH = N < 16 ? N : 16, K4 = (K + 3) & ~3;
+    constexpr bool SMALL = K4 * N <= 1024;  // the 16 / 32-wide GNN layers: straight-line code
+#pragma unroll 1
+    for (int o0 = 0; o0 < N; o0 += CH) {
+        float acc[CH];
+#pragma unroll
+        for (int c = 0; c < CH; c++) acc[c] = bias[o0 + c];
+        if constexpr (SMALL) {
+#pragma unroll
+            for (int k4 = 0; k4 < K4; k4 += 4) bwd_fwd_step<K, CH, N>(in, w, k4, o0, acc);
+        } else {
+#pragma unroll 2
+            for (int k4 = 0; k4 < K4; k4 += 4) bwd_fwd_step<K, CH, N>(in, w, k4, o0, acc);
+        }
+#pragma unroll
+        for (int c = 0; c < CH; c += 4)
+            *reinterpret_cast<float4 *>(out + o0 + c) = make_float4(act_tc<TANH>(acc[c]), act_tc<TANH>(acc[c + 1]),
+                                                                    act_tc<TANH>(acc[c + 2]), act_tc<TANH>(acc[c + 3]));
+    }
+}
+// the adjoint of a Linear: s[k] = sum_o w[k][o] d[o] for k < K (d = this thread's delta row, N of them, N % 4 == 0)
+template <int N>
+__device__ __forceinline__ void bwd_dot4(const float *w, int k, const float (&d)[N], float (&s)[4])
+{
+#pragma unroll
+    for (int kk = 0; kk < 4; kk++) {
+        float a0 = 0.0f, a1 = 0.0f;
+#pragma unroll
+        for (int o = 0; o < N; o += 4) {
+            const float4 wv = *reinterpret_cast<const float4 *>(w + (k + kk) * N + o);
+            a0 = fmaf(wv.x, d[o], a0);
+            a1 = fmaf(wv.y, d[o + 1], a1);
+            a0 = fmaf(wv.z, d[o + 2], a0);
+            a1 = fmaf(wv.w, d[o + 3], a1);
+        }
+        s[kk] = a0 + a1;
+    }
+}
+// delta of a hidden layer: dst[k] = dact(a[k]) * sum_o w[k][o] dout[o]  (k < K, K % 4 == 0)
+template <int K, int N, bool TANH>
+__device__ __forceinline__ void bwd_layer_delta(const float *dout, const float *w, const float *a, float *dst)
+{
+    float d[N];
+#pragma unroll
+    for (int o = 0; o < N; o += 4) {
+        const float4 v = *reinterpret_cast<const float4 *>(dout + o);
+        d[o] = v.x; d[o + 1] = v.y; d[o + 2] = v.z; d[o + 3] = v.w;
+    }
+    auto step = [&](int k) {
+        float s[4];
+        bwd_dot4<N>(w, k, d, s);
+        const float4 av = *reinterpret_cast<const float4 *>(a + k);
+        *reinterpret_cast<float4 *>(dst + k) = make_float4(s[0] * dact_tc<TANH>(av.x), s[1] * dact_tc<TANH>(av.y),
+                                                           s[2] * dact_tc<TANH>(av.z), s[3] * dact_tc<TANH>(av.w));
+    };
+    if constexpr (K * N <= 1024) {
+#pragma unroll 4
+        for (int k = 0; k < K; k += 4) step(k);
+    } else {
+#pragma unroll 2
+        for (int k = 0; k < K; k += 4) step(k);
     }
 }
 
 template <int ST>
 __global__ void __launch_bounds__(128)
-k_mlp_backward(Params p, TileArgs a, const float *g_out, float *dX, float *X_out, float *dW, BwdBufs bw)
+k_mlp_backward(Params p, TileArgs a, const float *g_out, float *dX, float *X_out, float *dW, BwdBufs bw,
+               const float *x_in)
 {
     using S = Spec<ST>;
     using L = BwdSmem<ST>;
-    extern __shared__ float bsm[];
+    extern __shared__ __align__(16) float bsm[];
     const int n_rows = *a.count;
     if (n_rows <= 0) return;
-    const int32_t *list = a.list + (a.offset ? *a.offset : 0);
+    const int list_off = a.offset ? *a.offset : 0;
+    const int32_t *list = a.list + list_off;
     const int n_tiles = (n_rows + 127) >> 7, tid = threadIdx.x;
     if ((int)blockIdx.x >= n_tiles) return;
-    float *X = bsm + L::X, *A1 = bsm + L::A1, *A2 = bsm + L::A2, *D1 = bsm + L::D1, *D2 = bsm + L::D2, *D3 = bsm + L::D3;
-    float *W = bsm + L::W;
+    float *T = bsm, *t = bsm + tid * L::LD, *W = bsm + L::W;
     for (int i = tid; i < L::WN; i += 128) W[i] = p.pol_w[S::W + i];
     // dd layout: per layer the transposed weight [in][out], then the bias, each padded to 4 floats
     const float *w1 = W, *b1 = w1 + dd::pad4(S::IN * S::H1);
     const float *w2 = W + dd::layer(S::IN, S::H1), *b2 = w2 + dd::pad4(S::H1 * S::H2);
-    const float *w3 = w2 + dd::layer(S::H1, S::H2), *b3 = w3 + dd::pad4(S::H2 * S::OUT);
-    (void)b3;
-    float *g = dW + DwOffset<ST>::V;  // ABI layout: W1 [H1][IN], b1, W2 [H2][H1], b2, W3 [OUT][H2], b3
-    constexpr int G_B1 = S::H1 * S::IN, G_W2 = G_B1 + S::H1, G_B2 = G_W2 + S::H2 * S::H1, G_W3 = G_B2 + S::H2,
-                  G_B3 = G_W3 + S::OUT * S::H2;
+    const float *w3 = w2 + dd::layer(S::H1, S::H2);
+    *reinterpret_cast<float4 *>(t + L::CONE) = make_float4(1.0f, 0.0f, 0.0f, 0.0f);
+    // this thread's gradient blocks: (left column, right column) in T
+    int colL[L::PER_THREAD], colR[L::PER_THREAD];
+    float acc[L::PER_THREAD][16];
+#pragma unroll
+    for (int j = 0; j < L::PER_THREAD; j++) {
+        const int blk = tid + 128 * j;
+        int cl = L::CONE, cr = L::CD3;  // (threads past the last block compute a block nobody reads)
+        if (blk < L::N1) { cl = L::CX + 4 * (blk / (S::H1 / 4)); cr = L::CD1 + 4 * (blk % (S::H1 / 4)); }
+        else if (blk < L::N1 + L::N2) { const int q = blk - L::N1; cl = L::CA1 + 4 * (q % (S::H1 / 4)); cr = L::CD2 + 4 * (q / (S::H1 / 4)); }
+        else if (blk < L::N1 + L::N2 + L::N3) { const int q = blk - L::N1 - L::N2; cl = L::CA2 + 4 * (q % (S::H2 / 4)); cr = L::CD3 + 4 * (q / (S::H2 / 4)); }
+        else if (blk < L::NBLK) cr = L::CD1 + 4 * (blk - L::N1 - L::N2 - L::N3);  // D1 | D2 | D3 are contiguous
+        colL[j] = cl; colR[j] = cr;
+#pragma unroll
+        for (int i = 0; i < 16; i++) acc[j][i] = 0.0f;
+    }
     __syncthreads();
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int row = tile * 128 + tid;
@@ -955,46 +1108,58 @@ k_mlp_backward(Params p, TileArgs a, const float *g_out, float *dX, float *X_out
         if (row < n_rows) id = (ST == ST_STAGE) ? row : list[row];
         {
             float in[S::K0];
-            gather_row<ST>(p, a, id, in);
+            if (x_in && (ST == ST_MSG || ST == ST_RCV)) {
 #pragma unroll
-            for (int k = 0; k < S::K0; k++) X[tid * L::SX + k] = in[k];
+                for (int k = 0; k < S::K0; k++) in[k] = 0.0f;
+                if (id >= 0) ld16(x_in + ((size_t)list_off + row) * 16, *reinterpret_cast<float(*)[16]>(in));
+            } else {
+                gather_row<ST>(p, a, id, in);
+            }
+#pragma unroll
+            for (int k = 0; k < S::K0; k += 4)
+                *reinterpret_cast<float4 *>(t + L::CX + k) = make_float4(in[k], in[k + 1], in[k + 2], in[k + 3]);
             if (X_out && row < n_rows) {
 #pragma unroll
                 for (int k = 0; k < S::K0; k++) X_out[(size_t)row * S::K0 + k] = in[k];
             }
         }
         // forward (recomputed)
-        for (int i = 0; i < S::H1; i++) {
-            float s = b1[i];
-            for (int k = 0; k < S::IN; k++) s = fmaf(X[tid * L::SX + k], w1[k * S::H1 + i], s);
-            A1[tid * L::S1 + i] = act_tc<S::TANH>(s);
+        bwd_layer_fwd<S::IN, S::H1, S::TANH>(t + L::CX, w1, b1, t + L::CA1);
+        bwd_layer_fwd<S::H1, S::H2, S::TANH>(t + L::CA1, w2, b2, t + L::CA2);
+        // backward, this thread's row (a padding row has zero upstream gradient, hence zero deltas)
+        upstream_row<ST>(p, g_out, bw, row, id, t + L::CD3);
+        if (!g_out) after_upstream<ST>(p, bw, id, t + L::CD3, 1);
+        if constexpr (S::OUT > 1) {
+            bwd_layer_delta<S::H2, S::OUT, S::TANH>(t + L::CD3, w3, t + L::CA2, t + L::CD2);
+        } else {
+            const float d3 = t[L::CD3];
+#pragma unroll 4
+            for (int j = 0; j < S::H2; j++) t[L::CD2 + j] = w3[j] * d3 * dact_tc<S::TANH>(t[L::CA2 + j]);
         }
-        for (int j = 0; j < S::H2; j++) {
-            float s = b2[j];
-            for (int i = 0; i < S::H1; i++) s = fmaf(A1[tid * L::S1 + i], w2[i * S::H2 + j], s);
-            A2[tid * L::S2 + j] = act_tc<S::TANH>(s);
-        }
-        // backward, this thread's row
-        for (int o = 0; o < S::OUT; o++) D3[tid * L::S3 + o] = upstream<ST>(p, g_out, bw, row, id, o);
-        if (!g_out) after_upstream<ST>(p, bw, id, D3 + tid * L::S3, 1);
-        for (int j = 0; j < S::H2; j++) {
-            float s = 0.0f;
-            for (int o = 0; o < S::OUT; o++) s = fmaf(w3[j * S::OUT + o], D3[tid * L::S3 + o], s);
-            D2[tid * L::S2 + j] = s * dact_tc<S::TANH>(A2[tid * L::S2 + j]);
-        }
-        for (int i = 0; i < S::H1; i++) {
-            float s = 0.0f;
-            for (int j = 0; j < S::H2; j++) s = fmaf(w2[i * S::H2 + j], D2[tid * L::S2 + j], s);
-            D1[tid * L::S1 + i] = s * dact_tc<S::TANH>(A1[tid * L::S1 + i]);
-        }
+        bwd_layer_delta<S::H1, S::H2, S::TANH>(t + L::CD2, w2, t + L::CA1, t + L::CD1);
         if (row < n_rows) {
-            float dx[S::K0];
+            float dx[S::K0], d1[S::H1];
 #pragma unroll
-            for (int k = 0; k < S::K0; k++) {
-                float s = 0.0f;
-                if (k < S::IN)
-                    for (int i = 0; i < S::H1; i++) s = fmaf(w1[k * S::H1 + i], D1[tid * L::S1 + i], s);
-                dx[k] = s;
+            for (int i = 0; i < S::H1; i += 4) {
+                const float4 v = *reinterpret_cast<const float4 *>(t + L::CD1 + i);
+                d1[i] = v.x; d1[i + 1] = v.y; d1[i + 2] = v.z; d1[i + 3] = v.w;
+            }
+#pragma unroll
+            for (int k = 0; k < S::K0; k += 4) {
+                float s4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                if (k + 3 < S::IN) {
+                    bwd_dot4<S::H1>(w1, k, d1, s4);
+                } else {
+#pragma unroll
+                    for (int kk = 0; kk < 4; kk++)
+                        if (k + kk < S::IN) {
+                            float sacc = 0.0f;
+#pragma unroll
+                            for (int i = 0; i < S::H1; i++) sacc = fmaf(w1[(k + kk) * S::H1 + i], d1[i], sacc);
+                            s4[kk] = sacc;
+                        }
+                }
+                dx[k] = s4[0]; dx[k + 1] = s4[1]; dx[k + 2] = s4[2]; dx[k + 3] = s4[3];
             }
             if (dX) {
 #pragma unroll
@@ -1003,39 +1168,69 @@ k_mlp_backward(Params p, TileArgs a, const float *g_out, float *dX, float *X_out
             consume_dx<ST>(p, bw, id, dx, a.level);
         }
         __syncthreads();
-        // the tile's weight and bias gradients: sums over its 128 rows
-        for (int idx = tid; idx < S::IN * S::H1; idx += 128) {
-            const int k = idx / S::H1, i = idx - k * S::H1;
-            float s = 0.0f;
-            for (int r = 0; r < 128; r++) s = fmaf(X[r * L::SX + k], D1[r * L::S1 + i], s);
-            atomicAdd(g + i * S::IN + k, s);
-        }
-        for (int idx = tid; idx < S::H1 * S::H2; idx += 128) {
-            const int i = idx / S::H2, j = idx - i * S::H2;
-            float s = 0.0f;
-            for (int r = 0; r < 128; r++) s = fmaf(A1[r * L::S1 + i], D2[r * L::S2 + j], s);
-            atomicAdd(g + G_W2 + j * S::H1 + i, s);
-        }
-        for (int idx = tid; idx < S::H2 * S::OUT; idx += 128) {
-            const int j = idx / S::OUT, o = idx - j * S::OUT;
-            float s = 0.0f;
-            for (int r = 0; r < 128; r++) s = fmaf(A2[r * L::S2 + j], D3[r * L::S3 + o], s);
-            atomicAdd(g + G_W3 + o * S::H2 + j, s);
-        }
-        for (int idx = tid; idx < S::H1 + S::H2 + S::OUT; idx += 128) {
-            float s = 0.0f;
-            if (idx < S::H1) {
-                for (int r = 0; r < 128; r++) s += D1[r * L::S1 + idx];
-                atomicAdd(g + G_B1 + idx, s);
-            } else if (idx < S::H1 + S::H2) {
-                for (int r = 0; r < 128; r++) s += D2[r * L::S2 + idx - S::H1];
-                atomicAdd(g + G_B2 + idx - S::H1, s);
-            } else {
-                for (int r = 0; r < 128; r++) s += D3[r * L::S3 + idx - S::H1 - S::H2];
-                atomicAdd(g + G_B3 + idx - S::H1 - S::H2, s);
+        // the tile's weight and bias gradients: this thread's blocks, summed over the 128 rows
+#pragma unroll 4
+        for (int r = 0; r < 128; r++) {
+            const float *tr = T + r * L::LD;
+#pragma unroll
+            for (int j = 0; j < L::PER_THREAD; j++) {
+                const float4 lv = *reinterpret_cast<const float4 *>(tr + colL[j]);
+                const float4 rv = *reinterpret_cast<const float4 *>(tr + colR[j]);
+                const float l4[4] = {lv.x, lv.y, lv.z, lv.w}, r4[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                for (int x = 0; x < 4; x++)
+#pragma unroll
+                    for (int y = 0; y < 4; y++) acc[j][4 * x + y] = fmaf(l4[x], r4[y], acc[j][4 * x + y]);
             }
         }
         __syncthreads();
+    }
+    // ABI layout of the MLP's gradient: W1 [H1][IN], b1, W2 [H2][H1], b2, W3 [OUT][H2], b3
+    float *g = dW + DwOffset<ST>::V;
+    constexpr int G_B1 = S::H1 * S::IN, G_W2 = G_B1 + S::H1, G_B2 = G_W2 + S::H2 * S::H1, G_W3 = G_B2 + S::H2,
+                  G_B3 = G_W3 + S::OUT * S::H2;
+#pragma unroll
+    for (int j = 0; j < L::PER_THREAD; j++) {
+        const int blk = tid + 128 * j;
+        if (blk >= L::NBLK) continue;
+        // out[x][y] -> g[base + x * sx + y * sy] for x < nx, y < ny
+        int base, sx = 1, sy, nx = 4, ny = 4;
+        if (blk < L::N1) {
+            const int k0 = 4 * (blk / (S::H1 / 4)), i0 = 4 * (blk % (S::H1 / 4));
+            base = i0 * S::IN + k0; sy = S::IN; nx = S::IN - k0;
+        } else if (blk < L::N1 + L::N2) {
+            const int q = blk - L::N1, i0 = 4 * (q % (S::H1 / 4)), j0 = 4 * (q / (S::H1 / 4));
+            base = G_W2 + j0 * S::H1 + i0; sy = S::H1;
+        } else if (blk < L::N1 + L::N2 + L::N3) {
+            const int q = blk - L::N1 - L::N2, j0 = 4 * (q % (S::H2 / 4)), o0 = 4 * (q / (S::H2 / 4));
+            base = G_W3 + o0 * S::H2 + j0; sy = S::H2; ny = S::OUT - o0;
+        } else {
+            const int c0 = 4 * (blk - L::N1 - L::N2 - L::N3);  // column of D1 | D2 | D3
+            nx = 1; sy = 1;
+            if (c0 < S::H1) base = G_B1 + c0;
+            else if (c0 < S::H1 + S::H2) base = G_B2 + c0 - S::H1;
+            else { base = G_B3 + c0 - S::H1 - S::H2; ny = S::OUT - (c0 - S::H1 - S::H2); }
+        }
+#pragma unroll
+        for (int x = 0; x < 4; x++)
+#pragma unroll
+            for (int y = 0; y < 4; y++)
+                if (x < nx && y < ny) atomicAdd(g + base + x * sx + y * sy, acc[j][4 * x + y]);
+    }
+}
+
+// the inputs of a message-passing level's rows, kept for the backward pass (see k_mlp_backward): one thread per row
+template <int ST>
+__global__ void __launch_bounds__(128) k_save_rows(Params p, TileArgs a, float *x_save)
+{
+    static_assert(Spec<ST>::K0 == 16, "level rows are 16 wide");
+    const int n_rows = *a.count;
+    const int list_off = a.offset ? *a.offset : 0;
+    const int32_t *list = a.list + list_off;
+    for (int row = blockIdx.x * 128 + threadIdx.x; row < n_rows; row += gridDim.x * 128) {
+        float in[16];
+        gather_row<ST>(p, a, list[row], in);
+        st16(x_save + ((size_t)list_off + row) * 16, in);
     }
 }
 

@@ -104,7 +104,7 @@ static int launch_mlp_rows(ssb_env *env, const float *x, int n, float *out, cuda
     return SSB_OK;
 }
 
-struct BackwardScratch { float *gs, *ge, *d_hdag, *d_hglob, *d_hinit, *d_msg; size_t floats; };
+struct BackwardScratch { float *gs, *ge, *d_hdag, *d_hglob, *d_hinit, *d_msg, *x_save; size_t save_rows, floats; };
 BackwardScratch backward_scratch(const Params &p, float *base)
 {
     BackwardScratch b{};
@@ -116,11 +116,16 @@ BackwardScratch backward_scratch(const Params &p, float *base)
     b.d_hglob = take((size_t)p.B * 16);
     b.d_hinit = take((size_t)p.B * p.Sc * 16);
     b.d_msg = take((size_t)p.B * p.Sc * 16);
+    // the message-passing levels' input rows, saved while the forward pass is replayed once (k_save_rows): room for
+    // three rows per node slot; a batch whose level lists are longer falls back to recomputing the levels
+    b.save_rows = std::min<size_t>((size_t)p.lvl_cap, (size_t)3 * p.B * p.Sc);
+    b.x_save = take(b.save_rows * 16);
     b.floats = off;
     return b;
 }
 int launch_mlp_backward(int stage, ssb_env *env, const int32_t *list, const int32_t *offset, const int32_t *count,
-                        int level, const float *g_out, float *dW, const bwd::Bufs &bw, cudaStream_t s);
+                        int level, const float *g_out, float *dW, const bwd::Bufs &bw, cudaStream_t s,
+                        const float *x_in = nullptr);
 template <int ST>
 int launch_tile(ssb_env *env, const int32_t *list, const int32_t *offset, const int32_t *count, int level,
                 int ctas_per_sm, cudaStream_t s)
@@ -145,10 +150,10 @@ int prepare_tile_kernel()
 }
 
 int launch_mlp_backward(int stage, ssb_env *env, const int32_t *list, const int32_t *offset, const int32_t *count,
-                        int level, const float *g_out, float *dW, const bwd::Bufs &bw, cudaStream_t s)
+                        int level, const float *g_out, float *dW, const bwd::Bufs &bw, cudaStream_t s, const float *x_in)
 {
     CUDA_TRY(bwd::mlp_backward(stage, env->p, env->num_sms, list, offset, count, level, g_out, nullptr, nullptr, dW, bw,
-                               true, s));
+                               true, x_in, s));
     return SSB_OK;
 }
 
@@ -468,9 +473,9 @@ int ssb_decima_head_backward(ssb_env *env, const float *grad_stage_logits, const
     }
     const bwd::Bufs none{nullptr, nullptr, nullptr, nullptr, nullptr};
     CUDA_TRY(bwd::mlp_backward(tc::ST_STAGE, p, env->num_sms, nullptr, nullptr, p.pl_cnt + tc::CNT_CAND, 0,
-                               grad_stage_logits, grad_stage_inputs, stage_inputs, grad_weights, none, false, s));
+                               grad_stage_logits, grad_stage_inputs, stage_inputs, grad_weights, none, false, nullptr, s));
     CUDA_TRY(bwd::mlp_backward(tc::ST_EXEC, p, env->num_sms, p.pl_exec, nullptr, p.pl_cnt + tc::CNT_EXEC, 0,
-                               grad_exec_logits, grad_exec_inputs, exec_inputs, grad_weights, none, false, s));
+                               grad_exec_logits, grad_exec_inputs, exec_inputs, grad_weights, none, false, nullptr, s));
     if (num_rows) {
         int32_t c[tc::CNT_OVERFLOW + 1];
         CUDA_TRY(cudaMemcpyAsync(c, p.pl_cnt, sizeof(c), cudaMemcpyDeviceToHost, s));
@@ -518,29 +523,65 @@ int ssb_decima_backward(ssb_env *env, const float *grad_lgprob, const float *gra
     if ((rc = launch_mlp_backward(tc::ST_DAG, env, p.pl_all, nullptr, cnt + tc::CNT_ALL, 0, nullptr, gw, bw, s))) return rc;
     if (!through_node_encoder) { SSB_MARK(env, s); return SSB_OK; }
     // NodeEncoder (scheduler.py:191-234), the levels in the reverse of the forward order.  Level k's backward needs
-    // the embeddings as they were BEFORE level k and the level's messages; the forward pass overwrites both in
-    // place, so they are recomputed: reset (PREP), sinks, levels dmax-1 .. k+1, then level k's messages.  First
-    // correct version: O(depth^2) tile passes instead of saving every level's rows.
+    // the embeddings as they were BEFORE level k (the senders' inputs) and the level's aggregated messages (the
+    // receivers' inputs); the forward pass overwrites both in place.  The forward level loop is therefore replayed
+    // ONCE here, every level's input rows saved at their list positions (k_save_rows), and the levels' backward
+    // kernels read them back -- 2 * depth tile passes.  (Round 1 recomputed reset .. level k+1 for every level k:
+    // O(depth^2) passes; that path remains for batches whose level lists exceed the save area.)
     CUDA_TRY(cudaMemsetAsync(b.d_hinit, 0, sizeof(float) * (size_t)p.B * p.Sc * 16, s));
     CUDA_TRY(cudaMemsetAsync(b.d_msg, 0, sizeof(float) * (size_t)p.B * p.Sc * 16, s));
+    int32_t hc[tc::CNT_TOTAL];  // the lists' lengths on the host: empty levels are skipped
+    CUDA_TRY(cudaMemcpyAsync(hc, p.pl_cnt, sizeof(hc), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (hc[tc::CNT_OVERFLOW]) return SSB_E_INVALID;
+    size_t lvl_rows = 0;
+    int top = 0;  // number of levels in use
     for (int k = 0; k < env->dmax; k++) {
-        if ((rc = launch_tile<tc::ST_PREP>(env, p.pl_all, nullptr, cnt + tc::CNT_ALL, 0, 4, s))) return rc;
-        if ((rc = launch_tile<tc::ST_SINK>(env, p.pl_sink, nullptr, cnt + tc::CNT_SINK, 0, 4, s))) return rc;
-        for (int j = env->dmax - 1; j > k; j--) {
-            if ((rc = launch_tile<tc::ST_MSG>(env, p.pl_lvl, cnt + tc::OFF_LVL + 2 * j, cnt + tc::CNT_LVL + 2 * j, j, 4, s)))
+        const size_t n = (size_t)hc[tc::CNT_LVL + 2 * k] + (size_t)hc[tc::CNT_LVL + 2 * k + 1];
+        if (n) top = k + 1;
+        lvl_rows += n;
+    }
+    const bool saved = lvl_rows <= b.save_rows && !getenv("SSB_BACKWARD_RECOMPUTE");
+    if (saved) {
+        if (top > 0) {
+            if ((rc = launch_tile<tc::ST_PREP>(env, p.pl_all, nullptr, cnt + tc::CNT_ALL, 0, 4, s))) return rc;
+            if ((rc = launch_tile<tc::ST_SINK>(env, p.pl_sink, nullptr, cnt + tc::CNT_SINK, 0, 4, s))) return rc;
+        }
+        for (int j = top - 1; j >= 0; j--) {
+            const int32_t *om = cnt + tc::OFF_LVL + 2 * j, *cm = cnt + tc::CNT_LVL + 2 * j;
+            CUDA_TRY(bwd::save_rows(tc::ST_MSG, p, env->num_sms, p.pl_lvl, om, cm, j, b.x_save, s));
+            if ((rc = launch_tile<tc::ST_MSG>(env, p.pl_lvl, om, cm, j, 4, s))) return rc;
+            CUDA_TRY(bwd::save_rows(tc::ST_RCV, p, env->num_sms, p.pl_lvl, om + 1, cm + 1, j, b.x_save, s));
+            if (j > 0 && (rc = launch_tile<tc::ST_RCV>(env, p.pl_lvl, om + 1, cm + 1, j, 4, s))) return rc;
+        }
+        // (level 0's receive pass is not replayed: nothing reads the embeddings after it.  They are left as of
+        // before level 0 -- the forward pass's outputs in pol_h are NOT restored; the heads' backward above has
+        // already consumed them, and the next policy / evaluate call recomputes everything.)
+        for (int k = 0; k < top; k++) {
+            const int32_t *om = cnt + tc::OFF_LVL + 2 * k, *cm = cnt + tc::CNT_LVL + 2 * k;
+            if ((rc = launch_mlp_backward(tc::ST_RCV, env, p.pl_lvl, om + 1, cm + 1, k, nullptr, gw, bw, s, b.x_save))) return rc;
+            if ((rc = launch_mlp_backward(tc::ST_MSG, env, p.pl_lvl, om, cm, k, nullptr, gw, bw, s, b.x_save))) return rc;
+        }
+    } else {
+        for (int k = 0; k < top; k++) {
+            if ((rc = launch_tile<tc::ST_PREP>(env, p.pl_all, nullptr, cnt + tc::CNT_ALL, 0, 4, s))) return rc;
+            if ((rc = launch_tile<tc::ST_SINK>(env, p.pl_sink, nullptr, cnt + tc::CNT_SINK, 0, 4, s))) return rc;
+            for (int j = top - 1; j > k; j--) {
+                if ((rc = launch_tile<tc::ST_MSG>(env, p.pl_lvl, cnt + tc::OFF_LVL + 2 * j, cnt + tc::CNT_LVL + 2 * j, j, 4, s)))
+                    return rc;
+                if ((rc = launch_tile<tc::ST_RCV>(env, p.pl_lvl, cnt + tc::OFF_LVL + 2 * j + 1,
+                                                  cnt + tc::CNT_LVL + 2 * j + 1, j, 4, s)))
+                    return rc;
+            }
+            if ((rc = launch_tile<tc::ST_MSG>(env, p.pl_lvl, cnt + tc::OFF_LVL + 2 * k, cnt + tc::CNT_LVL + 2 * k, k, 4, s)))
                 return rc;
-            if ((rc = launch_tile<tc::ST_RCV>(env, p.pl_lvl, cnt + tc::OFF_LVL + 2 * j + 1, cnt + tc::CNT_LVL + 2 * j + 1,
-                                              j, 4, s)))
+            if ((rc = launch_mlp_backward(tc::ST_RCV, env, p.pl_lvl, cnt + tc::OFF_LVL + 2 * k + 1,
+                                          cnt + tc::CNT_LVL + 2 * k + 1, k, nullptr, gw, bw, s)))
+                return rc;
+            if ((rc = launch_mlp_backward(tc::ST_MSG, env, p.pl_lvl, cnt + tc::OFF_LVL + 2 * k, cnt + tc::CNT_LVL + 2 * k, k,
+                                          nullptr, gw, bw, s)))
                 return rc;
         }
-        if ((rc = launch_tile<tc::ST_MSG>(env, p.pl_lvl, cnt + tc::OFF_LVL + 2 * k, cnt + tc::CNT_LVL + 2 * k, k, 4, s)))
-            return rc;
-        if ((rc = launch_mlp_backward(tc::ST_RCV, env, p.pl_lvl, cnt + tc::OFF_LVL + 2 * k + 1,
-                                                  cnt + tc::CNT_LVL + 2 * k + 1, k, nullptr, gw, bw, s)))
-            return rc;
-        if ((rc = launch_mlp_backward(tc::ST_MSG, env, p.pl_lvl, cnt + tc::OFF_LVL + 2 * k, cnt + tc::CNT_LVL + 2 * k, k,
-                                                  nullptr, gw, bw, s)))
-            return rc;
     }
     if ((rc = launch_mlp_backward(tc::ST_SINK, env, p.pl_sink, nullptr, cnt + tc::CNT_SINK, 0, nullptr, gw, bw, s))) return rc;
     if ((rc = launch_mlp_backward(tc::ST_PREP, env, p.pl_all, nullptr, cnt + tc::CNT_ALL, 0, nullptr, gw, bw, s))) return rc;

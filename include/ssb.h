@@ -61,8 +61,12 @@ typedef struct {
     int32_t num_executors;   /* env_cfg["num_executors"], 1..128 */
     int32_t job_arrival_cap; /* env_cfg["job_arrival_cap"]; <= 0: none (time limit required) */
     int32_t max_jobs;        /* capacity per env; >= job_arrival_cap.  Without a job cap (time-limited arrivals) an
-                                episode that needs more jobs fails at reset with SSB_ENV_CAPACITY and the env stops:
-                                size it for the longest time limit you expect (Exp-distributed limits have no bound) */
+                                episode that needs more jobs is refused at reset with SSB_ENV_CAPACITY in
+                                ssb_obs_hdr.error (never silently clipped); the capacity is carved out of the
+                                workspace once, so the remedy is a larger handle: the host layer re-creates it with
+                                twice the capacity and repeats the reset (batched_env.reset_host(grow=True), always on
+                                in the gym facade), or sizes it up front for Exp-distributed limits
+                                (required_job_capacity: geometric tail of the job count). */
     int32_t tape_capacity;   /* f64 durations per env for trace replay (0 = no replay support) */
     int32_t log_capacity;    /* event-log rows per env (0 = no event log) */
     double moving_delay;     /* ms */

@@ -30,6 +30,7 @@ class SsbConfig(C.Structure):
 
 
 FLAG_DECIMA_OBS = 1
+ENV_CAPACITY = 10  # SSB_ENV_CAPACITY (include/ssb.h)
 FLAG_DECIMA_POLICY = 2
 DECIMA_NUM_PARAMS = 20802
 

@@ -57,6 +57,15 @@ class BatchedSparkSchedSimEnv:
         if max_jobs is None:
             max_jobs = self.job_arrival_cap if self.job_arrival_cap > 0 else 256
         self.max_jobs = int(max_jobs)
+        self._ctor = (env_cfg, int(tape_capacity), int(log_capacity), bool(decima_obs), bool(decima_policy),
+                      int(history_capacity))
+        self._settings = {}   # what the setters changed on the handle (re-applied by grow())
+        self._weights = None
+        self._create()
+
+    def _create(self):
+        """(Re-)creates the native handle for self.max_jobs and maps its views."""
+        env_cfg, tape_capacity, log_capacity, decima_obs, decima_policy, history_capacity = self._ctor
         self.cfg = nat.SsbConfig(
             self.num_envs, self.num_executors, self.job_arrival_cap, self.max_jobs,
             int(tape_capacity), int(log_capacity), float(env_cfg["moving_delay"]),
@@ -122,6 +131,31 @@ class BatchedSparkSchedSimEnv:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def grow(self, max_jobs: int) -> None:
+        """Re-creates the handle with room for `max_jobs` jobs per env (node / edge / pool capacities follow).  The
+        capacity is fixed at creation (one workspace, carved once), so growing means a new handle: every env's
+        state is lost (reset afterwards); the policy weights, the auto-reset mode and the mean time limit are
+        carried over.  Time-limited arrivals without a job cap are the case that needs this: an episode that draws
+        more jobs than the capacity stops at its reset with SSB_ENV_CAPACITY (`reset_host(..., grow=True)` grows
+        and retries; `required_job_capacity` sizes the handle up front)."""
+        assert max_jobs > self.max_jobs
+        self.close()
+        self.max_jobs = int(max_jobs)
+        self._create()
+        if self._weights is not None:
+            self.set_decima_weights(self._weights)
+        if "autoreset" in self._settings:
+            self.set_autoreset(*self._settings["autoreset"])
+        if "mean_time_limit" in self._settings:
+            self.set_mean_time_limit(self._settings["mean_time_limit"])
+
+    @staticmethod
+    def required_job_capacity(job_arrival_rate: float, mean_time_limit: float, tail: float = 1e-9) -> int:
+        """Jobs per episode that Poisson arrivals (rate per ms) under an Exp(mean) time limit exceed with probability
+        `tail`: the count is geometric, P(N > n) = (rate * mean / (1 + rate * mean)) ** n  (+ the job at t = 0)."""
+        x = float(job_arrival_rate) * float(mean_time_limit)
+        return 2 + int(np.ceil(np.log(tail) / np.log(x / (1.0 + x))))
+
     def close(self):
         if getattr(self, "_h", None):
             self.L.ssb_destroy(self._h)
@@ -183,6 +217,7 @@ class BatchedSparkSchedSimEnv:
         seed + seed_step * reset_count (rollout_worker.py:118-120), ignores its action and returns the new
         episode's first observation with hdr["was_reset"] = 1."""
         nat.check(self.L.ssb_set_autoreset(self._h, int(bool(enable)), int(seed_step)), "ssb_set_autoreset")
+        self._settings["autoreset"] = (bool(enable), int(seed_step))
 
     def rollout_fair_async(self, max_decisions, rollout_duration, dynamic_partition=True, seed_step=1):
         """Fixed-duration rollouts spanning resets (RolloutWorkerAsync.collect_rollout, rollout_worker.py:160-206).
@@ -201,6 +236,7 @@ class BatchedSparkSchedSimEnv:
         """StochasticTimeLimit on the device: every reset without an explicit limit (and every auto-reset) draws
         the episode's time limit ~ Exp(mean_ms) from the episode seed's Philox LIMIT stream."""
         nat.check(self.L.ssb_set_mean_time_limit(self._h, float(mean_ms)), "ssb_set_mean_time_limit")
+        self._settings["mean_time_limit"] = float(mean_ms)
 
     def rollout_fair_traj(self, num_decisions, dynamic_partition=True, auto_reset=True, seed_step=1,
                           out: "torch.Tensor | None" = None, host: "torch.Tensor | None" = None):
@@ -224,14 +260,21 @@ class BatchedSparkSchedSimEnv:
 
     # ---------------------------------------------------------------- host-buffer API (e2e path)
     def reset_host(self, seeds: np.ndarray, time_limits: np.ndarray | None = None,
-                   mask: np.ndarray | None = None) -> np.ndarray:
+                   mask: np.ndarray | None = None, grow: bool = False, grow_limit: int = 1 << 16) -> np.ndarray:
+        """grow=True (only with mask=None, i.e. when every env is reset): if an episode needs more jobs than the
+        handle has room for (hdr["error"] == SSB_ENV_CAPACITY), the handle is re-created with twice the capacity and
+        the reset repeated -- resets are functions of the seed, so the result is what a large enough handle gives."""
         seeds = np.ascontiguousarray(seeds, dtype=np.uint64)
         tl = None if time_limits is None else np.ascontiguousarray(time_limits, dtype=np.float64)
         m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
-        nat.check(self.L.ssb_reset_host(self._h, seeds.ctypes.data, tl.ctypes.data if tl is not None else None,
-                                        m.ctypes.data if m is not None else None,
-                                        self._hdr_host.ctypes.data), "ssb_reset_host")
-        return self._hdr_host
+        while True:
+            nat.check(self.L.ssb_reset_host(self._h, seeds.ctypes.data, tl.ctypes.data if tl is not None else None,
+                                            m.ctypes.data if m is not None else None,
+                                            self._hdr_host.ctypes.data), "ssb_reset_host")
+            if not (grow and m is None and (self._hdr_host["error"] == nat.ENV_CAPACITY).any()
+                    and 2 * self.max_jobs <= grow_limit):
+                return self._hdr_host
+            self.grow(2 * self.max_jobs)
 
     def step_host(self, stage_idx: np.ndarray, num_exec: np.ndarray, mask: np.ndarray | None = None,
                   max_events: int = 0) -> np.ndarray:
@@ -376,6 +419,7 @@ class BatchedSparkSchedSimEnv:
         flat = np.ascontiguousarray(flat)
         nat.check(self.L.ssb_set_decima_weights(self._h, flat.ctypes.data, flat.size),
                   "ssb_set_decima_weights")
+        self._weights = flat
 
     def decima_policy(self, forced_stage=None, forced_num_exec=None):
         """One Decima decision per env on the device (observation adapter + GNN + sampling).

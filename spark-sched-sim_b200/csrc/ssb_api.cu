@@ -821,14 +821,17 @@ int ssb_decima_obs(ssb_env *env, void *stream)
 {
     if (!env || !env->p.dec_feat) return SSB_E_INVALID;  // needs SSB_FLAG_DECIMA_OBS
     SSB_ON_DEVICE(env);
-    k_decima_obs<<<env->grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(env->p);
-    CUDA_TRY(cudaGetLastError());
+    const int rc = ssb_i_decima_obs(env, (cudaStream_t)stream);
+    if (rc) return rc;
     SSB_MARK(env, stream);
     return SSB_OK;
 }
 
 int ssb_i_decima_obs(ssb_env *env, cudaStream_t s)
 {
+    // one CTA per env (ssb_policy.cu) unless SSB_DECIMA_ADAPTER=warp asks for the one-warp-per-env kernel (A/B)
+    static const bool warp_version = [] { const char *v = getenv("SSB_DECIMA_ADAPTER"); return v && !strcmp(v, "warp"); }();
+    if (!warp_version) return ssb_i_decima_obs_cta(env, s);
     k_decima_obs<<<env->grid, WARPS_PER_CTA * 32, 0, s>>>(env->p);
     CUDA_TRY(cudaGetLastError());
     return SSB_OK;

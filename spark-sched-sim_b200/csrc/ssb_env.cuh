@@ -126,7 +126,8 @@ extern "C" {
 int ssb_i_step_launch(ssb_env *env, const int32_t *stage_idx, const int32_t *num_exec, const uint8_t *mask,
                       int32_t max_events, int32_t *next_a, int32_t *next_n, int dyn, cudaStream_t s,
                       int force_autoreset, uint64_t force_seed_step);
-int ssb_i_decima_obs(ssb_env *env, cudaStream_t s);  // the observation adapter kernel (k_decima_obs)
+int ssb_i_decima_obs(ssb_env *env, cudaStream_t s);  // the observation adapter kernel
+int ssb_i_decima_obs_cta(ssb_env *env, cudaStream_t s);  // its one-CTA-per-env version (ssb_policy.cu)
 // ssb_policy.cu
 void ssb_i_policy_carve(Carver &cv, const ssb_config &c, const Dims &d, ssb::Params &p);
 int ssb_i_policy_init(ssb_env *env);

@@ -1,6 +1,7 @@
 // ssb_policy.cu -- the Decima policy's side of the C ABI (include/ssb.h): weights, the policy call (row lists + tile
 // kernels, or the fused kernel), stored observations and their re-evaluation, the backward pass, Decima rollouts.
 // A translation unit of its own so that nothing here sits next to the simulator kernels (see ssb_env.cuh).
+#define SSB_DECIMA_CTA_ADAPTER
 #include "ssb_env.cuh"
 #include "ssb_decima.cuh"
 #include "ssb_decima_tc.cuh"
@@ -10,6 +11,49 @@
 using namespace ssb;
 
 namespace {
+// The observation adapter (DecimaObsWrapper.observation + make_dag_layer_edge_masks), one CTA per environment:
+// pass 1, one thread per active job: the job's edge count in the observation; an exclusive scan gives every job's
+// first edge entry (its first node row is the observation's dag_ptr); pass 2: the CTA's warps take the jobs
+// round-robin (Sim::decima_obs_job_w).  Same outputs as k_decima_obs (one warp per env, jobs one after the other),
+// which stays in the simulator's translation unit for the fused policy kernel and as the A/B reference.
+constexpr int ADAPTER_WARPS = 4;
+__global__ void __launch_bounds__(ADAPTER_WARPS * 32) k_decima_obs_cta(Params p)
+{
+    extern __shared__ __align__(16) unsigned char ad_smem[];  // AdJob [Jc], then edge_off int32 [Jc]
+    __shared__ uint64_t Sk[ADAPTER_WARPS][64];
+    __shared__ int depth_s, scan_s[ADAPTER_WARPS];
+    const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    Sim sim(p, b, lane);
+    Sim::AdJob *aj = reinterpret_cast<Sim::AdJob *>(ad_smem);
+    int32_t *edge_off = reinterpret_cast<int32_t *>(aj + p.Jc);
+    const int n_active = sim.h->n_active;
+    if (tid == 0) depth_s = 0;
+    // pass 1 + block-wide exclusive scan of the edge counts, 128 jobs at a time
+    int carry = 0;
+    for (int i0 = 0; i0 < n_active; i0 += ADAPTER_WARPS * 32) {
+        const int i = i0 + tid;
+        int c = 0;
+        if (i < n_active) { aj[i] = sim.decima_job_fetch(i); c = aj[i].n_edges; }
+        int incl = c;
+        for (int off = 1; off < 32; off <<= 1) { const int v = __shfl_up_sync(FULL, incl, off); if (lane >= off) incl += v; }
+        if (lane == 31) scan_s[warp] = incl;
+        __syncthreads();
+        int base = carry;
+        for (int w = 0; w < warp; w++) base += scan_s[w];
+        if (i < n_active) edge_off[i] = base + incl - c;
+        for (int w = 0; w < ADAPTER_WARPS; w++) carry += scan_s[w];
+        __syncthreads();
+    }
+    const int ncommit = sim.num_committable(), src_job = sim.source_job_id();
+    const int32_t *dag_ptr = p.obs_dag_ptr + (size_t)b * (p.Jc + 1);
+    int D = 0;
+    for (int i = warp; i < n_active; i += ADAPTER_WARPS)
+        D = max(D, sim.decima_obs_job_w(aj[i], i, dag_ptr[i], edge_off[i], ncommit, src_job, Sk[warp]));
+    if (lane == 0 && D) atomicMax(&depth_s, D);
+    __syncthreads();
+    if (tid == 0) p.dec_depth[b] = depth_s > 1 ? depth_s - 1 : 0;
+}
+
 // rollout-buffer rows around one { policy ; step } call of ssb_rollout_decima
 // (the row index d lives in device memory so that one captured graph serves every decision of a call)
 __global__ void k_traj_pre(Params p, const int32_t *a, const int32_t *n, ssb_transition *traj, int K)
@@ -157,6 +201,13 @@ int launch_mlp_backward(int stage, ssb_env *env, const int32_t *list, const int3
     return SSB_OK;
 }
 
+
+int ssb_i_decima_obs_cta(ssb_env *env, cudaStream_t s)
+{
+    k_decima_obs_cta<<<env->p.B, ADAPTER_WARPS * 32, (sizeof(Sim::AdJob) + sizeof(int32_t)) * env->p.Jc, s>>>(env->p);
+    CUDA_TRY(cudaGetLastError());
+    return SSB_OK;
+}
 
 // The captured graph of ssb_rollout_decima holds Params and the auto-reset arguments BY VALUE: every setter that
 // changes one of them drops the graph, the next rollout call captures it again.

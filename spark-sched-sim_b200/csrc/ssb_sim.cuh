@@ -1983,6 +1983,139 @@ struct Sim {
         stage_idx = -1;
         num_exec = ncommit;
     }
+
+#ifdef SSB_DECIMA_CTA_ADAPTER
+    // ------------------------------------------------------------ Decima adapter, one CTA per environment
+    // (k_decima_obs_cta, ssb_policy.cu; compiled only there so that the simulator's translation unit is unchanged).
+    // decima_obs_w walks the active jobs one after the other -- a chain of dependent loads per job that one warp
+    // cannot hide.  Here the jobs' node offsets come from the observation's dag_ptr, their edge offsets from a count
+    // pass with one THREAD per job, and the warps of the CTA then take the jobs round-robin.
+    // what pass 2 needs of a job, fetched by pass 1 (one thread per job) into shared memory: the per-job chain of
+    // dependent loads (active list -> job record -> template -> edges) then runs for all jobs at once
+    struct AdJob { uint64_t active, sched, frontier; int32_t supply, ns, node_base, ts_base, eb, ne, j, n_edges; };
+    // pass 1 for the i-th active job; n_edges = its edges that stay in the observation (both ends active),
+    // utils.subgraph (utils.py:5-22)
+    __device__ AdJob decima_job_fetch(int i) const
+    {
+        AdJob a;
+        a.j = act[i];
+        const JobRec &J = jb[a.j];
+        a.active = J.active; a.sched = J.sched; a.frontier = J.frontier;
+        a.supply = J.supply; a.ns = J.n_stages; a.node_base = J.node_base; a.ts_base = J.ts_base;
+        a.eb = p.b_edge_base[J.tmpl];
+        a.ne = p.b_edge_base[J.tmpl + 1] - a.eb;
+        int c = 0;
+#pragma unroll 8
+        for (int k = 0; k < a.ne; k++) {
+            const int u = p.b_edges[2 * (a.eb + k)], v = p.b_edges[2 * (a.eb + k) + 1];
+            c += (int)((a.active >> u) & (a.active >> v) & 1);
+        }
+        a.n_edges = c;
+        return a;
+    }
+    // the i-th active job's share of decima_obs_w (env_wrapper.py:69-143, decima/utils.py:238-267): node rows N..,
+    // edge entries M..; returns the number of topological generations of the job's active sub-graph
+    __device__ int decima_obs_job_w(const AdJob &A, int i, int N, int M, int ncommit, int src_job, uint64_t *Sk)
+    {
+        float *feat = p.dec_feat + (size_t)b * p.Sc * 5;
+        uint8_t *smask = p.dec_stage_mask + (size_t)b * p.Sc;
+        uint8_t *fmask = p.dec_frontier_mask + (size_t)b * p.Sc;
+        uint64_t *ebits = p.dec_edge_bits + (size_t)b * p.Mc;
+        const double Ed = (double)p.E;
+        const int j = A.j;
+        const uint64_t active = A.active, sched = A.sched, frontier = A.frontier;
+        const int supply = A.supply, ns = A.ns;
+        int cap = min(max(p.E - supply, 0), ncommit);  // :74-77
+        if (j == src_job) cap = ncommit;               // :81-82
+        if (lane == 0) p.dec_caps[(size_t)b * p.Jc + i] = cap;
+        const float f0 = (float)((double)cap / Ed), f1 = (j == src_job) ? 1.0f : -1.0f, f2 = (float)((double)supply / Ed);
+        for (int s = lane; s < ns; s += 32) {
+            if (!((active >> s) & 1)) continue;
+            const StageRec r = st[A.node_base + s];
+            const int rank = N + popc64(active & (bit64(s) - 1));
+            const float rem = (float)r.remaining;
+            float *f = feat + (size_t)rank * 5;
+            f[0] = f0; f[1] = f1; f[2] = f2;
+            f[3] = __fdiv_rn(rem, 200.0f);                       // float32 / num_tasks_scale (:137)
+            f[4] = __fdiv_rn(__fmul_rn(rem, r.mrd), 100000.0f);  // float32 * float32 / work_scale (:141)
+            smask[rank] = (uint8_t)((sched >> s) & 1);
+            fmask[rank] = (uint8_t)((frontier >> s) & 1);
+        }
+        const uint64_t *pm = p.b_parent + A.ts_base, *cm = p.b_child + A.ts_base;
+        const int eb = A.eb, ne = A.ne;
+        int dj = 0;
+        if (ns <= 32) {  // one stage per lane, level sets in registers (see decima_obs_w)
+            const uint32_t act32 = (uint32_t)active;
+            const uint32_t pm32 = lane < ns ? (uint32_t)pm[lane] : 0u, cm32 = lane < ns ? (uint32_t)cm[lane] : 0u;
+            uint32_t assigned = 0;
+            uint64_t ls = 0;
+            while (assigned != act32 && dj < 64) {
+                const uint32_t open = act32 & ~assigned;
+                const bool r0 = ((open >> lane) & 1) && (pm32 & open) == 0;
+                const uint32_t Lk = __ballot_sync(FULL, r0);
+                const uint32_t S = Lk | __reduce_or_sync(FULL, r0 ? (cm32 & act32) : 0u);
+                if ((S >> lane) & 1) ls |= bit64(dj);
+                assigned |= Lk;
+                dj++;
+                if (Lk == 0) break;  // cannot happen in a DAG
+            }
+            Sk[lane] = ls;
+            __syncwarp();
+            for (int k0 = 0; k0 < ne; k0 += 32) {
+                const int k = k0 + lane;
+                int u = 0, v = 0;
+                bool keep = false;
+                if (k < ne) {
+                    u = p.b_edges[2 * (eb + k)];
+                    v = p.b_edges[2 * (eb + k) + 1];
+                    keep = ((act32 >> u) & 1) && ((act32 >> v) & 1);
+                }
+                const unsigned m = __ballot_sync(FULL, keep);
+                if (keep) ebits[M + __popc(m & ((1u << lane) - 1))] = Sk[u] & Sk[v];
+                M += __popc(m);
+            }
+        } else {
+            uint64_t assigned = 0;
+            while (assigned != active && dj < 64) {
+                const uint64_t open = active & ~assigned;
+                const int s0 = lane, s1 = lane + 32;
+                const bool r0 = s0 < ns && ((open >> s0) & 1) && (pm[s0] & open) == 0;
+                const bool r1 = s1 < ns && ((open >> s1) & 1) && (pm[s1] & open) == 0;
+                const uint64_t Lk = (uint64_t)__ballot_sync(FULL, r0) | ((uint64_t)__ballot_sync(FULL, r1) << 32);
+                const uint64_t mine = ((r0 ? cm[s0] : 0ull) | (r1 ? cm[s1] : 0ull)) & active;
+                const uint64_t succ = (uint64_t)__reduce_or_sync(FULL, (uint32_t)mine) |
+                                      ((uint64_t)__reduce_or_sync(FULL, (uint32_t)(mine >> 32)) << 32);
+                if (lane == 0) Sk[dj] = Lk | succ;
+                assigned |= Lk;
+                dj++;
+                if (Lk == 0) break;
+            }
+            __syncwarp();
+            for (int k0 = 0; k0 < ne; k0 += 32) {
+                const int k = k0 + lane;
+                int u = 0, v = 0;
+                bool keep = false;
+                if (k < ne) {
+                    u = p.b_edges[2 * (eb + k)];
+                    v = p.b_edges[2 * (eb + k) + 1];
+                    keep = ((active >> u) & 1) && ((active >> v) & 1);
+                }
+                const unsigned m = __ballot_sync(FULL, keep);
+                if (keep) {
+                    uint64_t bits = 0;
+                    for (int q = 0; q < dj; q++) {
+                        const uint64_t S = Sk[q];
+                        if (((S >> u) & 1) && ((S >> v) & 1)) bits |= bit64(q);
+                    }
+                    ebits[M + __popc(m & ((1u << lane) - 1))] = bits;
+                }
+                M += __popc(m);
+            }
+        }
+        __syncwarp();
+        return dj;
+    }
+#endif
 };
 
 }  // namespace ssb

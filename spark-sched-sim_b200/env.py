@@ -68,7 +68,9 @@ class SparkSchedSimEnv(Env):
         if seed is None:
             self._auto_seed += 1
             seed = (1 << 40) + self._auto_seed
-        hdr = self._batched.reset_host(np.array([seed], np.uint64), np.array([time_limit], np.float64))
+        # time-limited arrivals without a job cap: the handle grows until the episode's jobs fit (the reference's
+        # job list is unbounded, spark_sched_sim.py:150-154)
+        hdr = self._batched.reset_host(np.array([seed], np.uint64), np.array([time_limit], np.float64), grow=True)
         self._raise_on_error(int(hdr[0]["error"]))
         # per-episode host state starts empty (:145, :173); job_duration_buff survives resets (:83)
         self.jobs = {}

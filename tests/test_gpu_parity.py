@@ -346,6 +346,42 @@ def test_rollout_with_time_limit_truncation(bank):
     assert n_trunc > 0
 
 
+def test_capacity_is_reported_and_the_handle_grows(bank):
+    """Time-limited arrivals without a job cap on a handle that is too small: the reset reports SSB_ENV_CAPACITY
+    (nothing is clipped), reset_host(grow=True) re-creates the handle with twice the room until the episodes fit, and
+    the grown handle's rollout equals the oracle's -- i.e. what a large enough handle gives."""
+    import torch
+    from spark_sched_sim_b200 import _native as nat
+    from spark_sched_sim_b200.batched_env import BatchedSparkSchedSimEnv
+
+    B, K, TL = 4, 200, 4.0e5
+    cfg = {"num_executors": 10, "job_arrival_cap": 0, "job_arrival_rate": 4.0e-5,
+           "moving_delay": 2000.0, "warmup_delay": 1000.0}
+    env = BatchedSparkSchedSimEnv(cfg, num_envs=B, bank=bank, max_jobs=4)
+    env.set_autoreset(True, 50)
+    seeds = np.arange(900, 900 + B, dtype=np.uint64)
+    hdr = env.reset_host(seeds, time_limits=np.full(B, TL))
+    assert (hdr["error"] == nat.ENV_CAPACITY).any()
+    hdr = env.reset_host(seeds, time_limits=np.full(B, TL), grow=True)
+    assert (hdr["error"] == 0).all() and env.max_jobs > 4
+    assert env._settings["autoreset"] == (True, 50)
+    host = torch.empty(B * K * nat.TRANSITION_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+    # a grown handle can still be too small for a LATER episode of the rollout: size it for the tail first
+    need = BatchedSparkSchedSimEnv.required_job_capacity(cfg["job_arrival_rate"], TL, tail=1e-12)
+    if env.max_jobs < need:
+        env.grow(need)
+        env.reset_host(seeds, time_limits=np.full(B, TL))
+    tr = env.rollout_fair_traj(K, True, auto_reset=True, seed_step=50, host=host)
+    assert (env.hdr()["error"] == 0).all()
+    for b in range(B):
+        rows, _ = _oracle_transitions(bank, cfg, seeds[b], 50, K, time_limit=TL)
+        for k, (wall0, rew, a, n, term, trunc) in enumerate(rows):
+            r = tr[b, k]
+            assert (r["wall_time"], r["reward"], r["stage_idx"], r["num_exec"]) == (wall0, rew, a, n), (b, k)
+    # the geometric tail: with rate * limit = 16 jobs on average, 1e-12 is a few hundred jobs
+    assert 100 < need < 1000
+
+
 def test_step_api_autoreset_matches_oracle(bank):
     """ssb_set_autoreset: a step() on a finished env re-seeds it (seed + seed_step * reset_count), ignores the
     action and flags was_reset; the sequence of real transitions equals the oracle loop with explicit resets."""

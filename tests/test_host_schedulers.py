@@ -39,6 +39,49 @@ def test_host_policies_reproduce_recorded_actions(name):
         assert info == {}
 
 
+def _reference_policy(tr):
+    """The reference's own scheduler object for a recorded trace, or None outside the build container."""
+    import os.path as osp
+    import sys
+
+    sys.path.insert(0, osp.join(osp.dirname(osp.dirname(osp.abspath(__file__))), "oracle"))
+    import refrun
+
+    if not refrun.reference_available():
+        return None
+    refrun.setup()
+    return refrun.make_policy(tr["policy"], tr["num_executors"], tr["policy_seed"])
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names(slim=False) if not n.startswith("decima_")][:8])
+def test_reference_schedulers_agree_on_the_same_observations(name):
+    """The UNMODIFIED reference schedulers (imported from /root/reference, build container only) and this package's
+    classes, side by side on every recorded observation: same action, and the same keys left in the observation
+    dict.  Together with the GPU facade test (the facade's observations equal the recorded ones bit for bit) this is
+    "the reference's schedulers run on the facade unchanged"."""
+    import copy
+
+    tr = load_golden(name)
+    ref = _reference_policy(tr)
+    if ref is None:
+        pytest.skip("reference not present (GPU box)")
+    if tr["policy"] in ("fair", "fifo"):
+        ours = RoundRobinScheduler(tr["num_executors"], dynamic_partition=(tr["policy"] == "fair"))
+    else:
+        ours = RandomScheduler(seed=tr["policy_seed"])
+    assert ours.name == ref.name
+    for k, obs in enumerate(recorded_obs(tr)):
+        if k == len(tr["actions"]):
+            break
+        o_ref, o_ours = copy.deepcopy(obs), copy.deepcopy(obs)
+        a_ref, i_ref = ref.schedule(o_ref)
+        a_ours, i_ours = ours.schedule(o_ours)
+        assert {k_: int(v) for k_, v in a_ref.items()} == {k_: int(v) for k_, v in a_ours.items()}, k
+        assert i_ref == i_ours == {}
+        assert {int(x) for x in o_ref["frontier_stages"]} == o_ours["frontier_stages"]
+        assert {int(a): int(b) for a, b in o_ref["schedulable_stages"].items()} == o_ours["schedulable_stages"]
+
+
 def test_make_scheduler_factory():
     s = make_scheduler({"agent_cls": "RoundRobinScheduler", "num_executors": 10, "dynamic_partition": False})
     assert s.name == "FIFO"

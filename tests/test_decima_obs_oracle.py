@@ -40,3 +40,14 @@ def test_mask_helpers_roundtrip():
     em = decima_obs.edge_masks_from_bits(bits, 3)
     assert em.tolist() == [[True, False, False], [False, True, False], [True, False, False]]
     assert decima_obs.edge_masks_from_bits(bits, 0).shape == (0, 3)
+
+
+def test_float32_division_equals_the_reference_double_then_float32():
+    """The CTA adapter (Sim::decima_obs_job_w) computes cap / E and supply / E with one float32 division; the
+    reference divides Python floats (double) and stores into a float32 array (env_wrapper.py:110-127).  Same bits
+    for every integer pair the adapter can see (0 <= x <= E <= 128)."""
+    for E in range(1, 129):
+        x = np.arange(0, E + 1)
+        via_double = (x.astype(np.float64) / np.float64(E)).astype(np.float32)
+        direct = x.astype(np.float32) / np.float32(E)
+        assert (via_double == direct).all(), E

@@ -571,7 +571,7 @@ def run_decima(cx, args, with_update: bool):
     # multiple of that (operand splitting for fp32 accuracy, padded K / N), stated separately
     useful_tflops = 2.0 * work["macs"] / (pol_ms * 1e-3) / 1e12
     roofline = {
-        "bound": "tensor", "kernel": "ssb_decima_policy (k_decima_obs, planning, k_tile_mlp<*> x levels, sampling)",
+        "bound": "tensor", "kernel": "ssb_decima_policy (k_decima_obs_cta, planning, k_tile3<*> x (6 + 2 x depth), sampling)",
         "achieved": useful_tflops, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": useful_tflops / pk["tensor"],
         "traffic": None, "peak_source": pk["src"], "policy_call_ms": pol_ms, "rows": work,
         "useful_macs_per_call": work["macs"], "launches_per_call": "see profiles/ launch list",

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SSB_ABI_VERSION 5
+#define SSB_ABI_VERSION 6
 
 /* status codes of the entry points */
 enum {
@@ -392,6 +392,12 @@ int ssb_decima_snapshot_unload(ssb_env *env, void *stream);
  * (it reads the lists' lengths).
  * scratch: DEVICE, ssb_decima_backward_bytes, 16-byte aligned. */
 int ssb_decima_backward_bytes(ssb_env *env, size_t *bytes);
+/* Attaches (NULL: detaches) the scratch the coming ssb_decima_backward calls will be given.  While attached,
+ * ssb_decima_evaluate stores every message-passing level's input rows into it as a by-product of its forward pass
+ * (the tile kernels write the rows they gathered), and an ssb_decima_backward with this scratch that follows such an
+ * evaluation skips its own replay of the levels.  (List-driven policy modes; the fused small-batch kernel and any
+ * other policy call in between fall back to the replay.) */
+int ssb_decima_attach_backward_scratch(ssb_env *env, void *scratch);
 int ssb_decima_backward(ssb_env *env, const float *grad_lgprob, const float *grad_entropy, float *grad_weights,
                         float *grad_node_embeddings, int32_t through_node_encoder, void *scratch, void *stream);
 /* First stage of the backward pass of evaluate_actions -- the adjoint of utils.evaluate (decima/utils.py:26-42:

@@ -9,7 +9,7 @@ import numpy as np
 
 PKG_DIR = osp.dirname(osp.abspath(__file__))
 LIB_PATH = osp.join(PKG_DIR, "_lib", "libssb.so")
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 class SsbConfig(C.Structure):
@@ -143,7 +143,7 @@ EXPORTS = [
     "ssb_rollout_fair", "ssb_rollout_fair_traj", "ssb_rollout_fair_async", "ssb_discounted_returns", "ssb_differential_returns", "ssb_group_baselines", "ssb_ppo_loss", "ssb_adam_step", "ssb_fair_actions", "ssb_get_views", "ssb_get_stats", "ssb_collect_stats", "ssb_reset_stats",
     "ssb_get_jobs", "ssb_get_log", "ssb_get_history", "ssb_decima_obs", "ssb_get_decima_views",
     "ssb_set_decima_weights", "ssb_decima_policy", "ssb_rollout_decima", "ssb_rollout_decima_async", "ssb_decima_snapshot_bytes",
-    "ssb_decima_snapshot", "ssb_decima_snapshot_gather", "ssb_decima_snapshot_load", "ssb_decima_snapshot_unload", "ssb_decima_evaluate", "ssb_decima_head_adjoint", "ssb_decima_head_backward", "ssb_decima_backward_bytes", "ssb_decima_backward", "ssb_get_policy_views", "ssb_decima_work", "ssb_decima_mlp_rows", "ssb_packed_obs_bytes", "ssb_get_obs_host", "ssb_get_debug_counters",
+    "ssb_decima_snapshot", "ssb_decima_snapshot_gather", "ssb_decima_snapshot_load", "ssb_decima_snapshot_unload", "ssb_decima_evaluate", "ssb_decima_head_adjoint", "ssb_decima_head_backward", "ssb_decima_backward_bytes", "ssb_decima_attach_backward_scratch", "ssb_decima_backward", "ssb_get_policy_views", "ssb_decima_work", "ssb_decima_mlp_rows", "ssb_packed_obs_bytes", "ssb_get_obs_host", "ssb_get_debug_counters",
 ]
 
 _lib = None
@@ -194,6 +194,7 @@ def lib():
     L.ssb_decima_head_adjoint.argtypes = [vp, vp, vp, vp, vp, vp]
     L.ssb_decima_head_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(i32), vp]
     L.ssb_decima_backward_bytes.argtypes = [vp, C.POINTER(C.c_size_t)]
+    L.ssb_decima_attach_backward_scratch.argtypes = [vp, vp]
     L.ssb_decima_backward.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp]
     L.ssb_decima_snapshot_load.argtypes = [vp, vp, vp]
     L.ssb_decima_snapshot_unload.argtypes = [vp, vp]

@@ -498,10 +498,26 @@ class BatchedSparkSchedSimEnv:
     def decima_snapshot_unload(self):
         nat.check(self.L.ssb_decima_snapshot_unload(self._h, self._stream()), "ssb_decima_snapshot_unload")
 
-    def decima_evaluate(self, snapshot: "torch.Tensor | None", stage_sel, exec_sel):
+    def _backward_scratch(self) -> torch.Tensor:
+        """The backward pass's scratch, allocated once and attached to the handle: evaluations then leave the
+        message-passing levels' input rows in it and decima_backward does not have to replay the levels."""
+        n = C.c_size_t()
+        nat.check(self.L.ssb_decima_backward_bytes(self._h, C.byref(n)), "ssb_decima_backward_bytes")
+        if getattr(self, "_bwd_scratch", None) is None or self._bwd_scratch.numel() < n.value:
+            self._bwd_scratch = torch.empty(n.value, dtype=torch.uint8, device=self.device)
+            self._bwd_attached = None
+        if getattr(self, "_bwd_attached", None) != (self._h.value, self._bwd_scratch.data_ptr()):
+            nat.check(self.L.ssb_decima_attach_backward_scratch(self._h, self._bwd_scratch.data_ptr()),
+                      "ssb_decima_attach_backward_scratch")
+            self._bwd_attached = (self._h.value, self._bwd_scratch.data_ptr())
+        return self._bwd_scratch
+
+    def decima_evaluate(self, snapshot: "torch.Tensor | None", stage_sel, exec_sel, for_backward: bool = False):
         """DecimaScheduler.evaluate_actions (forward only) on a stored snapshot (None: the one decima_snapshot_load
         put in place): (lgprobs, entropies) f32[B] for the given Decima-format actions; the envs themselves are
-        left untouched."""
+        left untouched.  for_backward: a decima_backward call follows (the forward pass keeps what it needs)."""
+        if for_backward:
+            self._backward_scratch()
         a = self._dev(stage_sel, torch.int32)
         n = self._dev(exec_sel, torch.int32)
         lg = torch.empty(self.num_envs, dtype=torch.float32, device=self.device)
@@ -552,10 +568,7 @@ class BatchedSparkSchedSimEnv:
         above NodeEncoder (score heads, global and job summaries only) and returns d loss / d node embeddings
         [B, node_stride, 16]; otherwise the returned buffer is working storage."""
         assert grad_weights.is_cuda and grad_weights.dtype == torch.float32 and grad_weights.numel() == 20802
-        n = C.c_size_t()
-        nat.check(self.L.ssb_decima_backward_bytes(self._h, C.byref(n)), "ssb_decima_backward_bytes")
-        if getattr(self, "_bwd_scratch", None) is None or self._bwd_scratch.numel() < n.value:
-            self._bwd_scratch = torch.empty(n.value, dtype=torch.uint8, device=self.device)
+        self._backward_scratch()
         d_h = torch.empty(self.num_envs, self.pol_stage_logits.shape[1], 16, dtype=torch.float32, device=self.device)
         nat.check(self.L.ssb_decima_backward(self._h, grad_lgprob.data_ptr(), grad_entropy.data_ptr(),
                                              grad_weights.data_ptr(), d_h.data_ptr(), int(through_node_encoder),

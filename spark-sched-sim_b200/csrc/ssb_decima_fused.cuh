@@ -407,6 +407,10 @@ __global__ void __launch_bounds__(128, Spec<ST>::OUT > 1 ? 8 : 4) k_tile3(Params
             }
         } else {
             fused::gather<ST>(p, id, a.level, in);
+            if constexpr (ST == tc::ST_MSG || ST == tc::ST_RCV) {
+                const int pos = (a.offset ? *a.offset : 0) + row;
+                if (a.x_save && id >= 0 && pos < a.x_cap) st16(a.x_save + (size_t)pos * 16, *reinterpret_cast<float(*)[16]>(in));
+            }
         }
         mlp_tile<ST, COLS>(g, tsm, in, o);
         tc::scatter_row<ST>(p, id, o);

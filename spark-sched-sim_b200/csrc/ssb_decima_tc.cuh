@@ -218,6 +218,10 @@ struct TileArgs {
     const int32_t *offset;  // device pointer to the list's first index in `list` (nullptr: 0)
     const int32_t *count;   // device pointer to the list length
     int level;              // ST_RCV: the message-passing level whose masked edges are aggregated
+    // ST_MSG / ST_RCV, optional: the rows' gathered inputs are also stored at x_save[list position] (positions below
+    // x_cap) -- what the backward pass of the level needs once the embeddings have been overwritten
+    float *x_save = nullptr;
+    int x_cap = 0;
 };
 
 // ------------------------------------------------------------------ gather / scatter of one row
@@ -414,6 +418,10 @@ __device__ __forceinline__ void run_tile(const Params &p, const TileArgs &a, con
         {
             float in[S::K0];
             gather_row<ST>(p, a, id, in);
+            if constexpr (ST == ST_MSG || ST == ST_RCV) {
+                const int pos = (a.offset ? *a.offset : 0) + row;
+                if (a.x_save && id >= 0 && pos < a.x_cap) st16(a.x_save + (size_t)pos * 16, *reinterpret_cast<float(*)[16]>(in));
+            }
             if (STAMPS && tile == (int)blockIdx.x) TC_STAMP(3);
             write_a_row<S::K0>(a_hi, a_lo, tid, in);
         }

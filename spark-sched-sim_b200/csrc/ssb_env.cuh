@@ -114,6 +114,8 @@ struct ssb_env {
     int dg_k, dg_events, dg_autoreset, no_graph;
     uint64_t dg_seed_step;
     int policy_mode;    // POLICY_* below (SSB_DECIMA_MODE overrides the default)
+    void *bw_scratch;   // ssb_decima_attach_backward_scratch
+    int bw_saved;       // the last policy evaluation left its levels' input rows in bw_scratch
     int fused_group;    // environments per group of the fused policy kernel
     int snap_loaded;    // ssb_decima_snapshot_load: a stored observation is in place, the live one parked
     int auto_reset;     // ssb_set_autoreset

@@ -172,9 +172,11 @@ int launch_mlp_backward(int stage, ssb_env *env, const int32_t *list, const int3
                         const float *x_in = nullptr);
 template <int ST>
 int launch_tile(ssb_env *env, const int32_t *list, const int32_t *offset, const int32_t *count, int level,
-                int ctas_per_sm, cudaStream_t s)
+                int ctas_per_sm, cudaStream_t s, float *x_save = nullptr, size_t x_cap = 0)
 {
     tc::TileArgs a{list, offset, count, level};
+    a.x_save = x_save;
+    a.x_cap = (int)std::min<size_t>(x_cap, 0x7fffffff);
     if (env->policy_mode == POLICY_TILES_TF32)
         tc::k_tile_mlp<ST><<<env->num_sms * ctas_per_sm, 128, tc::Smem<ST>::BYTES, s>>>(env->p, a);
     else
@@ -332,10 +334,11 @@ static int replan(ssb_env *env, cudaStream_t s)
 // advance_draws = false: the Philox policy stream of the envs is left where it is (pure evaluation)
 static int decima_policy_impl(ssb_env *env, const int32_t *forced_stage, const int32_t *forced_num_exec,
                               int32_t *stage_idx_out, int32_t *num_exec_out, bool run_adapter, bool advance_draws,
-                              cudaStream_t s, const uint8_t *active = nullptr)
+                              cudaStream_t s, const uint8_t *active = nullptr, bool save_levels = false)
 {
     Params p = env->p;
     p.pol_active = active;
+    env->bw_saved = 0;
     if (env->policy_mode == POLICY_FUSED) {
         // the whole decision of every env in one persistent kernel (ssb_decima_fused.cuh)
         CUDA_TRY(cudaMemsetAsync(p.fz_cursor, 0, sizeof(int32_t) * 4, s));
@@ -359,11 +362,20 @@ static int decima_policy_impl(ssb_env *env, const int32_t *forced_stage, const i
     CUDA_TRY(cudaGetLastError());
     if ((rc = launch_tile<tc::ST_PREP>(env, p.pl_all, nullptr, cnt + tc::CNT_ALL, 0, 4, s))) return rc;
     if ((rc = launch_tile<tc::ST_SINK>(env, p.pl_sink, nullptr, cnt + tc::CNT_SINK, 0, 4, s))) return rc;
+    // (an evaluation with the backward pass's scratch attached leaves every level's input rows there)
+    float *xs = nullptr;
+    size_t xcap = 0;
+    if (save_levels && env->bw_scratch) {
+        const BackwardScratch bs = backward_scratch(p, static_cast<float *>(env->bw_scratch));
+        xs = bs.x_save;
+        xcap = bs.save_rows;
+    }
+    env->bw_saved = xs != nullptr;
     for (int k = env->dmax - 1; k >= 0; k--) {  // reversed(edge_masks) (scheduler.py:214-232)
-        if ((rc = launch_tile<tc::ST_MSG>(env, p.pl_lvl, cnt + tc::OFF_LVL + 2 * k, cnt + tc::CNT_LVL + 2 * k, k, 4, s)))
+        if ((rc = launch_tile<tc::ST_MSG>(env, p.pl_lvl, cnt + tc::OFF_LVL + 2 * k, cnt + tc::CNT_LVL + 2 * k, k, 4, s, xs, xcap)))
             return rc;
         if ((rc = launch_tile<tc::ST_RCV>(env, p.pl_lvl, cnt + tc::OFF_LVL + 2 * k + 1, cnt + tc::CNT_LVL + 2 * k + 1,
-                                          k, 4, s)))
+                                          k, 4, s, xs, xcap)))
             return rc;
     }
     if ((rc = launch_tile<tc::ST_DAG>(env, p.pl_all, nullptr, cnt + tc::CNT_ALL, 0, 4, s))) return rc;
@@ -538,6 +550,14 @@ int ssb_decima_head_backward(ssb_env *env, const float *grad_stage_logits, const
     return SSB_OK;
 }
 
+int ssb_decima_attach_backward_scratch(ssb_env *env, void *scratch)
+{
+    if (!env || !env->p.pol_w || (reinterpret_cast<uintptr_t>(scratch) & 15)) return SSB_E_INVALID;
+    env->bw_scratch = scratch;
+    env->bw_saved = 0;
+    return SSB_OK;
+}
+
 int ssb_decima_backward_bytes(ssb_env *env, size_t *bytes)
 {
     if (!env || !bytes || !env->p.pol_w) return SSB_E_INVALID;
@@ -594,16 +614,20 @@ int ssb_decima_backward(ssb_env *env, const float *grad_lgprob, const float *gra
     }
     const bool saved = lvl_rows <= b.save_rows && !getenv("SSB_BACKWARD_RECOMPUTE");
     if (saved) {
-        if (top > 0) {
+        // the rows are already there when the evaluation this call differentiates ran with this scratch attached
+        const bool have = env->bw_saved && env->bw_scratch == scratch && env->policy_mode != POLICY_FUSED;
+        if (top > 0 && !have) {
             if ((rc = launch_tile<tc::ST_PREP>(env, p.pl_all, nullptr, cnt + tc::CNT_ALL, 0, 4, s))) return rc;
             if ((rc = launch_tile<tc::ST_SINK>(env, p.pl_sink, nullptr, cnt + tc::CNT_SINK, 0, 4, s))) return rc;
         }
-        for (int j = top - 1; j >= 0; j--) {
+        for (int j = top - 1; j >= 0 && !have; j--) {
             const int32_t *om = cnt + tc::OFF_LVL + 2 * j, *cm = cnt + tc::CNT_LVL + 2 * j;
-            CUDA_TRY(bwd::save_rows(tc::ST_MSG, p, env->num_sms, p.pl_lvl, om, cm, j, b.x_save, s));
-            if ((rc = launch_tile<tc::ST_MSG>(env, p.pl_lvl, om, cm, j, 4, s))) return rc;
-            CUDA_TRY(bwd::save_rows(tc::ST_RCV, p, env->num_sms, p.pl_lvl, om + 1, cm + 1, j, b.x_save, s));
-            if (j > 0 && (rc = launch_tile<tc::ST_RCV>(env, p.pl_lvl, om + 1, cm + 1, j, 4, s))) return rc;
+            if ((rc = launch_tile<tc::ST_MSG>(env, p.pl_lvl, om, cm, j, 4, s, b.x_save, b.save_rows))) return rc;
+            if (j > 0) {
+                if ((rc = launch_tile<tc::ST_RCV>(env, p.pl_lvl, om + 1, cm + 1, j, 4, s, b.x_save, b.save_rows))) return rc;
+            } else {
+                CUDA_TRY(bwd::save_rows(tc::ST_RCV, p, env->num_sms, p.pl_lvl, om + 1, cm + 1, j, b.x_save, s));
+            }
         }
         // (level 0's receive pass is not replayed: nothing reads the embeddings after it.  They are left as of
         // before level 0 -- the forward pass's outputs in pol_h are NOT restored; the heads' backward above has
@@ -697,7 +721,7 @@ int ssb_decima_evaluate(ssb_env *env, const void *snapshot, const int32_t *stage
     int rc;
     if (snapshot && (rc = ssb_decima_snapshot_load(env, snapshot, stream))) return rc;
     // whatever happens below, a snapshot this call loaded is unloaded again (the live observation comes back)
-    rc = decima_policy_impl(env, stage_sel, exec_sel, nullptr, nullptr, false, false, s);
+    rc = decima_policy_impl(env, stage_sel, exec_sel, nullptr, nullptr, false, false, s, nullptr, true);
     if (!rc && lgprob_out &&
         cudaMemcpyAsync(lgprob_out, env->p.pol_lgprob, B * 4, cudaMemcpyDeviceToDevice, s) != cudaSuccess) rc = SSB_E_CUDA;
     if (!rc && entropy_out &&

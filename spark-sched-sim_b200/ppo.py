@@ -100,7 +100,7 @@ def ppo_minibatch_update(env, snapshot, stage_sel, exec_sel, old_lgprob, returns
     B = env.num_envs
     env.decima_snapshot_load(snapshot)
     try:
-        lg, en = env.decima_evaluate(None, stage_sel, exec_sel)
+        lg, en = env.decima_evaluate(None, stage_sel, exec_sel, for_backward=True)
         out, g_lp, g_en = loss_fn(lg, old_lgprob, en, returns, baselines)
         info = dict(zip(PPOLoss.KEYS, out.tolist()))
         if allreduce is not None:
@@ -216,7 +216,7 @@ def _evaluate_slots(env, store, staging, ks, bs):
     kk, bb = ks.clamp(min=0).long(), bs.clamp(min=0).long()
     stage_sel = store.stage_sel[kk, bb].contiguous()
     exec_sel = store.exec_sel[kk, bb].contiguous()
-    return env.decima_evaluate(None, stage_sel, exec_sel)
+    return env.decima_evaluate(None, stage_sel, exec_sel, for_backward=True)
 
 
 def ppo_train_samples(env, store: RolloutStore, returns: torch.Tensor, baselines: torch.Tensor, loss_fn: PPOLoss,

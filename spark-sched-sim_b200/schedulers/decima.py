@@ -112,7 +112,7 @@ class DecimaScheduler(Scheduler):
         env.decima_snapshot_gather(store.snapshots, ks, bs, out=self._staging)
         env.decima_snapshot_load(self._staging)
         self._pending = n
-        lg, en = env.decima_evaluate(None, stage_sel, exec_sel)
+        lg, en = env.decima_evaluate(None, stage_sel, exec_sel, for_backward=True)
         return {"lgprobs": lg[:n], "entropies": en[:n]}
 
     def update_parameters(self, loss=None) -> None:

@@ -745,14 +745,21 @@ def test_decima_async_rollouts_match_the_workers_loop(bank):
 
 
 @pytest.mark.parametrize("fixture", ["decima_grads_e10_j8_s5", "decima_grads_e50_j14_s4"])
-def test_backward_matches_the_reference_models_gradients(fixture):
-    """ssb_decima_evaluate + ssb_decima_backward against gradients recorded from the UNMODIFIED reference
+@pytest.mark.parametrize("mode,for_backward", [(None, False), ("0", False), ("0", True)],
+                         ids=["fused-replay", "tiles-replay", "tiles-saved-by-evaluate"])
+def test_backward_matches_the_reference_models_gradients(fixture, mode, for_backward, monkeypatch):
+    """(mode: the policy's execution mode for this small batch -- default = the fused kernel, "0" = the list-driven tile
+    kernels; for_backward: the evaluation leaves the levels' input rows in the attached scratch and the backward pass
+    does not replay them.)
+    ssb_decima_evaluate + ssb_decima_backward against gradients recorded from the UNMODIFIED reference
     DecimaScheduler (tests/golden/gen_decima_grad_golden.py: its own evaluate_actions, scheduler.py:101-139, and
     loss.backward() on a batch of observations of a recorded episode).  Env i replays the episode up to observation
     picks[i] and stops there; one evaluate / backward over the B live observations must reproduce the reference's
     lgprobs, entropies and all 42 parameter gradients (each tensor within 5e-4 of its largest entry: fp32 atomics)."""
     from spark_sched_sim_b200.batched_env import BatchedSparkSchedSimEnv
 
+    if mode is not None:
+        monkeypatch.setenv("SSB_DECIMA_MODE", mode)
     g = np.load(osp.join(GOLDEN_DIR, fixture + ".npz"))
     tr = load_golden(str(g["trace"]))
     picks = [int(k) for k in g["picks"]]
@@ -775,7 +782,7 @@ def test_backward_matches_the_reference_models_gradients(fixture):
     exec_sel = torch.tensor([int(tr["pol_actions"][k][2]) for k in picks], dtype=torch.int32, device="cuda")
     snap = env.decima_snapshot()
     env.decima_snapshot_load(snap)
-    lg, en = env.decima_evaluate(None, stage_sel, exec_sel)
+    lg, en = env.decima_evaluate(None, stage_sel, exec_sel, for_backward=for_backward)
     assert np.abs(lg.cpu().numpy() - g["lgprobs"]).max() < 2e-5
     assert np.abs(en.cpu().numpy() - g["entropies"]).max() < 2e-5
     grads = torch.zeros(20802, dtype=torch.float32, device="cuda")

@@ -131,7 +131,7 @@ class _StubEnv:
     def decima_snapshot_unload(self):
         self.loaded -= 1
 
-    def decima_evaluate(self, snapshot, stage_sel, exec_sel):
+    def decima_evaluate(self, snapshot, stage_sel, exec_sel, for_backward=False):
         return torch.zeros(4), torch.zeros(4)
 
     def decima_backward(self, g_lp, g_en, grads):

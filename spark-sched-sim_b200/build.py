@@ -23,15 +23,23 @@ NVCC_FLAGS = [
 ]
 
 
+LAST: dict = {}  # what the last build() call did (path, compiled or up to date, seconds, the nvcc command line)
+
+
 def build(force: bool = False, verbose: bool = False, variant: str | None = None,
           extra: list[str] | None = None) -> str:
     out = OUT if variant is None else osp.join(PKG_DIR, "_lib", f"libssb_{variant}.so")
-    if not force and osp.exists(out) and all(osp.getmtime(d) <= osp.getmtime(out) for d in DEPS):
-        return out
-    os.makedirs(osp.dirname(out), exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc] + NVCC_FLAGS + (extra or []) + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + SRC
+    if not force and osp.exists(out) and all(osp.getmtime(d) <= osp.getmtime(out) for d in DEPS):
+        LAST.update(path=out, compiled=False, seconds=0.0, command=" ".join(cmd))
+        return out
+    os.makedirs(osp.dirname(out), exist_ok=True)
+    import time
+
+    t0 = time.time()
     subprocess.check_call(cmd)
+    LAST.update(path=out, compiled=True, seconds=time.time() - t0, command=" ".join(cmd))
     return out
 
 

@@ -357,11 +357,22 @@ __global__ void __launch_bounds__(128) k_mlp_rows(const uint32_t *blob_all, cons
 // One MLP over a row list built by the planning kernels (ssb_decima_tc.cuh: all nodes, sinks, the senders / receivers
 // of one level, jobs, schedulable stages, executor-count rows): the launch sequence of round 1 with the tile routine
 // above.  128 threads = one warpgroup per CTA, 128 TMEM columns, four CTAs per SM.
+#ifndef SSB_TILE3_GATHER_CTAS
+#define SSB_TILE3_GATHER_CTAS 5
+#endif
+#ifndef SSB_TILE3_CTAS
+#define SSB_TILE3_CTAS 8
+#endif
 namespace fused {
 template <int ST> __device__ __forceinline__ void gather(const Params &p, int id, int level, float *in);
 }
+// resident CTAs per SM a stage's kernel is compiled for: eight 64-column TMEM contexts for the GNN MLPs, except the two
+// gather-heavy stages (receivers: children's messages, jobs: the job's node rows; four 16-float rows in flight), which
+// spill ~290 B per thread at the 64-register cap of eight -- six (85 registers) keeps them in registers; four 128-column
+// contexts for the score heads
+template <int ST> constexpr int tile3_ctas() { return Spec<ST>::OUT > 1 ? ((ST == tc::ST_RCV || ST == tc::ST_GLOB) ? SSB_TILE3_GATHER_CTAS : SSB_TILE3_CTAS) : 4; }
 template <int ST>
-__global__ void __launch_bounds__(128, Spec<ST>::OUT > 1 ? 8 : 4) k_tile3(Params p, tc::TileArgs a)
+__global__ void __launch_bounds__(128, tile3_ctas<ST>()) k_tile3(Params p, tc::TileArgs a)
 {
     using S = Spec<ST>;
     using L = Blob<ST>;

@@ -180,7 +180,7 @@ int launch_tile(ssb_env *env, const int32_t *list, const int32_t *offset, const 
     if (env->policy_mode == POLICY_TILES_TF32)
         tc::k_tile_mlp<ST><<<env->num_sms * ctas_per_sm, 128, tc::Smem<ST>::BYTES, s>>>(env->p, a);
     else
-        fz::k_tile3<ST><<<env->num_sms * (fz::Spec<ST>::OUT > 1 ? 2 * ctas_per_sm : ctas_per_sm), 128,
+        fz::k_tile3<ST><<<env->num_sms * (ctas_per_sm >= 4 ? fz::tile3_ctas<ST>() : ctas_per_sm), 128,
                           sizeof(uint32_t) * fz::Blob<ST>::WORDS, s>>>(env->p, a);
     CUDA_TRY(cudaGetLastError());
     return SSB_OK;

@@ -360,6 +360,9 @@ __global__ void __launch_bounds__(128) k_mlp_rows(const uint32_t *blob_all, cons
 #ifndef SSB_TILE3_GATHER_CTAS
 #define SSB_TILE3_GATHER_CTAS 5
 #endif
+#ifndef SSB_RCV_DEPTH
+#define SSB_RCV_DEPTH 3
+#endif
 #ifndef SSB_TILE3_CTAS
 #define SSB_TILE3_CTAS 8
 #endif
@@ -506,27 +509,28 @@ __device__ __forceinline__ void gather(const Params &p, int id, int level, float
         const int32_t *edges = p.obs_edges + (size_t)b * p.Mc * 2;
         const uint64_t *ebits = p.dec_edge_bits + (size_t)b * p.Mc;
         const int M = p.obs_hdr[b].num_edges;
-        for (int e0 = p.pol_row_start[id]; e0 < M; e0 += 4) {  // (a parent's edges are contiguous; four in flight)
-            int2 uv[4];
-            uint64_t bits[4];
+        constexpr int RD = SSB_RCV_DEPTH;  // edges / message rows in flight
+        for (int e0 = p.pol_row_start[id]; e0 < M; e0 += RD) {  // (a parent's edges are contiguous; RD in flight: 3 with 96 registers measured best)
+            int2 uv[RD];
+            uint64_t bits[RD];
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
+            for (int q = 0; q < RD; q++) {
                 const int e = e0 + q < M ? e0 + q : M - 1;
                 uv[q] = *reinterpret_cast<const int2 *>(edges + 2 * e);
                 bits[q] = ebits[e];
             }
-            bool use[4], more = true;
+            bool use[RD], more = true;
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
+            for (int q = 0; q < RD; q++) {
                 more = more && e0 + q < M && uv[q].x == u;
                 use[q] = more && ((bits[q] >> level) & 1);
             }
-            float m[4][16];
+            float m[RD][16];
 #pragma unroll
-            for (int q = 0; q < 4; q++)
+            for (int q = 0; q < RD; q++)
                 if (use[q]) ld16(p.pol_msg + ((size_t)b * p.Sc + uv[q].y) * 16, m[q]);
 #pragma unroll
-            for (int q = 0; q < 4; q++)
+            for (int q = 0; q < RD; q++)
                 if (use[q]) {
 #pragma unroll
                     for (int i = 0; i < 16; i++) in[i] += m[q][i];

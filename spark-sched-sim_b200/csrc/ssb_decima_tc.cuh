@@ -322,12 +322,11 @@ __device__ __forceinline__ void scatter_row(const Params &p, int id, const float
     if (id < 0) return;
     if constexpr (ST == ST_PREP) {
         st16(p.pol_h_init + (size_t)id * 16, *reinterpret_cast<const float(*)[16]>(out));
-        // _forward_no_mp (:236-241) when the observation has no edge masks; otherwise h starts at 0 (:204)
-        float h0[16];
-        const bool no_mp = p.dec_depth[id / p.Sc] == 0;
-#pragma unroll
-        for (int i = 0; i < 16; i++) h0[i] = no_mp ? out[i] : 0.0f;
-        st16(p.pol_h + (size_t)id * 16, h0);
+        // _forward_no_mp (:236-241) when the observation has no edge masks: h = h_init.  Otherwise the reference
+        // starts h at 0 (:204) -- not stored here: every node is then either a sink (no masked edge as a parent: h =
+        // update(h_init), the SINK pass) or a receiver at one level at least (h = h_init + update(agg)), and both
+        // passes write h before anything reads it (a level's senders were written by the sink pass or a deeper level).
+        if (p.dec_depth[id / p.Sc] == 0) st16(p.pol_h + (size_t)id * 16, *reinterpret_cast<const float(*)[16]>(out));
     } else if constexpr (ST == ST_SINK) {
         st16(p.pol_h + (size_t)id * 16, *reinterpret_cast<const float(*)[16]>(out));
     } else if constexpr (ST == ST_MSG) {

@@ -17,6 +17,9 @@
 #include "ssb_env.cuh"
 #include "ssb_sim.cuh"
 
+#ifndef SSB_NS1_CTAS
+#define SSB_NS1_CTAS 7  // resident CTAs per SM of the one-slot kernels: 4096 envs = 1024 CTAs of 4 warps must all be resident
+#endif
 #ifndef SSB_NS2_CTAS
 #define SSB_NS2_CTAS 5  // resident CTAs per SM the two-slot kernels (E > 32) are compiled for (96 registers; A/B in profiles/r02_ns2_occupancy.txt)
 #endif
@@ -43,7 +46,7 @@ k_reset(Params p, const uint64_t *seeds, const double *time_limits, const uint8_
 
 // NS: executor slots per lane of the batched fast path (1: E <= 32, 2: E <= 64), see ssb_sim.cuh
 template <int NS>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, NS == 1 ? 7 : SSB_NS2_CTAS)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, NS == 1 ? SSB_NS1_CTAS : SSB_NS2_CTAS)
 k_step(Params p, const int32_t *stage_idx, const int32_t *num_exec, const uint8_t *mask, int max_events,
        int auto_reset, uint64_t seed_step, int32_t *next_a, int32_t *next_n, int dynamic_partition)
 {
@@ -95,7 +98,7 @@ k_fair_actions(Params p, int dynamic_partition, int32_t *stage_idx, int32_t *num
 // 148 SMs; at 80 registers only 6 fit and the last 136 CTAs run as a second wave, +37 % time.
 // Two-slot kernel: 4 CTAs per SM = 128 registers, what it needs without spilling.)
 template <int NS>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, NS == 1 ? 7 : SSB_NS2_CTAS)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, NS == 1 ? SSB_NS1_CTAS : SSB_NS2_CTAS)
 k_rollout_fair(Params p, int num_decisions, int dynamic_partition, int auto_reset, uint64_t seed_step,
                ssb_transition *traj)
 {
@@ -149,7 +152,7 @@ k_rollout_fair(Params p, int num_decisions, int dynamic_partition, int auto_rese
 // simulated time reaches `duration` (or after max_decisions rows), resets do not end it, and the time axis of the
 // stored rows is that accumulated time.  (A kernel of its own, so that the default rollout kernel stays as measured.)
 template <int NS>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, NS == 1 ? 7 : SSB_NS2_CTAS)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, NS == 1 ? SSB_NS1_CTAS : SSB_NS2_CTAS)
 k_rollout_fair_async(Params p, int max_decisions, double duration, int dynamic_partition, uint64_t seed_step,
                      ssb_transition *traj, int32_t *num_steps, double *elapsed_out)
 {

@@ -1,7 +1,7 @@
 """A/B timing of the fused fair rollout (C2 unless overridden) for one build of the library.
 
 Usage on the GPU box:  SSB_LIB=/path/to/libssb_x.so python profiles/ab_rollout.py
-Env: AB_SEED_GROUP (G consecutive envs share a seed = run as twins; 1), AB_B (envs, 4096), AB_E (10), AB_J (50), AB_K (decisions per launch, 128), AB_ITERS (5)."""
+Env: AB_SEED_GROUP (G consecutive envs share a seed = run as twins; 1), AB_B (envs, 4096), AB_E (10), AB_J (50), AB_K (decisions per launch, 128), AB_PRE (untimed decisions per env first, 0), AB_ITERS (5)."""
 import os
 import os.path as osp
 import sys
@@ -23,6 +23,8 @@ cfg = {"num_executors": E, "job_arrival_cap": J, "job_arrival_rate": 4.0e-5,
 env = BatchedSparkSchedSimEnv(cfg, num_envs=B)
 G = int(os.environ.get("AB_SEED_GROUP", "1"))
 env.reset_host((1234 + np.arange(B) // G).astype(np.uint64))
+if int(os.environ.get("AB_PRE", "0")) > 0:  # untimed decisions first (mid-episode state, as bench.py's C4)
+    env.rollout_fair(int(os.environ["AB_PRE"]), True, True, B)
 for _ in range(3):
     env.rollout_fair(K, True, True, B)
 torch.cuda.synchronize()

@@ -585,6 +585,10 @@ def run_decima(cx, args, with_update: bool):
         "note": "K <= 64 three-layer MLP chains over gathered rows: bound by the per-layer hand-off and the launch "
                 "sequence, not by the tensor pipe; the fraction is reported, not hidden",
     }
+    tp = osp.join(REPO, "profiles", "policy_tensor_pipe.json")
+    if osp.exists(tp):  # sm__pipe_tensor_cycles_active of the tile kernels, from the committed ncu capture
+        with open(tp) as f:
+            roofline["tensor_pipe"] = json.load(f)
     # e2e: the rollout-collection call with every slab of transitions copied to pinned host memory (wall clock)
     env.reset_stats()
     barrier(cx)

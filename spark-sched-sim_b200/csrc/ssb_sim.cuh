@@ -1138,6 +1138,38 @@ struct Sim {
         }
         out[0] = aa; out[1] = ab; out[2] = ba; out[3] = bb;
     }
+    // The 32-bit order keys tie (with 50 pending events equal event times are common): instead of redoing all 64 x 64
+    // comparisons exactly (exact_less2_w), find the lanes that hold a pending event whose key equals one of another
+    // pending event's keys (U) and redo the comparisons against THOSE lanes only, on the full (t, seq) pairs.  Pairs
+    // whose keys differ are ordered by the keys (floor(16 t) is monotone in t), so the masks come out exact.
+    __device__ SSB_RARE void refine_ties2_w(uint32_t hia, uint32_t hib, bool pa, bool pb, unsigned penda, unsigned pendb,
+                                             unsigned long long kta, uint32_t ksa, unsigned long long ktb, uint32_t ksb,
+                                             unsigned *m)
+    {
+        unsigned tie = 0;
+#pragma unroll 1
+        for (int i = 0; i < 32; i++) {
+            const uint32_t oa = __shfl_sync(FULL, hia, i), ob = __shfl_sync(FULL, hib, i);
+            const bool ia = (penda >> i) & 1, ib = (pendb >> i) & 1;
+            const bool t = (pa && ((ia && oa == hia && i != lane) || (ib && ob == hia))) ||
+                           (pb && ((ia && oa == hib) || (ib && ob == hib && i != lane)));
+            tie |= t ? 1u << i : 0u;
+        }
+        unsigned U = __reduce_or_sync(FULL, tie);
+        unsigned aa = m[0], ab = m[1], ba = m[2], bb = m[3];
+        while (U) {
+            const int i = __ffs((int)U) - 1;
+            U &= U - 1;
+            const unsigned long long ota = __shfl_sync(FULL, kta, i), otb = __shfl_sync(FULL, ktb, i);
+            const uint32_t osa = __shfl_sync(FULL, ksa, i), osb = __shfl_sync(FULL, ksb, i);
+            const unsigned bit = 1u << i;
+            aa = (aa & ~bit) | ((ota < kta || (ota == kta && osa < ksa)) ? bit : 0u);
+            ab = (ab & ~bit) | ((otb < kta || (otb == kta && osb < ksa)) ? bit : 0u);
+            ba = (ba & ~bit) | ((ota < ktb || (ota == ktb && osa < ksb)) ? bit : 0u);
+            bb = (bb & ~bit) | ((otb < ktb || (otb == ktb && osb < ksb)) ? bit : 0u);
+        }
+        m[0] = aa; m[1] = ab; m[2] = ba; m[3] = bb;
+    }
     __device__ __forceinline__ int fast_batch2_w(HotLane &A, HotLane &Bq, const Same2 &S, HotEnv &H, int budget)
     {
         const unsigned long long INF_BITS = 0x7ff0000000000000ull;
@@ -1166,8 +1198,8 @@ struct Sim {
             const unsigned long long seen = (unsigned long long)__reduce_or_sync(FULL, (uint32_t)mine) |
                                             ((unsigned long long)__reduce_or_sync(FULL, (uint32_t)(mine >> 32)) << 32);
             if (seen != (n >= 64 ? ~0ull : (1ull << n) - 1ull)) {
-                unsigned ex4[4];
-                exact_less2_w(A.kt, A.ks, Bq.kt, Bq.ks, ex4);
+                unsigned ex4[4] = {aa, ab, ba, bb};
+                refine_ties2_w(hia, hib, pa, pb, penda, pendb, A.kt, A.ks, Bq.kt, Bq.ks, ex4);
                 aa = ex4[0] & penda; ab = ex4[1] & pendb; ba = ex4[2] & penda; bb = ex4[3] & pendb;
                 ranka = __popc(aa) + __popc(ab); rankb = __popc(ba) + __popc(bb);
             }

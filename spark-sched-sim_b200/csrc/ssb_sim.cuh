@@ -129,10 +129,14 @@ __device__ SSB_RARE void ps_resize(PSet<T> &s, int minused, T *tmp)  // set_tabl
     while (newsize <= minused) newsize <<= 1;
     int oldmask = s.mask;
     if (newsize == 8 && oldmask == 7 && s.fill == s.used) return;
+    // (tables are at least 8 entries and 8-byte aligned: copy and fill in 64-bit words, EMPTY is all ones)
+    {
+        unsigned long long *t8 = reinterpret_cast<unsigned long long *>(s.t), *m8 = reinterpret_cast<unsigned long long *>(tmp);
 #pragma unroll 1
-    for (int i = 0; i <= oldmask; i++) tmp[i] = s.t[i];
+        for (int i = 0; i < (oldmask + 1) * (int)sizeof(T) / 8; i++) m8[i] = t8[i];
 #pragma unroll 1
-    for (int i = 0; i < newsize; i++) s.t[i] = (T)PSet<T>::EMPTY;
+        for (int i = 0; i < newsize * (int)sizeof(T) / 8; i++) t8[i] = ~0ull;
+    }
     s.mask = newsize - 1;
     s.fill = s.used;
 #pragma unroll 1

@@ -223,8 +223,10 @@ __device__ SSB_RARE void ps_copy_into(PSet<T> &dst, T *table, const PSet<T> &oth
     if (other.used == 0) return;
     if (other.used * 5 >= 7 * 3) ps_resize(dst, other.used * 2, tmp);
     if (dst.mask == other.mask && other.fill == other.used) {
+        const unsigned long long *o8 = reinterpret_cast<const unsigned long long *>(other.t);
+        unsigned long long *d8 = reinterpret_cast<unsigned long long *>(dst.t);
 #pragma unroll 1
-        for (int i = 0; i <= other.mask; i++) dst.t[i] = other.t[i];
+        for (int i = 0; i < (other.mask + 1) * (int)sizeof(T) / 8; i++) d8[i] = o8[i];
         dst.fill = other.fill; dst.used = other.used;
         return;
     }

@@ -1438,8 +1438,9 @@ struct Sim {
         ps_init(ids, tab);
 #pragma unroll 1
         for (int i = 0; i < n_old; i++) ps_add(ids, old[i], tmp);
+        // (the new list = survivors of the old one, already in the set, + the arrivals, whose ids are larger)
 #pragma unroll 1
-        for (int i = 0; i < n_new; i++) ps_add(ids, act[i], tmp);
+        for (int i = 0; i < n_new; i++) if (act[i] > last_old) ps_add(ids, act[i], tmp);
         for (int i = 0; i <= ids.mask; i++)
             if (ids.t[i] < PSet<uint16_t>::DUMMY) ord[k++] = (int16_t)ids.t[i];
         return k;

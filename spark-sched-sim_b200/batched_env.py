@@ -281,10 +281,25 @@ class BatchedSparkSchedSimEnv:
         a = np.ascontiguousarray(stage_idx, dtype=np.int32)
         n = np.ascontiguousarray(num_exec, dtype=np.int32)
         m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
-        nat.check(self.L.ssb_step_host(self._h, a.ctypes.data, n.ctypes.data,
-                                       m.ctypes.data if m is not None else None, int(max_events),
-                                       self._hdr_host.ctypes.data), "ssb_step_host")
+        nat.check(self.L.ssb_step_host(self._h, self._ptr(a), self._ptr(n),
+                                       self._ptr(m) if m is not None else None, int(max_events),
+                                       self._ptr(self._hdr_host)), "ssb_step_host")
         return self._hdr_host
+
+    def _ptr(self, arr: np.ndarray) -> int:
+        """Address of a host array for the C ABI.  `arr.ctypes.data` builds a ctypes helper object on every access
+        (2 us each, five per step call); callers of the host-buffer API pass the same few (pinned) arrays call after call,
+        so the addresses of the last arrays seen are kept -- together with the arrays themselves, which keeps an id from
+        being reused by another object."""
+        c = self.__dict__.setdefault("_ptr_cache", {})
+        ent = c.get(id(arr))
+        if ent is not None and ent[0] is arr:
+            return ent[1]
+        if len(c) >= 16:
+            c.clear()
+        ptr = arr.ctypes.data
+        c[id(arr)] = (arr, ptr)
+        return ptr
 
     def step_fair_host(self, stage_idx: np.ndarray, num_exec: np.ndarray, next_stage_idx: np.ndarray,
                        next_num_exec: np.ndarray, dynamic_partition: bool = True, mask: np.ndarray | None = None,
@@ -295,10 +310,10 @@ class BatchedSparkSchedSimEnv:
         n = np.ascontiguousarray(num_exec, dtype=np.int32)
         m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
         assert next_stage_idx.dtype == np.int32 and next_num_exec.dtype == np.int32
-        nat.check(self.L.ssb_step_fair_host(self._h, a.ctypes.data, n.ctypes.data,
-                                            m.ctypes.data if m is not None else None, int(max_events),
-                                            int(dynamic_partition), self._hdr_host.ctypes.data,
-                                            next_stage_idx.ctypes.data, next_num_exec.ctypes.data),
+        nat.check(self.L.ssb_step_fair_host(self._h, self._ptr(a), self._ptr(n),
+                                            self._ptr(m) if m is not None else None, int(max_events),
+                                            int(dynamic_partition), self._ptr(self._hdr_host),
+                                            self._ptr(next_stage_idx), self._ptr(next_num_exec)),
                   "ssb_step_fair_host")
         return self._hdr_host
 
